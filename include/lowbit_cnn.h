@@ -1,0 +1,179 @@
+/*
+ * lowbit_cnn.h — C ABI of liblowbit-cnn (B200 / sm_100a int8 convolution library).
+ *
+ * This is the drop-in boundary for the reference's int8 convolution path.  The reference
+ * (alnfedorov/lowbitdnn-project) has no shared library: its operators are header-only C++
+ * templates over at::Tensor that are #included into the drivers.  Every entry point below
+ * names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   lbc_conv_plan_create / lbc_conv_run   <- conv2DForward3x3<batch,inC,outC,inH,inW,outH,outW>(Tensor,Tensor)
+ *                                            cpp/int8conv/conv2DForward3x3TensorCores.cuh:695-751 (host wrapper)
+ *                                            and the kernel it launches, :537-693
+ *   lbc_conv_prepack_weights              <- to_vect_c(kernel) + .contiguous() at
+ *                                            cpp/int8conv/check.cu:72,77 and ...TensorCores.cuh:715-716
+ *   lbc_to_vect_c / lbc_from_vect_c       <- to_vect_c / from_vect_c, cpp/int8conv/utils.cuh:11-26
+ *   epilogue (bias, scale, RNE, clamp)    <- quantize(), cpp/int8conv/conv2DForward3x3WinogradFused.cuh:39-46
+ *                                            _Quantize.forward, python/qtorch/nn/functional/quantization.py:27-49
+ *   elapsed_ms out-parameter              <- std::tuple<Tensor,float> second element (cudaEvent timing),
+ *                                            ...TensorCores.cuh:734-750
+ *   lbc_net_*                             <- the conv->relu chains of python/tmp.py:43-56 driven as one unit
+ *                                            (benchmark apps: cpp/apps/benchmark.cpp:54-81)
+ *
+ * Conventions
+ *   - Activations: int8, NHWC, dense.  Weights: int8, [K][R][S][C/groups] ("KRSC") or OIHW on input to prepack.
+ *   - Accumulation: exact int32 (two's-complement wraparound), cross-correlation (no kernel flip),
+ *     same orientation as refConv2DForwardImpl (cpp/int8conv/refConv2DForward.hpp:24-51).
+ *   - Epilogue (LBC_OUT_INT8):  t = acc + bias[k] (int32 wraparound); f = (float)t (round-to-nearest-even);
+ *     f = f * scale[k] (one fp32 multiply, no FMA); q = rint(f) (round-half-to-even);
+ *     q = clamp(q, relu ? 0 : -128, 127); store int8 NHWC.
+ *     LBC_OUT_INT32 stores t = acc + bias[k] (bias may be NULL -> 0) as int32 NHWC, no scaling.
+ *   - All buffers are caller-owned DEVICE pointers unless the function name ends in _host.
+ *   - Every function returns an lbc_status; nothing throws across this boundary.
+ *   - There is no CPU fallback: every compute entry point fails with LBC_ERR_NO_DEVICE when no
+ *     sm_100 device is usable.
+ */
+#ifndef LOWBIT_CNN_H
+#define LOWBIT_CNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBC_VERSION_MAJOR 0
+#define LBC_VERSION_MINOR 1
+
+typedef enum lbc_status {
+    LBC_OK = 0,
+    LBC_ERR_INVALID_ARG = 1,     /* NULL pointer, zero dimension, inconsistent descriptor            */
+    LBC_ERR_UNSUPPORTED = 2,     /* descriptor is valid but no kernel covers it                       */
+    LBC_ERR_NO_DEVICE = 3,       /* no CUDA device / not compute capability 10.x                      */
+    LBC_ERR_CUDA = 4,            /* a CUDA runtime/driver call failed; see lbc_last_error_string()    */
+    LBC_ERR_ALLOC = 5,           /* host or device allocation failed                                  */
+    LBC_ERR_KERNEL_TIMEOUT = 6   /* a device-side pipeline wait exceeded its watchdog (bug guard)     */
+} lbc_status;
+
+typedef enum lbc_out_mode {
+    LBC_OUT_INT8 = 0,            /* fused bias + per-channel scale + RNE + [relu] + saturate -> int8  */
+    LBC_OUT_INT32 = 1            /* raw accumulators (+ optional bias) -> int32                       */
+} lbc_out_mode;
+
+typedef enum lbc_weight_layout {
+    LBC_W_KRSC = 0,              /* [K][R][S][C/groups]  (NHWC-style filters)                         */
+    LBC_W_OIHW = 1               /* [K][C/groups][R][S]  (reference layout, refConv2DForward.hpp:27)  */
+} lbc_weight_layout;
+
+typedef enum lbc_kernel_kind {
+    LBC_KERNEL_AUTO = 0,         /* planner decides                                                   */
+    LBC_KERNEL_DIRECT = 1,       /* CUDA-core direct convolution (any shape)                          */
+    LBC_KERNEL_IGEMM_TC = 2,     /* tcgen05 implicit GEMM (TMA im2col + TMEM accumulators)            */
+    LBC_KERNEL_DEPTHWISE = 3,    /* CUDA-core depthwise (groups == C == K)                            */
+    LBC_KERNEL_STEM_TC = 4       /* tcgen05 GEMM over an in-kernel im2col for tiny C (C <= 4)         */
+} lbc_kernel_kind;
+
+/* Plain-old-data convolution descriptor.  All sizes in elements. */
+typedef struct lbc_conv_desc {
+    int32_t n, h, w, c;          /* input  NHWC                                                       */
+    int32_t k, r, s;             /* K filters of R x S x (C/groups)                                   */
+    int32_t stride_h, stride_w;
+    int32_t pad_h, pad_w;        /* symmetric zero padding                                            */
+    int32_t dil_h, dil_w;
+    int32_t groups;
+    int32_t relu;                /* 0/1, only used by LBC_OUT_INT8                                    */
+    int32_t out_mode;            /* lbc_out_mode                                                      */
+} lbc_conv_desc;
+
+typedef struct lbc_plan lbc_plan;     /* opaque, immutable after creation, thread-safe to share      */
+typedef struct lbc_net  lbc_net;      /* opaque: a fixed chain/list of planned convolutions           */
+typedef void* lbc_stream;             /* a cudaStream_t (NULL = legacy default stream)                */
+
+/* ---- library / device --------------------------------------------------------------------------- */
+int         lbc_version(void);                       /* major*1000 + minor                            */
+const char* lbc_last_error_string(void);             /* thread-local, never NULL                      */
+lbc_status  lbc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes);
+
+/* ---- shape helpers (pure host arithmetic; usable without a GPU) ------------------------------- */
+/* (in + 2p - (d(k-1)+1))/s + 1 : cpp/int8conv/cudnn2DConvolution.cuh:33-36 */
+lbc_status  lbc_conv_out_shape(const lbc_conv_desc* d, int32_t* p, int32_t* q);
+/* ops = 2*N*P*Q*K*(C/g)*R*S ; bytes = N*H*W*C + K*(C/g)*R*S + N*P*Q*K*out_elt + 8*K   */
+lbc_status  lbc_conv_work(const lbc_conv_desc* d, double* ops, double* bytes);
+
+/* ---- planning --------------------------------------------------------------------------------- */
+/* Chooses kernel + tiling for `d` on the current device.  `force` = LBC_KERNEL_AUTO for the planner's
+ * choice, or a specific kind (fails with LBC_ERR_UNSUPPORTED if that kernel cannot run the shape). */
+lbc_status  lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan);
+lbc_status  lbc_conv_plan_destroy(lbc_plan* plan);
+lbc_status  lbc_conv_plan_kernel(const lbc_plan* plan, int32_t* kind);           /* lbc_kernel_kind   */
+lbc_status  lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_len); /* human-readable */
+/* Number of kernels one lbc_conv_run() launches (for launch accounting in the harness). */
+lbc_status  lbc_conv_plan_launches(const lbc_plan* plan, int32_t* launches);
+
+/* ---- weights ---------------------------------------------------------------------------------- */
+/* Size in bytes of the packed-weight buffer the plan's kernel wants. */
+lbc_status  lbc_conv_packed_weight_bytes(const lbc_plan* plan, size_t* bytes);
+/* Re-lays `w_dev` (device, int8, `layout`) into the plan's kernel layout at `dst_dev` (device). */
+lbc_status  lbc_conv_prepack_weights(const lbc_plan* plan, const int8_t* w_dev, int32_t layout,
+                                     void* dst_dev, lbc_stream stream);
+
+/* ---- execution -------------------------------------------------------------------------------- */
+/* Asynchronous on `stream`.  If elapsed_ms != NULL the call brackets the launch with events on
+ * `stream`, synchronises, and returns the device time (the reference's `(out, ms)` convention). */
+lbc_status  lbc_conv_run(const lbc_plan* plan, const int8_t* x_nhwc, const void* w_packed,
+                         const int32_t* bias, const float* scale, void* y_nhwc,
+                         lbc_stream stream, float* elapsed_ms);
+
+/* Same, but x / y are HOST buffers (pinned or pageable); H2D and D2H copies are issued on `stream`
+ * around the kernel and the call returns after the result is in y_host.  w/bias/scale stay on device. */
+lbc_status  lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const void* w_packed,
+                              const int32_t* bias, const float* scale, void* y_host,
+                              lbc_stream stream, float* elapsed_ms);
+
+/* ---- layout converters (reference tensor formats) -------------------------------------------- */
+/* NCHW int8/int32 -> [N][C/V][H][W][V]  (utils.cuh:20-26) and back (utils.cuh:11-17). elt = 1 or 4. */
+lbc_status  lbc_to_vect_c(const void* src_nchw, void* dst_vect, int32_t n, int32_t c, int32_t h, int32_t w,
+                          int32_t v, int32_t elt_bytes, lbc_stream stream);
+lbc_status  lbc_from_vect_c(const void* src_vect, void* dst_nchw, int32_t n, int32_t c, int32_t h, int32_t w,
+                            int32_t v, int32_t elt_bytes, lbc_stream stream);
+/* NHWC <-> [N][C/V][H][W][V]: the regroup the reference-signature shims need around lbc_conv_run. */
+lbc_status  lbc_nhwc_to_vect_c(const void* src_nhwc, void* dst_vect, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t v, int32_t elt_bytes, lbc_stream stream);
+lbc_status  lbc_vect_c_to_nhwc(const void* src_vect, void* dst_nhwc, int32_t n, int32_t c, int32_t h, int32_t w,
+                               int32_t v, int32_t elt_bytes, lbc_stream stream);
+/* NCHW <-> NHWC (callers holding refConv2DForward-format tensors). */
+lbc_status  lbc_nchw_to_nhwc(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                             int32_t elt_bytes, lbc_stream stream);
+lbc_status  lbc_nhwc_to_nchw(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
+                             int32_t elt_bytes, lbc_stream stream);
+
+/* ---- networks: a list of convolutions run back to back (benchmark apps) ------------------------ */
+/* `input_of[i]` = index of the layer whose OUTPUT feeds layer i, or -1 for the network input.  The
+ * network owns its packed weights, bias, scale and activation buffers (synthetic or caller-loaded). */
+lbc_status  lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers, lbc_net** net);
+lbc_status  lbc_net_destroy(lbc_net* net);
+lbc_status  lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan** plan);
+/* Load parameters for one layer from HOST memory (weights in `layout`, bias int32[K], scale f32[K]). */
+lbc_status  lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w_host, int32_t layout,
+                                    const int32_t* bias_host, const float* scale_host);
+/* Device pointers of a layer's input/output activations (valid until lbc_net_destroy). */
+lbc_status  lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_dev, void** y_dev);
+/* Run all layers on `stream` with the network input already resident in HBM (x_dev NHWC of layer(s)
+ * with input_of == -1).  per_layer_ms (may be NULL) receives n_layers event-timed durations. */
+lbc_status  lbc_net_run(lbc_net* net, const int8_t* x_dev, lbc_stream stream, float* per_layer_ms, float* total_ms);
+/* End to end: x_host -> (H2D) -> all layers -> (D2H) -> y_host (the last layer's output). */
+lbc_status  lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lbc_stream stream, float* total_ms);
+lbc_status  lbc_net_launches(const lbc_net* net, int32_t* launches);
+
+/* ---- measurement helpers (cpp/libbenchmark role) ---------------------------------------------- */
+/* MMA-only tcgen05 kind::i8 peak probe: returns achieved dense int8 TOPS on the current device. */
+lbc_status  lbc_probe_int8_mma_peak(int32_t iters, double* tops, lbc_stream stream);
+/* Streaming-copy probe (int4 loads/stores), GB/s read+write. */
+lbc_status  lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stream stream);
+/* Writes `bytes` of zeros to an internal scratch buffer to evict L2 (timing hygiene). */
+lbc_status  lbc_flush_l2(lbc_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOWBIT_CNN_H */
