@@ -1,0 +1,94 @@
+"""ctypes declarations for include/lowbit_cnn.h.  The library is REQUIRED: nothing here falls back to
+PyTorch or to the CPU oracle — a missing or unloadable liblowbit_cnn.so raises immediately."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liblowbit_cnn.so")
+
+LBC_OK = 0
+STATUS_NAMES = {0: "LBC_OK", 1: "LBC_ERR_INVALID_ARG", 2: "LBC_ERR_UNSUPPORTED", 3: "LBC_ERR_NO_DEVICE",
+                4: "LBC_ERR_CUDA", 5: "LBC_ERR_ALLOC", 6: "LBC_ERR_KERNEL_TIMEOUT"}
+OUT_INT8, OUT_INT32 = 0, 1
+W_KRSC, W_OIHW = 0, 1
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_IGEMM_TC, KERNEL_DEPTHWISE, KERNEL_STEM_TC = 0, 1, 2, 3, 4
+KERNEL_NAMES = {1: "direct", 2: "igemm_tc", 3: "depthwise", 4: "stem_tc"}
+
+
+class LbcError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class CConvDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "n", "h", "w", "c", "k", "r", "s", "stride_h", "stride_w", "pad_h", "pad_w",
+        "dil_h", "dil_w", "groups", "relu", "out_mode")]
+
+
+_vp = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_PROTOS = {
+    "lbc_version": (ctypes.c_int, []),
+    "lbc_last_error_string": (ctypes.c_char_p, []),
+    "lbc_device_info": (ctypes.c_int, [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
+    "lbc_conv_out_shape": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
+    "lbc_conv_work": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "lbc_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _i32, ctypes.POINTER(_vp)]),
+    "lbc_conv_plan_destroy": (ctypes.c_int, [_vp]),
+    "lbc_conv_plan_kernel": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
+    "lbc_conv_plan_describe": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
+    "lbc_conv_plan_launches": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
+    "lbc_conv_packed_weight_bytes": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    "lbc_conv_prepack_weights": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
+    "lbc_conv_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "lbc_conv_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "lbc_to_vect_c": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
+    "lbc_from_vect_c": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
+    "lbc_nhwc_to_vect_c": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
+    "lbc_vect_c_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
+    "lbc_nchw_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i32] * 5 + [_vp]),
+    "lbc_nhwc_to_nchw": (ctypes.c_int, [_vp, _vp] + [_i32] * 5 + [_vp]),
+    "lbc_net_create": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), _i32, ctypes.POINTER(_vp)]),
+    "lbc_net_destroy": (ctypes.c_int, [_vp]),
+    "lbc_net_layer_plan": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp)]),
+    "lbc_net_set_params_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
+    "lbc_net_layer_io": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "lbc_net_run": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "lbc_net_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "lbc_net_launches": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
+    "lbc_probe_int8_mma_peak": (ctypes.c_int, [_i32, ctypes.POINTER(ctypes.c_double), _vp]),
+    "lbc_probe_hbm_copy": (ctypes.c_int, [ctypes.c_size_t, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
+    "lbc_flush_l2": (ctypes.c_int, [_vp]),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOS)
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Loads liblowbit_cnn.so.  Raises FileNotFoundError / OSError if it is missing — by design."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(
+            f"{p} is missing: build it with `python lowbitdnn-project_b200/build.py` "
+            "(liblowbit-cnn has no Python/CPU fallback)")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != LBC_OK:
+        raise LbcError(status, load_library().lbc_last_error_string().decode())

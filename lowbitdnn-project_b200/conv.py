@@ -1,0 +1,216 @@
+"""Host-side wrappers over the C ABI (plans, weight pre-pack, run, layout converters).
+
+PyTorch is used here only as the device allocator / stream provider: every tensor argument is a CUDA
+torch tensor whose ``data_ptr()`` is handed to liblowbit-cnn.  All arithmetic happens inside the library.
+
+The call surface mirrors the reference operators (names are the reference's, argument meaning too):
+  conv2DForward3x3(input_vect_c, kernel_vect_c) -> (out_int32_vect_c, ms)
+        cpp/int8conv/conv2DForward3x3TensorCores.cuh:695-751
+  to_vect_c / from_vect_c                         cpp/int8conv/utils.cuh:11-26
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import asdict, dataclass
+
+from . import _capi
+from ._capi import CConvDesc, check, load_library
+
+
+@dataclass(frozen=True)
+class ConvDesc:
+    """lbc_conv_desc (include/lowbit_cnn.h)."""
+    n: int
+    h: int
+    w: int
+    c: int
+    k: int
+    r: int
+    s: int
+    stride_h: int = 1
+    stride_w: int = 1
+    pad_h: int = 0
+    pad_w: int = 0
+    dil_h: int = 1
+    dil_w: int = 1
+    groups: int = 1
+    relu: int = 0
+    out_mode: int = _capi.OUT_INT8
+
+    def c_struct(self) -> CConvDesc:
+        return CConvDesc(**asdict(self))
+
+    def replace(self, **kw) -> "ConvDesc":
+        d = asdict(self)
+        d.update(kw)
+        return ConvDesc(**d)
+
+    @property
+    def out_hw(self) -> tuple[int, int]:
+        p, q = ctypes.c_int32(), ctypes.c_int32()
+        st = self.c_struct()
+        check(load_library().lbc_conv_out_shape(ctypes.byref(st), ctypes.byref(p), ctypes.byref(q)))
+        return p.value, q.value
+
+    @property
+    def work(self) -> tuple[float, float]:
+        """(ops, algorithmic bytes) — SURVEY.md 8d formulas, computed by the library."""
+        ops, byts = ctypes.c_double(), ctypes.c_double()
+        st = self.c_struct()
+        check(load_library().lbc_conv_work(ctypes.byref(st), ctypes.byref(ops), ctypes.byref(byts)))
+        return ops.value, byts.value
+
+
+def _stream_ptr(stream) -> ctypes.c_void_p:
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def _ptr(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class ConvPlan:
+    """An lbc_plan plus convenience methods on torch CUDA tensors."""
+
+    def __init__(self, desc: ConvDesc, force: int = _capi.KERNEL_AUTO):
+        self.desc = desc
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        st = desc.c_struct()
+        check(self._lib.lbc_conv_plan_create(ctypes.byref(st), force, ctypes.byref(self._h)))
+        self.p, self.q = desc.out_hw
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.lbc_conv_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel(self) -> str:
+        k = ctypes.c_int32()
+        check(self._lib.lbc_conv_plan_kernel(self._h, ctypes.byref(k)))
+        return _capi.KERNEL_NAMES[k.value]
+
+    def describe(self) -> str:
+        buf = ctypes.create_string_buffer(512)
+        check(self._lib.lbc_conv_plan_describe(self._h, buf, 512))
+        return buf.value.decode()
+
+    @property
+    def launches(self) -> int:
+        n = ctypes.c_int32()
+        check(self._lib.lbc_conv_plan_launches(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def packed_weight_bytes(self) -> int:
+        n = ctypes.c_size_t()
+        check(self._lib.lbc_conv_packed_weight_bytes(self._h, ctypes.byref(n)))
+        return n.value
+
+    def prepack(self, w, layout: int = _capi.W_KRSC, stream=None):
+        """w: int8 CUDA tensor in KRSC or OIHW order -> packed int8 CUDA tensor for this plan's kernel."""
+        import torch
+        assert w.is_cuda and w.dtype == torch.int8 and w.is_contiguous()
+        d = self.desc
+        assert w.numel() == d.k * d.r * d.s * (d.c // d.groups), "weight element count does not match the descriptor"
+        out = torch.empty(self.packed_weight_bytes, dtype=torch.int8, device=w.device)
+        check(self._lib.lbc_conv_prepack_weights(self._h, _ptr(w), layout, _ptr(out), _stream_ptr(stream)))
+        return out
+
+    def empty_output(self, device):
+        import torch
+        d = self.desc
+        dt = torch.int8 if d.out_mode == _capi.OUT_INT8 else torch.int32
+        return torch.empty((d.n, self.p, self.q, d.k), dtype=dt, device=device)
+
+    def run(self, x, w_packed, bias=None, scale=None, out=None, stream=None, timed: bool = False):
+        """x: int8 NHWC CUDA tensor.  Returns y, or (y, ms) when timed (the reference's (Tensor, float))."""
+        import torch
+        d = self.desc
+        assert x.is_cuda and x.dtype == torch.int8 and x.is_contiguous() and tuple(x.shape) == (d.n, d.h, d.w, d.c)
+        assert bias is None or (bias.dtype == torch.int32 and bias.numel() == d.k and bias.is_cuda)
+        assert scale is None or (scale.dtype == torch.float32 and scale.numel() == d.k and scale.is_cuda)
+        y = out if out is not None else self.empty_output(x.device)
+        ms = ctypes.c_float()
+        check(self._lib.lbc_conv_run(self._h, _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(scale), _ptr(y),
+                                     _stream_ptr(stream), ctypes.byref(ms) if timed else None))
+        return (y, ms.value) if timed else y
+
+    def run_host(self, x_host, w_packed, bias, scale, y_host, stream=None) -> float:
+        """x_host / y_host: CPU (ideally pinned) tensors; H2D + kernel + D2H inside the call. Returns ms."""
+        ms = ctypes.c_float()
+        check(self._lib.lbc_conv_run_host(self._h, _ptr(x_host), _ptr(w_packed), _ptr(bias), _ptr(scale),
+                                          _ptr(y_host), _stream_ptr(stream), ctypes.byref(ms)))
+        return ms.value
+
+
+# ---- layout converters (reference tensor formats) --------------------------------------------------
+def _convert(fn_name: str, src, n, c, h, w, v, out_shape, stream=None):
+    import torch
+    assert src.is_cuda and src.is_contiguous() and src.dtype in (torch.int8, torch.int32)
+    out = torch.empty(out_shape, dtype=src.dtype, device=src.device)
+    fn = getattr(load_library(), fn_name)
+    args = [_ptr(src), _ptr(out), n, c, h, w] + ([v] if v is not None else []) + [src.element_size(), _stream_ptr(stream)]
+    check(fn(*args))
+    return out
+
+
+def to_vect_c(t, v: int = 16, stream=None):
+    """[N,C,H,W] -> [N,C/V,H,W,V], materialised (utils.cuh:20-26)."""
+    n, c, h, w = t.shape
+    return _convert("lbc_to_vect_c", t, n, c, h, w, v, (n, c // v, h, w, v), stream)
+
+
+def from_vect_c(t, stream=None):
+    """[N,C/V,H,W,V] -> [N,C,H,W] (utils.cuh:11-17)."""
+    n, cg, h, w, v = t.shape
+    return _convert("lbc_from_vect_c", t, n, cg * v, h, w, v, (n, cg * v, h, w), stream)
+
+
+def nhwc_to_vect_c(t, v: int = 16, stream=None):
+    n, h, w, c = t.shape
+    return _convert("lbc_nhwc_to_vect_c", t, n, c, h, w, v, (n, c // v, h, w, v), stream)
+
+
+def vect_c_to_nhwc(t, stream=None):
+    n, cg, h, w, v = t.shape
+    return _convert("lbc_vect_c_to_nhwc", t, n, cg * v, h, w, v, (n, h, w, cg * v), stream)
+
+
+def nchw_to_nhwc(t, stream=None):
+    n, c, h, w = t.shape
+    return _convert("lbc_nchw_to_nhwc", t, n, c, h, w, None, (n, h, w, c), stream)
+
+
+def nhwc_to_nchw(t, stream=None):
+    n, h, w, c = t.shape
+    return _convert("lbc_nhwc_to_nchw", t, n, c, h, w, None, (n, c, h, w), stream)
+
+
+def conv2DForward3x3(rinput, rkernel):
+    """Reference-signature operator (conv2DForward3x3TensorCores.cuh:695-751): VECT_C=16 int8 input
+    [N][C/16][H][W][16] and kernel [K][C/16][3][3][16]; 3x3, stride 1, no padding; returns
+    (int32 [N][K/16][P][Q][16], elapsed_ms).  Unlike the reference there is no P,Q % 32 restriction."""
+    import torch
+    n, cg, h, w, v = rinput.shape
+    k, cg2, r, s, v2 = rkernel.shape
+    assert v == 16 and v2 == 16 and cg == cg2 and r == 3 and s == 3, "reference operator is 3x3 on VECT_C=16 tensors"
+    c = cg * v
+    x = vect_c_to_nhwc(rinput.contiguous())
+    wk = vect_c_to_nhwc(rkernel.contiguous())            # [K][3][3][C] == KRSC
+    plan = ConvPlan(ConvDesc(n=n, h=h, w=w, c=c, k=k, r=3, s=3, out_mode=_capi.OUT_INT32))
+    wp = plan.prepack(wk.reshape(-1), _capi.W_KRSC)
+    y, ms = plan.run(x, wp, timed=True)
+    out = nhwc_to_vect_c(y, 16)
+    torch.cuda.current_stream().synchronize()
+    plan.close()
+    return out, ms

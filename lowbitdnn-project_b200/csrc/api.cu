@@ -1,0 +1,686 @@
+// api.cu — the extern "C" surface declared in include/lowbit_cnn.h: planner, weight pre-pack, run,
+// layout converters, network runner and probes.  Host-side C++; every compute path ends in a CUDA launch
+// (there is no CPU fallback — without an sm_100 device every compute entry point returns LBC_ERR_NO_DEVICE).
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace lbc {
+
+// ---- errors ------------------------------------------------------------------------------------------
+static thread_local char t_err[512] = "no error";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return t_err; }
+
+// ---- geometry ----------------------------------------------------------------------------------------
+static int32_t out_dim(int32_t in, int32_t pad, int32_t dil, int32_t k, int32_t stride)
+{
+    return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;   // cudnn2DConvolution.cuh:33-36
+}
+
+lbc_status make_geom(const lbc_conv_desc* d, ConvGeom* g)
+{
+    LBC_REQUIRE(d && g, LBC_ERR_INVALID_ARG, "null descriptor");
+    LBC_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->k > 0 && d->r > 0 && d->s > 0,
+                LBC_ERR_INVALID_ARG, "descriptor has a non-positive extent");
+    LBC_REQUIRE(d->stride_h > 0 && d->stride_w > 0 && d->dil_h > 0 && d->dil_w > 0 && d->pad_h >= 0 && d->pad_w >= 0,
+                LBC_ERR_INVALID_ARG, "descriptor has a bad stride/dilation/padding");
+    LBC_REQUIRE(d->groups > 0 && d->c % d->groups == 0 && d->k % d->groups == 0, LBC_ERR_INVALID_ARG,
+                "groups must divide C and K");
+    LBC_REQUIRE(d->out_mode == LBC_OUT_INT8 || d->out_mode == LBC_OUT_INT32, LBC_ERR_INVALID_ARG, "bad out_mode");
+    g->d = *d;
+    g->p = out_dim(d->h, d->pad_h, d->dil_h, d->r, d->stride_h);
+    g->q = out_dim(d->w, d->pad_w, d->dil_w, d->s, d->stride_w);
+    LBC_REQUIRE(g->p > 0 && g->q > 0, LBC_ERR_INVALID_ARG, "empty output (%d x %d)", g->p, g->q);
+    LBC_REQUIRE(d->h + 2 * d->pad_h >= d->dil_h * (d->r - 1) + 1 && d->w + 2 * d->pad_w >= d->dil_w * (d->s - 1) + 1,
+                LBC_ERR_INVALID_ARG, "filter larger than the padded input");
+    g->cg = d->c / d->groups;
+    g->kg = d->k / d->groups;
+    g->m_total = (int64_t)d->n * g->p * g->q;
+    return LBC_OK;
+}
+
+// ---- device ------------------------------------------------------------------------------------------
+lbc_status current_device(DeviceInfo* info)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device (%s); liblowbit-cnn has no CPU fallback", e == cudaSuccess ? "count == 0" : cudaGetErrorString(e));
+        return LBC_ERR_NO_DEVICE;
+    }
+    int dev = 0;
+    LBC_CUDA_TRY(cudaGetDevice(&dev));
+    static std::mutex mu;
+    static std::vector<DeviceInfo> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)cache.size() <= dev) cache.resize(dev + 1);
+    if (cache[dev].device < 0) {
+        cudaDeviceProp p;
+        LBC_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+        DeviceInfo di;
+        di.device = dev;
+        di.sm_count = p.multiProcessorCount;
+        di.cc_major = p.major;
+        di.cc_minor = p.minor;
+        di.hbm_bytes = p.totalGlobalMem;
+        cudaDriverGetVersion(&di.driver_version);
+        cache[dev] = di;
+    }
+    *info = cache[dev];
+    if (info->cc_major != 10) {
+        set_error("device %d is sm_%d%d; liblowbit-cnn is built for sm_100a only", dev, info->cc_major, info->cc_minor);
+        return LBC_ERR_NO_DEVICE;
+    }
+    return LBC_OK;
+}
+
+}  // namespace lbc
+
+using namespace lbc;
+
+// ---- opaque types ------------------------------------------------------------------------------------
+struct lbc_plan {
+    ConvGeom g;
+    int32_t kind;
+    IgemmConfig cfg;
+    DeviceInfo dev;
+    // scratch for lbc_conv_run_host
+    mutable std::mutex mu;
+    mutable void* x_dev = nullptr;
+    mutable void* y_dev = nullptr;
+};
+
+namespace {
+
+size_t out_elt(const ConvGeom& g) { return g.d.out_mode == LBC_OUT_INT32 ? 4 : 1; }
+size_t in_bytes(const ConvGeom& g) { return (size_t)g.d.n * g.d.h * g.d.w * g.d.c; }
+size_t out_bytes(const ConvGeom& g) { return (size_t)g.m_total * g.d.k * out_elt(g); }
+
+size_t packed_weight_bytes(const lbc_plan* p)
+{
+    const lbc_conv_desc& d = p->g.d;
+    switch (p->kind) {
+        case LBC_KERNEL_IGEMM_TC: return (size_t)d.k * d.r * d.s * p->cfg.c_pad;
+        case LBC_KERNEL_DEPTHWISE: return (size_t)d.r * d.s * d.c;
+        default: return (size_t)d.k * d.r * d.s * p->g.cg;
+    }
+}
+
+// A fully resolved launch: everything needed to put the layer on a stream.
+struct ResolvedLaunch {
+    const lbc_plan* plan = nullptr;
+    const int8_t* x = nullptr;
+    const void* w = nullptr;
+    EpilogueParams ep{};
+    void* y = nullptr;
+    IgemmLaunch ig{};
+};
+
+lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const int32_t* bias, const float* scale,
+                   void* y, ResolvedLaunch* out)
+{
+    LBC_REQUIRE(plan && x && w && y, LBC_ERR_INVALID_ARG, "lbc_conv_run: null plan/x/w/y");
+    LBC_REQUIRE(plan->g.d.out_mode == LBC_OUT_INT32 || scale, LBC_ERR_INVALID_ARG,
+                "lbc_conv_run: int8 output needs a per-channel scale");
+    out->plan = plan;
+    out->x = x;
+    out->w = w;
+    out->y = y;
+    out->ep.bias = bias;
+    out->ep.scale = scale;
+    out->ep.relu = plan->g.d.relu;
+    out->ep.out_mode = plan->g.d.out_mode;
+    if (plan->kind == LBC_KERNEL_IGEMM_TC)
+        return igemm_encode(plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, &out->ig);
+    return LBC_OK;
+}
+
+lbc_status launch(const ResolvedLaunch& l, cudaStream_t stream)
+{
+    const lbc_plan* p = l.plan;
+    switch (p->kind) {
+        case LBC_KERNEL_IGEMM_TC: return igemm_launch(p->g, l.ig, l.ep, l.y, stream);
+        case LBC_KERNEL_DEPTHWISE: return launch_depthwise(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
+        case LBC_KERNEL_DIRECT: return launch_direct_conv(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
+        default: set_error("plan has unknown kernel kind %d", p->kind); return LBC_ERR_UNSUPPORTED;
+    }
+}
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    lbc_status init()
+    {
+        LBC_CUDA_TRY(cudaEventCreate(&a));
+        LBC_CUDA_TRY(cudaEventCreate(&b));
+        return LBC_OK;
+    }
+    ~EventPair()
+    {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+}  // namespace
+
+// ======================================================================================================
+extern "C" {
+
+int lbc_version(void) { return LBC_VERSION_MAJOR * 1000 + LBC_VERSION_MINOR; }
+const char* lbc_last_error_string(void) { return last_error(); }
+
+lbc_status lbc_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* hbm_bytes)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        set_error("no CUDA device %d", device);
+        return LBC_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp p;
+    LBC_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_out_shape(const lbc_conv_desc* d, int32_t* p, int32_t* q)
+{
+    ConvGeom g;
+    lbc_status st = make_geom(d, &g);
+    if (st != LBC_OK) return st;
+    if (p) *p = g.p;
+    if (q) *q = g.q;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_work(const lbc_conv_desc* d, double* ops, double* bytes)
+{
+    ConvGeom g;
+    lbc_status st = make_geom(d, &g);
+    if (st != LBC_OK) return st;
+    if (ops) *ops = 2.0 * (double)g.m_total * d->k * g.cg * d->r * d->s;
+    if (bytes)
+        *bytes = (double)in_bytes(g) + (double)d->k * g.cg * d->r * d->s + (double)out_bytes(g) + 8.0 * d->k;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan)
+{
+    LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan out-pointer");
+    *plan = nullptr;
+    ConvGeom g;
+    lbc_status st = make_geom(d, &g);
+    if (st != LBC_OK) return st;
+    DeviceInfo dev;
+    st = current_device(&dev);
+    if (st != LBC_OK) return st;
+
+    std::string why;
+    const bool tc_ok = igemm_supported(g, &why);
+    const bool dw_ok = (d->groups == d->c && d->k == d->c && d->c % 4 == 0);
+    int32_t kind = force;
+    if (force == LBC_KERNEL_AUTO) {
+        // Tile/layout planner: tensor cores for dense contractions, CUDA cores where they do not pay.
+        if (dw_ok) kind = LBC_KERNEL_DEPTHWISE;
+        else if (tc_ok) kind = LBC_KERNEL_IGEMM_TC;
+        else kind = LBC_KERNEL_DIRECT;
+    }
+    LBC_REQUIRE(kind == LBC_KERNEL_DIRECT || kind == LBC_KERNEL_IGEMM_TC || kind == LBC_KERNEL_DEPTHWISE,
+                LBC_ERR_UNSUPPORTED, "kernel kind %d is not available", kind);
+    LBC_REQUIRE(kind != LBC_KERNEL_IGEMM_TC || tc_ok, LBC_ERR_UNSUPPORTED, "tcgen05 implicit GEMM cannot run this shape: %s",
+                why.c_str());
+    LBC_REQUIRE(kind != LBC_KERNEL_DEPTHWISE || dw_ok, LBC_ERR_UNSUPPORTED,
+                "depthwise kernel needs groups == C == K and C %% 4 == 0");
+
+    lbc_plan* p = new (std::nothrow) lbc_plan();
+    LBC_REQUIRE(p, LBC_ERR_ALLOC, "out of host memory");
+    p->g = g;
+    p->kind = kind;
+    p->dev = dev;
+    if (kind == LBC_KERNEL_IGEMM_TC) {
+        st = igemm_make_config(g, dev, &p->cfg);
+        if (st != LBC_OK) {
+            delete p;
+            return st;
+        }
+    }
+    *plan = p;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_destroy(lbc_plan* plan)
+{
+    if (!plan) return LBC_OK;
+    if (plan->x_dev) cudaFree(plan->x_dev);
+    if (plan->y_dev) cudaFree(plan->y_dev);
+    delete plan;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_kernel(const lbc_plan* plan, int32_t* kind)
+{
+    LBC_REQUIRE(plan && kind, LBC_ERR_INVALID_ARG, "null argument");
+    *kind = plan->kind;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_len)
+{
+    LBC_REQUIRE(plan && buf && buf_len > 0, LBC_ERR_INVALID_ARG, "null argument");
+    const lbc_conv_desc& d = plan->g.d;
+    if (plan->kind == LBC_KERNEL_IGEMM_TC) {
+        const IgemmConfig& c = plan->cfg;
+        snprintf(buf, buf_len,
+                 "igemm_tc N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %d "
+                 "a=%s tiles %dx%d grid %d smem %zu tmem %u",
+                 d.n, d.h, d.w, d.c, d.k, d.r, d.s, d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc,
+                 c.k_blocks, c.stages, c.a_im2col ? "im2col" : "tiled", c.tiles_m, c.tiles_n, c.grid, c.smem_bytes,
+                 c.tmem_cols);
+    } else {
+        snprintf(buf, buf_len, "%s N%d %dx%dx%d->%d %dx%d s%d p%d g%d | M=%lld",
+                 plan->kind == LBC_KERNEL_DEPTHWISE ? "depthwise" : "direct", d.n, d.h, d.w, d.c, d.k, d.r, d.s,
+                 d.stride_h, d.pad_h, d.groups, (long long)plan->g.m_total);
+    }
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_launches(const lbc_plan* plan, int32_t* launches)
+{
+    LBC_REQUIRE(plan && launches, LBC_ERR_INVALID_ARG, "null argument");
+    *launches = 1;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_packed_weight_bytes(const lbc_plan* plan, size_t* bytes)
+{
+    LBC_REQUIRE(plan && bytes, LBC_ERR_INVALID_ARG, "null argument");
+    *bytes = packed_weight_bytes(plan);
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_prepack_weights(const lbc_plan* plan, const int8_t* w_dev, int32_t layout, void* dst_dev,
+                                    lbc_stream stream)
+{
+    LBC_REQUIRE(plan && w_dev && dst_dev, LBC_ERR_INVALID_ARG, "null argument");
+    LBC_REQUIRE(layout == LBC_W_KRSC || layout == LBC_W_OIHW, LBC_ERR_INVALID_ARG, "bad weight layout %d", layout);
+    const lbc_conv_desc& d = plan->g.d;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (plan->kind) {
+        case LBC_KERNEL_IGEMM_TC:
+            return launch_prepack_krsc(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, plan->g.cg, plan->cfg.c_pad, s);
+        case LBC_KERNEL_DEPTHWISE:
+            return launch_prepack_depthwise(w_dev, layout, (int8_t*)dst_dev, d.c, d.r, d.s, s);
+        default:
+            return launch_prepack_krsc(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, plan->g.cg, plan->g.cg, s);
+    }
+}
+
+lbc_status lbc_conv_run(const lbc_plan* plan, const int8_t* x, const void* w_packed, const int32_t* bias,
+                        const float* scale, void* y, lbc_stream stream, float* elapsed_ms)
+{
+    ResolvedLaunch l;
+    lbc_status st = resolve(plan, x, w_packed, bias, scale, y, &l);
+    if (st != LBC_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!elapsed_ms) return launch(l, s);
+    EventPair ev;
+    st = ev.init();
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaEventRecord(ev.a, s));
+    st = launch(l, s);
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaEventRecord(ev.b, s));
+    LBC_CUDA_TRY(cudaEventSynchronize(ev.b));
+    LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ev.a, ev.b));
+    if (plan->kind == LBC_KERNEL_IGEMM_TC) return igemm_check_timeout();
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const void* w_packed, const int32_t* bias,
+                             const float* scale, void* y_host, lbc_stream stream, float* elapsed_ms)
+{
+    LBC_REQUIRE(plan && x_host && y_host, LBC_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(plan->mu);
+    if (!plan->x_dev) {
+        if (cudaMalloc(&plan->x_dev, in_bytes(plan->g)) != cudaSuccess || cudaMalloc(&plan->y_dev, out_bytes(plan->g)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("lbc_conv_run_host: device allocation failed");
+            return LBC_ERR_ALLOC;
+        }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    EventPair ev;
+    lbc_status st = ev.init();
+    if (st != LBC_OK) return st;
+    ResolvedLaunch l;
+    st = resolve(plan, (const int8_t*)plan->x_dev, w_packed, bias, scale, plan->y_dev, &l);
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaEventRecord(ev.a, s));
+    LBC_CUDA_TRY(cudaMemcpyAsync(plan->x_dev, x_host, in_bytes(plan->g), cudaMemcpyHostToDevice, s));
+    st = launch(l, s);
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, plan->y_dev, out_bytes(plan->g), cudaMemcpyDeviceToHost, s));
+    LBC_CUDA_TRY(cudaEventRecord(ev.b, s));
+    LBC_CUDA_TRY(cudaEventSynchronize(ev.b));
+    if (elapsed_ms) LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ev.a, ev.b));
+    if (plan->kind == LBC_KERNEL_IGEMM_TC) return igemm_check_timeout();
+    return LBC_OK;
+}
+
+// ---- layout converters -------------------------------------------------------------------------------
+static lbc_status permute_checked(const void* src, void* dst, int32_t d0, int32_t d1, int32_t d2, int32_t d3,
+                                  int32_t d4, int p0, int p1, int p2, int p3, int p4, int32_t elt, lbc_stream stream)
+{
+    DeviceInfo dev;
+    lbc_status st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    const int32_t dims[5] = {d0, d1, d2, d3, d4};
+    const int32_t perm[5] = {p0, p1, p2, p3, p4};
+    return launch_permute5(src, dst, dims, perm, elt, (cudaStream_t)stream);
+}
+
+#define LBC_VECT_ARGS_OK()                                                                                  \
+    LBC_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && v > 0 && c % v == 0, LBC_ERR_INVALID_ARG,               \
+                "vect_c: C (%d) must be a positive multiple of V (%d)", c, v)
+
+lbc_status lbc_to_vect_c(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t v,
+                         int32_t elt, lbc_stream stream)
+{   // [N, C/V, V, H, W] -> [N, C/V, H, W, V]   (utils.cuh:20-26)
+    LBC_VECT_ARGS_OK();
+    return permute_checked(src, dst, n, c / v, v, h, w, 0, 1, 3, 4, 2, elt, stream);
+}
+
+lbc_status lbc_from_vect_c(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t v,
+                           int32_t elt, lbc_stream stream)
+{   // [N, C/V, H, W, V] -> [N, C/V, V, H, W]   (utils.cuh:11-17)
+    LBC_VECT_ARGS_OK();
+    return permute_checked(src, dst, n, c / v, h, w, v, 0, 1, 4, 2, 3, elt, stream);
+}
+
+lbc_status lbc_nhwc_to_vect_c(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t v,
+                              int32_t elt, lbc_stream stream)
+{   // [N, H, W, C/V, V] -> [N, C/V, H, W, V]
+    LBC_VECT_ARGS_OK();
+    return permute_checked(src, dst, n, h, w, c / v, v, 0, 3, 1, 2, 4, elt, stream);
+}
+
+lbc_status lbc_vect_c_to_nhwc(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t v,
+                              int32_t elt, lbc_stream stream)
+{   // [N, C/V, H, W, V] -> [N, H, W, C/V, V]
+    LBC_VECT_ARGS_OK();
+    return permute_checked(src, dst, n, c / v, h, w, v, 0, 2, 3, 1, 4, elt, stream);
+}
+
+lbc_status lbc_nchw_to_nhwc(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t elt,
+                            lbc_stream stream)
+{
+    LBC_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, LBC_ERR_INVALID_ARG, "bad extents");
+    return permute_checked(src, dst, n, c, h, w, 1, 0, 2, 3, 1, 4, elt, stream);
+}
+
+lbc_status lbc_nhwc_to_nchw(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w, int32_t elt,
+                            lbc_stream stream)
+{
+    LBC_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, LBC_ERR_INVALID_ARG, "bad extents");
+    return permute_checked(src, dst, n, h, w, c, 1, 0, 3, 1, 2, 4, elt, stream);
+}
+
+// ---- probes ------------------------------------------------------------------------------------------
+lbc_status lbc_probe_int8_mma_peak(int32_t iters, double* tops, lbc_stream stream)
+{
+    return probe_int8_mma_peak(iters, tops, (cudaStream_t)stream);
+}
+lbc_status lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stream stream)
+{
+    return probe_hbm_copy(bytes, iters, gbs, (cudaStream_t)stream);
+}
+lbc_status lbc_flush_l2(lbc_stream stream)
+{
+    DeviceInfo dev;
+    lbc_status st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    return flush_l2((cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ======================================================================================================
+// Networks
+// ======================================================================================================
+struct lbc_net {
+    struct Layer {
+        lbc_plan* plan = nullptr;
+        int32_t input_of = -1;
+        void* w = nullptr;       // packed weights
+        int32_t* bias = nullptr;
+        float* scale = nullptr;
+        void* x_own = nullptr;   // own input buffer when input_of == -1
+        void* y = nullptr;
+        ResolvedLaunch rl;
+        bool resolved = false;
+    };
+    std::vector<Layer> layers;
+    std::vector<cudaEvent_t> events;   // n_layers + 1
+    std::mutex mu;
+};
+
+namespace {
+
+const void* layer_input(const lbc_net* net, int i)
+{
+    const lbc_net::Layer& L = net->layers[i];
+    return L.input_of < 0 ? L.x_own : net->layers[L.input_of].y;
+}
+
+lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
+{
+    lbc_net::Layer& L = net->layers[i];
+    const int8_t* x = x_override ? x_override : (const int8_t*)layer_input(net, i);
+    if (L.resolved && L.rl.x == x) return LBC_OK;
+    lbc_status st = resolve(L.plan, x, L.w, L.bias, L.scale, L.y, &L.rl);
+    if (st == LBC_OK) L.resolved = true;
+    return st;
+}
+
+lbc_status net_enqueue(lbc_net* net, const int8_t* x_dev, cudaStream_t s, bool timed)
+{
+    const int n = (int)net->layers.size();
+    if (timed) LBC_CUDA_TRY(cudaEventRecord(net->events[0], s));
+    for (int i = 0; i < n; ++i) {
+        lbc_status st = net_resolve(net, i, (i == 0 && x_dev) ? x_dev : nullptr);
+        if (st != LBC_OK) return st;
+        st = launch(net->layers[i].rl, s);
+        if (st != LBC_OK) return st;
+        if (timed) LBC_CUDA_TRY(cudaEventRecord(net->events[i + 1], s));
+    }
+    return LBC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+lbc_status lbc_net_destroy(lbc_net* net)
+{
+    if (!net) return LBC_OK;
+    for (auto& L : net->layers) {
+        if (L.w) cudaFree(L.w);
+        if (L.bias) cudaFree(L.bias);
+        if (L.scale) cudaFree(L.scale);
+        if (L.x_own) cudaFree(L.x_own);
+        if (L.y) cudaFree(L.y);
+        lbc_conv_plan_destroy(L.plan);
+    }
+    for (auto e : net->events) cudaEventDestroy(e);
+    delete net;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers, lbc_net** out)
+{
+    LBC_REQUIRE(descs && out && n_layers > 0, LBC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    lbc_net* net = new (std::nothrow) lbc_net();
+    LBC_REQUIRE(net, LBC_ERR_ALLOC, "out of host memory");
+    net->layers.resize(n_layers);
+    lbc_status st = LBC_OK;
+    for (int i = 0; i < n_layers && st == LBC_OK; ++i) {
+        lbc_net::Layer& L = net->layers[i];
+        L.input_of = input_of ? input_of[i] : (i == 0 ? -1 : i - 1);
+        if (L.input_of >= i) {
+            set_error("layer %d: input_of (%d) must reference an earlier layer", i, L.input_of);
+            st = LBC_ERR_INVALID_ARG;
+            break;
+        }
+        st = lbc_conv_plan_create(&descs[i], LBC_KERNEL_AUTO, &L.plan);
+        if (st != LBC_OK) break;
+        const ConvGeom& g = L.plan->g;
+        if (L.input_of >= 0) {
+            const ConvGeom& pg = net->layers[L.input_of].plan->g;
+            if (pg.d.out_mode != LBC_OUT_INT8 || pg.d.n != g.d.n || pg.p != g.d.h || pg.q != g.d.w || pg.d.k != g.d.c) {
+                set_error("layer %d: input %dx%dx%dx%d does not match the output of layer %d (%dx%dx%dx%d)", i, g.d.n,
+                          g.d.h, g.d.w, g.d.c, L.input_of, pg.d.n, pg.p, pg.q, pg.d.k);
+                st = LBC_ERR_INVALID_ARG;
+                break;
+            }
+        }
+        const size_t wb = packed_weight_bytes(L.plan);
+        bool ok = cudaMalloc(&L.w, wb) == cudaSuccess && cudaMalloc((void**)&L.bias, sizeof(int32_t) * g.d.k) == cudaSuccess &&
+                  cudaMalloc((void**)&L.scale, sizeof(float) * g.d.k) == cudaSuccess && cudaMalloc(&L.y, out_bytes(g)) == cudaSuccess;
+        if (ok && L.input_of < 0) ok = cudaMalloc(&L.x_own, in_bytes(g)) == cudaSuccess;
+        if (!ok) {
+            cudaGetLastError();
+            set_error("layer %d: device allocation failed", i);
+            st = LBC_ERR_ALLOC;
+            break;
+        }
+        cudaMemset(L.w, 0, wb);
+        cudaMemset(L.bias, 0, sizeof(int32_t) * g.d.k);
+        cudaMemset(L.scale, 0, sizeof(float) * g.d.k);
+        if (L.x_own) cudaMemset(L.x_own, 0, in_bytes(g));
+    }
+    if (st == LBC_OK) {
+        net->events.resize(n_layers + 1);
+        for (auto& e : net->events)
+            if (cudaEventCreate(&e) != cudaSuccess) {
+                e = nullptr;
+                set_error("cudaEventCreate failed");
+                st = LBC_ERR_CUDA;
+                break;
+            }
+    }
+    if (st != LBC_OK) {
+        char keep[512];
+        strncpy(keep, last_error(), sizeof keep);
+        keep[sizeof keep - 1] = 0;
+        lbc_net_destroy(net);
+        set_error("%s", keep);
+        return st;
+    }
+    *out = net;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan** plan)
+{
+    LBC_REQUIRE(net && plan && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");
+    *plan = net->layers[layer].plan;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w_host, int32_t layout,
+                                   const int32_t* bias_host, const float* scale_host)
+{
+    LBC_REQUIRE(net && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");
+    lbc_net::Layer& L = net->layers[layer];
+    const ConvGeom& g = L.plan->g;
+    if (w_host) {
+        const size_t raw = (size_t)g.d.k * g.d.r * g.d.s * g.cg;
+        void* tmp = nullptr;
+        if (cudaMalloc(&tmp, raw) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("set_params: device allocation failed");
+            return LBC_ERR_ALLOC;
+        }
+        cudaError_t e = cudaMemcpy(tmp, w_host, raw, cudaMemcpyHostToDevice);
+        lbc_status st = e == cudaSuccess ? lbc_conv_prepack_weights(L.plan, (const int8_t*)tmp, layout, L.w, nullptr) : LBC_ERR_CUDA;
+        if (st == LBC_OK) e = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (st != LBC_OK) return st;
+        LBC_CUDA_TRY(e);
+    }
+    if (bias_host) LBC_CUDA_TRY(cudaMemcpy(L.bias, bias_host, sizeof(int32_t) * g.d.k, cudaMemcpyHostToDevice));
+    if (scale_host) LBC_CUDA_TRY(cudaMemcpy(L.scale, scale_host, sizeof(float) * g.d.k, cudaMemcpyHostToDevice));
+    return LBC_OK;
+}
+
+lbc_status lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_dev, void** y_dev)
+{
+    LBC_REQUIRE(net && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");
+    if (x_dev) *x_dev = layer_input(net, layer);
+    if (y_dev) *y_dev = net->layers[layer].y;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_run(lbc_net* net, const int8_t* x_dev, lbc_stream stream, float* per_layer_ms, float* total_ms)
+{
+    LBC_REQUIRE(net, LBC_ERR_INVALID_ARG, "null net");
+    std::lock_guard<std::mutex> lk(net->mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool timed = per_layer_ms || total_ms;
+    lbc_status st = net_enqueue(net, x_dev, s, timed);
+    if (st != LBC_OK) return st;
+    if (!timed) return LBC_OK;
+    const int n = (int)net->layers.size();
+    LBC_CUDA_TRY(cudaEventSynchronize(net->events[n]));
+    if (per_layer_ms)
+        for (int i = 0; i < n; ++i) LBC_CUDA_TRY(cudaEventElapsedTime(&per_layer_ms[i], net->events[i], net->events[i + 1]));
+    if (total_ms) LBC_CUDA_TRY(cudaEventElapsedTime(total_ms, net->events[0], net->events[n]));
+    return igemm_check_timeout();
+}
+
+lbc_status lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lbc_stream stream, float* total_ms)
+{
+    LBC_REQUIRE(net && x_host && y_host, LBC_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(net->mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = (int)net->layers.size();
+    lbc_net::Layer& first = net->layers[0];
+    lbc_net::Layer& last = net->layers[n - 1];
+    LBC_REQUIRE(first.x_own, LBC_ERR_INVALID_ARG, "layer 0 must take the network input");
+    LBC_CUDA_TRY(cudaEventRecord(net->events[0], s));
+    LBC_CUDA_TRY(cudaMemcpyAsync(first.x_own, x_host, in_bytes(first.plan->g), cudaMemcpyHostToDevice, s));
+    lbc_status st = net_enqueue(net, nullptr, s, false);
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, last.y, out_bytes(last.plan->g), cudaMemcpyDeviceToHost, s));
+    LBC_CUDA_TRY(cudaEventRecord(net->events[n], s));
+    LBC_CUDA_TRY(cudaEventSynchronize(net->events[n]));
+    if (total_ms) LBC_CUDA_TRY(cudaEventElapsedTime(total_ms, net->events[0], net->events[n]));
+    return igemm_check_timeout();
+}
+
+lbc_status lbc_net_launches(const lbc_net* net, int32_t* launches)
+{
+    LBC_REQUIRE(net && launches, LBC_ERR_INVALID_ARG, "null argument");
+    *launches = (int32_t)net->layers.size();
+    return LBC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// common.cuh — internal declarations shared by the liblowbit-cnn translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/lowbit_cnn.h"
+
+namespace lbc {
+
+// ---- error plumbing (never throws across the C boundary) ---------------------------------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define LBC_CUDA_TRY(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::lbc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return LBC_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define LBC_REQUIRE(cond, status, ...)        \
+    do {                                      \
+        if (!(cond)) {                        \
+            ::lbc::set_error(__VA_ARGS__);    \
+            return (status);                  \
+        }                                     \
+    } while (0)
+
+// ---- geometry ----------------------------------------------------------------------------------
+struct ConvGeom {
+    lbc_conv_desc d;
+    int32_t p, q;        // output spatial size
+    int32_t cg, kg;      // channels / filters per group
+    int64_t m_total;     // N*P*Q
+};
+
+lbc_status make_geom(const lbc_conv_desc* d, ConvGeom* g);
+
+// ---- device info (cached) ----------------------------------------------------------------------
+struct DeviceInfo {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    int driver_version = 0;
+};
+lbc_status current_device(DeviceInfo* info);  // LBC_ERR_NO_DEVICE unless cc 10.x
+
+// ---- kernels (one TU each) ---------------------------------------------------------------------
+struct EpilogueParams {
+    const int32_t* bias;   // may be null
+    const float* scale;    // null only for int32 output
+    int32_t relu;
+    int32_t out_mode;      // lbc_out_mode
+};
+
+// direct_conv.cu — CUDA-core direct convolution, any shape; weights [K][R][S][C/g].
+lbc_status launch_direct_conv(const ConvGeom& g, const int8_t* x, const int8_t* w_krsc, const EpilogueParams& ep,
+                              void* y, cudaStream_t stream);
+
+// depthwise.cu — groups == C == K; weights packed [R][S][C].
+lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
+                            void* y, cudaStream_t stream);
+
+// igemm_tc.cu — tcgen05 implicit GEMM.
+struct IgemmConfig {
+    int32_t bn;          // N tile (multiple of 16, <= 256)
+    int32_t bkc;         // K chunk in bytes per pipeline stage: 32 / 64 / 128 (== swizzle span)
+    int32_t c_pad;       // C rounded up to a multiple of bkc (packed-weight row pitch per tap)
+    int32_t stages;      // smem pipeline depth
+    int32_t a_im2col;    // 0: A is a plain [M][C] matrix (1x1, stride 1, no pad); 1: TMA im2col mode
+    int32_t tiles_m, tiles_n;
+    int32_t k_blocks;    // R*S*(c_pad/bkc)
+    int32_t grid;        // persistent CTAs
+    size_t smem_bytes;
+    uint32_t tmem_cols;  // power of two >= 2*bn
+};
+struct IgemmLaunch {
+    CUtensorMap tm_a;
+    CUtensorMap tm_b;
+    IgemmConfig cfg;
+};
+bool igemm_supported(const ConvGeom& g, std::string* why);
+lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConfig* cfg);
+lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceInfo& dev, const int8_t* x,
+                        const int8_t* w_packed, IgemmLaunch* out);
+lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
+                        cudaStream_t stream);
+lbc_status igemm_check_timeout();  // reads (and clears) the device watchdog flag; call after a sync
+
+// layout.cu
+lbc_status launch_prepack_krsc(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
+                               int32_t cg, int32_t c_pad, cudaStream_t stream);              // -> [K][R][S][c_pad]
+lbc_status launch_prepack_depthwise(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t c, int32_t r,
+                                    int32_t s, cudaStream_t stream);                         // -> [R][S][C]
+lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,
+                           cudaStream_t stream);
+
+// probes.cu
+lbc_status probe_int8_mma_peak(int32_t iters, double* tops, cudaStream_t stream);
+lbc_status probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, cudaStream_t stream);
+lbc_status flush_l2(cudaStream_t stream);
+
+// ---- the fused epilogue, shared by every kernel (bit-exact with oracle_requant) ----------------
+// t = acc + bias (int32 wraparound) ; f = float(t) RNE ; f *= scale (single multiply) ;
+// clamp to [lo,127] in fp32 (NaN -> lo, as fmaxf drops NaN) ; round-half-to-even via the 1.5*2^23
+// magic add ; the low byte of the result's bit pattern is the two's-complement int8.
+__device__ __forceinline__ uint32_t requant_u8bits(int32_t acc, int32_t bias, float scale, float lo)
+{
+    const int32_t t = acc + bias;
+    float f = __fmul_rn(__int2float_rn(t), scale);
+    f = fminf(fmaxf(f, lo), 127.0f);
+    return __float_as_uint(__fadd_rn(f, 12582912.0f));
+}
+
+__device__ __forceinline__ uint32_t pack4_u8(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    const uint32_t ab = __byte_perm(a, b, 0x0040);  // {a0, b0, ., .}
+    const uint32_t cd = __byte_perm(c, d, 0x0040);
+    return __byte_perm(ab, cd, 0x5410);
+}
+
+}  // namespace lbc

@@ -1,0 +1,84 @@
+"""lbc_net wrapper: a list of planned convolutions run back to back (cpp/apps/benchmark.cpp:54-81 role)."""
+from __future__ import annotations
+
+import ctypes
+
+from . import _capi
+from ._capi import CConvDesc, check, load_library
+from .conv import ConvDesc, _ptr, _stream_ptr
+
+
+class Net:
+    def __init__(self, layers):
+        """layers: [(name, ConvDesc, input_name_or_None)]"""
+        self._lib = load_library()
+        self.names = [l[0] for l in layers]
+        self.descs: list[ConvDesc] = [l[1] for l in layers]
+        idx = {n: i for i, n in enumerate(self.names)}
+        self.input_of = [(-1 if l[2] is None else idx[l[2]]) for l in layers]
+        n = len(layers)
+        arr = (CConvDesc * n)(*[d.c_struct() for d in self.descs])
+        inp = (ctypes.c_int32 * n)(*self.input_of)
+        self._h = ctypes.c_void_p()
+        check(self._lib.lbc_net_create(arr, inp, n, ctypes.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.lbc_net_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return len(self.descs)
+
+    def set_params(self, layer: int, w_host, bias_host, scale_host, layout: int = _capi.W_KRSC):
+        """numpy arrays (int8 KRSC/OIHW weights, int32 bias, f32 scale) -> device, pre-packed."""
+        def p(a):
+            return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        check(self._lib.lbc_net_set_params_host(self._h, layer, p(w_host), layout, p(bias_host), p(scale_host)))
+
+    def layer_io(self, layer: int) -> tuple[int, int]:
+        x, y = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._lib.lbc_net_layer_io(self._h, layer, ctypes.byref(x), ctypes.byref(y)))
+        return x.value, y.value
+
+    def layer_kernel(self, layer: int) -> str:
+        plan = ctypes.c_void_p()
+        check(self._lib.lbc_net_layer_plan(self._h, layer, ctypes.byref(plan)))
+        k = ctypes.c_int32()
+        check(self._lib.lbc_conv_plan_kernel(plan, ctypes.byref(k)))
+        return _capi.KERNEL_NAMES[k.value]
+
+    def layer_describe(self, layer: int) -> str:
+        plan = ctypes.c_void_p()
+        check(self._lib.lbc_net_layer_plan(self._h, layer, ctypes.byref(plan)))
+        buf = ctypes.create_string_buffer(512)
+        check(self._lib.lbc_conv_plan_describe(plan, buf, 512))
+        return buf.value.decode()
+
+    @property
+    def launches(self) -> int:
+        n = ctypes.c_int32()
+        check(self._lib.lbc_net_launches(self._h, ctypes.byref(n)))
+        return n.value
+
+    def run(self, x_dev=None, stream=None, timed: bool = False):
+        """Enqueue every layer. timed=True synchronises and returns (per_layer_ms list, total_ms)."""
+        n = len(self)
+        if not timed:
+            check(self._lib.lbc_net_run(self._h, _ptr(x_dev), _stream_ptr(stream), None, None))
+            return None
+        per = (ctypes.c_float * n)()
+        tot = ctypes.c_float()
+        check(self._lib.lbc_net_run(self._h, _ptr(x_dev), _stream_ptr(stream), per, ctypes.byref(tot)))
+        return list(per), tot.value
+
+    def run_host(self, x_host, y_host, stream=None) -> float:
+        tot = ctypes.c_float()
+        check(self._lib.lbc_net_run_host(self._h, _ptr(x_host), _ptr(y_host), _stream_ptr(stream), ctypes.byref(tot)))
+        return tot.value

@@ -1,0 +1,80 @@
+"""CPU tests: the C-ABI library builds, loads, exports every symbol include/lowbit_cnn.h declares,
+does its host arithmetic right, and FAILS LOUDLY (no fallback) when there is no GPU."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.fixture(scope="module")
+def lbc():
+    import lowbitdnn_project_b200 as m
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("lbc_build", os.path.join(ROOT, "lowbitdnn-project_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.build()
+    m.load_library()
+    return m
+
+
+def test_header_symbols_are_exported(lbc):
+    hdr = open(os.path.join(ROOT, "include", "lowbit_cnn.h")).read()
+    declared = set(re.findall(r"\b(lbc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = lbc.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/lowbit_cnn.h but not exported"
+    from lowbitdnn_project_b200 import _capi
+    assert declared == set(_capi.EXPORTED_SYMBOLS), declared ^ set(_capi.EXPORTED_SYMBOLS)
+
+
+def test_host_arithmetic(lbc):
+    d = lbc.ConvDesc(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1)
+    assert d.out_hw == (56, 56)
+    ops, byts = d.work
+    assert ops == 2 * 115605504 and byts == 438784
+    d = lbc.ConvDesc(n=512, h=224, w=224, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3)
+    assert d.out_hw == (112, 112)
+    with pytest.raises(lbc.LbcError):
+        _ = lbc.ConvDesc(n=1, h=2, w=2, c=4, k=4, r=5, s=5).out_hw      # filter larger than input
+    with pytest.raises(lbc.LbcError):
+        _ = lbc.ConvDesc(n=1, h=8, w=8, c=6, k=4, r=1, s=1, groups=4).out_hw
+
+
+def test_network_tables_match_survey(lbc):
+    nets = lbc.networks
+    want = {"resnet18": (20, 464.27, 1.206), "resnet50": (53, 2092.61, 11.173), "vgg16": (13, 1964.37, 2.911),
+            "mobilenet_v2": (52, 306.68, 13.769), "single_3x3": (1, 0.115605504, 0.000438784)}
+    for name, (n_layers, gmac, gb) in want.items():
+        layers = nets.NETWORKS[name](nets.DEFAULT_BATCH[name])
+        g, b = nets.total_work(layers)
+        assert len(layers) == n_layers
+        assert abs(g - gmac) / gmac < 1e-3 and abs(b - gb) / gb < 2e-3, (name, g, b)
+        names = [l[0] for l in layers]
+        for _, _, src in layers:
+            assert src is None or src in names
+
+
+def test_no_silent_fallback_without_gpu(lbc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(lbc.LbcError) as e:
+        lbc.ConvPlan(lbc.ConvDesc(n=1, h=8, w=8, c=16, k=16, r=1, s=1))
+    assert e.value.status == 3  # LBC_ERR_NO_DEVICE
+
+
+def test_product_path_does_not_import_oracle():
+    """The product path may never import, include, link or dlopen anything under oracle/."""
+    pkg = os.path.join(ROOT, "lowbitdnn-project_b200")
+    pat = re.compile(r"import\s+oracle|from\s+oracle|from\s+\.+oracle|oracle/|libcpu_ref|libref_conv|#include[^\n]*oracle")
+    for root, _, files in os.walk(pkg):
+        if os.path.basename(root) in ("build", "lib", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(root, f)).read()
+                assert not pat.search(src), f"{os.path.join(root, f)} reaches into oracle/"

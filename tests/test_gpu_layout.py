@@ -1,0 +1,42 @@
+"""GPU tests for the reference tensor-format converters and the reference-signature operator."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vect_c_converters_match_reference_definition():
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    rng = np.random.default_rng(0)
+    for v, dt in ((16, np.int8), (4, np.int8), (32, np.int8), (16, np.int32)):
+        a = rng.integers(-100, 100, size=(2, 2 * v, 5, 7)).astype(dt)
+        t = torch.from_numpy(a).cuda()
+        got = lbc.to_vect_c(t, v)
+        assert np.array_equal(got.cpu().numpy(), oracle.to_vect_c(a, v))
+        back = lbc.from_vect_c(got)
+        assert np.array_equal(back.cpu().numpy(), a)
+        nhwc = lbc.nchw_to_nhwc(t)
+        assert np.array_equal(nhwc.cpu().numpy(), a.transpose(0, 2, 3, 1))
+        assert np.array_equal(lbc.nhwc_to_nchw(nhwc).cpu().numpy(), a)
+        vc = lbc.nhwc_to_vect_c(nhwc, v)
+        assert np.array_equal(vc.cpu().numpy(), oracle.to_vect_c(a, v))
+        assert np.array_equal(lbc.vect_c_to_nhwc(vc).cpu().numpy(), a.transpose(0, 2, 3, 1))
+
+
+def test_reference_signature_operator():
+    """conv2DForward3x3(to_vect_c(x), to_vect_c(w)) == to_vect_c(refConv2DForward(x, w)) — the comparison
+    check.cu:107-129 makes, on a shape the reference kernel itself cannot run (P,Q not multiples of 32)."""
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    rng = np.random.default_rng(1)
+    x = rng.integers(-128, 128, size=(2, 32, 12, 14), dtype=np.int8)      # NCHW, pre-padded
+    w = rng.integers(-128, 128, size=(48, 32, 3, 3), dtype=np.int8)       # OIHW
+    want = oracle.ref_style_nchw_valid(x, w)                               # int32 NCHW
+    xv = lbc.to_vect_c(torch.from_numpy(x).cuda(), 16)
+    wv = lbc.to_vect_c(torch.from_numpy(w).cuda(), 16)
+    out, ms = lbc.conv2DForward3x3(xv, wv)
+    assert ms > 0
+    assert np.array_equal(out.cpu().numpy(), oracle.to_vect_c(want, 16))

@@ -1,0 +1,143 @@
+"""GPU parity tests (run with -m gpu on a B200): every kernel of liblowbit-cnn, called through the C ABI,
+must equal the CPU oracle bit for bit — int32 accumulators and requantised int8 alike."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from oracle.oracle import ConvDesc as D
+
+pytestmark = pytest.mark.gpu
+
+DIRECT, IGEMM, DW = 1, 2, 3
+
+
+def _check(d, **kw):
+    from tests.parity_util import check_case
+    nbad, total, name, detail = check_case(d, **kw)
+    assert nbad == 0, f"{name}: {detail}"
+    return name
+
+
+# ---- CUDA-core direct kernel: any shape -----------------------------------------------------------------
+DIRECT_CASES = [
+    D(n=2, h=9, w=7, c=8, k=12, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+    D(n=1, h=12, w=12, c=16, k=8, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1),
+    D(n=2, h=20, w=20, c=3, k=16, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),   # stem-like
+    D(n=1, h=6, w=5, c=32, k=24, r=1, s=1, relu=1),
+    D(n=1, h=10, w=10, c=8, k=8, r=3, s=3, pad_h=2, pad_w=2, dil_h=2, dil_w=2, groups=2, relu=1),
+    D(n=1, h=5, w=9, c=4, k=6, r=3, s=2, pad_h=0, pad_w=1, stride_h=1, stride_w=2),
+    D(n=1, h=7, w=7, c=5, k=3, r=3, s=3, pad_h=1, pad_w=1),                                      # odd C, K
+    D(n=2, h=9, w=9, c=6, k=6, r=3, s=3, pad_h=1, pad_w=1, groups=6, relu=1),                    # depthwise, C%4 != 0
+]
+
+
+@pytest.mark.parametrize("d", DIRECT_CASES, ids=lambda d: f"c{d.c}k{d.k}r{d.r}s{d.stride_h}g{d.groups}")
+@pytest.mark.parametrize("out_mode", [0, 1])
+def test_direct_kernel(d, out_mode):
+    _check(D(**{**d.__dict__, "out_mode": out_mode}), force=DIRECT)
+
+
+# ---- depthwise kernel ---------------------------------------------------------------------------------
+DW_CASES = [
+    D(n=2, h=9, w=9, c=24, k=24, r=3, s=3, pad_h=1, pad_w=1, groups=24, relu=1),
+    D(n=1, h=14, w=14, c=96, k=96, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, groups=96, relu=1),
+    D(n=1, h=7, w=7, c=960, k=960, r=3, s=3, pad_h=1, pad_w=1, groups=960),
+]
+
+
+@pytest.mark.parametrize("d", DW_CASES, ids=lambda d: f"c{d.c}s{d.stride_h}")
+@pytest.mark.parametrize("out_mode", [0, 1])
+def test_depthwise_kernel(d, out_mode):
+    assert _check(D(**{**d.__dict__, "out_mode": out_mode})) == "depthwise"
+
+
+# ---- tcgen05 implicit GEMM ----------------------------------------------------------------------------
+IGEMM_CASES = [
+    # pure GEMM (tiled TMA): 128B / 64B / 32B swizzle, N tiles, M tail
+    D(n=1, h=16, w=16, c=128, k=128, r=1, s=1),
+    D(n=2, h=14, w=14, c=64, k=256, r=1, s=1, relu=1),
+    D(n=1, h=9, w=11, c=32, k=64, r=1, s=1),
+    D(n=1, h=7, w=7, c=512, k=2048, r=1, s=1, relu=1),          # tiles_n = 8, many k-blocks
+    D(n=3, h=5, w=5, c=16, k=16, r=1, s=1),                     # C padded 16 -> 32, smallest N
+    D(n=1, h=12, w=12, c=144, k=48, r=1, s=1, relu=1),          # C=144 -> 160 zero-padded, bn = 48
+    D(n=1, h=8, w=8, c=256, k=320, r=1, s=1),                   # K_out tail tile (320 = 256 + 64)
+    # im2col TMA: 3x3 pad 1, stride 2, 1x1 stride 2, 7x7, dilation, rectangular
+    D(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),       # BASELINE config 1
+    D(n=2, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+    D(n=2, h=28, w=28, c=128, k=128, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),
+    D(n=2, h=28, w=28, c=256, k=512, r=1, s=1, stride_h=2, stride_w=2),
+    D(n=1, h=17, w=13, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1),
+    D(n=1, h=20, w=20, c=16, k=32, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),
+    D(n=1, h=15, w=15, c=64, k=64, r=3, s=3, pad_h=2, pad_w=2, dil_h=2, dil_w=2),
+    D(n=1, h=12, w=10, c=64, k=32, r=3, s=1, pad_h=1, pad_w=0),
+    D(n=1, h=10, w=10, c=64, k=64, r=3, s=3),                                 # VALID (reference style)
+]
+
+
+@pytest.mark.parametrize("d", IGEMM_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}p{d.pad_h}")
+@pytest.mark.parametrize("out_mode", [1, 0])
+def test_igemm_tc_kernel(d, out_mode):
+    assert _check(D(**{**d.__dict__, "out_mode": out_mode}), force=IGEMM) == "igemm_tc"
+
+
+def test_igemm_reference_style_inputs_and_oihw_weights():
+    """{0,1}-valued inputs (check.cu:43-44,69-75), weights handed over in the reference's OIHW order."""
+    d = D(n=2, h=34, w=34, c=128, k=128, r=3, s=3, out_mode=1)
+    _check(d, style="ref", force=IGEMM, use_bias=False, w_layout="oihw")
+
+
+def test_igemm_matches_reference_golden():
+    """The tensor-core path against outputs of the reference itself (tests/golden)."""
+    from tests.test_oracle import iter_golden
+    from tests.parity_util import run_gpu
+    n_run = 0
+    for key, shape, x, w, y in iter_golden():
+        b, ic, ih, iw, oc, oh, ow, kh, kw = shape
+        if ic % 16 or oc % 16:
+            continue
+        d = D(n=b, h=ih, w=iw, c=ic, k=oc, r=kh, s=kw, out_mode=1)
+        got, name, _ = run_gpu(d, np.ascontiguousarray(x.transpose(0, 2, 3, 1)),
+                               np.ascontiguousarray(w.transpose(0, 2, 3, 1)), None, None, force=IGEMM)
+        assert name == "igemm_tc"
+        assert np.array_equal(got.transpose(0, 3, 1, 2), y), key
+        n_run += 1
+    assert n_run >= 12
+
+
+def test_direct_matches_reference_golden():
+    from tests.test_oracle import iter_golden
+    from tests.parity_util import run_gpu
+    for key, shape, x, w, y in iter_golden():
+        b, ic, ih, iw, oc, oh, ow, kh, kw = shape
+        d = D(n=b, h=ih, w=iw, c=ic, k=oc, r=kh, s=kw, out_mode=1)
+        got, _, _ = run_gpu(d, np.ascontiguousarray(x.transpose(0, 2, 3, 1)),
+                            np.ascontiguousarray(w.transpose(0, 2, 3, 1)), None, None, force=DIRECT)
+        assert np.array_equal(got.transpose(0, 3, 1, 2), y), key
+
+
+def test_planner_choices():
+    import lowbitdnn_project_b200 as lbc
+    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1)).kernel == "igemm_tc"
+    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=56, w=56, c=64, k=256, r=1, s=1)).kernel == "igemm_tc"
+    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=28, w=28, c=192, k=192, r=3, s=3, pad_h=1, pad_w=1, groups=192)).kernel == "depthwise"
+    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=224, w=224, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3)).kernel == "direct"
+
+
+def test_requant_extremes_on_device():
+    """Saturation, ties and wraparound through the fused epilogue (bias/scale chosen to hit them)."""
+    from tests.parity_util import run_gpu
+    d = D(n=1, h=4, w=8, c=16, k=16, r=1, s=1, out_mode=0)
+    rng = np.random.default_rng(5)
+    x = rng.integers(-128, 128, size=(1, 4, 8, 16), dtype=np.int8)
+    w = np.zeros((16, 1, 1, 16), dtype=np.int8)
+    for k in range(16):
+        w[k, 0, 0, k] = 1                                  # acc[k] = x[..., k]
+    bias = np.array([0, 1, -1, 127, -128, 2**31 - 1, -2**31, 5, 0, 0, 0, 0, 3, 3, 3, 3], dtype=np.int32)
+    scale = np.array([0.5, 0.5, 0.5, 1.0, 1.0, 1.0, 1.0, 1e-9, 1e9, -1.0, np.inf, np.nan, 0.25, 1.5, 2.5, 0.75],
+                     dtype=np.float32)
+    for relu in (0, 1):
+        dd = D(**{**d.__dict__, "relu": relu})
+        want = oracle.conv_nhwc(dd, x, w, bias, scale)
+        for force in (DIRECT, IGEMM):
+            got, _, _ = run_gpu(dd, x, w, bias, scale, force=force)
+            assert np.array_equal(got, want), (relu, force)
