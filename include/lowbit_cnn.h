@@ -156,6 +156,8 @@ lbc_status  lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan
 /* Load parameters for one layer from HOST memory (weights in `layout`, bias int32[K], scale f32[K]). */
 lbc_status  lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w_host, int32_t layout,
                                     const int32_t* bias_host, const float* scale_host);
+/* Fill the resident input buffer of a layer whose input_of == -1 from HOST memory (NHWC int8). */
+lbc_status  lbc_net_set_input_host(lbc_net* net, int32_t layer, const int8_t* x_host);
 /* Device pointers of a layer's input/output activations (valid until lbc_net_destroy). */
 lbc_status  lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_dev, void** y_dev);
 /* Run all layers on `stream` with the network input already resident in HBM (x_dev NHWC of layer(s)

@@ -631,6 +631,15 @@ lbc_status lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w_
     return LBC_OK;
 }
 
+lbc_status lbc_net_set_input_host(lbc_net* net, int32_t layer, const int8_t* x_host)
+{
+    LBC_REQUIRE(net && x_host && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad argument");
+    lbc_net::Layer& L = net->layers[layer];
+    LBC_REQUIRE(L.x_own, LBC_ERR_INVALID_ARG, "layer %d takes its input from layer %d, not from a resident buffer", layer, L.input_of);
+    LBC_CUDA_TRY(cudaMemcpy(L.x_own, x_host, in_bytes(L.plan->g), cudaMemcpyHostToDevice));
+    return LBC_OK;
+}
+
 lbc_status lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_dev, void** y_dev)
 {
     LBC_REQUIRE(net && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");

@@ -42,6 +42,10 @@ class Net:
             return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
         check(self._lib.lbc_net_set_params_host(self._h, layer, p(w_host), layout, p(bias_host), p(scale_host)))
 
+    def set_input(self, layer: int, x_host):
+        """numpy int8 NHWC -> the resident input buffer of a layer fed from outside the conv chain."""
+        check(self._lib.lbc_net_set_input_host(self._h, layer, x_host.ctypes.data_as(ctypes.c_void_p)))
+
     def layer_io(self, layer: int) -> tuple[int, int]:
         x, y = ctypes.c_void_p(), ctypes.c_void_p()
         check(self._lib.lbc_net_layer_io(self._h, layer, ctypes.byref(x), ctypes.byref(y)))
