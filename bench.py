@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of liblowbit-cnn on B200: ResNet-50 int8 convolution stack, images/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--network resnet50] [--batch B]
+
+A "step" is one pass of the hot path (all 53 convolutions of ResNet-50, batch 512 per GPU, fused
+bias/requant/ReLU epilogues) over one batch of synthetic int8 input.  Rank 0 prints ONE JSON line.
+
+  value      images/s over all ranks with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same metric through lbc_net_run_host: pinned HOST input -> H2D -> 53 layers -> D2H -> HOST output
+  roofline   igemm_i8_kernel (the dominant kernel): algorithmic ops/bytes per launch (SURVEY 8d formulas) over
+             its event-timed launch durations inside this run, against MEASURED_PEAKS.json / the int8 MMA probe
+  cpu_baseline  the oracle port (oracle/cpu_ref.c, OpenMP) timed on this host on a bounded sample
+
+--impl reference times the reference's own CPU implementation (cpp/int8conv/refConv2DForward.hpp compiled
+unmodified into oracle/_ref) on a bounded sample, on rank 0 only.
+
+Multi-GPU: one process per GPU (torchrun), the batch dimension is sharded — every rank owns `batch` images
+and a replica of the weights; there is no collective on the convolution path.  NCCL is used only to gather
+per-rank timings and output checksums.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "resnet50_int8_conv_images_per_sec"
+UNIT = "images/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML; the recipe's "clocks line")
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            log("clock sampler unavailable:", e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def synth_params(d, layer: int):
+    """SURVEY.md 8d synthetic parameters (same generator as oracle.synth, restated to keep the product/bench
+    path free of oracle imports on the GPU arm)."""
+    cg = d.c // d.groups
+    rw = np.random.default_rng(4321 + layer)
+    w = rw.integers(-127, 128, size=(d.k, d.r, d.s, cg), dtype=np.int8)
+    bias = rw.integers(-2**15, 2**15, size=(d.k,), dtype=np.int32)
+    scale = (rw.uniform(0.5, 2.0, size=(d.k,)) * 2.0**-7 / np.sqrt(d.r * d.s * cg)).astype(np.float32)
+    return w, bias, scale
+
+
+def synth_input(d, layer: int):
+    return np.random.default_rng(1234 + layer).integers(-128, 128, size=(d.n, d.h, d.w, d.c), dtype=np.int8)
+
+
+def layer_work(d):
+    p = (d.h + 2 * d.pad_h - (d.dil_h * (d.r - 1) + 1)) // d.stride_h + 1
+    q = (d.w + 2 * d.pad_w - (d.dil_w * (d.s - 1) + 1)) // d.stride_w + 1
+    cg = d.c // d.groups
+    ops = 2.0 * d.n * p * q * d.k * cg * d.r * d.s
+    byts = d.n * d.h * d.w * d.c + d.k * cg * d.r * d.s + d.n * p * q * d.k + 8 * d.k
+    return ops, float(byts)
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops", 0)),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", 0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that touch oracle/)
+# ------------------------------------------------------------------------------------------------------
+def cpu_baseline_port(layers, budget_s: float = 20.0):
+    """Oracle port (oracle/cpu_ref.c, all host threads) on the same network at batch 1, repeated until
+    ~budget_s of CPU work; returns images/s."""
+    from oracle import oracle
+    from oracle.oracle import ConvDesc as OD
+    threads = oracle.max_threads()
+    prepared = []
+    for i, (_, d, _) in enumerate(layers):
+        od = OD(**{**d.__dict__, "n": 1})
+        x, w, b, s = oracle.synth(od, layer=i)
+        prepared.append((od, x, w, b, s))
+    t0 = time.perf_counter()
+    images = 0
+    while True:
+        for od, x, w, b, s in prepared:
+            oracle.conv_nhwc(od, x, w, b, s)
+        images += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or images >= 64:
+            break
+    return {"value": images / el, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{images} image(s) x all {len(layers)} layers at batch 1, oracle/cpu_ref.c with {threads} OpenMP threads, {el:.1f} s"}
+
+
+REF_SAMPLE = (1, 64, 10, 10, 64, 8, 8, 3, 3)   # config 1 (56x56x64->64 3x3) cropped to 8x8 outputs, pre-padded
+
+
+def reference_arm(args, layers):
+    """The reference's own CPU path (refConv2DForward.hpp, unmodified, oracle/_ref) on a bounded sample."""
+    from oracle import oracle
+    if not oracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_conv.so missing (built only where /root/reference exists)"}))
+        return
+    b, ic, ih, iw, oc, oh, ow, kh, kw = REF_SAMPLE
+    rng = np.random.default_rng(99)
+    x = rng.integers(-128, 128, size=(b, ic, ih, iw), dtype=np.int8)
+    w = rng.integers(-128, 128, size=(oc, ic, kh, kw), dtype=np.int8)
+    sample_macs = b * oc * oh * ow * ic * kh * kw
+    net_macs_per_image = sum(layer_work(d)[0] for _, d, _ in layers) / 2.0 / layers[0][1].n
+    for _ in range(args.warmup):
+        oracle.ref_conv2d_forward(x, w)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        y = oracle.ref_conv2d_forward(x, w)
+    el = time.perf_counter() - t0
+    assert np.array_equal(y, oracle.ref_style_nchw_valid(x, w))
+    ms = el / args.steps * 1e3
+    value = (sample_macs / (ms * 1e-3)) / net_macs_per_image
+    cores = oracle.ref_max_threads()
+    sample = (f"refConv2DForward<1,64,10,10,64,8,8,3,3> per step ({sample_macs / 1e6:.2f} MMAC: BASELINE config 1 cropped to 8x8 "
+              f"outputs), {cores} OpenMP threads; images/s = sample MAC rate / {net_macs_per_image / 1e9:.3f} GMAC per ResNet-50 image "
+              "(extrapolated from the reference CPU path)")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8", "data": "synthetic",
+        "config": {"workload": f"{args.network}_conv_stack_b{args.batch}", "network": args.network,
+                   "batch_per_gpu": args.batch, "layers": len(layers)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--network", default="resnet50")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-report", default=None, help="write the per-layer table (JSON) here")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import lowbitdnn_project_b200 as lbc   # raises if liblowbit_cnn.so is missing — no fallback
+    nets = lbc.networks
+    if args.batch is None:
+        args.batch = nets.DEFAULT_BATCH[args.network]
+    layers = nets.NETWORKS[args.network](args.batch)
+
+    if args.impl == "reference":
+        if rank == 0:
+            reference_arm(args, layers)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py (ours) needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- build the network, load synthetic parameters / resident inputs --------------------------------
+    t_setup = time.time()
+    net = lbc.Net(layers)
+    for i, (_, d, src) in enumerate(layers):
+        w, b, s = synth_params(d, i)
+        net.set_params(i, w, b, s)
+        if src is None:
+            net.set_input(i, synth_input(d, i + 1000 * rank))
+    d0, dl = layers[0][1], layers[-1][1]
+    pl, ql = dl.out_hw
+    x_host = torch.from_numpy(synth_input(d0, 1000 * rank)).pin_memory()
+    y_host = torch.empty((dl.n, pl, ql, dl.k), dtype=torch.int8).pin_memory()
+    stream = torch.cuda.current_stream()
+    log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s; kernels: "
+        + ", ".join(f"{k}x{v}" for k, v in sorted(_count(net).items())))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        net.run(stream=stream)
+    barrier()
+
+    # ---- timed region: K steps back to back, inputs resident in HBM ---------------------------------------
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        net.run(stream=stream)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+
+    # ---- instrumented pass: per-launch CUDA-event durations of every layer (same stream, same inputs) -----
+    per_layer = np.zeros(len(layers))
+    for _ in range(args.steps):
+        per, _tot = net.run(stream=stream, timed=True)
+        per_layer += np.array(per)
+    per_layer /= args.steps
+
+    # ---- e2e: host buffers through the C ABI (H2D + 53 layers + D2H inside the timed region) ---------------
+    for _ in range(2):
+        net.run_host(x_host, y_host, stream=stream)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_dev_ms = 0.0
+    for _ in range(args.steps):
+        e2e_dev_ms += net.run_host(x_host, y_host, stream=stream)
+    torch.cuda.synchronize()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_dev_ms, e2e_wall_ms) / args.steps
+    checksum = zlib.crc32(y_host.numpy().tobytes())
+
+    # ---- gather (NCCL): max over ranks; checksums ------------------------------------------------------------
+    stats = torch.tensor([ms_total, e2e_ms, float(checksum)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        ms_total = max(float(s[0]) for s in allst)
+        e2e_ms = max(float(s[1]) for s in allst)
+    ms_per_step = ms_total / args.steps
+    images_per_step = args.batch * world
+
+    if rank == 0:
+        peaks = read_peaks()
+        kinds = [net.layer_kernel(i) for i in range(len(layers))]
+        works = [layer_work(d) for _, d, _ in layers]
+        # dominant kernel = the one with the largest share of the step
+        share = {}
+        for k, ms in zip(kinds, per_layer):
+            share[k] = share.get(k, 0.0) + ms
+        dom = max(share, key=share.get)
+        sel = [i for i, k in enumerate(kinds) if k == dom]
+        dom_ms = sum(per_layer[i] for i in sel)
+        dom_ops = sum(works[i][0] for i in sel)
+        dom_bytes = sum(works[i][1] for i in sel)
+        int8_peak = None
+        try:
+            int8_peak = lbc.probe_int8_mma_peak(16384)
+        except Exception as e:  # noqa: BLE001
+            log("int8 peak probe failed:", e)
+        tops = dom_ops / (dom_ms * 1e-3) / 1e12
+        gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
+        # roofline time of the dominant kernel's launches: each launch is bound by its slower side
+        tc_peak = (int8_peak or 2 * peaks["bf16_tflops"]) * 1e12
+        roof_ms = sum(max(works[i][0] / tc_peak, works[i][1] / (peaks["hbm_gbs"] * 1e9)) for i in sel) * 1e3
+        hbm_bound_ms = sum(per_layer[i] for i in sel if works[i][1] / (peaks["hbm_gbs"] * 1e9) >= works[i][0] / tc_peak)
+        bound = "hbm" if hbm_bound_ms >= dom_ms / 2 else "tensor"
+        if bound == "hbm":
+            roofline = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+        else:
+            roofline = {"bound": "tensor", "achieved": tops, "peak": tc_peak / 1e12, "unit": "TFLOP/s",
+                        "frac": tops / (tc_peak / 1e12), "traffic": None}
+        roofline.update({
+            "kernel": {"igemm_tc": "igemm_i8_kernel", "direct": "direct_conv_kernel", "depthwise": "depthwise_kernel"}[dom],
+            "launches_per_step": len(sel), "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / float(per_layer.sum()),
+            "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs; int8 peak = on-box tcgen05 kind::i8 MMA-only probe)",
+            "achieved_tops": tops, "achieved_gbs": gbs, "int8_mma_peak_tops": int8_peak,
+            "roofline_ms": roof_ms, "frac_of_mixed_roofline": roof_ms / dom_ms,
+        })
+        total_ops = sum(w[0] for w in works)
+        out = {
+            "metric": METRIC, "value": images_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": f"{args.network}_conv_stack_b{args.batch}", "network": args.network,
+                       "batch_per_gpu": args.batch, "global_batch": images_per_step, "layers": len(layers),
+                       "parallelism": f"batch-sharded x{world}, no collective on the conv path",
+                       "l2": "no flush: every layer reads >= 25 MB produced by an earlier launch; 11.2 GB touched per step vs 126 MB L2"},
+            "tops_per_gpu": total_ops / (ms_per_step * 1e-3) / 1e12,
+            "clocks": clocks,
+            "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(x_host.numel()), "d2h_bytes_per_step": int(y_host.numel()),
+                    "ms_per_step": e2e_ms,
+                    "note": "lbc_net_run_host: pinned host input -> H2D -> all layers -> D2H of the last layer's output"},
+            "gpu_launches": int(args.steps * net.launches),
+            "roofline": roofline,
+            "output_crc32": checksum,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline_port(layers)
+            except Exception as e:  # noqa: BLE001
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        if args.layer_report:
+            rep = []
+            for i, (name, d, _) in enumerate(layers):
+                ops, byts = works[i]
+                ms = float(per_layer[i])
+                rep.append({"layer": name, "kernel": kinds[i], "plan": net.layer_describe(i), "ms": ms,
+                            "tops": ops / ms / 1e9, "gbs": byts / ms / 1e6, "ai": ops / byts,
+                            "frac_tc": ops / ms / 1e9 / (tc_peak / 1e12), "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"]})
+            with open(args.layer_report, "w") as fh:
+                json.dump({"network": args.network, "batch": args.batch, "int8_peak_tops": int8_peak,
+                           "hbm_gbs": peaks["hbm_gbs"], "layers": rep}, fh, indent=1)
+        print(json.dumps(out))
+    net.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _count(net):
+    c = {}
+    for i in range(len(net)):
+        k = net.layer_kernel(i)
+        c[k] = c.get(k, 0) + 1
+    return c
+
+
+if __name__ == "__main__":
+    main()
