@@ -114,7 +114,7 @@ size_t packed_weight_bytes(const lbc_plan* p)
 {
     const lbc_conv_desc& d = p->g.d;
     switch (p->kind) {
-        case LBC_KERNEL_IGEMM_TC: return (size_t)d.k * d.r * d.s * p->cfg.c_pad;
+        case LBC_KERNEL_IGEMM_TC: return (size_t)d.k * p->cfg.packed_row_bytes;
         case LBC_KERNEL_DEPTHWISE: return (size_t)d.r * d.s * d.c;
         default: return (size_t)d.k * d.r * d.s * p->g.cg;
     }
@@ -145,7 +145,7 @@ lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const i
     out->ep.relu = plan->g.d.relu;
     out->ep.out_mode = plan->g.d.out_mode;
     if (plan->kind == LBC_KERNEL_IGEMM_TC)
-        return igemm_encode(plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, &out->ig);
+        return igemm_encode(plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, y, &out->ig);
     return LBC_OK;
 }
 
@@ -287,12 +287,13 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
     const lbc_conv_desc& d = plan->g.d;
     if (plan->kind == LBC_KERNEL_IGEMM_TC) {
         const IgemmConfig& c = plan->cfg;
+        static const char* modes[] = {"tiled", "im2col", "window"};
         snprintf(buf, buf_len,
-                 "igemm_tc N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %d "
-                 "a=%s tiles %dx%d grid %d smem %zu tmem %u",
+                 "igemm_tc N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %d+%dw "
+                 "a=%s(%dx%d px/tile) tiles %dx%d grid %d smem %zu tmem %u",
                  d.n, d.h, d.w, d.c, d.k, d.r, d.s, d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc,
-                 c.k_blocks, c.stages, c.a_im2col ? "im2col" : "tiled", c.tiles_m, c.tiles_n, c.grid, c.smem_bytes,
-                 c.tmem_cols);
+                 c.k_blocks, c.stages, c.win_stages, modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
+                 c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols);
     } else {
         snprintf(buf, buf_len, "%s N%d %dx%dx%d->%d %dx%d s%d p%d g%d | M=%lld",
                  plan->kind == LBC_KERNEL_DEPTHWISE ? "depthwise" : "direct", d.n, d.h, d.w, d.c, d.k, d.r, d.s,
@@ -324,7 +325,8 @@ lbc_status lbc_conv_prepack_weights(const lbc_plan* plan, const int8_t* w_dev, i
     cudaStream_t s = (cudaStream_t)stream;
     switch (plan->kind) {
         case LBC_KERNEL_IGEMM_TC:
-            return launch_prepack_krsc(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, plan->g.cg, plan->cfg.c_pad, s);
+            return launch_prepack_igemm(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, plan->g.cg, plan->cfg.s_pad,
+                                        plan->cfg.bkc, plan->cfg.cblocks, plan->cfg.mode == 2, s);
         case LBC_KERNEL_DEPTHWISE:
             return launch_prepack_depthwise(w_dev, layout, (int8_t*)dst_dev, d.c, d.r, d.s, s);
         default:

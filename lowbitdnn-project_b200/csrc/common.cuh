@@ -69,13 +69,20 @@ lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_
 
 // igemm_tc.cu — tcgen05 implicit GEMM.
 struct IgemmConfig {
+    int32_t mode;        // 0 tiled (pure GEMM), 1 TMA im2col, 2 shifted window
     int32_t bn;          // N tile (multiple of 16, <= 256)
-    int32_t bkc;         // K chunk in bytes per pipeline stage: 32 / 64 / 128 (== swizzle span)
-    int32_t c_pad;       // C rounded up to a multiple of bkc (packed-weight row pitch per tap)
-    int32_t stages;      // smem pipeline depth
-    int32_t a_im2col;    // 0: A is a plain [M][C] matrix (1x1, stride 1, no pad); 1: TMA im2col mode
+    int32_t bkc;         // bytes of K per pixel row of an A block: 16 (window, C == 16) / 32 / 64 / 128
+    int32_t bkb;         // bytes of K per row of a B block
+    int32_t c_pad;       // C rounded up to a multiple of bkc
+    int32_t s_pad;       // filter width rounded up to even when taps are consumed in pairs (C == 16)
+    int32_t cblocks, inner, k_blocks;
+    size_t packed_row_bytes;   // bytes per output channel in the packed filter matrix
+    int32_t stages, win_stages;
+    uint32_t a_stage_bytes, b_stage_bytes, win_stage_bytes, win_tx_bytes;
+    int32_t wt, rows_per_tile, cols_per_tile, row_tiles, col_tiles;
     int32_t tiles_m, tiles_n;
-    int32_t k_blocks;    // R*S*(c_pad/bkc)
+    int32_t panel_bytes, panel_swz_bits, n_panels;
+    uint32_t off_b, off_stage, off_ctl;
     int32_t grid;        // persistent CTAs
     size_t smem_bytes;
     uint32_t tmem_cols;  // power of two >= 2*bn
@@ -83,12 +90,13 @@ struct IgemmConfig {
 struct IgemmLaunch {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
+    CUtensorMap tm_out;
     IgemmConfig cfg;
 };
 bool igemm_supported(const ConvGeom& g, std::string* why);
 lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConfig* cfg);
 lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceInfo& dev, const int8_t* x,
-                        const int8_t* w_packed, IgemmLaunch* out);
+                        const int8_t* w_packed, void* y, IgemmLaunch* out);
 lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
                         cudaStream_t stream);
 lbc_status igemm_check_timeout();  // reads (and clears) the device watchdog flag; call after a sync
@@ -96,6 +104,11 @@ lbc_status igemm_check_timeout();  // reads (and clears) the device watchdog fla
 // layout.cu
 lbc_status launch_prepack_krsc(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
                                int32_t cg, int32_t c_pad, cudaStream_t stream);              // -> [K][R][S][c_pad]
+// -> the tcgen05 kernel's filter matrix: per output channel `row_bytes`, K ordered [tap][chunk][bkc] (ring modes)
+// or [chunk][tap][bkc] (window mode); taps = R x s_pad with zero phantom taps / zero channel padding.
+lbc_status launch_prepack_igemm(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
+                                int32_t cg, int32_t s_pad, int32_t bkc, int32_t cblocks, int32_t chunk_outer,
+                                cudaStream_t stream);
 lbc_status launch_prepack_depthwise(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t c, int32_t r,
                                     int32_t s, cudaStream_t stream);                         // -> [R][S][C]
 lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,

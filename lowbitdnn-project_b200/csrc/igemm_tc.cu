@@ -1,20 +1,31 @@
 // igemm_tc.cu — tcgen05 implicit-GEMM int8 convolution for sm_100a.
 //
 //   GEMM view:  D[M = N*P*Q][K_out] = A[M][R*S*C] * B[K_out][R*S*C]^T     (int8 x int8 -> int32 in TMEM)
-//   A tiles  :  TMA im2col-mode loads of the NHWC activation tensor (one filter tap x <=128 channels per
-//               pipeline stage), or plain 2-D tiled loads when the conv is a pure GEMM (1x1, stride 1, no pad);
-//               hardware zero-fill implements the padding halo and the M tail.
-//   B tiles  :  TMA 2-D loads of the pre-packed [K_out][R][S][C_pad] filter matrix.
-//   MMA      :  tcgen05.mma.cta_group::1.kind::i8, M=128 x N=bn x K=32 per instruction, issued by one thread,
-//               operands straight from 128B/64B/32B-swizzled shared memory.
-//   Epilogue :  4 warps drain the TMEM accumulator (tcgen05.ld 32x32b), fuse bias + per-channel fp32 scale +
-//               round-to-nearest-even + ReLU/saturate, pack to int8 and write 16-byte vectors (NHWC).
-//   Schedule :  persistent CTAs (one per SM), static round-robin over (m,n) tiles, a `stages`-deep smem ring
-//               between the TMA warp and the MMA warp, and two TMEM accumulator stages so the epilogue of tile
-//               i overlaps the main loop of tile i+1.
+//
+//   A operand, three TMA modes (planner picks one per layer):
+//     TILED   1x1 / stride 1 / no pad: A is the plain [M][C] matrix, 2-D tiled loads.
+//     IM2COL  any R,S,stride,dilation: one TMA im2col-mode load per (filter tap, channel chunk) and stage;
+//             hardware zero-fill implements the padding halo and the M tail.
+//     WINDOW  stride-1 RxS: the (rows+R-1) x (cols+S-1) input halo window of a tile is loaded ONCE per channel
+//             chunk (4-D tiled load, OOB zero-fill = padding) and every filter tap is issued as an MMA whose
+//             shared-memory descriptor starts (r*Wt + s) pixel rows further into the same window.  Swizzled
+//             K-major descriptors may start on any row (measured: tools/exp/desc_shift.cu), so the 9 taps of a
+//             3x3 cost one L2->smem fill instead of nine.  Output positions that fall in the halo columns are
+//             computed and dropped (87.5% of the MMA rows are useful for 56/28/112/224-wide layers).
+//             For C == 16 (space-to-depth'd stems) pixel rows are 16 bytes, unswizzled, and one K=32 MMA covers
+//             two horizontally adjacent taps through the descriptor's leading-dimension offset.
+//   B operand:  TMA 2-D loads of the pre-packed filter matrix, one [bn][<=128 B] block per stage.
+//   MMA      :  tcgen05.mma.cta_group::1.kind::i8, M=128 x N=bn x K=32 per instruction, issued by one thread.
+//   Epilogue :  8 warps drain the TMEM accumulator (tcgen05.ld 32x32b, software-pipelined), fuse bias +
+//               per-channel fp32 scale + round-to-nearest-even + ReLU/saturate, pack to int8, stage the tile in
+//               swizzled shared memory and write it with TMA stores (full 128-byte lines).  int32 output mode
+//               writes 16-byte vectors directly.
+//   Schedule :  persistent CTAs (one per SM), static round-robin over tiles, mbarrier rings between the TMA
+//               warps and the MMA warp, two TMEM accumulator stages so the epilogue of tile i overlaps the main
+//               loop of tile i+1.
 //
 // Replaces CUDAConv2DForward3x3TensorCoures (cpp/int8conv/conv2DForward3x3TensorCores.cuh:537-693: wmma
-// m32n8k16, single-buffered smem, int32 stores, 3x3/stride-1/VALID only).
+// m32n8k16, single-buffered 34x34x16 halo tile in smem, int32 stores, 3x3/stride-1/VALID only).
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -26,97 +37,181 @@ namespace lbc {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kNumThreads = 192;          // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int kEpilogueThreads = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kFirstEpiWarp = 3;                       // warp 0: ring TMA, 1: MMA + TMEM alloc, 2: window TMA
+constexpr int kNumThreads = kFirstEpiWarp * 32 + kEpiThreads;   // 352
 constexpr int kMaxStages = 8;
+constexpr int kMaxWinStages = 4;
+
+enum : int32_t { A_TILED = 0, A_IM2COL = 1, A_WINDOW = 2 };
 
 struct IgemmParams {
     int64_t m_total;
-    int32_t k_out;
-    int32_t bn, bkc, stages, a_im2col;
-    int32_t tiles_m, tiles_n, k_blocks, cblocks;   // cblocks = c_pad / bkc
-    int32_t p, q, s_taps;                          // output rows/cols, filter width
+    int32_t k_out, n_img, p, q;
+    int32_t mode;                 // A_TILED / A_IM2COL / A_WINDOW
+    int32_t bn;                   // N tile
+    int32_t bkc;                  // bytes of K per pixel row of an A block: 16 (window only) / 32 / 64 / 128
+    int32_t bkb;                  // bytes of K per row of a B block (== bkc, or S_pad*16 when bkc == 16)
+    int32_t tiles_m, tiles_n;
+    int32_t cblocks;              // channel chunks
+    int32_t inner;                // B blocks per channel chunk: taps (bkc >= 32) or filter rows (bkc == 16); 1 for TILED
+    int32_t mma_outer, mma_inner; // MMA loop nest: (cblocks, inner) in WINDOW mode, (1, cblocks*inner) otherwise
+    int32_t s_taps;               // filter width S
     int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
+    int32_t stages;               // ring depth (B, and A in TILED/IM2COL)
+    uint32_t a_stage_bytes, b_stage_bytes;
+    // window mode
+    int32_t win_stages;
+    uint32_t win_stage_bytes, win_tx_bytes;
+    int32_t wt;                   // window pitch in pixels = cols_per_tile + (S_eff-1)*dil_w
+    int32_t rows_per_tile, cols_per_tile, row_tiles, col_tiles;
+    // epilogue
     int32_t relu, out_mode;
     uint32_t tmem_cols;
-    uint32_t a_stage_bytes, b_stage_bytes;
+    int32_t panel_bytes, panel_swz_bits, n_panels;
+    // smem carve-up (byte offsets from the 1024-aligned base)
+    uint32_t off_b, off_stage, off_ctl;
 };
 
 __device__ int g_timeout_flag = 0;
 
-struct SmemLayout {
-    // dynamic smem: [stages x A tile][stages x B tile] (1024-aligned), then this control block.
+struct Ctl {
     uint64_t full[kMaxStages];
     uint64_t empty[kMaxStages];
+    uint64_t wfull[kMaxWinStages];
+    uint64_t wempty[kMaxWinStages];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
-    uint32_t pad_;
+    uint32_t pad_[3];
+    alignas(16) float scale[256];
+    alignas(16) int32_t bias[256];
 };
 
-// Requantise / bias NCOLS consecutive accumulator columns of one output pixel and store them with 16-byte
-// vectors.  bias/scale are read straight from global memory: every lane of the warp reads the same address
-// (one broadcast transaction, L1-resident), which needs no cross-warp staging barrier.
-template <int NCOLS>
-__device__ __forceinline__ void epilogue_store_chunk(const uint32_t* v, const float* __restrict__ sc,
-                                                     const int32_t* __restrict__ bi, float lo, int32_t out_mode,
-                                                     void* y, int64_t out_off)
+struct TileCoord {
+    int32_t n_blk;
+    int64_t m0;                   // TILED / IM2COL: first GEMM row of the tile
+    int32_t img, p0, q0;          // WINDOW: image and first output row / column
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& prm, int32_t tile)
 {
-    if (out_mode == LBC_OUT_INT32) {
-        int32_t* yo = reinterpret_cast<int32_t*>(y) + out_off;
-#pragma unroll
-        for (int j = 0; j < NCOLS; j += 4) {
-            const int4 b = bi ? __ldg(reinterpret_cast<const int4*>(bi + j)) : make_int4(0, 0, 0, 0);
-            ptx::st_global_v4(yo + j, v[j] + (uint32_t)b.x, v[j + 1] + (uint32_t)b.y, v[j + 2] + (uint32_t)b.z,
-                              v[j + 3] + (uint32_t)b.w);
-        }
+    TileCoord t;
+    t.n_blk = tile % prm.tiles_n;
+    const int32_t mt = tile / prm.tiles_n;
+    if (prm.mode == A_WINDOW) {
+        const int32_t ct = mt % prm.col_tiles;
+        const int32_t rt = (mt / prm.col_tiles) % prm.row_tiles;
+        t.img = mt / (prm.col_tiles * prm.row_tiles);
+        t.p0 = rt * prm.rows_per_tile;
+        t.q0 = ct * prm.cols_per_tile;
+        t.m0 = 0;
     } else {
-        int8_t* yo = reinterpret_cast<int8_t*>(y) + out_off;
+        t.m0 = (int64_t)mt * kBlockM;
+        t.img = t.p0 = t.q0 = 0;
+    }
+    return t;
+}
+
+// bounded wait for the single-thread roles: false => give up (the watchdog flag is set)
+__device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, volatile int* flag)
+{
+    return ptx::mbar_wait(bar, parity, flag);
+}
+
+__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask)
+{
+    return off ^ (((off >> 7) & mask) << 4);
+}
+
+// One 16-column group of one output pixel: requantise (bias/scale from smem) and return 16 packed int8.
+__device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi, float lo)
+{
+    uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < NCOLS; j += 16) {
-            uint32_t w[4];
+    for (int t = 0; t < 4; ++t) {
+        const float4 f = *reinterpret_cast<const float4*>(sc + 4 * t);
+        const int4 b = *reinterpret_cast<const int4*>(bi + 4 * t);
+        const uint32_t b0 = requant_u8bits((int32_t)v[4 * t + 0], b.x, f.x, lo);
+        const uint32_t b1 = requant_u8bits((int32_t)v[4 * t + 1], b.y, f.y, lo);
+        const uint32_t b2 = requant_u8bits((int32_t)v[4 * t + 2], b.z, f.z, lo);
+        const uint32_t b3 = requant_u8bits((int32_t)v[4 * t + 3], b.w, f.w, lo);
+        w[t] = pack4_u8(b0, b1, b2, b3);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct EpiThread {
+    bool valid;          // this TMEM lane holds a real output pixel of the tile (window mode may drop halo lanes)
+    uint32_t srow;       // row of the tile's staging buffer
+    int32_t wrow, wcol;  // window mode: output row / column inside the tile
+};
+
+// Process NG 16-column groups held in v[] starting at tile column c.
+template <int NG>
+__device__ __forceinline__ void epi_consume(const IgemmParams& prm, const Ctl* ctl, const uint32_t* v, int32_t c,
+                                            const EpiThread& et, uint8_t* staging, float lo, int32_t* y32,
+                                            int64_t out_row, int32_t col0)
+{
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int c = j + 4 * t;
-                const int4 b = bi ? __ldg(reinterpret_cast<const int4*>(bi + c)) : make_int4(0, 0, 0, 0);
-                const float4 f = __ldg(reinterpret_cast<const float4*>(sc + c));
-                const uint32_t b0 = requant_u8bits((int32_t)v[c + 0], b.x, f.x, lo);
-                const uint32_t b1 = requant_u8bits((int32_t)v[c + 1], b.y, f.y, lo);
-                const uint32_t b2 = requant_u8bits((int32_t)v[c + 2], b.z, f.z, lo);
-                const uint32_t b3 = requant_u8bits((int32_t)v[c + 3], b.w, f.w, lo);
-                w[t] = pack4_u8(b0, b1, b2, b3);
+    for (int g = 0; g < NG; ++g) {
+        const int32_t cc = c + 16 * g;
+        if (prm.out_mode == LBC_OUT_INT8) {
+            const uint4 r = requant16(v + 16 * g, ctl->scale + cc, ctl->bias + cc, lo);
+            if (et.valid) {
+                const uint32_t panel = (uint32_t)cc / (uint32_t)prm.panel_bytes;
+                const uint32_t cb = (uint32_t)cc - panel * (uint32_t)prm.panel_bytes;
+                const uint32_t off = swz(et.srow * (uint32_t)prm.panel_bytes + cb, (1u << prm.panel_swz_bits) - 1u);
+                *reinterpret_cast<uint4*>(staging + panel * (uint32_t)(kBlockM * prm.panel_bytes) + off) = r;
             }
-            ptx::st_global_v4(yo + j, w[0], w[1], w[2], w[3]);
+        } else if (et.valid && out_row >= 0 && col0 + cc < prm.k_out) {
+            int32_t* yo = y32 + out_row * prm.k_out + col0 + cc;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const int4 b = *reinterpret_cast<const int4*>(ctl->bias + cc + j);
+                ptx::st_global_v4(yo + j, v[16 * g + j] + (uint32_t)b.x, v[16 * g + j + 1] + (uint32_t)b.y,
+                                  v[16 * g + j + 2] + (uint32_t)b.z, v[16 * g + j + 3] + (uint32_t)b.w);
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                const IgemmParams prm, const int32_t* __restrict__ bias, const float* __restrict__ scale,
-                void* __restrict__ y)
+                const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
+                const int32_t* __restrict__ bias, const float* __restrict__ scale, void* __restrict__ y)
 {
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B-swizzle atoms (the dynamic smem base is only 16B-aligned by contract).
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + (size_t)prm.stages * prm.a_stage_bytes;
-    SmemLayout* ctl = reinterpret_cast<SmemLayout*>(smem_b + (size_t)prm.stages * prm.b_stage_bytes);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* smem_a = smem;                         // A ring (TILED/IM2COL) or window ring (WINDOW)
+    uint8_t* smem_b = smem + prm.off_b;
+    uint8_t* staging = smem + prm.off_stage;
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem + prm.off_ctl);
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     volatile int* tflag = &g_timeout_flag;
 
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {       // swizzle atoms need a 1024-byte aligned base
+        if (threadIdx.x == 0) *tflag = 2;
+        return;
+    }
+
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_b);
+        ptx::prefetch_tensormap(&tm_out);
         for (int i = 0; i < prm.stages; ++i) {
             ptx::mbar_init(&ctl->full[i], 1);
             ptx::mbar_init(&ctl->empty[i], 1);
         }
+        for (int i = 0; i < prm.win_stages; ++i) {
+            ptx::mbar_init(&ctl->wfull[i], 1);
+            ptx::mbar_init(&ctl->wempty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
-            ptx::mbar_init(&ctl->tmem_empty[i], kEpilogueThreads / 32);
+            ptx::mbar_init(&ctl->tmem_empty[i], kEpiWarps);
         }
         ptx::fence_barrier_init();
     }
@@ -128,127 +223,252 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
-
     const int32_t num_tiles = prm.tiles_m * prm.tiles_n;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== ring producer: B blocks (+ A blocks in TILED / IM2COL) =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint32_t tx_bytes = prm.b_stage_bytes + (prm.mode == A_WINDOW ? 0u : prm.a_stage_bytes);
             bool ok = true;
-            const uint32_t tx_bytes = prm.a_stage_bytes + prm.b_stage_bytes;
             for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const int32_t n_blk = tile % prm.tiles_n;
-                const int32_t m_blk = tile / prm.tiles_n;
-                const int64_t m0 = (int64_t)m_blk * kBlockM;
-                // base pixel of the tile in input coordinates (im2col mode)
-                const int32_t q0 = (int32_t)(m0 % prm.q);
-                const int32_t p0 = (int32_t)((m0 / prm.q) % prm.p);
-                const int32_t n0 = (int32_t)(m0 / ((int64_t)prm.q * prm.p));
-                const int32_t w_base = q0 * prm.stride_w - prm.pad_w;
-                const int32_t h_base = p0 * prm.stride_h - prm.pad_h;
-                for (int32_t kb = 0; kb < prm.k_blocks; ++kb) {
-                    ok = ptx::mbar_wait(&ctl->empty[stage], phase ^ 1, tflag);
+                const TileCoord tc = decode_tile(prm, tile);
+                int32_t w_base = 0, h_base = 0, n0 = 0;
+                if (prm.mode == A_IM2COL) {
+                    const int32_t q0 = (int32_t)(tc.m0 % prm.q);
+                    const int32_t p0 = (int32_t)((tc.m0 / prm.q) % prm.p);
+                    n0 = (int32_t)(tc.m0 / ((int64_t)prm.q * prm.p));
+                    w_base = q0 * prm.stride_w - prm.pad_w;
+                    h_base = p0 * prm.stride_h - prm.pad_h;
+                }
+                const int32_t blocks = prm.cblocks * prm.inner;
+                for (int32_t kb = 0; kb < blocks; ++kb) {
+                    ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
                     if (!ok) break;
                     ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
-                    const int32_t tap = kb / prm.cblocks;
-                    const int32_t c0 = (kb - tap * prm.cblocks) * prm.bkc;
-                    uint8_t* dst_a = smem_a + (size_t)stage * prm.a_stage_bytes;
                     uint8_t* dst_b = smem_b + (size_t)stage * prm.b_stage_bytes;
-                    if (prm.a_im2col) {
-                        const int32_t fr = tap / prm.s_taps;
-                        const int32_t fs = tap - fr * prm.s_taps;
-                        ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0,
-                                                (uint16_t)(fs * prm.dil_w), (uint16_t)(fr * prm.dil_h));
-                    } else {
-                        ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, (int32_t)m0);
+                    if (prm.mode != A_WINDOW) {
+                        // K order [tap][channel chunk]
+                        const int32_t tap = kb / prm.cblocks;
+                        const int32_t c0 = (kb - tap * prm.cblocks) * prm.bkc;
+                        uint8_t* dst_a = smem_a + (size_t)stage * prm.a_stage_bytes;
+                        if (prm.mode == A_IM2COL) {
+                            const int32_t fr = tap / prm.s_taps;
+                            const int32_t fs = tap - fr * prm.s_taps;
+                            ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0,
+                                                    (uint16_t)(fs * prm.dil_w), (uint16_t)(fr * prm.dil_h));
+                        } else {
+                            ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, (int32_t)tc.m0);
+                        }
                     }
-                    ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], kb * prm.bkc, n_blk * prm.bn);
+                    ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], kb * prm.bkb, tc.n_blk * prm.bn);
                     if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== window producer (WINDOW mode only) =====================
+        if (lane == 0 && prm.mode == A_WINDOW) {
+            uint32_t ws = 0, wphase = 0;
+            bool ok = true;
+            for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(prm, tile);
+                for (int32_t cb = 0; cb < prm.cblocks; ++cb) {
+                    ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
+                    if (!ok) break;
+                    ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
+                    ptx::tma_load_4d(smem_a + (size_t)ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], cb * prm.bkc,
+                                     tc.q0 - prm.pad_w, tc.p0 - prm.pad_h, tc.img);
+                    if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
             uint32_t acc_stage = 0, acc_phase = 0;
             bool ok = true;
             const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
-            const uint32_t k_steps = (uint32_t)prm.bkc / 32;
+            const uint32_t k_steps = (uint32_t)prm.bkb / 32;
             for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                ok = ptx::mbar_wait(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
+                ok = wait_or_quit(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
                 if (!ok) break;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc_stage * (uint32_t)prm.bn;
-                for (int32_t kb = 0; kb < prm.k_blocks; ++kb) {
-                    ok = ptx::mbar_wait(&ctl->full[stage], phase, tflag);
-                    if (!ok) break;
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * prm.a_stage_bytes);
-                    const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * prm.b_stage_bytes);
-                    const uint64_t da = ptx::make_kmajor_desc(a_addr, (uint32_t)prm.bkc);
-                    const uint64_t db = ptx::make_kmajor_desc(b_addr, (uint32_t)prm.bkc);
-                    for (uint32_t k = 0; k < k_steps; ++k) {
-                        // advance 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-                        ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                uint32_t accumulate = 0;
+                for (int32_t cb = 0; cb < prm.mma_outer && ok; ++cb) {
+                    uint32_t win_addr = 0;
+                    if (prm.mode == A_WINDOW) {
+                        ok = wait_or_quit(&ctl->wfull[ws], wphase, tflag);
+                        if (!ok) break;
+                        ptx::tc_fence_after();
+                        win_addr = ptx::smem_u32(smem_a + (size_t)ws * prm.win_stage_bytes);
                     }
-                    ptx::mma_commit(&ctl->empty[stage]);      // smem slot reusable once these MMAs retire
-                    if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
+                    // TILED / IM2COL iterate [tap][chunk] in the producer; here the order only matters for WINDOW,
+                    // where `inner` blocks share one window.  For the ring modes cblocks*inner blocks are consumed
+                    // in ring order, so a flat loop is equivalent.
+                    for (int32_t i = 0; i < prm.mma_inner; ++i) {
+                        ok = wait_or_quit(&ctl->full[stage], phase, tflag);
+                        if (!ok) break;
+                        ptx::tc_fence_after();
+                        const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * prm.b_stage_bytes);
+                        const uint64_t db = ptx::make_kmajor_desc(b_addr, (uint32_t)prm.bkb);
+                        if (prm.mode != A_WINDOW) {
+                            const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * prm.a_stage_bytes);
+                            const uint64_t da = ptx::make_kmajor_desc(a_addr, (uint32_t)prm.bkc);
+                            for (uint32_t k = 0; k < k_steps; ++k) {
+                                ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        } else if (prm.bkc >= 32) {
+                            const int32_t fr = i / prm.s_taps;
+                            const int32_t fs = i - fr * prm.s_taps;
+                            const uint32_t shift = (uint32_t)(fr * prm.dil_h * prm.wt + fs * prm.dil_w) * (uint32_t)prm.bkc;
+                            const uint64_t da = ptx::make_kmajor_desc(win_addr + shift, (uint32_t)prm.bkc);
+                            for (uint32_t k = 0; k < k_steps; ++k) {
+                                ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        } else {
+                            // 16-byte pixels: block i = filter row i; K-step k covers taps (i, 2k) and (i, 2k+1)
+                            for (uint32_t k = 0; k < k_steps; ++k) {
+                                const uint32_t shift = (uint32_t)(i * prm.dil_h * prm.wt + 2 * (int32_t)k * prm.dil_w) * 16u;
+                                const uint64_t da = ptx::make_kmajor_desc_nosw(win_addr + shift, (uint32_t)prm.dil_w * 16u, 128u);
+                                ptx::mma_i8_ss(tmem_d, da, db + 2ull * k, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        ptx::mma_commit(&ctl->empty[stage]);      // slot reusable once these MMAs retire
+                        if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
+                    }
+                    if (!ok) break;
+                    if (prm.mode == A_WINDOW) {
+                        ptx::mma_commit(&ctl->wempty[ws]);
+                        if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                    }
                 }
                 if (!ok) break;
-                ptx::mma_commit(&ctl->tmem_full[acc_stage]);  // accumulator complete -> epilogue
+                ptx::mma_commit(&ctl->tmem_full[acc_stage]);      // accumulator complete -> epilogue
                 acc_stage ^= 1;
                 if (acc_stage == 0) acc_phase ^= 1;
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const uint32_t quarter = warp & 3;                    // TMEM lanes [32*quarter, 32*quarter+32)
+        // ===================== epilogue (warps 3..10) =====================
+        // Control flow here is uniform across all 256 threads (named barriers): a watchdog trip only stops the
+        // waiting, never the loop.
+        const uint32_t e = warp - kFirstEpiWarp;                 // 0..7
+        const uint32_t quarter = warp & 3;                        // TMEM lanes [32*quarter, +32) for this warp
+        const uint32_t half = e >> 2;                             // which half of the tile's columns
+        const uint32_t et_id = threadIdx.x - kFirstEpiWarp * 32;  // 0..255
+        const bool issuer = (et_id == 0);
         const float lo = prm.relu ? 0.0f : -128.0f;
+        const bool int8_out = (prm.out_mode == LBC_OUT_INT8);
+        const int32_t split = ((prm.bn / 16 + 1) / 2) * 16;
+        const int32_t c_begin = half ? split : 0;
+        const int32_t c_end = half ? prm.bn : split;
+
+        const uint32_t lane_row = quarter * 32 + lane;            // TMEM lane == row of the MMA tile
+        EpiThread et;
+        if (prm.mode == A_WINDOW) {
+            et.wrow = (int32_t)lane_row / prm.wt;
+            et.wcol = (int32_t)lane_row - et.wrow * prm.wt;
+            et.valid = et.wcol < prm.cols_per_tile && et.wrow < prm.rows_per_tile;
+            et.srow = (uint32_t)(et.wrow * prm.cols_per_tile + et.wcol);
+        } else {
+            et.wrow = et.wcol = 0;
+            et.valid = true;
+            et.srow = lane_row;
+        }
+
         uint32_t acc_stage = 0, acc_phase = 0;
-        bool ok = true;
-        for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            const int32_t n_blk = tile % prm.tiles_n;
-            const int32_t m_blk = tile / prm.tiles_n;
-            const int32_t col0 = n_blk * prm.bn;
-            ok = ptx::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, tflag);
-            if (!ok) break;
+        for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(prm, tile);
+            const int32_t col0 = tc.n_blk * prm.bn;
+            // (a) the previous tile's TMA store must have finished READING the staging buffer
+            if (issuer && int8_out) ptx::tma_store_wait_read<0>();
+            // (b) per-channel parameters of this N tile -> smem
+            for (int32_t c = (int32_t)et_id; c < prm.bn; c += kEpiThreads) {
+                const int32_t kc = col0 + c;
+                const bool in = kc < prm.k_out;
+                ctl->scale[c] = (in && scale) ? __ldg(scale + kc) : 0.0f;
+                ctl->bias[c] = (in && bias) ? __ldg(bias + kc) : 0;
+            }
+            ptx::named_bar_sync(1, kEpiThreads);
+            // (c) accumulator ready?
+            ptx::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, tflag);
             ptx::tc_fence_after();
 
-            const int64_t row = (int64_t)m_blk * kBlockM + quarter * 32 + lane;
-            const bool row_ok = row < prm.m_total;
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc_stage * (uint32_t)prm.bn;
-            const float* sc = scale ? scale + col0 : nullptr;
-            const int32_t* bi = bias ? bias + col0 : nullptr;
-            int32_t c = 0;
-            for (; c + 32 <= prm.bn; c += 32) {
-                uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
-                ptx::tmem_ld_wait();
-                if (row_ok) {
-                    const int64_t off = row * prm.k_out + col0 + c;
-                    if (col0 + c + 32 <= prm.k_out)
-                        epilogue_store_chunk<32>(v, sc + c, bi ? bi + c : nullptr, lo, prm.out_mode, y, off);
-                    else if (col0 + c < prm.k_out)      // N tail: K_out % 16 == 0, so exactly 16 valid columns
-                        epilogue_store_chunk<16>(v, sc + c, bi ? bi + c : nullptr, lo, prm.out_mode, y, off);
+            // int32 mode: global row of this lane (or -1)
+            int64_t out_row = -1;
+            if (!int8_out) {
+                if (prm.mode == A_WINDOW) {
+                    const int32_t pp = tc.p0 + et.wrow, qq = tc.q0 + et.wcol;
+                    if (et.valid && pp < prm.p && qq < prm.q) out_row = ((int64_t)tc.img * prm.p + pp) * prm.q + qq;
+                } else {
+                    const int64_t r = tc.m0 + lane_row;
+                    if (r < prm.m_total) out_row = r;
                 }
             }
-            if (c < prm.bn) {   // bn % 32 == 16
-                uint32_t v[16];
-                ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v);
-                ptx::tmem_ld_wait();
-                if (row_ok && col0 + c < prm.k_out)
-                    epilogue_store_chunk<16>(v, sc + c, bi ? bi + c : nullptr, lo, prm.out_mode, y,
-                                             row * prm.k_out + col0 + c);
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc_stage * (uint32_t)prm.bn;
+            int32_t* y32 = reinterpret_cast<int32_t*>(y);
+
+            // (d) drain: 32-column chunks, the load of chunk i+1 in flight while chunk i is converted
+            int32_t c = c_begin;
+            uint32_t va[32], vb[32];
+            if (c + 32 <= c_end) {
+                ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, va);
+                ptx::tmem_ld_wait_dep(va);
+                while (true) {
+                    const bool more = c + 64 <= c_end;
+                    if (more) ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c + 32), vb);
+                    epi_consume<2>(prm, ctl, va, c, et, staging, lo, y32, out_row, col0);
+                    c += 32;
+                    if (!more) break;
+                    ptx::tmem_ld_wait_dep(vb);
+                    const bool more2 = c + 64 <= c_end;
+                    if (more2) ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c + 32), va);
+                    epi_consume<2>(prm, ctl, vb, c, et, staging, lo, y32, out_row, col0);
+                    c += 32;
+                    if (!more2) break;
+                    ptx::tmem_ld_wait_dep(va);
+                }
             }
-            // accumulator drained: hand the TMEM stage back to the MMA warp
+            if (c + 16 <= c_end) {
+                uint32_t v16[16];
+                ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
+                ptx::tmem_ld_wait_dep16(v16);
+                epi_consume<1>(prm, ctl, v16, c, et, staging, lo, y32, out_row, col0);
+                c += 16;
+            }
+            // (e) accumulator drained: hand the TMEM stage back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc_stage]);
             acc_stage ^= 1;
             if (acc_stage == 0) acc_phase ^= 1;
+            // (f) staging complete -> one thread issues the TMA store(s)
+            if (int8_out) {
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(2, kEpiThreads);
+                if (issuer) {
+                    for (int32_t pnl = 0; pnl < prm.n_panels; ++pnl) {
+                        const int32_t cbyte = col0 + pnl * prm.panel_bytes;
+                        if (cbyte >= prm.k_out) break;
+                        const uint8_t* src = staging + (size_t)pnl * kBlockM * prm.panel_bytes;
+                        if (prm.mode == A_WINDOW)
+                            ptx::tma_store_4d(&tm_out, src, cbyte, tc.q0, tc.p0, tc.img);
+                        else
+                            ptx::tma_store_2d(&tm_out, src, cbyte, (int32_t)tc.m0);
+                    }
+                    ptx::tma_store_commit();
+                }
+            } else {
+                ptx::named_bar_sync(2, kEpiThreads);   // keep ctl->bias stable until every warp is done with it
+            }
         }
+        if (issuer && int8_out) ptx::tma_store_wait<0>();
     }
 
     // ---- teardown ----
@@ -292,9 +512,12 @@ lbc_status resolve_driver_entry_points()
     return LBC_OK;
 }
 
-CUtensorMapSwizzle swizzle_for(int bkc)
+CUtensorMapSwizzle swizzle_for(int row_bytes)
 {
-    return bkc == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : bkc == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+         : row_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+         : row_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                            : CU_TENSOR_MAP_SWIZZLE_NONE;
 }
 
 // Driver quirk handled the way CUTLASS does it (cute/atom/copy_traits_sm90_im2col.hpp, "driver_version <=
@@ -307,6 +530,8 @@ void small_tensor_fixup(CUtensorMap* tm, size_t tensor_bytes, int driver_version
 
 bool g_attr_set = false;
 std::mutex g_attr_mu;
+
+uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
@@ -328,65 +553,136 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
 {
     const lbc_conv_desc& d = g.d;
     IgemmConfig c{};
-    c.bkc = (d.c % 128 == 0) ? 128 : (d.c % 64 == 0) ? 64 : 32;
-    c.c_pad = (d.c + c.bkc - 1) / c.bkc * c.bkc;
-    // N tile: the whole K_out when it fits one 256-wide tile, else the largest of 256/128/... dividing it.
+    // ---- N tile: the whole K_out when it fits one 256-wide tile, else the largest of 256/128 dividing it
     if (d.k <= 256) c.bn = d.k;
     else if (d.k % 256 == 0) c.bn = 256;
     else if (d.k % 128 == 0) c.bn = 128;
-    else c.bn = 256;   // tail tile handled by TMA zero-fill + masked stores
+    else c.bn = 256;   // tail tile handled by TMA zero-fill (loads) and clipping (stores)
     c.tiles_n = (d.k + c.bn - 1) / c.bn;
-    c.tiles_m = (int32_t)((g.m_total + kBlockM - 1) / kBlockM);
-    c.k_blocks = d.r * d.s * (c.c_pad / c.bkc);
-    c.a_im2col = !(d.r == 1 && d.s == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0);
-    if (getenv("LBC_FORCE_IM2COL")) c.a_im2col = 1;   // debugging aid: exercise the im2col path on 1x1 layers
-    const size_t stage_bytes = (size_t)(kBlockM + c.bn) * c.bkc;
-    const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - sizeof(SmemLayout);
-    int stages = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
+
+    // ---- A mode
+    const bool pure_gemm = d.r == 1 && d.s == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0;
+    c.mode = pure_gemm ? A_TILED : A_IM2COL;
+    if (getenv("LBC_FORCE_IM2COL")) c.mode = A_IM2COL;   // debugging aid
+    const bool c16 = (d.c == 16);
+    c.s_pad = d.s;
+    c.rows_per_tile = c.cols_per_tile = c.row_tiles = c.col_tiles = c.wt = 0;
+    if (!pure_gemm && d.stride_h == 1 && d.stride_w == 1 && !getenv("LBC_FORCE_IM2COL") && !getenv("LBC_NO_WINDOW")) {
+        const int s_eff = c16 ? ((d.s + 1) / 2) * 2 : d.s;        // 16-byte pixels: taps are consumed in pairs
+        const int ext_w = (s_eff - 1) * d.dil_w, ext_h = (d.r - 1) * d.dil_h;
+        int col_tiles = (g.q + kBlockM - 1) / kBlockM;
+        int cols = (g.q + col_tiles - 1) / col_tiles;
+        int wt = cols + ext_w;
+        int rows = 1;
+        while (rows < g.p && rows * wt + cols <= kBlockM) ++rows;   // (rows-1)*wt + cols <= 128
+        const int row_tiles = (g.p + rows - 1) / rows;
+        const double eff = (double)g.p * g.q / ((double)row_tiles * col_tiles * kBlockM);
+        const bool s_ok = !c16 || (s_eff * 16 == 32 || s_eff * 16 == 64 || s_eff * 16 == 128);
+        if (eff >= 0.55 && wt <= 256 && rows + ext_h <= 256 && s_ok && (rows - 1) * wt + cols <= kBlockM) {
+            c.mode = A_WINDOW;
+            c.s_pad = s_eff;
+            c.rows_per_tile = rows; c.cols_per_tile = cols; c.row_tiles = row_tiles; c.col_tiles = col_tiles; c.wt = wt;
+        }
+    }
+
+    // ---- K chunking
+    if (c.mode == A_WINDOW && c16) {
+        c.bkc = 16; c.c_pad = 16;
+        c.bkb = c.s_pad * 16;
+        c.cblocks = 1;
+        c.inner = d.r;
+    } else {
+        c.bkc = (d.c % 128 == 0) ? 128 : (d.c % 64 == 0) ? 64 : 32;
+        c.c_pad = (d.c + c.bkc - 1) / c.bkc * c.bkc;
+        c.bkb = c.bkc;
+        c.cblocks = c.c_pad / c.bkc;
+        c.inner = (c.mode == A_TILED) ? 1 : d.r * d.s;
+    }
+    c.k_blocks = c.cblocks * c.inner;
+    c.packed_row_bytes = (size_t)c.k_blocks * c.bkb;
+
+    // ---- M tiles
+    if (c.mode == A_WINDOW) c.tiles_m = d.n * c.row_tiles * c.col_tiles;
+    else c.tiles_m = (int32_t)((g.m_total + kBlockM - 1) / kBlockM);
+
+    // ---- output staging (int8 mode): panels of <= 128 bytes per row
+    if (c.bn % 128 == 0) c.panel_bytes = 128;
+    else if (c.bn == 64 || c.bn == 32) c.panel_bytes = c.bn;
+    else c.panel_bytes = c.bn;                      // unswizzled single panel (rare channel counts)
+    c.n_panels = c.bn / c.panel_bytes;
+    c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
+    const uint32_t stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(kBlockM * c.bn), 1024) : 0;
+
+    // ---- smem carve-up
+    const uint32_t ctl_bytes = round_up((uint32_t)sizeof(Ctl), 256);
+    const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
+    c.a_stage_bytes = (c.mode == A_WINDOW) ? 0 : (uint32_t)(kBlockM * c.bkc);
+    c.b_stage_bytes = (uint32_t)(c.bn * c.bkb);
+    c.win_stage_bytes = c.win_tx_bytes = 0;
+    c.win_stages = 0;
+    uint32_t win_total = 0;
+    if (c.mode == A_WINDOW) {
+        const int s_eff = c.s_pad;
+        const int ext_w = (s_eff - 1) * d.dil_w, ext_h = (d.r - 1) * d.dil_h;
+        const uint32_t box_bytes = (uint32_t)(c.wt * (c.rows_per_tile + ext_h) * c.bkc);
+        const uint32_t reach = (uint32_t)((kBlockM + ext_h * c.wt + ext_w + 1) * c.bkc);   // furthest row an MMA reads
+        c.win_tx_bytes = box_bytes;
+        c.win_stage_bytes = round_up(std::max(box_bytes, reach), 1024);
+        c.win_stages = std::min(kMaxWinStages, std::max(2, c.cblocks > 1 ? 3 : 2));
+        win_total = c.win_stages * c.win_stage_bytes;
+        LBC_REQUIRE(win_total + 2 * c.b_stage_bytes <= budget, LBC_ERR_UNSUPPORTED, "igemm: window does not fit in smem");
+    }
+    const uint32_t ring_stage = c.a_stage_bytes + c.b_stage_bytes;
+    int stages = (int)std::min<uint32_t>(kMaxStages, (budget - win_total) / ring_stage);
     stages = std::max(2, std::min(stages, std::max(2, c.k_blocks * 2)));
     c.stages = stages;
-    c.smem_bytes = 1024 + (size_t)stages * stage_bytes + sizeof(SmemLayout);
+    c.off_b = (c.mode == A_WINDOW) ? win_total : (uint32_t)stages * c.a_stage_bytes;
+    c.off_stage = c.off_b + (uint32_t)stages * c.b_stage_bytes;
+    c.off_ctl = c.off_stage + stage_bytes;
+    c.smem_bytes = c.off_ctl + ctl_bytes;
+    LBC_REQUIRE(c.smem_bytes <= 227 * 1024, LBC_ERR_UNSUPPORTED, "igemm: smem %zu too large", c.smem_bytes);
+
     uint32_t cols = 32;
     while (cols < 2u * (uint32_t)c.bn) cols <<= 1;
     c.tmem_cols = cols;
     c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
-    LBC_REQUIRE(c.smem_bytes <= 227 * 1024, LBC_ERR_UNSUPPORTED, "igemm: smem %zu too large", c.smem_bytes);
     *cfg = c;
     return LBC_OK;
 }
 
 lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceInfo& dev, const int8_t* x,
-                        const int8_t* w_packed, IgemmLaunch* out)
+                        const int8_t* w_packed, void* y, IgemmLaunch* out)
 {
     lbc_status st = resolve_driver_entry_points();
     if (st != LBC_OK) return st;
     const lbc_conv_desc& d = g.d;
-    LBC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
-                LBC_ERR_INVALID_ARG, "igemm: x and packed weights must be 16-byte aligned");
+    LBC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+                LBC_ERR_INVALID_ARG, "igemm: x, packed weights and y must be 16-byte aligned");
     out->cfg = cfg;
-    const CUtensorMapSwizzle swz = swizzle_for(cfg.bkc);
     const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 
-    // ---- B: [K_out rows][R*S*c_pad bytes], box {bkc, bn}
+    // ---- B: [K_out rows][packed_row_bytes], box {bkb, bn}
     {
-        const cuuint64_t dims[2] = {(cuuint64_t)d.r * d.s * cfg.c_pad, (cuuint64_t)d.k};
-        const cuuint64_t strides[1] = {(cuuint64_t)d.r * d.s * cfg.c_pad};
-        const cuuint32_t box[2] = {(cuuint32_t)cfg.bkc, (cuuint32_t)cfg.bn};
+        const cuuint64_t dims[2] = {(cuuint64_t)cfg.packed_row_bytes, (cuuint64_t)d.k};
+        const cuuint64_t strides[1] = {(cuuint64_t)cfg.packed_row_bytes};
+        const cuuint32_t box[2] = {(cuuint32_t)cfg.bkb, (cuuint32_t)cfg.bn};
         CUresult r = g_encode_tiled(&out->tm_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)w_packed, dims, strides, box,
-                                    ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cfg.bkb), promo,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
     // ---- A
-    if (!cfg.a_im2col) {
+    if (cfg.mode == A_TILED) {
         const cuuint64_t dims[2] = {(cuuint64_t)d.c, (cuuint64_t)g.m_total};
         const cuuint64_t strides[1] = {(cuuint64_t)d.c};
         const cuuint32_t box[2] = {(cuuint32_t)cfg.bkc, (cuuint32_t)kBlockM};
         CUresult r = g_encode_tiled(&out->tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)x, dims, strides, box, ones,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cfg.bkc), promo,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
-    } else {
+    } else if (cfg.mode == A_IM2COL) {
         // rank-4 (C, W, H, N); corners in (W, H) order.  lower = -pad ; upper = pad - (filter-1)*dilation.
         const cuuint64_t dims[4] = {(cuuint64_t)d.c, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
         const cuuint64_t strides[3] = {(cuuint64_t)d.c, (cuuint64_t)d.c * d.w, (cuuint64_t)d.c * d.w * d.h};
@@ -395,10 +691,44 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
         const cuuint32_t trav[4] = {1, (cuuint32_t)d.stride_w, (cuuint32_t)d.stride_h, 1};
         CUresult r = g_encode_im2col(&out->tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)x, dims, strides, lower,
                                      upper, (cuuint32_t)cfg.bkc, (cuuint32_t)kBlockM, trav,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cfg.bkc), promo,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeIm2col(A) failed: %d", (int)r);
         small_tensor_fixup(&out->tm_a, (size_t)d.n * d.h * d.w * d.c, dev.driver_version);
+    } else {
+        // WINDOW: rank-4 tiled (C, W, H, N), box {bkc, wt, rows + (R-1)*dil_h, 1}; OOB zero-fill is the padding
+        const cuuint64_t dims[4] = {(cuuint64_t)d.c, (cuuint64_t)d.w, (cuuint64_t)d.h, (cuuint64_t)d.n};
+        const cuuint64_t strides[3] = {(cuuint64_t)d.c, (cuuint64_t)d.c * d.w, (cuuint64_t)d.c * d.w * d.h};
+        const cuuint32_t box[4] = {(cuuint32_t)cfg.bkc, (cuuint32_t)cfg.wt,
+                                   (cuuint32_t)(cfg.rows_per_tile + (d.r - 1) * d.dil_h), 1};
+        CUresult r = g_encode_tiled(&out->tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)x, dims, strides, box, ones,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cfg.bkc), promo,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(A window) failed: %d", (int)r);
+    }
+    // ---- output (int8 mode): staged tile -> TMA store
+    if (d.out_mode == LBC_OUT_INT8) {
+        const CUtensorMapSwizzle oswz = cfg.panel_swz_bits ? swizzle_for(cfg.panel_bytes) : CU_TENSOR_MAP_SWIZZLE_NONE;
+        CUresult r;
+        if (cfg.mode == A_WINDOW) {
+            const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)g.q, (cuuint64_t)g.p, (cuuint64_t)d.n};
+            const cuuint64_t strides[3] = {(cuuint64_t)d.k, (cuuint64_t)d.k * g.q, (cuuint64_t)d.k * g.q * g.p};
+            const cuuint32_t box[4] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)cfg.cols_per_tile,
+                                       (cuuint32_t)cfg.rows_per_tile, 1};
+            r = g_encode_tiled(&out->tm_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, y, dims, strides, box, ones,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        } else {
+            const cuuint64_t dims[2] = {(cuuint64_t)d.k, (cuuint64_t)g.m_total};
+            const cuuint64_t strides[1] = {(cuuint64_t)d.k};
+            const cuuint32_t box[2] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)kBlockM};
+            r = g_encode_tiled(&out->tm_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, y, dims, strides, box, ones,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+    } else {
+        out->tm_out = out->tm_b;   // unused in int32 mode; keep the parameter a valid descriptor
     }
     return LBC_OK;
 }
@@ -410,17 +740,24 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     const lbc_conv_desc& d = g.d;
     IgemmParams prm{};
     prm.m_total = g.m_total;
-    prm.k_out = d.k;
-    prm.bn = c.bn; prm.bkc = c.bkc; prm.stages = c.stages; prm.a_im2col = c.a_im2col;
-    prm.tiles_m = c.tiles_m; prm.tiles_n = c.tiles_n; prm.k_blocks = c.k_blocks; prm.cblocks = c.c_pad / c.bkc;
-    prm.p = g.p; prm.q = g.q; prm.s_taps = d.s;
+    prm.k_out = d.k; prm.n_img = d.n; prm.p = g.p; prm.q = g.q;
+    prm.mode = c.mode; prm.bn = c.bn; prm.bkc = c.bkc; prm.bkb = c.bkb;
+    prm.tiles_m = c.tiles_m; prm.tiles_n = c.tiles_n; prm.cblocks = c.cblocks; prm.inner = c.inner;
+    prm.s_taps = d.s;
     prm.stride_h = d.stride_h; prm.stride_w = d.stride_w; prm.pad_h = d.pad_h; prm.pad_w = d.pad_w;
     prm.dil_h = d.dil_h; prm.dil_w = d.dil_w;
+    prm.stages = c.stages; prm.a_stage_bytes = c.a_stage_bytes; prm.b_stage_bytes = c.b_stage_bytes;
+    prm.win_stages = c.win_stages; prm.win_stage_bytes = c.win_stage_bytes; prm.win_tx_bytes = c.win_tx_bytes;
+    prm.wt = c.wt; prm.rows_per_tile = c.rows_per_tile; prm.cols_per_tile = c.cols_per_tile;
+    prm.row_tiles = c.row_tiles; prm.col_tiles = c.col_tiles;
     prm.relu = ep.relu; prm.out_mode = ep.out_mode;
     prm.tmem_cols = c.tmem_cols;
-    prm.a_stage_bytes = (uint32_t)(kBlockM * c.bkc);
-    prm.b_stage_bytes = (uint32_t)(c.bn * c.bkc);
-    LBC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0, LBC_ERR_INVALID_ARG, "igemm: y must be 16-byte aligned");
+    prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
+    prm.off_b = c.off_b; prm.off_stage = c.off_stage; prm.off_ctl = c.off_ctl;
+    // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one
+    // "channel chunk" of cblocks*inner blocks.
+    if (c.mode == A_WINDOW) { prm.mma_outer = c.cblocks; prm.mma_inner = c.inner; }
+    else { prm.mma_outer = 1; prm.mma_inner = c.cblocks * c.inner; }
     {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (!g_attr_set) {
@@ -428,7 +765,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
             g_attr_set = true;
         }
     }
-    igemm_i8_kernel<<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, prm, ep.bias, ep.scale, y);
+    igemm_i8_kernel<<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }
@@ -440,7 +777,8 @@ lbc_status igemm_check_timeout()
     if (flag) {
         int zero = 0;
         cudaMemcpyToSymbol(g_timeout_flag, &zero, sizeof(int));
-        set_error("igemm: device pipeline watchdog fired (mbarrier wait exceeded 2 s)");
+        set_error(flag == 2 ? "igemm: dynamic shared memory base is not 1024-byte aligned"
+                            : "igemm: device pipeline watchdog fired (mbarrier wait exceeded 2 s)");
         return LBC_ERR_KERNEL_TIMEOUT;
     }
     return LBC_OK;

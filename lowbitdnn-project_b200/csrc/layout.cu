@@ -52,6 +52,34 @@ __global__ void __launch_bounds__(256) prepack_krsc_kernel(const int8_t* __restr
     }
 }
 
+// tcgen05 filter matrix (see common.cuh::launch_prepack_igemm).
+__global__ void __launch_bounds__(256) prepack_igemm_kernel(const int8_t* __restrict__ src, int32_t oihw,
+                                                            int8_t* __restrict__ dst, int32_t k, int32_t r, int32_t s,
+                                                            int32_t cg, int32_t s_pad, int32_t bkc, int32_t cblocks,
+                                                            int32_t chunk_outer)
+{
+    const int32_t taps = r * s_pad;
+    const int64_t row_bytes = (int64_t)taps * cblocks * bkc;
+    const int64_t total = (int64_t)k * row_bytes;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t ik = (int32_t)(i / row_bytes);
+        const int32_t rest = (int32_t)(i - (int64_t)ik * row_bytes);
+        const int32_t cin = rest % bkc;
+        int32_t tap, cb;
+        if (chunk_outer) { cb = rest / (taps * bkc); tap = (rest / bkc) % taps; }
+        else             { tap = rest / (cblocks * bkc); cb = (rest / bkc) % cblocks; }
+        const int32_t c = cb * bkc + cin;
+        const int32_t ir = tap / s_pad, is = tap % s_pad;
+        int8_t v = 0;
+        if (c < cg && is < s) {
+            const int64_t so = oihw ? ((((int64_t)ik * cg + c) * r + ir) * s + is)
+                                    : ((((int64_t)ik * r + ir) * s + is) * cg + c);
+            v = src[so];
+        }
+        dst[i] = v;
+    }
+}
+
 // depthwise: dst [R][S][C] <- src [C][R][S] (KRSC with cg==1 and OIHW with I==1 coincide).
 __global__ void __launch_bounds__(256) prepack_dw_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst,
                                                          int32_t c, int32_t rs)
@@ -79,6 +107,17 @@ lbc_status launch_prepack_krsc(const int8_t* src, int32_t src_layout, int8_t* ds
 {
     const int64_t total = (int64_t)k * r * s * c_pad;
     prepack_krsc_kernel<<<grid_for(total), 256, 0, stream>>>(src, src_layout == LBC_W_OIHW, dst, k, r, s, cg, c_pad);
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
+
+lbc_status launch_prepack_igemm(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
+                                int32_t cg, int32_t s_pad, int32_t bkc, int32_t cblocks, int32_t chunk_outer,
+                                cudaStream_t stream)
+{
+    const int64_t total = (int64_t)k * r * s_pad * cblocks * bkc;
+    prepack_igemm_kernel<<<grid_for(total), 256, 0, stream>>>(src, src_layout == LBC_W_OIHW, dst, k, r, s, cg, s_pad,
+                                                              bkc, cblocks, chunk_outer);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

@@ -130,6 +130,17 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3)
+        : "memory");
+}
+
 // im2col-mode load of a rank-4 (C,W,H,N) tensor: coordinates are the base pixel (input space) and the
 // first channel; (off_w, off_h) is the filter-tap offset (s*dil_w, r*dil_h).
 __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t c,
@@ -148,6 +159,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(tm)),
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1,
+                                             int32_t c2, int32_t c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 
@@ -210,6 +230,30 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar)
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Wait for outstanding tcgen05.ld AND tie the destination registers to the wait, so the compiler cannot
+// schedule arithmetic on them above it (the loads are asynchronous until wait::ld).
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                   "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                   "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                   "+r"(r[15])
+                 :
+                 : "memory");
+}
+
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -249,6 +293,18 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
     d |= (uint64_t)((8u * row_bytes) >> 4) << 32;         // SBO
     d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
     d |= layout << 61;
+    return d;
+}
+
+// Unswizzled K-major operand: 8-row x 16-byte core matrices; `lbo` = byte distance between the two 16-byte
+// K chunks of one MMA, `sbo` = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_kmajor_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
     return d;
 }
 

@@ -71,6 +71,17 @@ IGEMM_CASES = [
     D(n=1, h=15, w=15, c=64, k=64, r=3, s=3, pad_h=2, pad_w=2, dil_h=2, dil_w=2),
     D(n=1, h=12, w=10, c=64, k=32, r=3, s=1, pad_h=1, pad_w=0),
     D(n=1, h=10, w=10, c=64, k=64, r=3, s=3),                                 # VALID (reference style)
+    # shifted-window path: tiles of whole rows, column tiles, ragged edges, N tiles, 16-byte pixels
+    D(n=3, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+    D(n=5, h=7, w=7, c=512, k=512, r=3, s=3, pad_h=1, pad_w=1),
+    D(n=1, h=20, w=224, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+    D(n=2, h=9, w=150, c=32, k=48, r=3, s=3, pad_h=1, pad_w=1),
+    D(n=2, h=19, w=23, c=32, k=32, r=5, s=5, pad_h=2, pad_w=2, relu=1),
+    D(n=2, h=14, w=14, c=128, k=512, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+    D(n=2, h=30, w=40, c=16, k=32, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # C=16: paired taps, phantom 4th tap
+    D(n=2, h=33, w=115, c=16, k=64, r=4, s=4, relu=1),                         # the space-to-depth'd 7x7 stem shape
+    D(n=2, h=20, w=57, c=16, k=32, r=2, s=2),
+    D(n=1, h=8, w=40, c=64, k=64, r=1, s=3, pad_h=0, pad_w=1),
 ]
 
 
@@ -78,6 +89,14 @@ IGEMM_CASES = [
 @pytest.mark.parametrize("out_mode", [1, 0])
 def test_igemm_tc_kernel(d, out_mode):
     assert _check(D(**{**d.__dict__, "out_mode": out_mode}), force=IGEMM) == "igemm_tc"
+
+
+@pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.stride_h == 1 and c.r > 1][:6],
+                         ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}")
+def test_igemm_im2col_path_on_stride1_shapes(d, monkeypatch):
+    """The same stride-1 layers with the window planner disabled: the TMA im2col path stays covered."""
+    monkeypatch.setenv("LBC_NO_WINDOW", "1")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
 
 
 def test_igemm_reference_style_inputs_and_oihw_weights():

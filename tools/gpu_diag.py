@@ -52,6 +52,22 @@ CASES = [
     ("i2c_rect", D(n=1, h=17, w=13, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1), IGEMM),
     ("i2c_small_tensor", D(n=1, h=6, w=6, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1), IGEMM),
     ("i2c_resnet_l3", D(n=8, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
+    # --- same stride-1 shapes with the window path disabled (pure im2col coverage)
+    ("nowin_3x3_p1_c64", D(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1), IGEMM, {"LBC_NO_WINDOW": "1"}),
+    ("nowin_3x3_c256_i8", D(n=2, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM, {"LBC_NO_WINDOW": "1"}),
+    # --- window path specifics
+    ("win_56_c64_i8", D(n=3, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
+    ("win_28_c128_i8", D(n=3, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
+    ("win_14_c256_i32", D(n=3, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1), IGEMM),
+    ("win_7_c512_i8", D(n=5, h=7, w=7, c=512, k=512, r=3, s=3, pad_h=1, pad_w=1, out_mode=0), IGEMM),
+    ("win_224_c64_coltiles", D(n=1, h=20, w=224, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
+    ("win_150_c32_ragged", D(n=2, h=9, w=150, c=32, k=48, r=3, s=3, pad_h=1, pad_w=1, out_mode=0), IGEMM),
+    ("win_5x5_p2", D(n=2, h=19, w=23, c=32, k=32, r=5, s=5, pad_h=2, pad_w=2, out_mode=0, relu=1), IGEMM),
+    ("win_k512_ntiles", D(n=2, h=14, w=14, c=128, k=512, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
+    ("win_c16_3x3", D(n=2, h=30, w=40, c=16, k=32, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
+    ("win_c16_4x4", D(n=2, h=33, w=115, c=16, k=64, r=4, s=4, out_mode=0, relu=1), IGEMM),
+    ("win_c16_2x2_i32", D(n=2, h=20, w=57, c=16, k=32, r=2, s=2), IGEMM),
+    ("win_1xS", D(n=1, h=8, w=40, c=64, k=64, r=1, s=3, pad_h=0, pad_w=1, out_mode=0), IGEMM),
 ]
 
 
