@@ -120,22 +120,30 @@ lbc_status probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, cudaStream_t
 lbc_status flush_l2(cudaStream_t stream);
 
 // ---- the fused epilogue, shared by every kernel (bit-exact with oracle_requant) ----------------
-// t = acc + bias (int32 wraparound) ; f = float(t) RNE ; f *= scale (single multiply) ;
-// clamp to [lo,127] in fp32 (NaN -> lo, as fmaxf drops NaN) ; round-half-to-even via the 1.5*2^23
-// magic add ; the low byte of the result's bit pattern is the two's-complement int8.
-__device__ __forceinline__ uint32_t requant_u8bits(int32_t acc, int32_t bias, float scale, float lo)
+// t = acc + bias (int32 wraparound) ; f = float(t) RNE ; f *= scale (single multiply) ; f = fmaxf(f, lo)
+// (drops NaN to lo) ; q = cvt.rni.s32.f32(f) (round-half-to-even, saturating) ; the upper clamp to 127 (and the
+// lower one, already guaranteed by lo >= -128) is done by the saturating int32->int8 pack.
+// Measured on B200 (tools/exp/epi_bench.cu): this F2I + cvt.pack.sat form is ~25% faster than a float clamp +
+// magic-number rounding + PRMT packing.
+__device__ __forceinline__ int32_t requant_s32(int32_t acc, int32_t bias, float scale, float lo)
 {
     const int32_t t = acc + bias;
-    float f = __fmul_rn(__int2float_rn(t), scale);
-    f = fminf(fmaxf(f, lo), 127.0f);
-    return __float_as_uint(__fadd_rn(f, 12582912.0f));
+    const float f = fmaxf(__fmul_rn(__int2float_rn(t), scale), lo);
+    return __float2int_rn(f);
 }
 
-__device__ __forceinline__ uint32_t pack4_u8(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+// {a, b, c, d} (int32, already >= -128) -> four saturated int8 packed little-endian.
+__device__ __forceinline__ uint32_t pack4_sat_s8(int32_t a, int32_t b, int32_t c, int32_t d)
 {
-    const uint32_t ab = __byte_perm(a, b, 0x0040);  // {a0, b0, ., .}
-    const uint32_t cd = __byte_perm(c, d, 0x0040);
-    return __byte_perm(ab, cd, 0x5410);
+    uint32_t hi, r;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(d), "r"(c));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r;
+}
+
+__device__ __forceinline__ int8_t requant_s8(int32_t acc, int32_t bias, float scale, float lo)
+{
+    return (int8_t)min(requant_s32(acc, bias, scale, lo), 127);
 }
 
 }  // namespace lbc

@@ -82,16 +82,16 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(DirectParams g, const 
     } else {
         int8_t* yo = reinterpret_cast<int8_t*>(y) + o;
         if (KT == 4 && (g.k & 3) == 0) {
-            uint32_t b[4];
+            int32_t b[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                b[j] = requant_u8bits(acc[j], bias ? bias[k0 + j] : 0, scale[k0 + j], lo);
-            *reinterpret_cast<uint32_t*>(yo) = pack4_u8(b[0], b[1], b[2], b[3]);
+                b[j] = requant_s32(acc[j], bias ? bias[k0 + j] : 0, scale[k0 + j], lo);
+            *reinterpret_cast<uint32_t*>(yo) = pack4_sat_s8(b[0], b[1], b[2], b[3]);
         } else {
 #pragma unroll
             for (int j = 0; j < KT; ++j)
                 if (k0 + j < g.k)
-                    yo[j] = (int8_t)(requant_u8bits(acc[j], bias ? bias[k0 + j] : 0, scale[k0 + j], lo) & 0xFF);
+                    yo[j] = requant_s8(acc[j], bias ? bias[k0 + j] : 0, scale[k0 + j], lo);
         }
     }
 }
@@ -135,10 +135,10 @@ __global__ void __launch_bounds__(256) depthwise_kernel(DirectParams g, const in
         v.w = acc[3] + (bias ? bias[c0 + 3] : 0);
         *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(y) + o) = v;
     } else {
-        uint32_t b[4];
+        int32_t b[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = requant_u8bits(acc[j], bias ? bias[c0 + j] : 0, scale[c0 + j], lo);
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(y) + o) = pack4_u8(b[0], b[1], b[2], b[3]);
+        for (int j = 0; j < 4; ++j) b[j] = requant_s32(acc[j], bias ? bias[c0 + j] : 0, scale[c0 + j], lo);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(y) + o) = pack4_sat_s8(b[0], b[1], b[2], b[3]);
     }
 }
 

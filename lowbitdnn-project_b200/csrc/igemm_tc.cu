@@ -37,10 +37,11 @@ namespace lbc {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kFirstEpiWarp = 3;                       // warp 0: ring TMA, 1: MMA + TMEM alloc, 2: window TMA
-constexpr int kNumThreads = kFirstEpiWarp * 32 + kEpiThreads;   // 352
+constexpr int kTeams = 2;                              // epilogue teams; team t drains TMEM accumulator stage t
+constexpr int kTeamWarps = 8;
+constexpr int kTeamThreads = kTeamWarps * 32;
+constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA + TMEM alloc, 2: window TMA, 3: idle
+constexpr int kNumThreads = (kFirstEpiWarp + kTeams * kTeamWarps) * 32;   // 640
 constexpr int kMaxStages = 8;
 constexpr int kMaxWinStages = 4;
 
@@ -85,8 +86,8 @@ struct Ctl {
     uint64_t tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad_[3];
-    alignas(16) float scale[256];
-    alignas(16) int32_t bias[256];
+    alignas(16) float scale[kTeams][256];
+    alignas(16) int32_t bias[kTeams][256];
 };
 
 struct TileCoord {
@@ -133,11 +134,8 @@ __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, c
     for (int t = 0; t < 4; ++t) {
         const float4 f = *reinterpret_cast<const float4*>(sc + 4 * t);
         const int4 b = *reinterpret_cast<const int4*>(bi + 4 * t);
-        const uint32_t b0 = requant_u8bits((int32_t)v[4 * t + 0], b.x, f.x, lo);
-        const uint32_t b1 = requant_u8bits((int32_t)v[4 * t + 1], b.y, f.y, lo);
-        const uint32_t b2 = requant_u8bits((int32_t)v[4 * t + 2], b.z, f.z, lo);
-        const uint32_t b3 = requant_u8bits((int32_t)v[4 * t + 3], b.w, f.w, lo);
-        w[t] = pack4_u8(b0, b1, b2, b3);
+        w[t] = pack4_sat_s8(requant_s32((int32_t)v[4 * t + 0], b.x, f.x, lo), requant_s32((int32_t)v[4 * t + 1], b.y, f.y, lo),
+                            requant_s32((int32_t)v[4 * t + 2], b.z, f.z, lo), requant_s32((int32_t)v[4 * t + 3], b.w, f.w, lo));
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -148,28 +146,28 @@ struct EpiThread {
     int32_t wrow, wcol;  // window mode: output row / column inside the tile
 };
 
-// Process NG 16-column groups held in v[] starting at tile column c.
+// Process NG 16-column groups held in v[] starting at tile column c (columns of staging panel `pnl0`..).
 template <int NG>
-__device__ __forceinline__ void epi_consume(const IgemmParams& prm, const Ctl* ctl, const uint32_t* v, int32_t c,
-                                            const EpiThread& et, uint8_t* staging, float lo, int32_t* y32,
-                                            int64_t out_row, int32_t col0)
+__device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
+                                            const uint32_t* v, int32_t c, const EpiThread& et, uint8_t* staging,
+                                            float lo, int32_t* y32, int64_t out_row, int32_t col0)
 {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         const int32_t cc = c + 16 * g;
         if (prm.out_mode == LBC_OUT_INT8) {
-            const uint4 r = requant16(v + 16 * g, ctl->scale + cc, ctl->bias + cc, lo);
+            const uint4 r = requant16(v + 16 * g, sc + cc, bi + cc, lo);
             if (et.valid) {
-                const uint32_t panel = (uint32_t)cc / (uint32_t)prm.panel_bytes;
-                const uint32_t cb = (uint32_t)cc - panel * (uint32_t)prm.panel_bytes;
+                // staging holds ONE panel (panel_bytes columns) at a time
+                const uint32_t cb = (uint32_t)cc % (uint32_t)prm.panel_bytes;
                 const uint32_t off = swz(et.srow * (uint32_t)prm.panel_bytes + cb, (1u << prm.panel_swz_bits) - 1u);
-                *reinterpret_cast<uint4*>(staging + panel * (uint32_t)(kBlockM * prm.panel_bytes) + off) = r;
+                *reinterpret_cast<uint4*>(staging + off) = r;
             }
-        } else if (et.valid && out_row >= 0 && col0 + cc < prm.k_out) {
+        } else if (out_row >= 0 && col0 + cc < prm.k_out) {
             int32_t* yo = y32 + out_row * prm.k_out + col0 + cc;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                const int4 b = *reinterpret_cast<const int4*>(ctl->bias + cc + j);
+                const int4 b = *reinterpret_cast<const int4*>(bi + cc + j);
                 ptx::st_global_v4(yo + j, v[16 * g + j] + (uint32_t)b.x, v[16 * g + j + 1] + (uint32_t)b.y,
                                   v[16 * g + j + 2] + (uint32_t)b.z, v[16 * g + j + 3] + (uint32_t)b.w);
             }
@@ -211,7 +209,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
-            ptx::mbar_init(&ctl->tmem_empty[i], kEpiWarps);
+            ptx::mbar_init(&ctl->tmem_empty[i], kTeamWarps);
         }
         ptx::fence_barrier_init();
     }
@@ -225,107 +223,123 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t tmem_base = ctl->tmem_base;
     const int32_t num_tiles = prm.tiles_m * prm.tiles_n;
 
+    // The three issue roles below run with ALL 32 lanes of their warp executing the (warp-uniform) loops; only
+    // the TMA / MMA / commit instructions themselves are predicated on one elected lane.  Keeping the loops
+    // convergent lets the compiler hold addresses and descriptors in uniform registers; a `lane == 0` branch
+    // around the whole loop made every tcgen05.mma cost ~150 scalar instructions (ncu, r01 v2).
     if (warp == 0) {
         // ===================== ring producer: B blocks (+ A blocks in TILED / IM2COL) =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint32_t tx_bytes = prm.b_stage_bytes + (prm.mode == A_WINDOW ? 0u : prm.a_stage_bytes);
-            bool ok = true;
-            for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(prm, tile);
-                int32_t w_base = 0, h_base = 0, n0 = 0;
-                if (prm.mode == A_IM2COL) {
-                    const int32_t q0 = (int32_t)(tc.m0 % prm.q);
-                    const int32_t p0 = (int32_t)((tc.m0 / prm.q) % prm.p);
-                    n0 = (int32_t)(tc.m0 / ((int64_t)prm.q * prm.p));
-                    w_base = q0 * prm.stride_w - prm.pad_w;
-                    h_base = p0 * prm.stride_h - prm.pad_h;
-                }
-                const int32_t blocks = prm.cblocks * prm.inner;
-                for (int32_t kb = 0; kb < blocks; ++kb) {
-                    ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
-                    if (!ok) break;
+        uint32_t stage = 0, phase = 0;
+        const uint32_t tx_bytes = prm.b_stage_bytes + (prm.mode == A_WINDOW ? 0u : prm.a_stage_bytes);
+        const int32_t blocks = prm.cblocks * prm.inner;
+        const bool leader = ptx::elect_one();
+        bool ok = true;
+        for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(prm, tile);
+            int32_t w_base = 0, h_base = 0, n0 = 0;
+            if (prm.mode == A_IM2COL) {
+                const int32_t q0 = (int32_t)(tc.m0 % prm.q);
+                const int32_t p0 = (int32_t)((tc.m0 / prm.q) % prm.p);
+                n0 = (int32_t)(tc.m0 / ((int64_t)prm.q * prm.p));
+                w_base = q0 * prm.stride_w - prm.pad_w;
+                h_base = p0 * prm.stride_h - prm.pad_h;
+            }
+            const int32_t brow = tc.n_blk * prm.bn;
+            // ring modes walk K as [tap][channel chunk]: (fr, fs) filter tap, c0 channel offset
+            int32_t c0 = 0, cbi = 0, off_w = 0, off_h = 0, fs = 0, bcol = 0;
+            for (int32_t kb = 0; kb < blocks; ++kb) {
+                ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
+                if (!ok) break;
+                if (leader) {
                     ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
-                    uint8_t* dst_b = smem_b + (size_t)stage * prm.b_stage_bytes;
-                    if (prm.mode != A_WINDOW) {
-                        // K order [tap][channel chunk]
-                        const int32_t tap = kb / prm.cblocks;
-                        const int32_t c0 = (kb - tap * prm.cblocks) * prm.bkc;
-                        uint8_t* dst_a = smem_a + (size_t)stage * prm.a_stage_bytes;
-                        if (prm.mode == A_IM2COL) {
-                            const int32_t fr = tap / prm.s_taps;
-                            const int32_t fs = tap - fr * prm.s_taps;
-                            ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0,
-                                                    (uint16_t)(fs * prm.dil_w), (uint16_t)(fr * prm.dil_h));
-                        } else {
-                            ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, (int32_t)tc.m0);
-                        }
+                    uint8_t* dst_b = smem_b + stage * prm.b_stage_bytes;
+                    if (prm.mode == A_IM2COL) {
+                        ptx::tma_load_im2col_4d(smem_a + stage * prm.a_stage_bytes, &tm_a, &ctl->full[stage], c0, w_base,
+                                                h_base, n0, (uint16_t)off_w, (uint16_t)off_h);
+                    } else if (prm.mode == A_TILED) {
+                        ptx::tma_load_2d(smem_a + stage * prm.a_stage_bytes, &tm_a, &ctl->full[stage], c0, (int32_t)tc.m0);
                     }
-                    ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], kb * prm.bkb, tc.n_blk * prm.bn);
-                    if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
+                    ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
                 }
+                bcol += prm.bkb;
+                c0 += prm.bkc;
+                if (++cbi == prm.cblocks) {
+                    cbi = 0; c0 = 0;
+                    off_w += prm.dil_w;
+                    if (++fs == prm.s_taps) { fs = 0; off_w = 0; off_h += prm.dil_h; }
+                }
+                if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 2) {
         // ===================== window producer (WINDOW mode only) =====================
-        if (lane == 0 && prm.mode == A_WINDOW) {
+        if (prm.mode == A_WINDOW) {
             uint32_t ws = 0, wphase = 0;
+            const bool leader = ptx::elect_one();
             bool ok = true;
             for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(prm, tile);
-                for (int32_t cb = 0; cb < prm.cblocks; ++cb) {
+                int32_t c0 = 0;
+                for (int32_t cb = 0; cb < prm.cblocks; ++cb, c0 += prm.bkc) {
                     ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
                     if (!ok) break;
-                    ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
-                    ptx::tma_load_4d(smem_a + (size_t)ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], cb * prm.bkc,
-                                     tc.q0 - prm.pad_w, tc.p0 - prm.pad_h, tc.img);
+                    if (leader) {
+                        ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
+                        ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, tc.q0 - prm.pad_w,
+                                         tc.p0 - prm.pad_h, tc.img);
+                    }
                     if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
-            uint32_t acc_stage = 0, acc_phase = 0;
-            bool ok = true;
-            const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
-            const uint32_t k_steps = (uint32_t)prm.bkb / 32;
-            for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                ok = wait_or_quit(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
-                if (!ok) break;
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc_stage * (uint32_t)prm.bn;
-                uint32_t accumulate = 0;
-                for (int32_t cb = 0; cb < prm.mma_outer && ok; ++cb) {
-                    uint32_t win_addr = 0;
-                    if (prm.mode == A_WINDOW) {
-                        ok = wait_or_quit(&ctl->wfull[ws], wphase, tflag);
-                        if (!ok) break;
-                        ptx::tc_fence_after();
-                        win_addr = ptx::smem_u32(smem_a + (size_t)ws * prm.win_stage_bytes);
-                    }
-                    // TILED / IM2COL iterate [tap][chunk] in the producer; here the order only matters for WINDOW,
-                    // where `inner` blocks share one window.  For the ring modes cblocks*inner blocks are consumed
-                    // in ring order, so a flat loop is equivalent.
-                    for (int32_t i = 0; i < prm.mma_inner; ++i) {
-                        ok = wait_or_quit(&ctl->full[stage], phase, tflag);
-                        if (!ok) break;
-                        ptx::tc_fence_after();
-                        const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)stage * prm.b_stage_bytes);
-                        const uint64_t db = ptx::make_kmajor_desc(b_addr, (uint32_t)prm.bkb);
+        uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
+        uint32_t acc_stage = 0, acc_phase = 0;
+        const bool leader = ptx::elect_one();
+        bool ok = true;
+        const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
+        const uint32_t k_steps = (uint32_t)prm.bkb / 32;
+        // descriptor templates: everything but the 14-bit (address >> 4) field
+        const uint64_t db_tmpl = ptx::make_kmajor_desc(0, (uint32_t)prm.bkb);
+        const uint64_t da_tmpl = (prm.bkc >= 32) ? ptx::make_kmajor_desc(0, (uint32_t)prm.bkc)
+                                                 : ptx::make_kmajor_desc_nosw(0, (uint32_t)prm.dil_w * 16u, 128u);
+        const uint32_t a_base16 = ptx::smem_u32(smem_a) >> 4;
+        const uint32_t b_base16 = ptx::smem_u32(smem_b) >> 4;
+        const uint32_t a_stage16 = (prm.mode == A_WINDOW ? prm.win_stage_bytes : prm.a_stage_bytes) >> 4;
+        const uint32_t b_stage16 = prm.b_stage_bytes >> 4;
+        // window mode: per-block advance of the A start address (16-byte units)
+        const uint32_t s_step16 = (uint32_t)(prm.dil_w * prm.bkc) >> 4;                 // next tap in the filter row
+        const uint32_t r_step16 = (uint32_t)(prm.dil_h * prm.wt * prm.bkc) >> 4;        // next filter row
+        for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+            ok = wait_or_quit(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
+            if (!ok) break;
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc_stage * (uint32_t)prm.bn;
+            uint32_t accumulate = 0;
+            for (int32_t cb = 0; cb < prm.mma_outer && ok; ++cb) {
+                uint32_t win16 = 0;
+                if (prm.mode == A_WINDOW) {
+                    ok = wait_or_quit(&ctl->wfull[ws], wphase, tflag);
+                    if (!ok) break;
+                    win16 = a_base16 + ws * a_stage16;
+                }
+                uint32_t row16 = 0, tap16 = 0;
+                int32_t fs = 0;
+                for (int32_t i = 0; i < prm.mma_inner; ++i) {
+                    ok = wait_or_quit(&ctl->full[stage], phase, tflag);
+                    if (!ok) break;
+                    ptx::tc_fence_after();
+                    if (leader) {
+                        const uint64_t db = db_tmpl | (uint64_t)((b_base16 + stage * b_stage16) & 0x3FFF);
                         if (prm.mode != A_WINDOW) {
-                            const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)stage * prm.a_stage_bytes);
-                            const uint64_t da = ptx::make_kmajor_desc(a_addr, (uint32_t)prm.bkc);
+                            const uint64_t da = da_tmpl | (uint64_t)((a_base16 + stage * a_stage16) & 0x3FFF);
                             for (uint32_t k = 0; k < k_steps; ++k) {
                                 ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, accumulate);
                                 accumulate = 1;
                             }
                         } else if (prm.bkc >= 32) {
-                            const int32_t fr = i / prm.s_taps;
-                            const int32_t fs = i - fr * prm.s_taps;
-                            const uint32_t shift = (uint32_t)(fr * prm.dil_h * prm.wt + fs * prm.dil_w) * (uint32_t)prm.bkc;
-                            const uint64_t da = ptx::make_kmajor_desc(win_addr + shift, (uint32_t)prm.bkc);
+                            const uint64_t da = da_tmpl | (uint64_t)((win16 + row16 + tap16) & 0x3FFF);
                             for (uint32_t k = 0; k < k_steps; ++k) {
                                 ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, accumulate);
                                 accumulate = 1;
@@ -333,41 +347,59 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         } else {
                             // 16-byte pixels: block i = filter row i; K-step k covers taps (i, 2k) and (i, 2k+1)
                             for (uint32_t k = 0; k < k_steps; ++k) {
-                                const uint32_t shift = (uint32_t)(i * prm.dil_h * prm.wt + 2 * (int32_t)k * prm.dil_w) * 16u;
-                                const uint64_t da = ptx::make_kmajor_desc_nosw(win_addr + shift, (uint32_t)prm.dil_w * 16u, 128u);
+                                const uint64_t da = da_tmpl | (uint64_t)((win16 + row16 + 2u * k * s_step16) & 0x3FFF);
                                 ptx::mma_i8_ss(tmem_d, da, db + 2ull * k, idesc, accumulate);
                                 accumulate = 1;
                             }
                         }
                         ptx::mma_commit(&ctl->empty[stage]);      // slot reusable once these MMAs retire
-                        if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
                     }
-                    if (!ok) break;
-                    if (prm.mode == A_WINDOW) {
-                        ptx::mma_commit(&ctl->wempty[ws]);
-                        if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                    accumulate = 1;
+                    if (prm.bkc >= 32) {
+                        tap16 += s_step16;
+                        if (++fs == prm.s_taps) { fs = 0; tap16 = 0; row16 += r_step16; }
+                    } else {
+                        row16 += r_step16;
                     }
+                    if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
                 }
                 if (!ok) break;
-                ptx::mma_commit(&ctl->tmem_full[acc_stage]);      // accumulator complete -> epilogue
-                acc_stage ^= 1;
-                if (acc_stage == 0) acc_phase ^= 1;
+                if (prm.mode == A_WINDOW) {
+                    if (leader) ptx::mma_commit(&ctl->wempty[ws]);
+                    if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                }
             }
+            if (!ok) break;
+            if (leader) ptx::mma_commit(&ctl->tmem_full[acc_stage]);      // accumulator complete -> epilogue
+            acc_stage ^= 1;
+            if (acc_stage == 0) acc_phase ^= 1;
         }
-    } else {
-        // ===================== epilogue (warps 3..10) =====================
-        // Control flow here is uniform across all 256 threads (named barriers): a watchdog trip only stops the
-        // waiting, never the loop.
-        const uint32_t e = warp - kFirstEpiWarp;                 // 0..7
+    } else if (warp >= kFirstEpiWarp) {
+        // ===================== epilogue: two teams of 8 warps =====================
+        // Team t owns TMEM accumulator stage t, i.e. every second tile of this CTA, and its own one-panel staging
+        // buffer; while one team waits (TMA-store read-out, accumulator not ready, barrier) the other converts.
+        // Per tile a team walks the N tile panel by panel (<= 128 columns): drain + requantise into the swizzled
+        // staging panel, then one thread issues the TMA store of that panel.
+        // Control flow is uniform across a team (named barriers): a watchdog trip only stops the waiting.
+        const uint32_t e = warp - kFirstEpiWarp;                  // 0..15
+        const uint32_t team = e / kTeamWarps;
+        const uint32_t tw = e % kTeamWarps;                       // warp inside the team
         const uint32_t quarter = warp & 3;                        // TMEM lanes [32*quarter, +32) for this warp
-        const uint32_t half = e >> 2;                             // which half of the tile's columns
-        const uint32_t et_id = threadIdx.x - kFirstEpiWarp * 32;  // 0..255
-        const bool issuer = (et_id == 0);
+        const uint32_t half = tw >> 2;                            // which half of a panel's columns
+        const uint32_t tt_id = (tw << 5) | lane;                  // thread inside the team, 0..255
+        const bool issuer = (tt_id == 0);
+        const uint32_t bar_id = 1 + team;                         // named barrier of this team
         const float lo = prm.relu ? 0.0f : -128.0f;
         const bool int8_out = (prm.out_mode == LBC_OUT_INT8);
-        const int32_t split = ((prm.bn / 16 + 1) / 2) * 16;
-        const int32_t c_begin = half ? split : 0;
-        const int32_t c_end = half ? prm.bn : split;
+        uint8_t* my_staging = staging + (size_t)team * kBlockM * prm.panel_bytes;
+        float* sc = ctl->scale[team];
+        int32_t* bi = ctl->bias[team];
+        // columns of a panel handled by this warp: [pc_begin, pc_end), multiples of 16
+        const int32_t pcols = int8_out ? prm.panel_bytes : prm.bn;   // int32 mode: the whole N tile is one "panel"
+        const int32_t psplit = ((pcols / 16 + 1) / 2) * 16;
+        const int32_t pc_begin = half ? psplit : 0;
+        const int32_t pc_end = half ? pcols : psplit;
+        const int32_t n_panels = int8_out ? prm.n_panels : 1;
 
         const uint32_t lane_row = quarter * 32 + lane;            // TMEM lane == row of the MMA tile
         EpiThread et;
@@ -382,26 +414,28 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             et.srow = lane_row;
         }
 
-        uint32_t acc_stage = 0, acc_phase = 0;
-        for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t acc_phase = 0;
+        int32_t cur_nblk = -1;
+        for (int32_t tile = blockIdx.x + (int32_t)team * gridDim.x; tile < num_tiles; tile += kTeams * gridDim.x) {
             const TileCoord tc = decode_tile(prm, tile);
             const int32_t col0 = tc.n_blk * prm.bn;
-            // (a) the previous tile's TMA store must have finished READING the staging buffer
-            if (issuer && int8_out) ptx::tma_store_wait_read<0>();
-            // (b) per-channel parameters of this N tile -> smem
-            for (int32_t c = (int32_t)et_id; c < prm.bn; c += kEpiThreads) {
-                const int32_t kc = col0 + c;
-                const bool in = kc < prm.k_out;
-                ctl->scale[c] = (in && scale) ? __ldg(scale + kc) : 0.0f;
-                ctl->bias[c] = (in && bias) ? __ldg(bias + kc) : 0;
+            // per-channel parameters of this N tile -> smem (only when the N tile changes)
+            if (tc.n_blk != cur_nblk) {
+                ptx::named_bar_sync(bar_id, kTeamThreads);       // everyone done with the previous parameters
+                for (int32_t c = (int32_t)tt_id; c < prm.bn; c += kTeamThreads) {
+                    const int32_t kc = col0 + c;
+                    const bool in = kc < prm.k_out;
+                    sc[c] = (in && scale) ? __ldg(scale + kc) : 0.0f;
+                    bi[c] = (in && bias) ? __ldg(bias + kc) : 0;
+                }
+                cur_nblk = tc.n_blk;
             }
-            ptx::named_bar_sync(1, kEpiThreads);
-            // (c) accumulator ready?
-            ptx::mbar_wait(&ctl->tmem_full[acc_stage], acc_phase, tflag);
+            // accumulator ready?
+            ptx::mbar_wait(&ctl->tmem_full[team], acc_phase, tflag);
+            acc_phase ^= 1;
             ptx::tc_fence_after();
 
-            // int32 mode: global row of this lane (or -1)
-            int64_t out_row = -1;
+            int64_t out_row = -1;   // int32 mode: global output row of this lane
             if (!int8_out) {
                 if (prm.mode == A_WINDOW) {
                     const int32_t pp = tc.p0 + et.wrow, qq = tc.q0 + et.wcol;
@@ -411,61 +445,48 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (r < prm.m_total) out_row = r;
                 }
             }
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc_stage * (uint32_t)prm.bn;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + team * (uint32_t)prm.bn;
             int32_t* y32 = reinterpret_cast<int32_t*>(y);
 
-            // (d) drain: 32-column chunks, the load of chunk i+1 in flight while chunk i is converted
-            int32_t c = c_begin;
-            uint32_t va[32], vb[32];
-            if (c + 32 <= c_end) {
-                ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, va);
-                ptx::tmem_ld_wait_dep(va);
-                while (true) {
-                    const bool more = c + 64 <= c_end;
-                    if (more) ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c + 32), vb);
-                    epi_consume<2>(prm, ctl, va, c, et, staging, lo, y32, out_row, col0);
-                    c += 32;
-                    if (!more) break;
-                    ptx::tmem_ld_wait_dep(vb);
-                    const bool more2 = c + 64 <= c_end;
-                    if (more2) ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c + 32), va);
-                    epi_consume<2>(prm, ctl, vb, c, et, staging, lo, y32, out_row, col0);
-                    c += 32;
-                    if (!more2) break;
-                    ptx::tmem_ld_wait_dep(va);
+            for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
+                const int32_t pbase = pnl * pcols;
+                // staging panel free (previous store has read it) + parameters visible
+                if (issuer && int8_out) ptx::tma_store_wait_read<0>();
+                ptx::named_bar_sync(bar_id, kTeamThreads);
+                int32_t c = pbase + pc_begin;
+                const int32_t cend = pbase + pc_end;
+                for (; c + 32 <= cend; c += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
+                    ptx::tmem_ld_wait_dep(v);
+                    epi_consume<2>(prm, sc, bi, v, c, et, my_staging, lo, y32, out_row, col0);
                 }
-            }
-            if (c + 16 <= c_end) {
-                uint32_t v16[16];
-                ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
-                ptx::tmem_ld_wait_dep16(v16);
-                epi_consume<1>(prm, ctl, v16, c, et, staging, lo, y32, out_row, col0);
-                c += 16;
-            }
-            // (e) accumulator drained: hand the TMEM stage back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc_stage]);
-            acc_stage ^= 1;
-            if (acc_stage == 0) acc_phase ^= 1;
-            // (f) staging complete -> one thread issues the TMA store(s)
-            if (int8_out) {
-                ptx::fence_proxy_async();
-                ptx::named_bar_sync(2, kEpiThreads);
-                if (issuer) {
-                    for (int32_t pnl = 0; pnl < prm.n_panels; ++pnl) {
-                        const int32_t cbyte = col0 + pnl * prm.panel_bytes;
-                        if (cbyte >= prm.k_out) break;
-                        const uint8_t* src = staging + (size_t)pnl * kBlockM * prm.panel_bytes;
-                        if (prm.mode == A_WINDOW)
-                            ptx::tma_store_4d(&tm_out, src, cbyte, tc.q0, tc.p0, tc.img);
-                        else
-                            ptx::tma_store_2d(&tm_out, src, cbyte, (int32_t)tc.m0);
+                if (c + 16 <= cend) {
+                    uint32_t v16[16];
+                    ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
+                    ptx::tmem_ld_wait_dep16(v16);
+                    epi_consume<1>(prm, sc, bi, v16, c, et, my_staging, lo, y32, out_row, col0);
+                }
+                if (pnl == n_panels - 1) {
+                    // accumulator drained: hand the TMEM stage back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[team]);
+                }
+                if (int8_out) {
+                    ptx::fence_proxy_async();
+                    ptx::named_bar_sync(bar_id, kTeamThreads);
+                    if (issuer) {
+                        const int32_t cbyte = col0 + pbase;
+                        if (cbyte < prm.k_out) {
+                            if (prm.mode == A_WINDOW)
+                                ptx::tma_store_4d(&tm_out, my_staging, cbyte, tc.q0, tc.p0, tc.img);
+                            else
+                                ptx::tma_store_2d(&tm_out, my_staging, cbyte, (int32_t)tc.m0);
+                        }
+                        ptx::tma_store_commit();
                     }
-                    ptx::tma_store_commit();
                 }
-            } else {
-                ptx::named_bar_sync(2, kEpiThreads);   // keep ctl->bias stable until every warp is done with it
             }
         }
         if (issuer && int8_out) ptx::tma_store_wait<0>();
@@ -611,7 +632,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     else c.panel_bytes = c.bn;                      // unswizzled single panel (rare channel counts)
     c.n_panels = c.bn / c.panel_bytes;
     c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
-    const uint32_t stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(kBlockM * c.bn), 1024) : 0;
+    const uint32_t stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(kTeams * kBlockM * c.panel_bytes), 1024) : 0;
 
     // ---- smem carve-up
     const uint32_t ctl_bytes = round_up((uint32_t)sizeof(Ctl), 256);
