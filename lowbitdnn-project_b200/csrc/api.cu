@@ -98,6 +98,10 @@ struct lbc_plan {
     int32_t kind;
     IgemmConfig cfg;
     DeviceInfo dev;
+    // LBC_KERNEL_STEM_TC: the rewritten stride-1 / 16-channel problem the tcgen05 kernel actually runs
+    ConvGeom g_inner;
+    int32_t stem_sh = 1, stem_sw = 1;
+    void* stem_x = nullptr;     // [N][Hs][Ws][16] transformed input, owned by the plan
     // scratch for lbc_conv_run_host
     mutable std::mutex mu;
     mutable void* x_dev = nullptr;
@@ -114,7 +118,8 @@ size_t packed_weight_bytes(const lbc_plan* p)
 {
     const lbc_conv_desc& d = p->g.d;
     switch (p->kind) {
-        case LBC_KERNEL_IGEMM_TC: return (size_t)d.k * p->cfg.packed_row_bytes;
+        case LBC_KERNEL_IGEMM_TC:
+        case LBC_KERNEL_STEM_TC: return (size_t)d.k * p->cfg.packed_row_bytes;
         case LBC_KERNEL_DEPTHWISE: return (size_t)d.r * d.s * d.c;
         default: return (size_t)d.k * d.r * d.s * p->g.cg;
     }
@@ -146,6 +151,8 @@ lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const i
     out->ep.out_mode = plan->g.d.out_mode;
     if (plan->kind == LBC_KERNEL_IGEMM_TC)
         return igemm_encode(plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, y, &out->ig);
+    if (plan->kind == LBC_KERNEL_STEM_TC)
+        return igemm_encode(plan->g_inner, plan->cfg, plan->dev, (const int8_t*)plan->stem_x, (const int8_t*)w, y, &out->ig);
     return LBC_OK;
 }
 
@@ -154,6 +161,13 @@ lbc_status launch(const ResolvedLaunch& l, cudaStream_t stream)
     const lbc_plan* p = l.plan;
     switch (p->kind) {
         case LBC_KERNEL_IGEMM_TC: return igemm_launch(p->g, l.ig, l.ep, l.y, stream);
+        case LBC_KERNEL_STEM_TC: {
+            const lbc_conv_desc& d = p->g.d;
+            lbc_status st = launch_stem_xform(l.x, p->stem_x, d.n, d.h, d.w, d.c, p->g_inner.d.h, p->g_inner.d.w, p->stem_sh,
+                                              p->stem_sw, d.pad_h, d.pad_w, stream);
+            if (st != LBC_OK) return st;
+            return igemm_launch(p->g_inner, l.ig, l.ep, l.y, stream);
+        }
         case LBC_KERNEL_DEPTHWISE: return launch_depthwise(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
         case LBC_KERNEL_DIRECT: return launch_direct_conv(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
         default: set_error("plan has unknown kernel kind %d", p->kind); return LBC_ERR_UNSUPPORTED;
@@ -235,15 +249,38 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
     std::string why;
     const bool tc_ok = igemm_supported(g, &why);
     const bool dw_ok = (d->groups == d->c && d->k == d->c && d->c % 4 == 0);
+    // small-C rewrite (stems): C*stride^2 <= 16 channels after zero-pad + space-to-depth
+    ConvGeom gi{};
+    IgemmConfig stem_cfg{};
+    bool stem_ok = d->groups == 1 && d->c < 16 && d->k % 16 == 0 && d->dil_h == 1 && d->dil_w == 1 &&
+                   d->stride_h == d->stride_w && (d->stride_h == 1 || d->stride_h == 2) &&
+                   d->c * d->stride_h * d->stride_w <= 16;
+    if (stem_ok) {
+        lbc_conv_desc di = *d;
+        const int sh = d->stride_h, sw = d->stride_w;
+        di.r = (d->r + sh - 1) / sh;
+        di.s = (d->s + sw - 1) / sw;
+        di.h = g.p + di.r - 1;
+        di.w = g.q + di.s - 1;
+        di.c = 16;
+        di.stride_h = di.stride_w = 1;
+        di.pad_h = di.pad_w = 0;
+        stem_ok = make_geom(&di, &gi) == LBC_OK && gi.p == g.p && gi.q == g.q && igemm_supported(gi, nullptr) &&
+                  igemm_make_config(gi, dev, &stem_cfg) == LBC_OK && stem_cfg.mode == 2 && stem_cfg.bkc == 16;
+    }
     int32_t kind = force;
     if (force == LBC_KERNEL_AUTO) {
         // Tile/layout planner: tensor cores for dense contractions, CUDA cores where they do not pay.
         if (dw_ok) kind = LBC_KERNEL_DEPTHWISE;
         else if (tc_ok) kind = LBC_KERNEL_IGEMM_TC;
+        else if (stem_ok) kind = LBC_KERNEL_STEM_TC;
         else kind = LBC_KERNEL_DIRECT;
     }
-    LBC_REQUIRE(kind == LBC_KERNEL_DIRECT || kind == LBC_KERNEL_IGEMM_TC || kind == LBC_KERNEL_DEPTHWISE,
+    LBC_REQUIRE(kind == LBC_KERNEL_DIRECT || kind == LBC_KERNEL_IGEMM_TC || kind == LBC_KERNEL_DEPTHWISE ||
+                    kind == LBC_KERNEL_STEM_TC,
                 LBC_ERR_UNSUPPORTED, "kernel kind %d is not available", kind);
+    LBC_REQUIRE(kind != LBC_KERNEL_STEM_TC || stem_ok, LBC_ERR_UNSUPPORTED,
+                "small-C tensor-core path needs groups 1, C*stride^2 <= 16, stride 1 or 2, dilation 1, K %% 16 == 0");
     LBC_REQUIRE(kind != LBC_KERNEL_IGEMM_TC || tc_ok, LBC_ERR_UNSUPPORTED, "tcgen05 implicit GEMM cannot run this shape: %s",
                 why.c_str());
     LBC_REQUIRE(kind != LBC_KERNEL_DEPTHWISE || dw_ok, LBC_ERR_UNSUPPORTED,
@@ -261,6 +298,19 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
             return st;
         }
     }
+    if (kind == LBC_KERNEL_STEM_TC) {
+        p->g_inner = gi;
+        p->cfg = stem_cfg;
+        p->stem_sh = d->stride_h;
+        p->stem_sw = d->stride_w;
+        const size_t bytes = (size_t)gi.d.n * gi.d.h * gi.d.w * 16;
+        if (cudaMalloc(&p->stem_x, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            delete p;
+            set_error("small-C path: cannot allocate the %zu-byte transformed input", bytes);
+            return LBC_ERR_ALLOC;
+        }
+    }
     *plan = p;
     return LBC_OK;
 }
@@ -270,6 +320,7 @@ lbc_status lbc_conv_plan_destroy(lbc_plan* plan)
     if (!plan) return LBC_OK;
     if (plan->x_dev) cudaFree(plan->x_dev);
     if (plan->y_dev) cudaFree(plan->y_dev);
+    if (plan->stem_x) cudaFree(plan->stem_x);
     delete plan;
     return LBC_OK;
 }
@@ -285,14 +336,15 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
 {
     LBC_REQUIRE(plan && buf && buf_len > 0, LBC_ERR_INVALID_ARG, "null argument");
     const lbc_conv_desc& d = plan->g.d;
-    if (plan->kind == LBC_KERNEL_IGEMM_TC) {
+    if (plan->kind == LBC_KERNEL_IGEMM_TC || plan->kind == LBC_KERNEL_STEM_TC) {
         const IgemmConfig& c = plan->cfg;
         static const char* modes[] = {"tiled", "im2col", "window"};
         snprintf(buf, buf_len,
-                 "igemm_tc N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %d+%dw "
+                 "%s N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %d+%dw "
                  "a=%s(%dx%d px/tile) tiles %dx%d grid %d smem %zu tmem %u",
-                 d.n, d.h, d.w, d.c, d.k, d.r, d.s, d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc,
-                 c.k_blocks, c.stages, c.win_stages, modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
+                 plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : "igemm_tc", d.n, d.h, d.w, d.c, d.k, d.r, d.s,
+                 d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.win_stages,
+                 modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols);
     } else {
         snprintf(buf, buf_len, "%s N%d %dx%dx%d->%d %dx%d s%d p%d g%d | M=%lld",
@@ -305,7 +357,7 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
 lbc_status lbc_conv_plan_launches(const lbc_plan* plan, int32_t* launches)
 {
     LBC_REQUIRE(plan && launches, LBC_ERR_INVALID_ARG, "null argument");
-    *launches = 1;
+    *launches = plan->kind == LBC_KERNEL_STEM_TC ? 2 : 1;
     return LBC_OK;
 }
 
@@ -327,6 +379,9 @@ lbc_status lbc_conv_prepack_weights(const lbc_plan* plan, const int8_t* w_dev, i
         case LBC_KERNEL_IGEMM_TC:
             return launch_prepack_igemm(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, plan->g.cg, plan->cfg.s_pad,
                                         plan->cfg.bkc, plan->cfg.cblocks, plan->cfg.mode == 2, s);
+        case LBC_KERNEL_STEM_TC:
+            return launch_prepack_stem(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, d.c, plan->stem_sh, plan->stem_sw,
+                                       plan->g_inner.d.r, plan->cfg.s_pad, s);
         case LBC_KERNEL_DEPTHWISE:
             return launch_prepack_depthwise(w_dev, layout, (int8_t*)dst_dev, d.c, d.r, d.s, s);
         default:
@@ -351,7 +406,7 @@ lbc_status lbc_conv_run(const lbc_plan* plan, const int8_t* x, const void* w_pac
     LBC_CUDA_TRY(cudaEventRecord(ev.b, s));
     LBC_CUDA_TRY(cudaEventSynchronize(ev.b));
     LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ev.a, ev.b));
-    if (plan->kind == LBC_KERNEL_IGEMM_TC) return igemm_check_timeout();
+    if (plan->kind == LBC_KERNEL_IGEMM_TC || plan->kind == LBC_KERNEL_STEM_TC) return igemm_check_timeout();
     return LBC_OK;
 }
 
@@ -690,7 +745,9 @@ lbc_status lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lb
 lbc_status lbc_net_launches(const lbc_net* net, int32_t* launches)
 {
     LBC_REQUIRE(net && launches, LBC_ERR_INVALID_ARG, "null argument");
-    *launches = (int32_t)net->layers.size();
+    int32_t n = 0;
+    for (const auto& L : net->layers) n += (L.plan->kind == LBC_KERNEL_STEM_TC) ? 2 : 1;
+    *launches = n;
     return LBC_OK;
 }
 

@@ -109,6 +109,11 @@ lbc_status launch_prepack_krsc(const int8_t* src, int32_t src_layout, int8_t* ds
 lbc_status launch_prepack_igemm(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
                                 int32_t cg, int32_t s_pad, int32_t bkc, int32_t cblocks, int32_t chunk_outer,
                                 cudaStream_t stream);
+// small-C ("stem") rewrite: zero-pad + space-to-depth into 16-channel pixels, and the matching filter matrix
+lbc_status launch_stem_xform(const int8_t* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t hs,
+                             int32_t ws, int32_t sh, int32_t sw, int32_t pad_h, int32_t pad_w, cudaStream_t stream);
+lbc_status launch_prepack_stem(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
+                               int32_t c, int32_t sh, int32_t sw, int32_t r2, int32_t s_pad, cudaStream_t stream);
 lbc_status launch_prepack_depthwise(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t c, int32_t r,
                                     int32_t s, cudaStream_t stream);                         // -> [R][S][C]
 lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,

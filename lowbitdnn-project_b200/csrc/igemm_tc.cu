@@ -589,7 +589,8 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     c.s_pad = d.s;
     c.rows_per_tile = c.cols_per_tile = c.row_tiles = c.col_tiles = c.wt = 0;
     if (!pure_gemm && d.stride_h == 1 && d.stride_w == 1 && !getenv("LBC_FORCE_IM2COL") && !getenv("LBC_NO_WINDOW")) {
-        const int s_eff = c16 ? ((d.s + 1) / 2) * 2 : d.s;        // 16-byte pixels: taps are consumed in pairs
+        // 16-byte pixels: taps are consumed in pairs and a B block is one filter row of 32/64/128 bytes
+        const int s_eff = !c16 ? d.s : (d.s <= 2 ? 2 : d.s <= 4 ? 4 : 8);
         const int ext_w = (s_eff - 1) * d.dil_w, ext_h = (d.r - 1) * d.dil_h;
         int col_tiles = (g.q + kBlockM - 1) / kBlockM;
         int cols = (g.q + col_tiles - 1) / col_tiles;
@@ -598,7 +599,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         while (rows < g.p && rows * wt + cols <= kBlockM) ++rows;   // (rows-1)*wt + cols <= 128
         const int row_tiles = (g.p + rows - 1) / rows;
         const double eff = (double)g.p * g.q / ((double)row_tiles * col_tiles * kBlockM);
-        const bool s_ok = !c16 || (s_eff * 16 == 32 || s_eff * 16 == 64 || s_eff * 16 == 128);
+        const bool s_ok = !c16 || d.s <= 8;
         if (eff >= 0.55 && wt <= 256 && rows + ext_h <= 256 && s_ok && (rows - 1) * wt + cols <= kBlockM) {
             c.mode = A_WINDOW;
             c.s_pad = s_eff;

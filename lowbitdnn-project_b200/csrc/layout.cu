@@ -80,6 +80,67 @@ __global__ void __launch_bounds__(256) prepack_igemm_kernel(const int8_t* __rest
     }
 }
 
+// Small-C ("stem") path.  A conv with C*sh*sw <= 16 input channels and stride (sh, sw) in {1, 2} is rewritten as a
+// stride-1, pad-0 conv over 16-channel pixels: the input is zero-padded and (for stride 2) space-to-depth'd,
+//   X'[n][hs][ws][(dr*sw + ds)*C + c] = Xpad[n][hs*sh + dr][ws*sw + ds][c],
+// and the filter likewise, W'[k][r2][s2][(dr*sw + ds)*C + c] = W[k][r2*sh + dr][s2*sw + ds][c] (0 outside R x S).
+struct StemXformParams {
+    int32_t n, h, w, c, hs, ws, sh, sw, pad_h, pad_w;
+};
+
+__global__ void __launch_bounds__(256) stem_xform_kernel(StemXformParams p, const int8_t* __restrict__ x,
+                                                         uint4* __restrict__ out)
+{
+    const int64_t total = (int64_t)p.n * p.hs * p.ws;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t ws = (int32_t)(i % p.ws);
+        const int32_t hs = (int32_t)((i / p.ws) % p.hs);
+        const int32_t n = (int32_t)(i / ((int64_t)p.ws * p.hs));
+        uint32_t v[4] = {0, 0, 0, 0};
+        int slot = 0;
+        for (int dr = 0; dr < p.sh; ++dr) {
+            const int32_t ih = hs * p.sh + dr - p.pad_h;
+            for (int ds = 0; ds < p.sw; ++ds) {
+                const int32_t iw = ws * p.sw + ds - p.pad_w;
+                const bool in = ih >= 0 && ih < p.h && iw >= 0 && iw < p.w;
+                const int8_t* src = x + (((int64_t)n * p.h + ih) * p.w + iw) * p.c;
+                for (int c = 0; c < p.c; ++c, ++slot) {
+                    const uint32_t b = in ? (uint32_t)(uint8_t)src[c] : 0u;
+                    v[slot >> 2] |= b << (8 * (slot & 3));
+                }
+            }
+        }
+        out[i] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// dst [K][r2][s_pad][16] <- src KRSC [K][R][S][C] or OIHW [K][C][R][S]
+__global__ void __launch_bounds__(256) prepack_stem_kernel(const int8_t* __restrict__ src, int32_t oihw,
+                                                           int8_t* __restrict__ dst, int32_t k, int32_t r, int32_t s,
+                                                           int32_t c, int32_t sh, int32_t sw, int32_t r2, int32_t s_pad)
+{
+    const int64_t total = (int64_t)k * r2 * s_pad * 16;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t ch = (int32_t)(i % 16);
+        int64_t t = i / 16;
+        const int32_t is2 = (int32_t)(t % s_pad); t /= s_pad;
+        const int32_t ir2 = (int32_t)(t % r2); t /= r2;
+        const int32_t ik = (int32_t)t;
+        int8_t v = 0;
+        if (ch < sh * sw * c) {
+            const int32_t sub = ch / c, cc = ch % c;
+            const int32_t dr = sub / sw, ds = sub % sw;
+            const int32_t ir = ir2 * sh + dr, is = is2 * sw + ds;
+            if (ir < r && is < s) {
+                const int64_t so = oihw ? ((((int64_t)ik * c + cc) * r + ir) * s + is)
+                                        : ((((int64_t)ik * r + ir) * s + is) * c + cc);
+                v = src[so];
+            }
+        }
+        dst[i] = v;
+    }
+}
+
 // depthwise: dst [R][S][C] <- src [C][R][S] (KRSC with cg==1 and OIHW with I==1 coincide).
 __global__ void __launch_bounds__(256) prepack_dw_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst,
                                                          int32_t c, int32_t rs)
@@ -118,6 +179,24 @@ lbc_status launch_prepack_igemm(const int8_t* src, int32_t src_layout, int8_t* d
     const int64_t total = (int64_t)k * r * s_pad * cblocks * bkc;
     prepack_igemm_kernel<<<grid_for(total), 256, 0, stream>>>(src, src_layout == LBC_W_OIHW, dst, k, r, s, cg, s_pad,
                                                               bkc, cblocks, chunk_outer);
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
+
+lbc_status launch_stem_xform(const int8_t* x, void* out, int32_t n, int32_t h, int32_t w, int32_t c, int32_t hs,
+                             int32_t ws, int32_t sh, int32_t sw, int32_t pad_h, int32_t pad_w, cudaStream_t stream)
+{
+    StemXformParams p{n, h, w, c, hs, ws, sh, sw, pad_h, pad_w};
+    stem_xform_kernel<<<grid_for((int64_t)n * hs * ws), 256, 0, stream>>>(p, x, reinterpret_cast<uint4*>(out));
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
+
+lbc_status launch_prepack_stem(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
+                               int32_t c, int32_t sh, int32_t sw, int32_t r2, int32_t s_pad, cudaStream_t stream)
+{
+    prepack_stem_kernel<<<grid_for((int64_t)k * r2 * s_pad * 16), 256, 0, stream>>>(src, src_layout == LBC_W_OIHW, dst, k,
+                                                                                    r, s, c, sh, sw, r2, s_pad);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

@@ -99,6 +99,30 @@ def test_igemm_im2col_path_on_stride1_shapes(d, monkeypatch):
     assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
 
 
+# ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
+STEM_CASES = [
+    D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),    # ResNet stem
+    D(n=1, h=37, w=45, c=3, k=32, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3),            # odd sizes
+    D(n=2, h=30, w=30, c=3, k=32, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),    # MobileNetV2 stem
+    D(n=1, h=24, w=40, c=3, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),                            # VGG conv1_1
+    D(n=1, h=300, w=300, c=3, k=16, r=3, s=3, pad_h=1, pad_w=1),                                  # wide rows: column tiles
+    D(n=2, h=20, w=20, c=4, k=16, r=5, s=5, stride_h=2, stride_w=2, pad_h=2, pad_w=2),
+    D(n=2, h=17, w=19, c=8, k=32, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+    D(n=1, h=40, w=40, c=1, k=16, r=5, s=5, pad_h=2, pad_w=2),
+]
+
+
+@pytest.mark.parametrize("d", STEM_CASES, ids=lambda d: f"h{d.h}w{d.w}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+@pytest.mark.parametrize("out_mode", [0, 1])
+def test_stem_tc_kernel(d, out_mode):
+    assert _check(D(**{**d.__dict__, "out_mode": out_mode})) == "stem_tc"
+
+
+def test_stem_tc_oihw_weights():
+    d = D(n=1, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1)
+    assert _check(d, w_layout="oihw") == "stem_tc"
+
+
 def test_igemm_reference_style_inputs_and_oihw_weights():
     """{0,1}-valued inputs (check.cu:43-44,69-75), weights handed over in the reference's OIHW order."""
     d = D(n=2, h=34, w=34, c=128, k=128, r=3, s=3, out_mode=1)
@@ -139,7 +163,8 @@ def test_planner_choices():
     assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1)).kernel == "igemm_tc"
     assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=56, w=56, c=64, k=256, r=1, s=1)).kernel == "igemm_tc"
     assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=28, w=28, c=192, k=192, r=3, s=3, pad_h=1, pad_w=1, groups=192)).kernel == "depthwise"
-    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=224, w=224, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3)).kernel == "direct"
+    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=224, w=224, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3)).kernel == "stem_tc"
+    assert lbc.ConvPlan(lbc.ConvDesc(n=1, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, groups=4)).kernel == "direct"
 
 
 def test_requant_extremes_on_device():
