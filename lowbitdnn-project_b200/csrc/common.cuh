@@ -77,7 +77,8 @@ struct IgemmConfig {
     int32_t s_pad;       // filter width rounded up to even when taps are consumed in pairs (C == 16)
     int32_t cblocks, inner, k_blocks;
     size_t packed_row_bytes;   // bytes per output channel in the packed filter matrix
-    int32_t stages, win_stages;
+    int32_t stages, win_stages, tps;
+    uint32_t a_block_bytes, b_block_bytes;
     uint32_t a_stage_bytes, b_stage_bytes, win_stage_bytes, win_tx_bytes;
     int32_t wt, rows_per_tile, cols_per_tile, row_tiles, col_tiles;
     int32_t tiles_m, tiles_n;

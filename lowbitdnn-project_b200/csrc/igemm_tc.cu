@@ -61,6 +61,8 @@ struct IgemmParams {
     int32_t s_taps;               // filter width S
     int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
     int32_t stages;               // ring depth (B, and A in TILED/IM2COL)
+    int32_t tps;                  // blocks per ring stage (one mbarrier round trip covers tps blocks)
+    uint32_t a_block_bytes, b_block_bytes;   // one block; a ring stage holds tps of each
     uint32_t a_stage_bytes, b_stage_bytes;
     // window mode
     int32_t win_stages;
@@ -175,6 +177,17 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
     }
 }
 
+// Opaque copy: keeps a loop-invariant in a register instead of letting the compiler re-read it from the constant
+// bank (LDCU, ~25 cycles of latency) inside the single-warp issue loops.
+template <typename T>
+__device__ __forceinline__ T keep(T v)
+{
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
+// KM: 0 tiled A, 1 im2col A, 2 window A (>= 32-byte pixels), 3 window A with 16-byte pixels (paired taps)
+template <int KM>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
@@ -227,17 +240,23 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // the TMA / MMA / commit instructions themselves are predicated on one elected lane.  Keeping the loops
     // convergent lets the compiler hold addresses and descriptors in uniform registers; a `lane == 0` branch
     // around the whole loop made every tcgen05.mma cost ~150 scalar instructions (ncu, r01 v2).
+    constexpr bool kWindow = (KM >= 2);
     if (warp == 0) {
         // ===================== ring producer: B blocks (+ A blocks in TILED / IM2COL) =====================
         uint32_t stage = 0, phase = 0;
-        const uint32_t tx_bytes = prm.b_stage_bytes + (prm.mode == A_WINDOW ? 0u : prm.a_stage_bytes);
-        const int32_t blocks = prm.cblocks * prm.inner;
+        const uint32_t tx_bytes = keep(prm.b_stage_bytes + (kWindow ? 0u : prm.a_stage_bytes));
+        const int32_t stages_per_tile = keep(prm.cblocks * prm.inner / prm.tps);
+        const int32_t tps = keep(prm.tps), nstages = keep(prm.stages), cblocks = keep(prm.cblocks);
+        const int32_t bkb = keep(prm.bkb), bkc = keep(prm.bkc), s_taps = keep(prm.s_taps);
+        const int32_t dil_w = keep(prm.dil_w), dil_h = keep(prm.dil_h);
+        const uint32_t a_block = keep(prm.a_block_bytes), b_block = keep(prm.b_block_bytes);
+        const uint32_t a_stage = keep(prm.a_stage_bytes), b_stage = keep(prm.b_stage_bytes);
         const bool leader = ptx::elect_one();
         bool ok = true;
         for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
             const TileCoord tc = decode_tile(prm, tile);
             int32_t w_base = 0, h_base = 0, n0 = 0;
-            if (prm.mode == A_IM2COL) {
+            if (KM == A_IM2COL) {
                 const int32_t q0 = (int32_t)(tc.m0 % prm.q);
                 const int32_t p0 = (int32_t)((tc.m0 / prm.q) % prm.p);
                 n0 = (int32_t)(tc.m0 / ((int64_t)prm.q * prm.p));
@@ -245,35 +264,41 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 h_base = p0 * prm.stride_h - prm.pad_h;
             }
             const int32_t brow = tc.n_blk * prm.bn;
-            // ring modes walk K as [tap][channel chunk]: (fr, fs) filter tap, c0 channel offset
+            // ring modes walk K as [tap][channel chunk]: (off_h, off_w) filter tap offset, c0 channel offset
             int32_t c0 = 0, cbi = 0, off_w = 0, off_h = 0, fs = 0, bcol = 0;
-            for (int32_t kb = 0; kb < blocks; ++kb) {
+            for (int32_t st = 0; st < stages_per_tile; ++st) {
                 ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
                 if (!ok) break;
-                if (leader) {
-                    ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
-                    uint8_t* dst_b = smem_b + stage * prm.b_stage_bytes;
-                    if (prm.mode == A_IM2COL) {
-                        ptx::tma_load_im2col_4d(smem_a + stage * prm.a_stage_bytes, &tm_a, &ctl->full[stage], c0, w_base,
-                                                h_base, n0, (uint16_t)off_w, (uint16_t)off_h);
-                    } else if (prm.mode == A_TILED) {
-                        ptx::tma_load_2d(smem_a + stage * prm.a_stage_bytes, &tm_a, &ctl->full[stage], c0, (int32_t)tc.m0);
+                if (leader) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
+                uint8_t* dst_a = smem_a + stage * a_stage;
+                uint8_t* dst_b = smem_b + stage * b_stage;
+                for (int32_t t = 0; t < tps; ++t) {
+                    if (leader) {
+                        if (KM == A_IM2COL)
+                            ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0, (uint16_t)off_w,
+                                                    (uint16_t)off_h);
+                        else if (KM == A_TILED)
+                            ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, (int32_t)tc.m0);
+                        ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
                     }
-                    ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
+                    dst_a += a_block;
+                    dst_b += b_block;
+                    bcol += bkb;
+                    if (!kWindow) {
+                        c0 += bkc;
+                        if (++cbi == cblocks) {
+                            cbi = 0; c0 = 0;
+                            off_w += dil_w;
+                            if (++fs == s_taps) { fs = 0; off_w = 0; off_h += dil_h; }
+                        }
+                    }
                 }
-                bcol += prm.bkb;
-                c0 += prm.bkc;
-                if (++cbi == prm.cblocks) {
-                    cbi = 0; c0 = 0;
-                    off_w += prm.dil_w;
-                    if (++fs == prm.s_taps) { fs = 0; off_w = 0; off_h += prm.dil_h; }
-                }
-                if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
+                if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 2) {
-        // ===================== window producer (WINDOW mode only) =====================
-        if (prm.mode == A_WINDOW) {
+        // ===================== window producer (WINDOW modes only) =====================
+        if (kWindow) {
             uint32_t ws = 0, wphase = 0;
             const bool leader = ptx::elect_one();
             bool ok = true;
@@ -298,75 +323,88 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         uint32_t acc_stage = 0, acc_phase = 0;
         const bool leader = ptx::elect_one();
         bool ok = true;
-        const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
-        const uint32_t k_steps = (uint32_t)prm.bkb / 32;
-        // descriptor templates: everything but the 14-bit (address >> 4) field
-        const uint64_t db_tmpl = ptx::make_kmajor_desc(0, (uint32_t)prm.bkb);
-        const uint64_t da_tmpl = (prm.bkc >= 32) ? ptx::make_kmajor_desc(0, (uint32_t)prm.bkc)
-                                                 : ptx::make_kmajor_desc_nosw(0, (uint32_t)prm.dil_w * 16u, 128u);
-        const uint32_t a_base16 = ptx::smem_u32(smem_a) >> 4;
-        const uint32_t b_base16 = ptx::smem_u32(smem_b) >> 4;
-        const uint32_t a_stage16 = (prm.mode == A_WINDOW ? prm.win_stage_bytes : prm.a_stage_bytes) >> 4;
-        const uint32_t b_stage16 = prm.b_stage_bytes >> 4;
-        // window mode: per-block advance of the A start address (16-byte units)
-        const uint32_t s_step16 = (uint32_t)(prm.dil_w * prm.bkc) >> 4;                 // next tap in the filter row
-        const uint32_t r_step16 = (uint32_t)(prm.dil_h * prm.wt * prm.bkc) >> 4;        // next filter row
+        const uint32_t idesc = keep(ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn));
+        const uint32_t k_steps = keep((uint32_t)prm.bkb / 32);
+        // descriptor templates: everything but the 14-bit (address >> 4) field, split in 32-bit halves
+        const uint64_t db_t = ptx::make_kmajor_desc(0, (uint32_t)prm.bkb);
+        const uint64_t da_t = (KM != 3) ? ptx::make_kmajor_desc(0, (uint32_t)prm.bkc)
+                                        : ptx::make_kmajor_desc_nosw(0, (uint32_t)prm.dil_w * 16u, 128u);
+        const uint32_t db_hi = keep((uint32_t)(db_t >> 32)), db_lo = keep((uint32_t)db_t);
+        const uint32_t da_hi = keep((uint32_t)(da_t >> 32)), da_lo = keep((uint32_t)da_t);
+        const uint32_t a_base16 = keep(ptx::smem_u32(smem_a) >> 4);
+        const uint32_t b_base16 = keep(ptx::smem_u32(smem_b) >> 4);
+        const uint32_t a_stage16 = keep((kWindow ? prm.win_stage_bytes : prm.a_stage_bytes) >> 4);
+        const uint32_t b_stage16 = keep(prm.b_stage_bytes >> 4);
+        const uint32_t a_block16 = keep(prm.a_block_bytes >> 4), b_block16 = keep(prm.b_block_bytes >> 4);
+        // window modes: per-block advance of the A start address (16-byte units)
+        const uint32_t s_step16 = keep((uint32_t)(prm.dil_w * prm.bkc) >> 4);           // next tap in the filter row
+        const uint32_t r_step16 = keep((uint32_t)(prm.dil_h * prm.wt * prm.bkc) >> 4);  // next filter row
+        const int32_t tps = keep(prm.tps), nstages = keep(prm.stages), s_taps = keep(prm.s_taps);
+        const int32_t outer = keep(prm.mma_outer), inner_stages = keep(prm.mma_inner / prm.tps);
+        const int32_t win_stages = keep(prm.win_stages);
+        const uint32_t bn = keep((uint32_t)prm.bn);
+
+        bool ready = ptx::mbar_test(&ctl->full[0], 0);
         for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
             ok = wait_or_quit(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
             if (!ok) break;
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc_stage * (uint32_t)prm.bn;
+            const uint32_t tmem_d = tmem_base + acc_stage * bn;
             uint32_t accumulate = 0;
-            for (int32_t cb = 0; cb < prm.mma_outer && ok; ++cb) {
+            for (int32_t cb = 0; cb < outer && ok; ++cb) {
                 uint32_t win16 = 0;
-                if (prm.mode == A_WINDOW) {
+                if (kWindow) {
                     ok = wait_or_quit(&ctl->wfull[ws], wphase, tflag);
                     if (!ok) break;
                     win16 = a_base16 + ws * a_stage16;
                 }
                 uint32_t row16 = 0, tap16 = 0;
                 int32_t fs = 0;
-                for (int32_t i = 0; i < prm.mma_inner; ++i) {
-                    ok = wait_or_quit(&ctl->full[stage], phase, tflag);
-                    if (!ok) break;
+                for (int32_t st = 0; st < inner_stages; ++st) {
+                    if (!ready) {
+                        ok = wait_or_quit(&ctl->full[stage], phase, tflag);
+                        if (!ok) break;
+                    }
                     ptx::tc_fence_after();
-                    if (leader) {
-                        const uint64_t db = db_tmpl | (uint64_t)((b_base16 + stage * b_stage16) & 0x3FFF);
-                        if (prm.mode != A_WINDOW) {
-                            const uint64_t da = da_tmpl | (uint64_t)((a_base16 + stage * a_stage16) & 0x3FFF);
+                    // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
+                    uint32_t nstage = stage + 1, nphase = phase;
+                    if (nstage == (uint32_t)nstages) { nstage = 0; nphase ^= 1; }
+                    const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
+                    uint32_t a16 = kWindow ? 0u : (a_base16 + stage * a_stage16);
+                    uint32_t b16 = b_base16 + stage * b_stage16;
+                    for (int32_t t = 0; t < tps; ++t) {
+                        uint32_t al;
+                        if (KM == 2) al = win16 + row16 + tap16;
+                        else if (KM == 3) al = win16 + row16;
+                        else al = a16;
+                        if (leader) {
                             for (uint32_t k = 0; k < k_steps; ++k) {
-                                ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, accumulate);
-                                accumulate = 1;
-                            }
-                        } else if (prm.bkc >= 32) {
-                            const uint64_t da = da_tmpl | (uint64_t)((win16 + row16 + tap16) & 0x3FFF);
-                            for (uint32_t k = 0; k < k_steps; ++k) {
-                                ptx::mma_i8_ss(tmem_d, da + 2ull * k, db + 2ull * k, idesc, accumulate);
-                                accumulate = 1;
-                            }
-                        } else {
-                            // 16-byte pixels: block i = filter row i; K-step k covers taps (i, 2k) and (i, 2k+1)
-                            for (uint32_t k = 0; k < k_steps; ++k) {
-                                const uint64_t da = da_tmpl | (uint64_t)((win16 + row16 + 2u * k * s_step16) & 0x3FFF);
-                                ptx::mma_i8_ss(tmem_d, da, db + 2ull * k, idesc, accumulate);
+                                // KM 3: K-step k covers taps (row, 2k) and (row, 2k+1) -> advance by two pixels
+                                const uint32_t ak = (KM == 3) ? al + 2u * k * s_step16 : al + 2u * k;
+                                const uint64_t da = ((uint64_t)da_hi << 32) | (uint64_t)(da_lo | (ak & 0x3FFFu));
+                                const uint64_t db = ((uint64_t)db_hi << 32) | (uint64_t)(db_lo | ((b16 + 2u * k) & 0x3FFFu));
+                                ptx::mma_i8_ss(tmem_d, da, db, idesc, accumulate);
                                 accumulate = 1;
                             }
                         }
-                        ptx::mma_commit(&ctl->empty[stage]);      // slot reusable once these MMAs retire
+                        accumulate = 1;
+                        b16 += b_block16;
+                        if (KM == 2) {
+                            tap16 += s_step16;
+                            if (++fs == s_taps) { fs = 0; tap16 = 0; row16 += r_step16; }
+                        } else if (KM == 3) {
+                            row16 += r_step16;
+                        } else {
+                            a16 += a_block16;
+                        }
                     }
-                    accumulate = 1;
-                    if (prm.bkc >= 32) {
-                        tap16 += s_step16;
-                        if (++fs == prm.s_taps) { fs = 0; tap16 = 0; row16 += r_step16; }
-                    } else {
-                        row16 += r_step16;
-                    }
-                    if (++stage == (uint32_t)prm.stages) { stage = 0; phase ^= 1; }
+                    if (leader) ptx::mma_commit(&ctl->empty[stage]);      // slot reusable once these MMAs retire
+                    stage = nstage; phase = nphase; ready = ready_next;
                 }
                 if (!ok) break;
-                if (prm.mode == A_WINDOW) {
+                if (kWindow) {
                     if (leader) ptx::mma_commit(&ctl->wempty[ws]);
-                    if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                    if (++ws == (uint32_t)win_stages) { ws = 0; wphase ^= 1; }
                 }
             }
             if (!ok) break;
@@ -638,8 +676,16 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     // ---- smem carve-up
     const uint32_t ctl_bytes = round_up((uint32_t)sizeof(Ctl), 256);
     const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
-    c.a_stage_bytes = (c.mode == A_WINDOW) ? 0 : (uint32_t)(kBlockM * c.bkc);
-    c.b_stage_bytes = (uint32_t)(c.bn * c.bkb);
+    c.a_block_bytes = (c.mode == A_WINDOW) ? 0 : (uint32_t)(kBlockM * c.bkc);
+    c.b_block_bytes = (uint32_t)(c.bn * c.bkb);
+    // blocks per ring stage: group small B blocks (window mode) so one mbarrier round trip feeds several MMAs
+    c.tps = 1;
+    if (c.mode == A_WINDOW) {
+        for (int t = c.inner; t >= 1; --t)
+            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= 48u * 1024u) { c.tps = t; break; }
+    }
+    c.a_stage_bytes = c.tps * c.a_block_bytes;
+    c.b_stage_bytes = c.tps * c.b_block_bytes;
     c.win_stage_bytes = c.win_tx_bytes = 0;
     c.win_stages = 0;
     uint32_t win_total = 0;
@@ -656,7 +702,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     }
     const uint32_t ring_stage = c.a_stage_bytes + c.b_stage_bytes;
     int stages = (int)std::min<uint32_t>(kMaxStages, (budget - win_total) / ring_stage);
-    stages = std::max(2, std::min(stages, std::max(2, c.k_blocks * 2)));
+    stages = std::max(2, std::min(stages, std::max(2, c.k_blocks / c.tps * 2)));
     c.stages = stages;
     c.off_b = (c.mode == A_WINDOW) ? win_total : (uint32_t)stages * c.a_stage_bytes;
     c.off_stage = c.off_b + (uint32_t)stages * c.b_stage_bytes;
@@ -769,6 +815,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.stride_h = d.stride_h; prm.stride_w = d.stride_w; prm.pad_h = d.pad_h; prm.pad_w = d.pad_w;
     prm.dil_h = d.dil_h; prm.dil_w = d.dil_w;
     prm.stages = c.stages; prm.a_stage_bytes = c.a_stage_bytes; prm.b_stage_bytes = c.b_stage_bytes;
+    prm.tps = c.tps; prm.a_block_bytes = c.a_block_bytes; prm.b_block_bytes = c.b_block_bytes;
     prm.win_stages = c.win_stages; prm.win_stage_bytes = c.win_stage_bytes; prm.win_tx_bytes = c.win_tx_bytes;
     prm.wt = c.wt; prm.rows_per_tile = c.rows_per_tile; prm.cols_per_tile = c.cols_per_tile;
     prm.row_tiles = c.row_tiles; prm.col_tiles = c.col_tiles;
@@ -783,11 +830,20 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (!g_attr_set) {
-            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             g_attr_set = true;
         }
     }
-    igemm_i8_kernel<<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y);
+    const int km = c.mode == A_WINDOW ? (c.bkc == 16 ? 3 : 2) : c.mode;
+    switch (km) {
+        case 0: igemm_i8_kernel<0><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
+        case 1: igemm_i8_kernel<1><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
+        case 2: igemm_i8_kernel<2><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
+        default: igemm_i8_kernel<3><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
+    }
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

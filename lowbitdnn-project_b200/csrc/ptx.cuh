@@ -82,6 +82,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 
+// Non-blocking probe of a phase (result may be consumed much later; the latency is scoreboarded).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 // Bounded wait: a wrong expect_tx or a lost arrive must never hang the GPU.  After `budget_ns` the
 // waiter raises *timeout_flag and returns false; every role then drains and the host reports
 // LBC_ERR_KERNEL_TIMEOUT.  The fast path is a single try_wait (HW-suspended, not a spin).
