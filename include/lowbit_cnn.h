@@ -172,6 +172,9 @@ lbc_status  lbc_net_launches(const lbc_net* net, int32_t* launches);
 lbc_status  lbc_probe_int8_mma_peak(int32_t iters, double* tops, lbc_stream stream);
 /* Streaming-copy probe (int4 loads/stores), GB/s read+write. */
 lbc_status  lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stream stream);
+/* Development aid: when device_buf != NULL, CTA 0 of the tcgen05 kernel records clock64 stamps of its pipeline
+ * events (16 int64 slots per local tile, `tiles` tiles) into it.  NULL switches tracing off. */
+lbc_status  lbc_debug_set_trace(void* device_buf, int32_t tiles);
 /* Writes `bytes` of zeros to an internal scratch buffer to evict L2 (timing hygiene). */
 lbc_status  lbc_flush_l2(lbc_stream stream);
 

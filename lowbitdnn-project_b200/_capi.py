@@ -63,6 +63,7 @@ _PROTOS = {
     "lbc_net_launches": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "lbc_probe_int8_mma_peak": (ctypes.c_int, [_i32, ctypes.POINTER(ctypes.c_double), _vp]),
     "lbc_probe_hbm_copy": (ctypes.c_int, [ctypes.c_size_t, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
+    "lbc_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "lbc_flush_l2": (ctypes.c_int, [_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

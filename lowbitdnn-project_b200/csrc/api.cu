@@ -508,6 +508,12 @@ lbc_status lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stre
 {
     return probe_hbm_copy(bytes, iters, gbs, (cudaStream_t)stream);
 }
+lbc_status lbc_debug_set_trace(void* device_buf, int32_t tiles)
+{
+    igemm_set_trace(reinterpret_cast<long long*>(device_buf), tiles);
+    return LBC_OK;
+}
+
 lbc_status lbc_flush_l2(lbc_stream stream)
 {
     DeviceInfo dev;

@@ -100,6 +100,7 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
                         const int8_t* w_packed, void* y, IgemmLaunch* out);
 lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
                         cudaStream_t stream);
+void igemm_set_trace(long long* device_buf, int32_t tiles);   // development aid: CTA 0 pipeline time stamps
 lbc_status igemm_check_timeout();  // reads (and clears) the device watchdog flag; call after a sync
 
 // layout.cu

@@ -75,7 +75,21 @@ struct IgemmParams {
     int32_t panel_bytes, panel_swz_bits, n_panels;
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
+    // optional pipeline trace (development aid): CTA 0 writes clock64 stamps, 16 slots per local tile
+    long long* trace;
+    int32_t trace_tiles;
 };
+
+enum : int { EV_P_ISSUE = 0, EV_W_ISSUE, EV_M_START, EV_M_WIN, EV_M_FULL, EV_M_DONE, EV_E_START, EV_E_DRAINED, EV_E_STORED,
+             EV_P_DONE };
+
+__device__ __forceinline__ void trace_ev(const IgemmParams& prm, int32_t tile, int ev)
+{
+    if (prm.trace != nullptr && blockIdx.x == 0) {
+        const int32_t local = tile / (int32_t)gridDim.x;
+        if (local < prm.trace_tiles) prm.trace[local * 16 + ev] = clock64();
+    }
+}
 
 __device__ int g_timeout_flag = 0;
 
@@ -148,23 +162,20 @@ struct EpiThread {
     int32_t wrow, wcol;  // window mode: output row / column inside the tile
 };
 
-// Process NG 16-column groups held in v[] starting at tile column c (columns of staging panel `pnl0`..).
-template <int NG>
+// Process NG 16-column groups held in v[]: tile columns [c, c + 16*NG), which are staging-panel columns
+// [pc, pc + 16*NG).  OUT8 selects the fused int8 path (requantise -> swizzled staging panel) or raw int32 stores.
+template <int NG, bool OUT8>
 __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
-                                            const uint32_t* v, int32_t c, const EpiThread& et, uint8_t* staging,
-                                            float lo, int32_t* y32, int64_t out_row, int32_t col0)
+                                            const uint32_t* v, int32_t c, int32_t pc, const EpiThread& et,
+                                            uint8_t* staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32,
+                                            int64_t out_row, int32_t col0)
 {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         const int32_t cc = c + 16 * g;
-        if (prm.out_mode == LBC_OUT_INT8) {
+        if (OUT8) {
             const uint4 r = requant16(v + 16 * g, sc + cc, bi + cc, lo);
-            if (et.valid) {
-                // staging holds ONE panel (panel_bytes columns) at a time
-                const uint32_t cb = (uint32_t)cc % (uint32_t)prm.panel_bytes;
-                const uint32_t off = swz(et.srow * (uint32_t)prm.panel_bytes + cb, (1u << prm.panel_swz_bits) - 1u);
-                *reinterpret_cast<uint4*>(staging + off) = r;
-            }
+            if (et.valid) *reinterpret_cast<uint4*>(staging + swz(row_off + (uint32_t)(pc + 16 * g), swz_mask)) = r;
         } else if (out_row >= 0 && col0 + cc < prm.k_out) {
             int32_t* yo = y32 + out_row * prm.k_out + col0 + cc;
 #pragma unroll
@@ -177,17 +188,37 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
     }
 }
 
-// Opaque copy: keeps a loop-invariant in a register instead of letting the compiler re-read it from the constant
-// bank (LDCU, ~25 cycles of latency) inside the single-warp issue loops.
-template <typename T>
-__device__ __forceinline__ T keep(T v)
+// Drain this warp's share [c0, c1) of one panel out of TMEM.
+template <bool OUT8>
+__device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* sc, const int32_t* bi, uint32_t taddr,
+                                          int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint8_t* staging,
+                                          uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
+                                          int32_t col0)
 {
-    asm volatile("" : "+r"(v));
-    return v;
+    int32_t c = c0;
+    for (; c + 32 <= c1; c += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
+        ptx::tmem_ld_wait_dep(v);
+        epi_consume<2, OUT8>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+    }
+    if (c + 16 <= c1) {
+        uint32_t v16[16];
+        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
+        ptx::tmem_ld_wait_dep16(v16);
+        epi_consume<1, OUT8>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+    }
 }
 
+// Opaque copy: keeps a loop-invariant in a register instead of letting the compiler re-read it from the constant
+// bank (LDCU, ~25 cycles of latency) inside the single-warp issue loops.
+__device__ __forceinline__ uint32_t keep(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ int32_t keep(int32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ uint64_t keep(uint64_t v) { asm volatile("" : "+l"(v)); return v; }
+
 // KM: 0 tiled A, 1 im2col A, 2 window A (>= 32-byte pixels), 3 window A with 16-byte pixels (paired taps)
-template <int KM>
+// KS: MMA K-steps (32 bytes each) per B block = bkb / 32
+template <int KM, int KS>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
@@ -269,6 +300,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int32_t st = 0; st < stages_per_tile; ++st) {
                 ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
                 if (!ok) break;
+                if (st == 0 && leader) trace_ev(prm, tile, EV_P_ISSUE);
                 if (leader) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
                 uint8_t* dst_a = smem_a + stage * a_stage;
                 uint8_t* dst_b = smem_b + stage * b_stage;
@@ -295,6 +327,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
                 if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
             }
+            if (leader) trace_ev(prm, tile, EV_P_DONE);
         }
     } else if (warp == 2) {
         // ===================== window producer (WINDOW modes only) =====================
@@ -309,6 +342,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
                     if (!ok) break;
                     if (leader) {
+                        if (cb == 0) trace_ev(prm, tile, EV_W_ISSUE);
                         ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
                         ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, tc.q0 - prm.pad_w,
                                          tc.p0 - prm.pad_h, tc.img);
@@ -319,96 +353,82 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // Convergent, exit-free loops (a watchdog trip only makes the waits return early): every address below is
+        // derived from kernel parameters and loop counters, so it lives in uniform registers; the tcgen05
+        // instructions are predicated on the elected lane inside their asm blocks.
         uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
         uint32_t acc_stage = 0, acc_phase = 0;
-        const bool leader = ptx::elect_one();
-        bool ok = true;
-        const uint32_t idesc = keep(ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn));
-        const uint32_t k_steps = keep((uint32_t)prm.bkb / 32);
-        // descriptor templates: everything but the 14-bit (address >> 4) field, split in 32-bit halves
-        const uint64_t db_t = ptx::make_kmajor_desc(0, (uint32_t)prm.bkb);
-        const uint64_t da_t = (KM != 3) ? ptx::make_kmajor_desc(0, (uint32_t)prm.bkc)
-                                        : ptx::make_kmajor_desc_nosw(0, (uint32_t)prm.dil_w * 16u, 128u);
-        const uint32_t db_hi = keep((uint32_t)(db_t >> 32)), db_lo = keep((uint32_t)db_t);
-        const uint32_t da_hi = keep((uint32_t)(da_t >> 32)), da_lo = keep((uint32_t)da_t);
-        const uint32_t a_base16 = keep(ptx::smem_u32(smem_a) >> 4);
-        const uint32_t b_base16 = keep(ptx::smem_u32(smem_b) >> 4);
-        const uint32_t a_stage16 = keep((kWindow ? prm.win_stage_bytes : prm.a_stage_bytes) >> 4);
-        const uint32_t b_stage16 = keep(prm.b_stage_bytes >> 4);
-        const uint32_t a_block16 = keep(prm.a_block_bytes >> 4), b_block16 = keep(prm.b_block_bytes >> 4);
-        // window modes: per-block advance of the A start address (16-byte units)
-        const uint32_t s_step16 = keep((uint32_t)(prm.dil_w * prm.bkc) >> 4);           // next tap in the filter row
-        const uint32_t r_step16 = keep((uint32_t)(prm.dil_h * prm.wt * prm.bkc) >> 4);  // next filter row
-        const int32_t tps = keep(prm.tps), nstages = keep(prm.stages), s_taps = keep(prm.s_taps);
-        const int32_t outer = keep(prm.mma_outer), inner_stages = keep(prm.mma_inner / prm.tps);
-        const int32_t win_stages = keep(prm.win_stages);
-        const uint32_t bn = keep((uint32_t)prm.bn);
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
+        const uint64_t db_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_b), (uint32_t)prm.bkb);
+        const uint64_t da_base = (KM != 3) ? ptx::make_kmajor_desc(ptx::smem_u32(smem_a), (uint32_t)prm.bkc)
+                                           : ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem_a), (uint32_t)prm.dil_w * 16u, 128u);
+        const uint32_t a_stage16 = (kWindow ? prm.win_stage_bytes : prm.a_stage_bytes) >> 4;
+        const uint32_t b_stage16 = prm.b_stage_bytes >> 4;
+        const uint32_t a_block16 = prm.a_block_bytes >> 4, b_block16 = prm.b_block_bytes >> 4;
+        const uint32_t s_step16 = (uint32_t)(prm.dil_w * prm.bkc) >> 4;             // next tap in the filter row
+        const uint32_t r_step16 = (uint32_t)(prm.dil_h * prm.wt * prm.bkc) >> 4;    // next filter row
+        const uint32_t k_step16 = (KM == 3) ? 2 * s_step16 : 2;   // A advance per K-step (KM 3: two taps = two pixels)
+        const int32_t inner_stages = prm.mma_inner / prm.tps;
 
         bool ready = ptx::mbar_test(&ctl->full[0], 0);
-        for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            ok = wait_or_quit(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
-            if (!ok) break;
+        bool wready = kWindow ? ptx::mbar_test(&ctl->wfull[0], 0) : true;
+        for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            ptx::mbar_wait_soft(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
             ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc_stage * bn;
+            if (leader) trace_ev(prm, tile, EV_M_START);
+            const uint32_t tmem_d = tmem_base + acc_stage * (uint32_t)prm.bn;
             uint32_t accumulate = 0;
-            for (int32_t cb = 0; cb < outer && ok; ++cb) {
-                uint32_t win16 = 0;
+            for (int32_t cb = 0; cb < prm.mma_outer; ++cb) {
+                uint64_t da_win = da_base;
                 if (kWindow) {
-                    ok = wait_or_quit(&ctl->wfull[ws], wphase, tflag);
-                    if (!ok) break;
-                    win16 = a_base16 + ws * a_stage16;
+                    if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
+                    da_win = da_base + (uint64_t)(ws * a_stage16);
+                    if (cb == 0 && leader) trace_ev(prm, tile, EV_M_WIN);
                 }
                 uint32_t row16 = 0, tap16 = 0;
                 int32_t fs = 0;
                 for (int32_t st = 0; st < inner_stages; ++st) {
-                    if (!ready) {
-                        ok = wait_or_quit(&ctl->full[stage], phase, tflag);
-                        if (!ok) break;
-                    }
+                    if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
                     ptx::tc_fence_after();
+                    if (st == 0 && cb == 0 && leader) trace_ev(prm, tile, EV_M_FULL);
                     // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
                     uint32_t nstage = stage + 1, nphase = phase;
-                    if (nstage == (uint32_t)nstages) { nstage = 0; nphase ^= 1; }
+                    if (nstage == (uint32_t)prm.stages) { nstage = 0; nphase ^= 1; }
                     const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
-                    uint32_t a16 = kWindow ? 0u : (a_base16 + stage * a_stage16);
-                    uint32_t b16 = b_base16 + stage * b_stage16;
-                    for (int32_t t = 0; t < tps; ++t) {
-                        uint32_t al;
-                        if (KM == 2) al = win16 + row16 + tap16;
-                        else if (KM == 3) al = win16 + row16;
-                        else al = a16;
-                        if (leader) {
-                            for (uint32_t k = 0; k < k_steps; ++k) {
-                                // KM 3: K-step k covers taps (row, 2k) and (row, 2k+1) -> advance by two pixels
-                                const uint32_t ak = (KM == 3) ? al + 2u * k * s_step16 : al + 2u * k;
-                                const uint64_t da = ((uint64_t)da_hi << 32) | (uint64_t)(da_lo | (ak & 0x3FFFu));
-                                const uint64_t db = ((uint64_t)db_hi << 32) | (uint64_t)(db_lo | ((b16 + 2u * k) & 0x3FFFu));
-                                ptx::mma_i8_ss(tmem_d, da, db, idesc, accumulate);
-                                accumulate = 1;
-                            }
+                    uint64_t da_blk = kWindow ? da_win : da_base + (uint64_t)(stage * a_stage16);
+                    uint64_t db_blk = db_base + (uint64_t)(stage * b_stage16);
+                    for (int32_t t = 0; t < prm.tps; ++t) {
+                        uint64_t da = da_blk;
+                        if (KM == 2) da = da_win + (uint64_t)(row16 + tap16);
+                        else if (KM == 3) da = da_win + (uint64_t)row16;
+#pragma unroll
+                        for (int k = 0; k < KS; ++k) {
+                            ptx::mma_i8_ss_pred(tmem_d, da + (uint64_t)(k * k_step16), db_blk + (uint64_t)(2 * k), idesc,
+                                                accumulate, leader);
+                            accumulate = 1;
                         }
-                        accumulate = 1;
-                        b16 += b_block16;
+                        db_blk += b_block16;
                         if (KM == 2) {
                             tap16 += s_step16;
-                            if (++fs == s_taps) { fs = 0; tap16 = 0; row16 += r_step16; }
+                            if (++fs == prm.s_taps) { fs = 0; tap16 = 0; row16 += r_step16; }
                         } else if (KM == 3) {
                             row16 += r_step16;
                         } else {
-                            a16 += a_block16;
+                            da_blk += a_block16;
                         }
                     }
-                    if (leader) ptx::mma_commit(&ctl->empty[stage]);      // slot reusable once these MMAs retire
+                    ptx::mma_commit_pred(&ctl->empty[stage], leader);     // slot reusable once these MMAs retire
                     stage = nstage; phase = nphase; ready = ready_next;
                 }
-                if (!ok) break;
                 if (kWindow) {
-                    if (leader) ptx::mma_commit(&ctl->wempty[ws]);
-                    if (++ws == (uint32_t)win_stages) { ws = 0; wphase ^= 1; }
+                    ptx::mma_commit_pred(&ctl->wempty[ws], leader);
+                    if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                    wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
                 }
             }
-            if (!ok) break;
-            if (leader) ptx::mma_commit(&ctl->tmem_full[acc_stage]);      // accumulator complete -> epilogue
+            ptx::mma_commit_pred(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue
+            if (leader) trace_ev(prm, tile, EV_M_DONE);
             acc_stage ^= 1;
             if (acc_stage == 0) acc_phase ^= 1;
         }
@@ -452,6 +472,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             et.srow = lane_row;
         }
 
+        const uint32_t row_off = et.srow * (uint32_t)prm.panel_bytes;     // byte offset of this lane's staging row
+        const uint32_t swz_mask = (1u << prm.panel_swz_bits) - 1u;
         uint32_t acc_phase = 0;
         int32_t cur_nblk = -1;
         for (int32_t tile = blockIdx.x + (int32_t)team * gridDim.x; tile < num_tiles; tile += kTeams * gridDim.x) {
@@ -472,6 +494,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             ptx::mbar_wait(&ctl->tmem_full[team], acc_phase, tflag);
             acc_phase ^= 1;
             ptx::tc_fence_after();
+            if (issuer) trace_ev(prm, tile, EV_E_START);
 
             int64_t out_row = -1;   // int32 mode: global output row of this lane
             if (!int8_out) {
@@ -491,25 +514,18 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 // staging panel free (previous store has read it) + parameters visible
                 if (issuer && int8_out) ptx::tma_store_wait_read<0>();
                 ptx::named_bar_sync(bar_id, kTeamThreads);
-                int32_t c = pbase + pc_begin;
-                const int32_t cend = pbase + pc_end;
-                for (; c + 32 <= cend; c += 32) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
-                    ptx::tmem_ld_wait_dep(v);
-                    epi_consume<2>(prm, sc, bi, v, c, et, my_staging, lo, y32, out_row, col0);
-                }
-                if (c + 16 <= cend) {
-                    uint32_t v16[16];
-                    ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
-                    ptx::tmem_ld_wait_dep16(v16);
-                    epi_consume<1>(prm, sc, bi, v16, c, et, my_staging, lo, y32, out_row, col0);
-                }
+                if (int8_out)
+                    epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
+                                    swz_mask, lo, y32, out_row, col0);
+                else
+                    epi_drain<false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
+                                     swz_mask, lo, y32, out_row, col0);
                 if (pnl == n_panels - 1) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[team]);
+                    if (issuer) trace_ev(prm, tile, EV_E_DRAINED);
                 }
                 if (int8_out) {
                     ptx::fence_proxy_async();
@@ -523,6 +539,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                 ptx::tma_store_2d(&tm_out, my_staging, cbyte, (int32_t)tc.m0);
                         }
                         ptx::tma_store_commit();
+                        if (pnl == n_panels - 1) trace_ev(prm, tile, EV_E_STORED);
                     }
                 }
             }
@@ -589,6 +606,8 @@ void small_tensor_fixup(CUtensorMap* tm, size_t tensor_bytes, int driver_version
 
 bool g_attr_set = false;
 std::mutex g_attr_mu;
+long long* g_trace_buf = nullptr;   // development aid, see igemm_set_trace()
+int32_t g_trace_tiles = 0;
 
 uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
@@ -823,29 +842,41 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.tmem_cols = c.tmem_cols;
     prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
     prm.off_b = c.off_b; prm.off_stage = c.off_stage; prm.off_ctl = c.off_ctl;
+    prm.trace = g_trace_buf; prm.trace_tiles = g_trace_tiles;
     // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one
     // "channel chunk" of cblocks*inner blocks.
     if (c.mode == A_WINDOW) { prm.mma_outer = c.cblocks; prm.mma_inner = c.inner; }
     else { prm.mma_outer = 1; prm.mma_inner = c.cblocks * c.inner; }
+    const int km = c.mode == A_WINDOW ? (c.bkc == 16 ? 3 : 2) : c.mode;
+    const int ks = c.bkb / 32;
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams, const int32_t*,
+                              const float*, void*);
+    static const KernelFn table[4][3] = {
+        {igemm_i8_kernel<0, 1>, igemm_i8_kernel<0, 2>, igemm_i8_kernel<0, 4>},
+        {igemm_i8_kernel<1, 1>, igemm_i8_kernel<1, 2>, igemm_i8_kernel<1, 4>},
+        {igemm_i8_kernel<2, 1>, igemm_i8_kernel<2, 2>, igemm_i8_kernel<2, 4>},
+        {igemm_i8_kernel<3, 1>, igemm_i8_kernel<3, 2>, igemm_i8_kernel<3, 4>},
+    };
+    LBC_REQUIRE(ks == 1 || ks == 2 || ks == 4, LBC_ERR_UNSUPPORTED, "igemm: unsupported K block of %d bytes", c.bkb);
+    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1];
     {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (!g_attr_set) {
-            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_i8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 3; ++j)
+                    LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             g_attr_set = true;
         }
     }
-    const int km = c.mode == A_WINDOW ? (c.bkc == 16 ? 3 : 2) : c.mode;
-    switch (km) {
-        case 0: igemm_i8_kernel<0><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
-        case 1: igemm_i8_kernel<1><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
-        case 2: igemm_i8_kernel<2><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
-        default: igemm_i8_kernel<3><<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y); break;
-    }
+    fn<<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
+}
+
+void igemm_set_trace(long long* device_buf, int32_t tiles)
+{
+    g_trace_buf = device_buf;
+    g_trace_tiles = tiles;
 }
 
 lbc_status igemm_check_timeout()

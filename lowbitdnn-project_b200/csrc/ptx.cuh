@@ -236,6 +236,54 @@ __device__ __forceinline__ void mma_i8_ss(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+// Same, issued by ALL lanes of a convergent warp but executed only where `leader` != 0: no C++-level branch, so
+// the compiler keeps the (warp-uniform) descriptors in uniform registers.
+__device__ __forceinline__ void mma_i8_ss_pred(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+
+__device__ __forceinline__ void mma_commit_pred(uint64_t* bar, uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(leader)
+        : "memory");
+}
+
+// Unbounded-in-control-flow wait for the convergent issue loops: spins on try_wait, gives up silently once the
+// watchdog flag is set or the time budget is exhausted (never breaks out of the caller's loop).
+__device__ __forceinline__ void mbar_wait_soft(uint64_t* bar, uint32_t parity, volatile int* timeout_flag,
+                                               uint64_t budget_ns = 2000000000ull)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0) {
+            if (*timeout_flag != 0) return;
+            if (globaltimer_ns() - t0 > budget_ns) {
+                *timeout_flag = 1;
+                __threadfence();
+                return;
+            }
+        }
+    }
+}
+
 // Arrives (count 1) on `bar` once every previously issued tcgen05.mma of this thread has completed.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint64_t* bar)

@@ -1,0 +1,63 @@
+"""trace_layer.py — dump CTA 0's pipeline time line (clock64 stamps) for one layer of a benchmark network."""
+import argparse
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+EV = ["P_ISSUE", "W_ISSUE", "M_START", "M_WIN", "M_FULL", "M_DONE", "E_START", "E_DRAIN", "E_STORE", "P_DONE"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--network", default="resnet50")
+    ap.add_argument("--layers", default="l1.1.conv2")
+    ap.add_argument("--tiles", type=int, default=24)
+    ap.add_argument("--skip", type=int, default=6)
+    a = ap.parse_args()
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    from lowbitdnn_project_b200 import _capi
+    lib = lbc.load_library()
+    nets = lbc.networks
+    layers = nets.NETWORKS[a.network](nets.DEFAULT_BATCH[a.network])
+    dev = torch.device("cuda:0")
+    for i, (name, d, _) in enumerate(layers):
+        if name not in a.layers.split(","):
+            continue
+        plan = lbc.ConvPlan(d)
+        cg = d.c // d.groups
+        w = torch.randint(-127, 128, (d.k * d.r * d.s * cg,), dtype=torch.int8, device=dev)
+        wp = plan.prepack(w)
+        x = torch.randint(-128, 128, (d.n, d.h, d.w, d.c), dtype=torch.int8, device=dev)
+        bias = torch.randint(-1000, 1000, (d.k,), dtype=torch.int32, device=dev)
+        scale = torch.full((d.k,), 2.0**-7 / (d.r * d.s * cg) ** 0.5, dtype=torch.float32, device=dev)
+        y = plan.empty_output(dev)
+        for _ in range(2):
+            plan.run(x, wp, bias, scale, out=y)
+        ntile = a.tiles + a.skip
+        buf = torch.zeros(ntile * 16, dtype=torch.int64, device=dev)
+        _capi.check(lib.lbc_debug_set_trace(ctypes.c_void_p(buf.data_ptr()), ntile))
+        _, ms = plan.run(x, wp, bias, scale, out=y, timed=True)
+        _capi.check(lib.lbc_debug_set_trace(None, 0))
+        t = buf.cpu().numpy().reshape(ntile, 16)
+        t0 = t[a.skip][t[a.skip] > 0].min()
+        print(f"== {name}: {ms * 1e3:.1f} us | {plan.describe()}")
+        print("tile " + " ".join(f"{e:>8s}" for e in EV) + "   | dM(start->done) dE(start->drain) tile-to-tile(M_DONE)")
+        prev = None
+        for k in range(a.skip, ntile):
+            row = t[k]
+            cells = " ".join(f"{(int(row[e]) - int(t0)) if row[e] else -1:8d}" for e in range(len(EV)))
+            dm = int(row[5] - row[2]) if row[5] and row[2] else -1
+            de = int(row[7] - row[6]) if row[7] and row[6] else -1
+            dd = int(row[5] - prev) if prev else -1
+            prev = row[5]
+            print(f"{k:4d} {cells}   | {dm:6d} {de:6d} {dd:6d}")
+        plan.close()
+
+
+if __name__ == "__main__":
+    main()
