@@ -1,0 +1,291 @@
+// depthwise.cu — CUDA-core depthwise convolution (groups == C == K), NHWC int8.
+//
+// A depthwise layer is a per-channel stencil: 9 MACs and 2 bytes of HBM traffic per output, no contraction a
+// 128-row MMA could use.  It is HBM-bound if the integer pipe keeps up, so the 3x3 kernel is built around the
+// instruction count per output:
+//
+//   * a thread owns 4 consecutive channels (one 32-bit word per pixel; the lanes of a warp cover 128 consecutive
+//     bytes of the NHWC row, so every load and store is a full line) and walks a strip of output pixels along W;
+//   * for every input column it loads the 3 (stride 2) or 4 (stride 1) input rows and transposes them with 6-8
+//     PRMTs into per-channel words whose BYTES are the vertically adjacent pixels (r0, r1, r2[, r3]);
+//   * one __dp4a of such a word with the matching column of the filter (w[0][s], w[1][s], w[2][s], 0) does the
+//     three vertical taps of one channel at once: 3 dp4a per output instead of 9 multiply-adds plus byte
+//     extraction.  With stride 1 the fourth byte carries the next input row, and the same word dotted with
+//     (0, w0, w1, w2) gives the output row below: two output rows per thread from one set of loads;
+//   * the three live columns roll through registers (each input column is loaded once per thread);
+//   * bias / scale of the thread's 4 channels sit in registers for the whole strip (no shared memory at all).
+//
+// Anything that is not 3x3 / dilation 1 / stride 1 or 2 runs the generic kernel at the bottom.
+//
+// Replaces nothing in the reference (it has no depthwise path: `groups` is accepted but never forwarded,
+// python/qtorch/cpp/conv2d.cuh:96,140); the shape family comes from BASELINE.json config 5 (MobileNetV2).
+#include "common.cuh"
+
+namespace lbc {
+
+namespace {
+
+struct DwParams {
+    int32_t n, h, w, c, p, q;
+    int32_t stride, pad_h, pad_w;
+    int32_t cq;           // C / 4
+    int32_t tw, strips;   // strip width (output pixels per thread along W), strips per output row
+    int32_t row_groups;   // ceil(P / ROWS)
+    int32_t relu, out_mode;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// rows (a, b, c, d) x 4 channels  ->  4 channel words of bytes (a_ch, b_ch, c_ch, d_ch)
+template <bool FOUR>
+__device__ __forceinline__ void rows_to_channels(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t (&v)[4])
+{
+    const uint32_t t0 = prmt(a, b, 0x5140);   // a0 b0 a1 b1
+    const uint32_t t1 = prmt(a, b, 0x7362);   // a2 b2 a3 b3
+    if (FOUR) {
+        const uint32_t u0 = prmt(c, d, 0x5140);   // c0 d0 c1 d1
+        const uint32_t u1 = prmt(c, d, 0x7362);   // c2 d2 c3 d3
+        v[0] = prmt(t0, u0, 0x5410);
+        v[1] = prmt(t0, u0, 0x7632);
+        v[2] = prmt(t1, u1, 0x5410);
+        v[3] = prmt(t1, u1, 0x7632);
+    } else {   // fourth byte: don't care (the filter word has a zero there)
+        v[0] = prmt(t0, c, 0x4410);
+        v[1] = prmt(t0, c, 0x5532);
+        v[2] = prmt(t1, c, 0x6610);
+        v[3] = prmt(t1, c, 0x7732);
+    }
+}
+
+// STRIDE 1: two output rows per thread (4 input rows per column); STRIDE 2: one output row (3 input rows).
+template <int STRIDE>
+__global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, const int8_t* __restrict__ x,
+                                                           const int8_t* __restrict__ w_rsc,
+                                                           const int32_t* __restrict__ bias,
+                                                           const float* __restrict__ scale, void* __restrict__ y)
+{
+    constexpr int ROWS = (STRIDE == 1) ? 2 : 1;
+    constexpr int IN_ROWS = (STRIDE == 1) ? 4 : 3;
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cqi = idx % (uint32_t)g.cq;
+    idx /= (uint32_t)g.cq;
+    const uint32_t strip = idx % (uint32_t)g.strips;
+    idx /= (uint32_t)g.strips;
+    const uint32_t rg = idx % (uint32_t)g.row_groups;
+    const uint32_t n = idx / (uint32_t)g.row_groups;
+    if (n >= (uint32_t)g.n) return;
+    const int32_t c0 = (int32_t)cqi * 4;
+    const int32_t p0 = (int32_t)rg * ROWS;
+    const int32_t q0 = (int32_t)strip * g.tw;
+    const int32_t q1 = min(q0 + g.tw, g.q);
+
+    // ---- filter columns: wv[s][ch] = bytes (w[0][s][ch], w[1][s][ch], w[2][s][ch], 0)
+    uint32_t wv[3][4];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (0 * 3 + s) * g.c + c0));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (1 * 3 + s) * g.c + c0));
+        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (2 * 3 + s) * g.c + c0));
+        rows_to_channels<false>(a, b, c, 0u, wv[s]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) wv[s][ch] &= 0x00ffffffu;
+    }
+
+    // ---- input rows of this thread
+    const int32_t ih0 = p0 * STRIDE - g.pad_h;
+    const int8_t* xr[IN_ROWS];
+    bool rok[IN_ROWS];
+#pragma unroll
+    for (int r = 0; r < IN_ROWS; ++r) {
+        const int32_t ih = ih0 + r;
+        rok[r] = ih >= 0 && ih < g.h;
+        xr[r] = x + (((int64_t)n * g.h + (rok[r] ? ih : 0)) * g.w) * g.c + c0;
+    }
+    auto load_col = [&](int32_t iw, uint32_t(&v)[4]) {
+        uint32_t rw[4] = {0u, 0u, 0u, 0u};
+        const bool cok = iw >= 0 && iw < g.w;
+        const int64_t off = (int64_t)iw * g.c;
+#pragma unroll
+        for (int r = 0; r < IN_ROWS; ++r)
+            if (cok && rok[r]) rw[r] = *reinterpret_cast<const uint32_t*>(xr[r] + off);
+        rows_to_channels<(IN_ROWS == 4)>(rw[0], rw[1], rw[2], rw[3], v);
+    };
+
+    // ---- epilogue parameters of the 4 channels
+    const float lo = g.relu ? 0.0f : -128.0f;
+    int32_t bi[4] = {0, 0, 0, 0};
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias) {
+        const int4 b = __ldg(reinterpret_cast<const int4*>(bias + c0));
+        bi[0] = b.x; bi[1] = b.y; bi[2] = b.z; bi[3] = b.w;
+    }
+    if (g.out_mode == LBC_OUT_INT8) {
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c0));
+        sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+    }
+    const bool row1 = (ROWS == 2) && (p0 + 1 < g.p);
+    const int64_t yrow0 = (((int64_t)n * g.p + p0) * g.q) * g.c + c0;   // element offset of (n, p0, 0, c0)
+    const int64_t yrow1 = yrow0 + (int64_t)g.q * g.c;
+
+    auto emit = [&](const int32_t(&acc)[4], int64_t o) {
+        if (g.out_mode == LBC_OUT_INT32) {
+            *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(y) + o) =
+                make_int4(acc[0] + bi[0], acc[1] + bi[1], acc[2] + bi[2], acc[3] + bi[3]);
+        } else {
+            *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(y) + o) =
+                pack4_sat_s8(requant_s32(acc[0], bi[0], sc[0], lo), requant_s32(acc[1], bi[1], sc[1], lo),
+                             requant_s32(acc[2], bi[2], sc[2], lo), requant_s32(acc[3], bi[3], sc[3], lo));
+        }
+    };
+
+    // ---- walk the strip; three live input columns roll through v0, v1, v2
+    uint32_t v0[4], v1[4], v2[4];
+    int32_t iw = q0 * STRIDE - g.pad_w;
+    load_col(iw, v0);
+    if (STRIDE == 1) load_col(iw + 1, v1);
+    for (int32_t q = q0; q < q1; ++q) {
+        if (STRIDE == 1) {
+            load_col(iw + 2, v2);
+        } else {
+            load_col(iw + 1, v1);
+            load_col(iw + 2, v2);
+        }
+        int32_t a0[4], a1[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            a0[ch] = __dp4a((int32_t)v0[ch], (int32_t)wv[0][ch], 0);
+            a0[ch] = __dp4a((int32_t)v1[ch], (int32_t)wv[1][ch], a0[ch]);
+            a0[ch] = __dp4a((int32_t)v2[ch], (int32_t)wv[2][ch], a0[ch]);
+            if (ROWS == 2) {   // output row p0 + 1: the same columns against (0, w0, w1, w2)
+                a1[ch] = __dp4a((int32_t)v0[ch], (int32_t)(wv[0][ch] << 8), 0);
+                a1[ch] = __dp4a((int32_t)v1[ch], (int32_t)(wv[1][ch] << 8), a1[ch]);
+                a1[ch] = __dp4a((int32_t)v2[ch], (int32_t)(wv[2][ch] << 8), a1[ch]);
+            }
+        }
+        const int64_t qo = (int64_t)q * g.c;
+        emit(a0, yrow0 + qo);
+        if (ROWS == 2 && row1) emit(a1, yrow1 + qo);
+        if (STRIDE == 1) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) { v0[ch] = v1[ch]; v1[ch] = v2[ch]; }
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) v0[ch] = v2[ch];
+        }
+        iw += STRIDE;
+    }
+}
+
+// ---- generic depthwise (any R, S, stride, dilation): one thread = one output pixel x 4 channels ------------
+struct DwGenericParams {
+    int32_t n, h, w, c, r, s, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, p, q, cq;
+    int32_t relu, out_mode;
+    int64_t total;
+};
+
+__device__ __forceinline__ int32_t sbyte(uint32_t v, int j) { return (int32_t)(int8_t)(v >> (8 * j)); }
+
+__global__ void __launch_bounds__(256) depthwise_generic_kernel(const DwGenericParams g, const int8_t* __restrict__ x,
+                                                                const int8_t* __restrict__ w_rsc,
+                                                                const int32_t* __restrict__ bias,
+                                                                const float* __restrict__ scale, void* __restrict__ y)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= g.total) return;
+    const int32_t c0 = (int32_t)(idx % g.cq) * 4;
+    const int64_t m = idx / g.cq;
+    const int32_t q = (int32_t)(m % g.q);
+    const int32_t p = (int32_t)((m / g.q) % g.p);
+    const int32_t n = (int32_t)(m / ((int64_t)g.q * g.p));
+
+    int32_t acc[4] = {0, 0, 0, 0};
+    for (int32_t r = 0; r < g.r; ++r) {
+        const int32_t ih = p * g.stride_h - g.pad_h + r * g.dil_h;
+        if (ih < 0 || ih >= g.h) continue;
+        for (int32_t s = 0; s < g.s; ++s) {
+            const int32_t iw = q * g.stride_w - g.pad_w + s * g.dil_w;
+            if (iw < 0 || iw >= g.w) continue;
+            const uint32_t xv = *reinterpret_cast<const uint32_t*>(x + (((int64_t)n * g.h + ih) * g.w + iw) * g.c + c0);
+            const uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + ((int64_t)r * g.s + s) * g.c + c0));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += sbyte(xv, j) * sbyte(wv, j);
+        }
+    }
+    const int64_t o = m * g.c + c0;
+    const float lo = g.relu ? 0.0f : -128.0f;
+    if (g.out_mode == LBC_OUT_INT32) {
+        int4 v;
+        v.x = acc[0] + (bias ? bias[c0 + 0] : 0);
+        v.y = acc[1] + (bias ? bias[c0 + 1] : 0);
+        v.z = acc[2] + (bias ? bias[c0 + 2] : 0);
+        v.w = acc[3] + (bias ? bias[c0 + 3] : 0);
+        *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(y) + o) = v;
+    } else {
+        int32_t b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = requant_s32(acc[j], bias ? bias[c0 + j] : 0, scale[c0 + j], lo);
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(y) + o) = pack4_sat_s8(b[0], b[1], b[2], b[3]);
+    }
+}
+
+// strip width: whole rows when short, else a divisor of Q in [8, 16], else 8 (the last strip is clipped)
+int32_t pick_strip(int32_t q)
+{
+    if (q <= 16) return q;
+    for (int32_t t = 16; t >= 8; --t)
+        if (q % t == 0) return t;
+    return 8;
+}
+
+}  // namespace
+
+lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
+                            void* y, cudaStream_t stream)
+{
+    const lbc_conv_desc& d = g.d;
+    LBC_REQUIRE(d.groups == d.c && d.k == d.c && (d.c % 4) == 0, LBC_ERR_UNSUPPORTED,
+                "depthwise kernel needs groups == C == K and C %% 4 == 0");
+    LBC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(w_rsc) & 3) == 0,
+                LBC_ERR_INVALID_ARG, "depthwise: x / w must be 4-byte aligned and y 16-byte aligned");
+    const bool fast = d.r == 3 && d.s == 3 && d.dil_h == 1 && d.dil_w == 1 && d.stride_h == d.stride_w &&
+                      (d.stride_h == 1 || d.stride_h == 2);
+    const int block = 256;
+    if (fast) {
+        DwParams p{};
+        p.n = d.n; p.h = d.h; p.w = d.w; p.c = d.c; p.p = g.p; p.q = g.q;
+        p.stride = d.stride_h; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+        p.cq = d.c / 4;
+        p.tw = pick_strip(g.q);
+        p.strips = (g.q + p.tw - 1) / p.tw;
+        const int rows = d.stride_h == 1 ? 2 : 1;
+        p.row_groups = (g.p + rows - 1) / rows;
+        p.relu = ep.relu; p.out_mode = ep.out_mode;
+        const int64_t threads = (int64_t)d.n * p.row_groups * p.strips * p.cq;
+        LBC_REQUIRE(threads < (1ll << 31), LBC_ERR_UNSUPPORTED, "depthwise: problem too large (%lld threads)", (long long)threads);
+        const unsigned grid = (unsigned)((threads + block - 1) / block);
+        if (d.stride_h == 1)
+            depthwise3x3_kernel<1><<<grid, block, 0, stream>>>(p, x, w_rsc, ep.bias, ep.scale, y);
+        else
+            depthwise3x3_kernel<2><<<grid, block, 0, stream>>>(p, x, w_rsc, ep.bias, ep.scale, y);
+    } else {
+        DwGenericParams p{};
+        p.n = d.n; p.h = d.h; p.w = d.w; p.c = d.c; p.r = d.r; p.s = d.s;
+        p.stride_h = d.stride_h; p.stride_w = d.stride_w; p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+        p.dil_h = d.dil_h; p.dil_w = d.dil_w; p.p = g.p; p.q = g.q; p.cq = d.c / 4;
+        p.relu = ep.relu; p.out_mode = ep.out_mode;
+        p.total = g.m_total * p.cq;
+        const int64_t grid = (p.total + block - 1) / block;
+        LBC_REQUIRE(grid <= 0x7fffffffLL, LBC_ERR_UNSUPPORTED, "depthwise: grid too large");
+        depthwise_generic_kernel<<<(unsigned)grid, block, 0, stream>>>(p, x, w_rsc, ep.bias, ep.scale, y);
+    }
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
+
+}  // namespace lbc

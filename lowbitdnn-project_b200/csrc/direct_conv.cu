@@ -1,6 +1,6 @@
-// direct_conv.cu — CUDA-core direct convolution (any R,S,stride,pad,dilation,groups) and the
-// depthwise kernel.  These carry the layers where tensor cores do not pay (depthwise, tiny C, grouped)
-// and are the always-available correct path for every descriptor.
+// direct_conv.cu — CUDA-core direct convolution (any R,S,stride,pad,dilation,groups): the always-available
+// correct path for every descriptor (grouped convolutions, channel counts the tensor-core path cannot tile).
+// The depthwise kernel lives in depthwise.cu.
 //
 // Replaces, functionally: CUDAConv2DForward3x3CudaV1 (cpp/int8conv/conv2DForward3x3.cuh:602-676), which is
 // 3x3/stride-1 only and atomically accumulates partial sums; here each thread owns its outputs.
@@ -9,8 +9,6 @@
 namespace lbc {
 
 namespace {
-
-__device__ __forceinline__ int32_t sbyte(uint32_t v, int j) { return (int32_t)(int8_t)(v >> (8 * j)); }
 
 struct DirectParams {
     int32_t n, h, w, c, k, r, s, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
@@ -96,52 +94,6 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(DirectParams g, const 
     }
 }
 
-// Depthwise: one thread = one output pixel x 4 consecutive channels.  Weights packed [R][S][C] so that a
-// warp reads 128 contiguous bytes of activations and of weights per tap (NHWC channel-innermost).
-__global__ void __launch_bounds__(256) depthwise_kernel(DirectParams g, const int8_t* __restrict__ x,
-                                                        const int8_t* __restrict__ w_rsc,
-                                                        const int32_t* __restrict__ bias,
-                                                        const float* __restrict__ scale, void* __restrict__ y)
-{
-    const int32_t cq = g.c >> 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= g.m_total * cq) return;
-    const int32_t c0 = (int32_t)(idx % cq) * 4;
-    const int64_t m = idx / cq;
-    const int32_t q = (int32_t)(m % g.q);
-    const int32_t p = (int32_t)((m / g.q) % g.p);
-    const int32_t n = (int32_t)(m / ((int64_t)g.q * g.p));
-
-    int32_t acc[4] = {0, 0, 0, 0};
-    for (int32_t r = 0; r < g.r; ++r) {
-        const int32_t ih = p * g.stride_h - g.pad_h + r * g.dil_h;
-        if (ih < 0 || ih >= g.h) continue;
-        for (int32_t s = 0; s < g.s; ++s) {
-            const int32_t iw = q * g.stride_w - g.pad_w + s * g.dil_w;
-            if (iw < 0 || iw >= g.w) continue;
-            const uint32_t xv = *reinterpret_cast<const uint32_t*>(x + (((int64_t)n * g.h + ih) * g.w + iw) * g.c + c0);
-            const uint32_t wv = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + ((int64_t)r * g.s + s) * g.c + c0));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] += sbyte(xv, j) * sbyte(wv, j);
-        }
-    }
-    const int64_t o = m * g.k + c0;
-    const float lo = g.relu ? 0.0f : -128.0f;
-    if (g.out_mode == LBC_OUT_INT32) {
-        int4 v;
-        v.x = acc[0] + (bias ? bias[c0 + 0] : 0);
-        v.y = acc[1] + (bias ? bias[c0 + 1] : 0);
-        v.z = acc[2] + (bias ? bias[c0 + 2] : 0);
-        v.w = acc[3] + (bias ? bias[c0 + 3] : 0);
-        *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(y) + o) = v;
-    } else {
-        int32_t b[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = requant_s32(acc[j], bias ? bias[c0 + j] : 0, scale[c0 + j], lo);
-        *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(y) + o) = pack4_sat_s8(b[0], b[1], b[2], b[3]);
-    }
-}
-
 DirectParams to_params(const ConvGeom& g, int kt, const EpilogueParams& ep)
 {
     DirectParams p{};
@@ -177,21 +129,6 @@ lbc_status launch_direct_conv(const ConvGeom& g, const int8_t* x, const int8_t* 
         direct_conv_kernel<1, true><<<(unsigned)grid, block, 0, stream>>>(p, x, w, ep.bias, ep.scale, y);
     else
         direct_conv_kernel<1, false><<<(unsigned)grid, block, 0, stream>>>(p, x, w, ep.bias, ep.scale, y);
-    LBC_CUDA_TRY(cudaGetLastError());
-    return LBC_OK;
-}
-
-lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
-                            void* y, cudaStream_t stream)
-{
-    LBC_REQUIRE(g.d.groups == g.d.c && g.d.k == g.d.c && (g.d.c % 4) == 0, LBC_ERR_UNSUPPORTED,
-                "depthwise kernel needs groups == C == K and C %% 4 == 0");
-    DirectParams p = to_params(g, 4, ep);
-    const int64_t threads = g.m_total * (g.d.c / 4);
-    const int block = 256;
-    const int64_t grid = (threads + block - 1) / block;
-    LBC_REQUIRE(grid <= 0x7fffffffLL, LBC_ERR_UNSUPPORTED, "depthwise: grid too large");
-    depthwise_kernel<<<(unsigned)grid, block, 0, stream>>>(p, x, w_rsc, ep.bias, ep.scale, y);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

@@ -42,10 +42,20 @@ DW_CASES = [
     D(n=2, h=9, w=9, c=24, k=24, r=3, s=3, pad_h=1, pad_w=1, groups=24, relu=1),
     D(n=1, h=14, w=14, c=96, k=96, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, groups=96, relu=1),
     D(n=1, h=7, w=7, c=960, k=960, r=3, s=3, pad_h=1, pad_w=1, groups=960),
+    # 3x3 fast path: odd output height (half-used row pair), strips with a clipped tail, W != H, no padding
+    D(n=2, h=13, w=37, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1, groups=32, relu=1),
+    D(n=1, h=11, w=19, c=16, k=16, r=3, s=3, groups=16, relu=1),
+    D(n=2, h=23, w=41, c=8, k=8, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, groups=8, relu=1),
+    D(n=1, h=112, w=112, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1, groups=32, relu=1),
+    D(n=1, h=56, w=56, c=144, k=144, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, groups=144, relu=1),
+    # generic depthwise kernel: 5x5, dilation, stride 3
+    D(n=1, h=15, w=15, c=12, k=12, r=5, s=5, pad_h=2, pad_w=2, groups=12, relu=1),
+    D(n=1, h=15, w=17, c=8, k=8, r=3, s=3, pad_h=2, pad_w=2, dil_h=2, dil_w=2, groups=8),
+    D(n=1, h=16, w=16, c=8, k=8, r=3, s=3, stride_h=3, stride_w=3, pad_h=1, pad_w=1, groups=8),
 ]
 
 
-@pytest.mark.parametrize("d", DW_CASES, ids=lambda d: f"c{d.c}s{d.stride_h}")
+@pytest.mark.parametrize("d", DW_CASES, ids=lambda d: f"h{d.h}w{d.w}c{d.c}r{d.r}s{d.stride_h}d{d.dil_h}")
 @pytest.mark.parametrize("out_mode", [0, 1])
 def test_depthwise_kernel(d, out_mode):
     assert _check(D(**{**d.__dict__, "out_mode": out_mode})) == "depthwise"

@@ -37,6 +37,29 @@ __device__ __forceinline__ uint32_t q4(const int* acc, const int4 b, const float
         asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q3), "r"(q2));
         asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q1), "r"(q0), "r"(hi));
         return r;
+    } else if (V == 4) {   // V2 without the float clamp (non-ReLU, NaN ignored)
+        auto f = [&](int a, int bb, float sc) { return __float2int_rn(__fmul_rn(__int2float_rn(a + bb), sc)); };
+        int q0 = f(acc[0], b.x, s.x), q1 = f(acc[1], b.y, s.y), q2 = f(acc[2], b.z, s.z), q3 = f(acc[3], b.w, s.w);
+        uint32_t hi, r;
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q3), "r"(q2));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q1), "r"(q0), "r"(hi));
+        return r;
+    } else if (V == 5) {   // ReLU on the packed word: pack.sat.s8 then signed-byte max with 0 = clear bytes whose sign bit is set
+        auto f = [&](int a, int bb, float sc) { return __float2int_rn(__fmul_rn(__int2float_rn(a + bb), sc)); };
+        int q0 = f(acc[0], b.x, s.x), q1 = f(acc[1], b.y, s.y), q2 = f(acc[2], b.z, s.z), q3 = f(acc[3], b.w, s.w);
+        uint32_t hi, r;
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q3), "r"(q2));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q1), "r"(q0), "r"(hi));
+        const uint32_t neg = (r >> 7) & 0x01010101u;          // 1 per negative byte
+        return r & ~(neg * 0xffu);                             // IMAD + LOP3
+    } else if (V == 6) {   // V4 with scale/bias in registers (no LDS) - lower bound
+        auto f = [&](int a, int bb, float sc) { return __float2int_rn(__fmul_rn(__int2float_rn(a + bb), sc)); };
+        int q0 = f(acc[0], lo > 1.f ? b.x : 77, lo > 1.f ? s.x : 0.013f), q1 = f(acc[1], lo > 1.f ? b.y : 78, lo > 1.f ? s.y : 0.014f),
+            q2 = f(acc[2], lo > 1.f ? b.z : 79, lo > 1.f ? s.z : 0.015f), q3 = f(acc[3], lo > 1.f ? b.w : 80, lo > 1.f ? s.w : 0.016f);
+        uint32_t hi, r;
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi) : "r"(q3), "r"(q2));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q1), "r"(q0), "r"(hi));
+        return r;
     } else {   // V == 3: float clamp + magic add, pack via I2IP-free shifts: (a&255)|(b&255)<<8 ... using LOP3/prmt alt
         auto f = [&](int a, int bb, float sc) {
             float x = __fmul_rn(__int2float_rn(a + bb), sc);
@@ -101,6 +124,8 @@ int main()
         run<1>("V1 cvt.rni.sat.s8.f32+prmt", th);
         run<2>("V2 f2i + cvt.pack.sat", th);
         run<3>("V3 fclamp+magic+cvt.pack", th);
+        run<4>("V4 V2 minus fmax", th);
+        run<5>("V5 relu on packed word", th);
     }
     return 0;
 }
