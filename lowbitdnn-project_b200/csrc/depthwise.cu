@@ -63,8 +63,16 @@ __device__ __forceinline__ void rows_to_channels(uint32_t a, uint32_t b, uint32_
 }
 
 // STRIDE 1: two output rows per thread (4 input rows per column); STRIDE 2: one output row (3 input rows).
+//
+// Instruction diet (the kernel is issue-bound, not HBM-bound, until this is right):
+//   * input rows outside the image are not predicated in the loop: their pointer is clamped to a valid row and the
+//     matching BYTE of every filter word is zeroed once, so whatever is loaded there multiplies by zero;
+//   * all addresses are 32-bit word offsets from the (warp-uniform) tensor base: one IMAD.WIDE per access;
+//   * the bias is the initial value of the dp4a chain (same int32 wraparound as acc + bias);
+//   * the strip loop is unrolled by the column-reuse period (3 for stride 1, 2 for stride 2) so the rolling window
+//     is a renaming of registers, not a set of moves.
 template <int STRIDE>
-__global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, const int8_t* __restrict__ x,
+__global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, const uint32_t* __restrict__ x32,
                                                            const int8_t* __restrict__ w_rsc,
                                                            const int32_t* __restrict__ bias,
                                                            const float* __restrict__ scale, void* __restrict__ y)
@@ -84,37 +92,34 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, con
     const int32_t q0 = (int32_t)strip * g.tw;
     const int32_t q1 = min(q0 + g.tw, g.q);
 
-    // ---- filter columns: wv[s][ch] = bytes (w[0][s][ch], w[1][s][ch], w[2][s][ch], 0)
-    uint32_t wv[3][4];
+    // ---- input rows: clamped word offsets + a byte mask that removes out-of-image rows from the filter
+    const int32_t ih0 = p0 * STRIDE - g.pad_h;
+    uint32_t rowoff[IN_ROWS];
+    uint32_t keep_mask = 0;
+#pragma unroll
+    for (int r = 0; r < IN_ROWS; ++r) {
+        const int32_t ih = ih0 + r;
+        const bool ok = ih >= 0 && ih < g.h;
+        if (ok) keep_mask |= 0xffu << (8 * r);
+        rowoff[r] = ((n * (uint32_t)g.h + (uint32_t)(ok ? ih : 0)) * (uint32_t)g.w) * (uint32_t)g.cq + cqi;
+    }
+
+    // ---- filter columns: wa[s][ch] = bytes (w[0][s][ch], w[1][s][ch], w[2][s][ch], 0) for output row p0 and
+    //      wb = the same shifted up one byte for output row p0 + 1 (stride 1 only)
+    uint32_t wa[3][4], wb[3][4];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
         const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (0 * 3 + s) * g.c + c0));
         const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (1 * 3 + s) * g.c + c0));
         const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (2 * 3 + s) * g.c + c0));
-        rows_to_channels<false>(a, b, c, 0u, wv[s]);
+        rows_to_channels<false>(a, b, c, 0u, wa[s]);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) wv[s][ch] &= 0x00ffffffu;
+        for (int ch = 0; ch < 4; ++ch) {
+            const uint32_t w3 = wa[s][ch] & 0x00ffffffu;
+            wa[s][ch] = w3 & keep_mask;
+            wb[s][ch] = (w3 << 8) & keep_mask;
+        }
     }
-
-    // ---- input rows of this thread
-    const int32_t ih0 = p0 * STRIDE - g.pad_h;
-    const int8_t* xr[IN_ROWS];
-    bool rok[IN_ROWS];
-#pragma unroll
-    for (int r = 0; r < IN_ROWS; ++r) {
-        const int32_t ih = ih0 + r;
-        rok[r] = ih >= 0 && ih < g.h;
-        xr[r] = x + (((int64_t)n * g.h + (rok[r] ? ih : 0)) * g.w) * g.c + c0;
-    }
-    auto load_col = [&](int32_t iw, uint32_t(&v)[4]) {
-        uint32_t rw[4] = {0u, 0u, 0u, 0u};
-        const bool cok = iw >= 0 && iw < g.w;
-        const int64_t off = (int64_t)iw * g.c;
-#pragma unroll
-        for (int r = 0; r < IN_ROWS; ++r)
-            if (cok && rok[r]) rw[r] = *reinterpret_cast<const uint32_t*>(xr[r] + off);
-        rows_to_channels<(IN_ROWS == 4)>(rw[0], rw[1], rw[2], rw[3], v);
-    };
 
     // ---- epilogue parameters of the 4 channels
     const float lo = g.relu ? 0.0f : -128.0f;
@@ -129,55 +134,94 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, con
         sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
     }
     const bool row1 = (ROWS == 2) && (p0 + 1 < g.p);
-    const int64_t yrow0 = (((int64_t)n * g.p + p0) * g.q) * g.c + c0;   // element offset of (n, p0, 0, c0)
-    const int64_t yrow1 = yrow0 + (int64_t)g.q * g.c;
+    // word offset (4 channels = one 32-bit word of int8 output) of (n, p0, 0, c0)
+    const uint32_t yoff0 = ((n * (uint32_t)g.p + (uint32_t)p0) * (uint32_t)g.q) * (uint32_t)g.cq + cqi;
+    const uint32_t yoff1 = yoff0 + (uint32_t)g.q * (uint32_t)g.cq;
+    uint32_t* y8 = reinterpret_cast<uint32_t*>(y);
+    int4* y32 = reinterpret_cast<int4*>(y);
 
-    auto emit = [&](const int32_t(&acc)[4], int64_t o) {
-        if (g.out_mode == LBC_OUT_INT32) {
-            *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(y) + o) =
-                make_int4(acc[0] + bi[0], acc[1] + bi[1], acc[2] + bi[2], acc[3] + bi[3]);
-        } else {
-            *reinterpret_cast<uint32_t*>(reinterpret_cast<int8_t*>(y) + o) =
-                pack4_sat_s8(requant_s32(acc[0], bi[0], sc[0], lo), requant_s32(acc[1], bi[1], sc[1], lo),
-                             requant_s32(acc[2], bi[2], sc[2], lo), requant_s32(acc[3], bi[3], sc[3], lo));
+    // raw row words of one input column (zero outside the image); transposed later, one iteration after the load
+    // was issued, so the memory latency is covered by the previous column's arithmetic
+    auto load_raw = [&](int32_t iw, uint32_t(&rw)[4]) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) rw[r] = 0u;
+        if ((uint32_t)iw < (uint32_t)g.w) {
+            const uint32_t co = (uint32_t)iw * (uint32_t)g.cq;
+#pragma unroll
+            for (int r = 0; r < IN_ROWS; ++r) rw[r] = __ldg(x32 + (rowoff[r] + co));
         }
     };
-
-    // ---- walk the strip; three live input columns roll through v0, v1, v2
-    uint32_t v0[4], v1[4], v2[4];
-    int32_t iw = q0 * STRIDE - g.pad_w;
-    load_col(iw, v0);
-    if (STRIDE == 1) load_col(iw + 1, v1);
-    for (int32_t q = q0; q < q1; ++q) {
-        if (STRIDE == 1) {
-            load_col(iw + 2, v2);
+    auto xpose = [&](const uint32_t(&rw)[4], uint32_t(&v)[4]) {
+        rows_to_channels<(IN_ROWS == 4)>(rw[0], rw[1], rw[2], rw[3], v);
+    };
+    auto emit = [&](const int32_t(&acc)[4], uint32_t o) {
+        if (g.out_mode == LBC_OUT_INT32) {
+            y32[o] = make_int4(acc[0], acc[1], acc[2], acc[3]);
         } else {
-            load_col(iw + 1, v1);
-            load_col(iw + 2, v2);
+            y8[o] = pack4_sat_s8(requant_s32(acc[0], 0, sc[0], lo), requant_s32(acc[1], 0, sc[1], lo),
+                                 requant_s32(acc[2], 0, sc[2], lo), requant_s32(acc[3], 0, sc[3], lo));
         }
+    };
+    auto compute = [&](const uint32_t(&va)[4], const uint32_t(&vb)[4], const uint32_t(&vc)[4], int32_t q) {
         int32_t a0[4], a1[4];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-            a0[ch] = __dp4a((int32_t)v0[ch], (int32_t)wv[0][ch], 0);
-            a0[ch] = __dp4a((int32_t)v1[ch], (int32_t)wv[1][ch], a0[ch]);
-            a0[ch] = __dp4a((int32_t)v2[ch], (int32_t)wv[2][ch], a0[ch]);
-            if (ROWS == 2) {   // output row p0 + 1: the same columns against (0, w0, w1, w2)
-                a1[ch] = __dp4a((int32_t)v0[ch], (int32_t)(wv[0][ch] << 8), 0);
-                a1[ch] = __dp4a((int32_t)v1[ch], (int32_t)(wv[1][ch] << 8), a1[ch]);
-                a1[ch] = __dp4a((int32_t)v2[ch], (int32_t)(wv[2][ch] << 8), a1[ch]);
+            a0[ch] = __dp4a((int32_t)va[ch], (int32_t)wa[0][ch], bi[ch]);
+            a0[ch] = __dp4a((int32_t)vb[ch], (int32_t)wa[1][ch], a0[ch]);
+            a0[ch] = __dp4a((int32_t)vc[ch], (int32_t)wa[2][ch], a0[ch]);
+            if (ROWS == 2) {
+                a1[ch] = __dp4a((int32_t)va[ch], (int32_t)wb[0][ch], bi[ch]);
+                a1[ch] = __dp4a((int32_t)vb[ch], (int32_t)wb[1][ch], a1[ch]);
+                a1[ch] = __dp4a((int32_t)vc[ch], (int32_t)wb[2][ch], a1[ch]);
             }
         }
-        const int64_t qo = (int64_t)q * g.c;
-        emit(a0, yrow0 + qo);
-        if (ROWS == 2 && row1) emit(a1, yrow1 + qo);
-        if (STRIDE == 1) {
+        const uint32_t qo = (uint32_t)q * (uint32_t)g.cq;
+        emit(a0, yoff0 + qo);
+        if (ROWS == 2 && row1) emit(a1, yoff1 + qo);
+    };
+
+    uint32_t v0[4], v1[4], v2[4], ra[4], rb[4];
+    int32_t iw = q0 * STRIDE - g.pad_w;
+    if (STRIDE == 1) {
+        load_raw(iw, ra);
+        load_raw(iw + 1, rb);
+        xpose(ra, v0);
+        load_raw(iw + 2, ra);
+        xpose(rb, v1);
+        // invariant at the top of a step for output q: ra holds the raw words of column iw + 2
+        for (int32_t q = q0; q < q1; q += 3, iw += 3) {
+            load_raw(iw + 3, rb);
+            xpose(ra, v2);
+            compute(v0, v1, v2, q);
+            if (q + 1 < q1) {
+                load_raw(iw + 4, ra);
+                xpose(rb, v0);
+                compute(v1, v2, v0, q + 1);
+            }
+            if (q + 2 < q1) {
+                load_raw(iw + 5, rb);
+                xpose(ra, v1);
+                compute(v2, v0, v1, q + 2);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) { v0[ch] = v1[ch]; v1[ch] = v2[ch]; }
-        } else {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) v0[ch] = v2[ch];
+                for (int r = 0; r < 4; ++r) ra[r] = rb[r];
+            }
         }
-        iw += STRIDE;
+    } else {
+        uint32_t rc[4], rd[4];
+        load_raw(iw, ra);
+        load_raw(iw + 1, rb);
+        load_raw(iw + 2, rc);
+        xpose(ra, v0);
+        // invariant: rb, rc hold the raw words of columns iw + 1, iw + 2
+        for (int32_t q = q0; q < q1; ++q, iw += 2) {
+            load_raw(iw + 3, ra);
+            load_raw(iw + 4, rd);
+            xpose(rb, v1);
+            xpose(rc, v2);
+            compute(v0, v1, v2, q);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { v0[r] = v2[r]; rb[r] = ra[r]; rc[r] = rd[r]; }
+        }
     }
 }
 
@@ -233,13 +277,13 @@ __global__ void __launch_bounds__(256) depthwise_generic_kernel(const DwGenericP
     }
 }
 
-// strip width: whole rows when short, else a divisor of Q in [8, 16], else 8 (the last strip is clipped)
+// strip width: whole rows when short, else a divisor of Q in [12, 28], else 16 (the last strip is clipped)
 int32_t pick_strip(int32_t q)
 {
-    if (q <= 16) return q;
-    for (int32_t t = 16; t >= 8; --t)
+    if (q <= 28) return q;
+    for (int32_t t = 28; t >= 12; --t)
         if (q % t == 0) return t;
-    return 8;
+    return 16;
 }
 
 }  // namespace
@@ -253,8 +297,10 @@ lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_
     LBC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(w_rsc) & 3) == 0,
                 LBC_ERR_INVALID_ARG, "depthwise: x / w must be 4-byte aligned and y 16-byte aligned");
+    // the fast kernel addresses x and y with 32-bit word offsets
+    const bool small = (int64_t)d.n * d.h * d.w * d.c < (1ll << 32) && g.m_total * d.c < (1ll << 32);
     const bool fast = d.r == 3 && d.s == 3 && d.dil_h == 1 && d.dil_w == 1 && d.stride_h == d.stride_w &&
-                      (d.stride_h == 1 || d.stride_h == 2);
+                      (d.stride_h == 1 || d.stride_h == 2) && small;
     const int block = 256;
     if (fast) {
         DwParams p{};
@@ -270,9 +316,9 @@ lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_
         LBC_REQUIRE(threads < (1ll << 31), LBC_ERR_UNSUPPORTED, "depthwise: problem too large (%lld threads)", (long long)threads);
         const unsigned grid = (unsigned)((threads + block - 1) / block);
         if (d.stride_h == 1)
-            depthwise3x3_kernel<1><<<grid, block, 0, stream>>>(p, x, w_rsc, ep.bias, ep.scale, y);
+            depthwise3x3_kernel<1><<<grid, block, 0, stream>>>(p, reinterpret_cast<const uint32_t*>(x), w_rsc, ep.bias, ep.scale, y);
         else
-            depthwise3x3_kernel<2><<<grid, block, 0, stream>>>(p, x, w_rsc, ep.bias, ep.scale, y);
+            depthwise3x3_kernel<2><<<grid, block, 0, stream>>>(p, reinterpret_cast<const uint32_t*>(x), w_rsc, ep.bias, ep.scale, y);
     } else {
         DwGenericParams p{};
         p.n = d.n; p.h = d.h; p.w = d.w; p.c = d.c; p.r = d.r; p.s = d.s;
