@@ -340,11 +340,11 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
         const IgemmConfig& c = plan->cfg;
         static const char* modes[] = {"tiled", "im2col", "window"};
         snprintf(buf, buf_len,
-                 "%s N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %dx%d+%dw "
+                 "%s N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %dx%d+%dw b=%s "
                  "a=%s(%dx%d px/tile) tiles %dx%d grid %d smem %zu tmem %u",
                  plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : "igemm_tc", d.n, d.h, d.w, d.c, d.k, d.r, d.s,
                  d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.tps, c.win_stages,
-                 modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
+                 c.res_b ? "resident" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols);
     } else {
         snprintf(buf, buf_len, "%s N%d %dx%dx%d->%d %dx%d s%d p%d g%d | M=%lld",

@@ -83,10 +83,18 @@ struct IgemmConfig {
     int32_t wt, rows_per_tile, cols_per_tile, row_tiles, col_tiles;
     int32_t tiles_m, tiles_n;
     int32_t panel_bytes, panel_swz_bits, n_panels;
+    int32_t stage_bufs;  // staging panels per epilogue team
+    int32_t k_mod;       // bias/scale index modulo (pixel-group rewrite), 0 = none
+    int32_t n_tab;       // MMA issue table: A-descriptor offsets (16-byte units) of one channel chunk
+    uint16_t a_tab[192];
+    uint16_t b_tab[192]; // resident-B window mode: matching B-descriptor offsets
+    int32_t res_b;       // filter matrix resident in shared memory (loaded once per CTA)
+    uint32_t b_total_bytes;
     uint32_t off_b, off_stage, off_ctl;
     int32_t grid;        // persistent CTAs
     size_t smem_bytes;
-    uint32_t tmem_cols;  // power of two >= 2*bn
+    uint32_t tmem_cols;  // power of two >= n_acc*bn
+    int32_t n_acc;       // TMEM accumulator stages (2 or 4)
 };
 struct IgemmLaunch {
     CUtensorMap tm_a;

@@ -43,7 +43,8 @@ constexpr int kTeamThreads = kTeamWarps * 32;
 constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA + TMEM alloc, 2: window TMA, 3: idle
 constexpr int kNumThreads = (kFirstEpiWarp + kTeams * kTeamWarps) * 32;   // 640
 constexpr int kMaxStages = 8;
-constexpr int kMaxWinStages = 4;
+constexpr int kMaxWinStages = 6;
+constexpr int kMaxTab = 192;                           // A-descriptor offsets per channel chunk (taps x K-steps)
 
 enum : int32_t { A_TILED = 0, A_IM2COL = 1, A_WINDOW = 2 };
 
@@ -72,9 +73,23 @@ struct IgemmParams {
     // epilogue
     int32_t relu, out_mode;
     uint32_t tmem_cols;
+    int32_t n_acc;                // TMEM accumulator stages (2 or 4): how far the MMA warp may run ahead of the epilogue
     int32_t panel_bytes, panel_swz_bits, n_panels;
+    int32_t stage_bufs;           // staging panels per epilogue team (2 = a TMA store drains while the next panel fills)
+    int32_t k_mod;                // bias/scale index = channel % k_mod (pixel-group rewrite replicates them), 0 = plain
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
+    // MMA issue table: A-descriptor offset (16-byte units, relative to the A stage / window base) of every MMA of one
+    // channel chunk, in issue order.  Lives in the kernel-parameter bank so the issue loop reads it with uniform loads.
+    int32_t n_tab;
+    uint16_t a_tab[kMaxTab];
+    uint16_t b_tab[kMaxTab];      // resident-B window mode: B-descriptor offsets of the same MMAs (relative to the chunk)
+    int32_t res_b;                // 1: the whole filter matrix stays in shared memory (loaded once per CTA)
+    uint32_t b_total_bytes;       // resident B: bytes of the filter matrix
+    // division-free tile iteration: a tile index is the mixed-radix number (img | rt | ct | n_blk) with radices
+    // (it_rows, it_cols, tiles_n); step_* are the digits of gridDim.x in that system
+    int32_t it_cols, it_rows;
+    int32_t step_nb, step_ct, step_rt, step_img;
     // optional pipeline trace (development aid): CTA 0 writes clock64 stamps, 16 slots per local tile
     long long* trace;
     int32_t trace_tiles;
@@ -83,12 +98,10 @@ struct IgemmParams {
 enum : int { EV_P_ISSUE = 0, EV_W_ISSUE, EV_M_START, EV_M_WIN, EV_M_FULL, EV_M_DONE, EV_E_START, EV_E_DRAINED, EV_E_STORED,
              EV_P_DONE };
 
-__device__ __forceinline__ void trace_ev(const IgemmParams& prm, int32_t tile, int ev)
+// `local` = index of the tile in this CTA's own sequence (0, 1, 2, ...)
+__device__ __forceinline__ void trace_ev(const IgemmParams& prm, int32_t local, int ev)
 {
-    if (prm.trace != nullptr && blockIdx.x == 0) {
-        const int32_t local = tile / (int32_t)gridDim.x;
-        if (local < prm.trace_tiles) prm.trace[local * 16 + ev] = clock64();
-    }
+    if (prm.trace != nullptr && blockIdx.x == 0 && local < prm.trace_tiles) prm.trace[local * 16 + ev] = clock64();
 }
 
 __device__ int g_timeout_flag = 0;
@@ -98,38 +111,46 @@ struct Ctl {
     uint64_t empty[kMaxStages];
     uint64_t wfull[kMaxWinStages];
     uint64_t wempty[kMaxWinStages];
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
+    uint64_t tmem_full[4];
+    uint64_t tmem_empty[4];
+    uint64_t bfull;               // resident filter matrix has landed
     uint32_t tmem_base;
-    uint32_t pad_[3];
+    uint32_t pad_[1];
     alignas(16) float scale[kTeams][256];
     alignas(16) int32_t bias[kTeams][256];
 };
 
-struct TileCoord {
-    int32_t n_blk;
-    int64_t m0;                   // TILED / IM2COL: first GEMM row of the tile
-    int32_t img, p0, q0;          // WINDOW: image and first output row / column
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& prm, int32_t tile)
-{
-    TileCoord t;
-    t.n_blk = tile % prm.tiles_n;
-    const int32_t mt = tile / prm.tiles_n;
-    if (prm.mode == A_WINDOW) {
-        const int32_t ct = mt % prm.col_tiles;
-        const int32_t rt = (mt / prm.col_tiles) % prm.row_tiles;
-        t.img = mt / (prm.col_tiles * prm.row_tiles);
-        t.p0 = rt * prm.rows_per_tile;
-        t.q0 = ct * prm.cols_per_tile;
-        t.m0 = 0;
-    } else {
-        t.m0 = (int64_t)mt * kBlockM;
-        t.img = t.p0 = t.q0 = 0;
+// Persistent tile walk without divisions in the loop: the digits are decoded once (init) and then advanced by the
+// digits of gridDim.x with carries (next).  In the ring modes it_cols == it_rows == 1 and `img` is the M-tile index.
+struct TileIter {
+    int32_t tile, n_blk, ct, rt, img, local;
+    __device__ __forceinline__ void init(const IgemmParams& prm, int32_t t0)
+    {
+        tile = t0;
+        local = 0;
+        n_blk = t0 % prm.tiles_n;
+        const int32_t mt = t0 / prm.tiles_n;
+        ct = mt % prm.it_cols;
+        rt = (mt / prm.it_cols) % prm.it_rows;
+        img = mt / (prm.it_cols * prm.it_rows);
     }
-    return t;
-}
+    __device__ __forceinline__ void next(const IgemmParams& prm)
+    {
+        tile += (int32_t)gridDim.x;
+        ++local;
+        n_blk += prm.step_nb;
+        if (n_blk >= prm.tiles_n) { n_blk -= prm.tiles_n; ++ct; }
+        ct += prm.step_ct;
+        if (ct >= prm.it_cols) { ct -= prm.it_cols; ++rt; }
+        rt += prm.step_rt;
+        if (rt >= prm.it_rows) { rt -= prm.it_rows; ++img; }
+        img += prm.step_img;
+    }
+    // WINDOW: first output row / column of the tile; ring modes: first GEMM row
+    __device__ __forceinline__ int32_t p0(const IgemmParams& prm) const { return rt * prm.rows_per_tile; }
+    __device__ __forceinline__ int32_t q0(const IgemmParams& prm) const { return ct * prm.cols_per_tile; }
+    __device__ __forceinline__ int32_t m0() const { return img * kBlockM; }
+};
 
 // bounded wait for the single-thread roles: false => give up (the watchdog flag is set)
 __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, volatile int* flag)
@@ -218,7 +239,9 @@ __device__ __forceinline__ uint64_t keep(uint64_t v) { asm volatile("" : "+l"(v)
 
 // KM: 0 tiled A, 1 im2col A, 2 window A (>= 32-byte pixels), 3 window A with 16-byte pixels (paired taps)
 // KS: MMA K-steps (32 bytes each) per B block = bkb / 32
-template <int KM, int KS>
+// RESB: the filter matrix is resident in shared memory (one N tile, loaded once per CTA); the ring then carries
+//       only A blocks (tiled / im2col) or does not exist at all (window modes)
+template <int KM, int KS, bool RESB>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
@@ -251,10 +274,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             ptx::mbar_init(&ctl->wfull[i], 1);
             ptx::mbar_init(&ctl->wempty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < prm.n_acc; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
             ptx::mbar_init(&ctl->tmem_empty[i], kTeamWarps);
         }
+        ptx::mbar_init(&ctl->bfull, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -272,62 +296,80 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // convergent lets the compiler hold addresses and descriptors in uniform registers; a `lane == 0` branch
     // around the whole loop made every tcgen05.mma cost ~150 scalar instructions (ncu, r01 v2).
     constexpr bool kWindow = (KM >= 2);
+    constexpr bool kRing = !(kWindow && RESB);      // resident B + window A: no ring at all
     if (warp == 0) {
         // ===================== ring producer: B blocks (+ A blocks in TILED / IM2COL) =====================
-        uint32_t stage = 0, phase = 0;
-        const uint32_t tx_bytes = keep(prm.b_stage_bytes + (kWindow ? 0u : prm.a_stage_bytes));
-        const int32_t stages_per_tile = keep(prm.cblocks * prm.inner / prm.tps);
-        const int32_t tps = keep(prm.tps), nstages = keep(prm.stages), cblocks = keep(prm.cblocks);
-        const int32_t bkb = keep(prm.bkb), bkc = keep(prm.bkc), s_taps = keep(prm.s_taps);
-        const int32_t dil_w = keep(prm.dil_w), dil_h = keep(prm.dil_h);
-        const uint32_t a_block = keep(prm.a_block_bytes), b_block = keep(prm.b_block_bytes);
-        const uint32_t a_stage = keep(prm.a_stage_bytes), b_stage = keep(prm.b_stage_bytes);
         const bool leader = ptx::elect_one();
-        bool ok = true;
-        for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(prm, tile);
-            int32_t w_base = 0, h_base = 0, n0 = 0;
-            if (KM == A_IM2COL) {
-                const int32_t q0 = (int32_t)(tc.m0 % prm.q);
-                const int32_t p0 = (int32_t)((tc.m0 / prm.q) % prm.p);
-                n0 = (int32_t)(tc.m0 / ((int64_t)prm.q * prm.p));
-                w_base = q0 * prm.stride_w - prm.pad_w;
-                h_base = p0 * prm.stride_h - prm.pad_h;
+        if (RESB) {
+            // the whole filter matrix, once: k_blocks boxes of [bn][bkb] side by side
+            if (leader) {
+                ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes);
+                const int32_t nblk = prm.cblocks * prm.inner;
+                uint8_t* dst = smem_b;
+                int32_t bcol = 0;
+                for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb)
+                    ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, 0);
             }
-            const int32_t brow = tc.n_blk * prm.bn;
-            // ring modes walk K as [tap][channel chunk]: (off_h, off_w) filter tap offset, c0 channel offset
-            int32_t c0 = 0, cbi = 0, off_w = 0, off_h = 0, fs = 0, bcol = 0;
-            for (int32_t st = 0; st < stages_per_tile; ++st) {
-                ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
-                if (!ok) break;
-                if (st == 0 && leader) trace_ev(prm, tile, EV_P_ISSUE);
-                if (leader) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
-                uint8_t* dst_a = smem_a + stage * a_stage;
-                uint8_t* dst_b = smem_b + stage * b_stage;
-                for (int32_t t = 0; t < tps; ++t) {
-                    if (leader) {
-                        if (KM == A_IM2COL)
-                            ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0, (uint16_t)off_w,
-                                                    (uint16_t)off_h);
-                        else if (KM == A_TILED)
-                            ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, (int32_t)tc.m0);
-                        ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
-                    }
-                    dst_a += a_block;
-                    dst_b += b_block;
-                    bcol += bkb;
-                    if (!kWindow) {
-                        c0 += bkc;
-                        if (++cbi == cblocks) {
-                            cbi = 0; c0 = 0;
-                            off_w += dil_w;
-                            if (++fs == s_taps) { fs = 0; off_w = 0; off_h += dil_h; }
+            __syncwarp();
+        }
+        if (kRing) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t tx_bytes = (RESB ? 0u : prm.b_stage_bytes) + (kWindow ? 0u : prm.a_stage_bytes);
+            const int32_t stages_per_tile = prm.cblocks * prm.inner / prm.tps;
+            const int32_t tps = prm.tps, nstages = prm.stages, cblocks = prm.cblocks;
+            const int32_t bkb = prm.bkb, bkc = prm.bkc, s_taps = prm.s_taps;
+            const int32_t dil_w = prm.dil_w, dil_h = prm.dil_h;
+            const uint32_t a_block = prm.a_block_bytes, b_block = prm.b_block_bytes;
+            const uint32_t a_stage = prm.a_stage_bytes, b_stage = prm.b_stage_bytes;
+            bool ok = true;
+            TileIter it;
+            for (it.init(prm, blockIdx.x); it.tile < num_tiles && ok; it.next(prm)) {
+                const int32_t m0 = it.m0();
+                int32_t w_base = 0, h_base = 0, n0 = 0;
+                if (KM == A_IM2COL) {
+                    const uint32_t um = (uint32_t)m0, uq = (uint32_t)prm.q, up = (uint32_t)prm.p;
+                    const uint32_t row = um / uq;
+                    const int32_t q0 = (int32_t)(um - row * uq);
+                    n0 = (int32_t)(row / up);
+                    const int32_t p0 = (int32_t)(row - (uint32_t)n0 * up);
+                    w_base = q0 * prm.stride_w - prm.pad_w;
+                    h_base = p0 * prm.stride_h - prm.pad_h;
+                }
+                const int32_t brow = it.n_blk * prm.bn;
+                // ring modes walk K as [tap][channel chunk]: (off_h, off_w) filter tap offset, c0 channel offset
+                int32_t c0 = 0, cbi = 0, off_w = 0, off_h = 0, fs = 0, bcol = 0;
+                for (int32_t st = 0; st < stages_per_tile; ++st) {
+                    ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
+                    if (!ok) break;
+                    if (st == 0 && leader) trace_ev(prm, it.local, EV_P_ISSUE);
+                    if (leader) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
+                    uint8_t* dst_a = smem_a + stage * a_stage;
+                    uint8_t* dst_b = smem_b + stage * b_stage;
+                    for (int32_t t = 0; t < tps; ++t) {
+                        if (leader) {
+                            if (KM == A_IM2COL)
+                                ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0, (uint16_t)off_w,
+                                                        (uint16_t)off_h);
+                            else if (KM == A_TILED)
+                                ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, m0);
+                            if (!RESB) ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
+                        }
+                        dst_a += a_block;
+                        dst_b += b_block;
+                        bcol += bkb;
+                        if (!kWindow) {
+                            c0 += bkc;
+                            if (++cbi == cblocks) {
+                                cbi = 0; c0 = 0;
+                                off_w += dil_w;
+                                if (++fs == s_taps) { fs = 0; off_w = 0; off_h += dil_h; }
+                            }
                         }
                     }
+                    if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+                if (leader) trace_ev(prm, it.local, EV_P_DONE);
             }
-            if (leader) trace_ev(prm, tile, EV_P_DONE);
         }
     } else if (warp == 2) {
         // ===================== window producer (WINDOW modes only) =====================
@@ -335,17 +377,17 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             uint32_t ws = 0, wphase = 0;
             const bool leader = ptx::elect_one();
             bool ok = true;
-            for (int32_t tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(prm, tile);
+            TileIter it;
+            for (it.init(prm, blockIdx.x); it.tile < num_tiles && ok; it.next(prm)) {
+                const int32_t wq = it.q0(prm) - prm.pad_w, wp = it.p0(prm) - prm.pad_h;
                 int32_t c0 = 0;
                 for (int32_t cb = 0; cb < prm.cblocks; ++cb, c0 += prm.bkc) {
                     ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
                     if (!ok) break;
                     if (leader) {
-                        if (cb == 0) trace_ev(prm, tile, EV_W_ISSUE);
+                        if (cb == 0) trace_ev(prm, it.local, EV_W_ISSUE);
                         ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
-                        ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, tc.q0 - prm.pad_w,
-                                         tc.p0 - prm.pad_h, tc.img);
+                        ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
                     }
                     if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
                 }
@@ -353,9 +395,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // Convergent, exit-free loops (a watchdog trip only makes the waits return early): every address below is
-        // derived from kernel parameters and loop counters, so it lives in uniform registers; the tcgen05
-        // instructions are predicated on the elected lane inside their asm blocks.
+        // Convergent, exit-free loops (a watchdog trip only makes the waits return early).  One tcgen05.mma of
+        // M=128 x N<=128 takes 48-64 cycles (tools/exp/mma_rates.cu), so the issue loop has to stay well below that
+        // per MMA: the descriptor offsets of a channel chunk come from tables in the kernel-parameter bank, only the
+        // low 32 bits of the descriptors are ever touched (the smem address field cannot carry into the LBO field),
+        // and with a resident filter matrix there is no per-block handshake at all.
         uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
         uint32_t acc_stage = 0, acc_phase = 0;
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
@@ -363,74 +407,89 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint64_t db_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_b), (uint32_t)prm.bkb);
         const uint64_t da_base = (KM != 3) ? ptx::make_kmajor_desc(ptx::smem_u32(smem_a), (uint32_t)prm.bkc)
                                            : ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem_a), (uint32_t)prm.dil_w * 16u, 128u);
+        const uint32_t da_lo = (uint32_t)da_base, da_hi = (uint32_t)(da_base >> 32);
+        const uint32_t db_lo = (uint32_t)db_base, db_hi = (uint32_t)(db_base >> 32);
         const uint32_t a_stage16 = (kWindow ? prm.win_stage_bytes : prm.a_stage_bytes) >> 4;
         const uint32_t b_stage16 = prm.b_stage_bytes >> 4;
-        const uint32_t a_block16 = prm.a_block_bytes >> 4, b_block16 = prm.b_block_bytes >> 4;
-        const uint32_t s_step16 = (uint32_t)(prm.dil_w * prm.bkc) >> 4;             // next tap in the filter row
-        const uint32_t r_step16 = (uint32_t)(prm.dil_h * prm.wt * prm.bkc) >> 4;    // next filter row
-        const uint32_t k_step16 = (KM == 3) ? 2 * s_step16 : 2;   // A advance per K-step (KM 3: two taps = two pixels)
+        const uint32_t b_block16 = prm.b_block_bytes >> 4;
+        const uint32_t b_chunk16 = b_block16 * (uint32_t)prm.inner;          // resident B: one channel chunk of blocks
         const int32_t inner_stages = prm.mma_inner / prm.tps;
+        const int32_t tps = prm.tps, mma_outer = prm.mma_outer, n_tab = prm.n_tab;
+        const uint32_t nstages = (uint32_t)prm.stages, nwin = (uint32_t)prm.win_stages;
+        const uint32_t bn = (uint32_t)prm.bn;
 
-        bool ready = ptx::mbar_test(&ctl->full[0], 0);
+        bool ready = kRing ? ptx::mbar_test(&ctl->full[0], 0) : true;
         bool wready = kWindow ? ptx::mbar_test(&ctl->wfull[0], 0) : true;
-        for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        if (RESB) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
+        int32_t local = 0;
+        for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             ptx::mbar_wait_soft(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
             ptx::tc_fence_after();
-            if (leader) trace_ev(prm, tile, EV_M_START);
-            const uint32_t tmem_d = tmem_base + acc_stage * (uint32_t)prm.bn;
+            if (leader) trace_ev(prm, local, EV_M_START);
+            const uint32_t tmem_d = tmem_base + acc_stage * bn;
             uint32_t accumulate = 0;
-            for (int32_t cb = 0; cb < prm.mma_outer; ++cb) {
-                uint64_t da_win = da_base;
-                if (kWindow) {
+            if (kWindow && RESB) {
+                // ---- window A, resident B: per channel chunk one wait, then a flat run of table-driven MMAs
+                uint32_t b_base = db_lo;
+                for (int32_t cb = 0; cb < mma_outer; ++cb, b_base += b_chunk16) {
                     if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
-                    da_win = da_base + (uint64_t)(ws * a_stage16);
-                    if (cb == 0 && leader) trace_ev(prm, tile, EV_M_WIN);
-                }
-                uint32_t row16 = 0, tap16 = 0;
-                int32_t fs = 0;
-                for (int32_t st = 0; st < inner_stages; ++st) {
-                    if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
                     ptx::tc_fence_after();
-                    if (st == 0 && cb == 0 && leader) trace_ev(prm, tile, EV_M_FULL);
-                    // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
-                    uint32_t nstage = stage + 1, nphase = phase;
-                    if (nstage == (uint32_t)prm.stages) { nstage = 0; nphase ^= 1; }
-                    const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
-                    uint64_t da_blk = kWindow ? da_win : da_base + (uint64_t)(stage * a_stage16);
-                    uint64_t db_blk = db_base + (uint64_t)(stage * b_stage16);
-                    for (int32_t t = 0; t < prm.tps; ++t) {
-                        uint64_t da = da_blk;
-                        if (KM == 2) da = da_win + (uint64_t)(row16 + tap16);
-                        else if (KM == 3) da = da_win + (uint64_t)row16;
-#pragma unroll
-                        for (int k = 0; k < KS; ++k) {
-                            ptx::mma_i8_ss_pred(tmem_d, da + (uint64_t)(k * k_step16), db_blk + (uint64_t)(2 * k), idesc,
-                                                accumulate, leader);
-                            accumulate = 1;
-                        }
-                        db_blk += b_block16;
-                        if (KM == 2) {
-                            tap16 += s_step16;
-                            if (++fs == prm.s_taps) { fs = 0; tap16 = 0; row16 += r_step16; }
-                        } else if (KM == 3) {
-                            row16 += r_step16;
-                        } else {
-                            da_blk += a_block16;
-                        }
+                    const uint32_t a_base = da_lo + ws * a_stage16;
+                    if (cb == 0 && leader) trace_ev(prm, local, EV_M_WIN);
+#pragma unroll 4
+                    for (int32_t j = 0; j < n_tab; ++j) {
+                        ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j], da_hi, b_base + (uint32_t)prm.b_tab[j], db_hi,
+                                              idesc, accumulate, leader);
+                        accumulate = 1;
                     }
-                    ptx::mma_commit_pred(&ctl->empty[stage], leader);     // slot reusable once these MMAs retire
-                    stage = nstage; phase = nphase; ready = ready_next;
-                }
-                if (kWindow) {
                     ptx::mma_commit_pred(&ctl->wempty[ws], leader);
-                    if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                    if (++ws == nwin) { ws = 0; wphase ^= 1; }
                     wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
+                }
+            } else {
+                uint32_t b_res = db_lo;   // resident B (ring modes): walks the blocks of the tile in order
+                for (int32_t cb = 0; cb < mma_outer; ++cb) {
+                    uint32_t a_base = da_lo;
+                    if (kWindow) {
+                        if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
+                        a_base = da_lo + ws * a_stage16;
+                        if (cb == 0 && leader) trace_ev(prm, local, EV_M_WIN);
+                    }
+                    int32_t j = 0;   // index into the chunk's A-offset table
+                    for (int32_t st = 0; st < inner_stages; ++st) {
+                        if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
+                        ptx::tc_fence_after();
+                        if (st == 0 && cb == 0 && leader) trace_ev(prm, local, EV_M_FULL);
+                        // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
+                        uint32_t nstage = stage + 1, nphase = phase;
+                        if (nstage == nstages) { nstage = 0; nphase ^= 1; }
+                        const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
+                        if (!kWindow) a_base = da_lo + stage * a_stage16;
+                        uint32_t b_lo = RESB ? b_res : db_lo + stage * b_stage16;
+                        for (int32_t t = 0; t < tps; ++t) {
+#pragma unroll
+                            for (int k = 0; k < KS; ++k) {
+                                const uint32_t a_lo = a_base + (uint32_t)prm.a_tab[kWindow ? j + k : k];
+                                ptx::mma_i8_ss_pred32(tmem_d, a_lo, da_hi, b_lo + 2u * k, db_hi, idesc, accumulate, leader);
+                                accumulate = 1;
+                            }
+                            j += KS;
+                            b_lo += b_block16;
+                        }
+                        if (RESB) b_res = b_lo;
+                        ptx::mma_commit_pred(&ctl->empty[stage], leader);     // slot reusable once these MMAs retire
+                        stage = nstage; phase = nphase; ready = ready_next;
+                    }
+                    if (kWindow) {
+                        ptx::mma_commit_pred(&ctl->wempty[ws], leader);
+                        if (++ws == nwin) { ws = 0; wphase ^= 1; }
+                        wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
+                    }
                 }
             }
             ptx::mma_commit_pred(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue
-            if (leader) trace_ev(prm, tile, EV_M_DONE);
-            acc_stage ^= 1;
-            if (acc_stage == 0) acc_phase ^= 1;
+            if (leader) trace_ev(prm, local, EV_M_DONE);
+            if (++acc_stage == (uint32_t)prm.n_acc) { acc_stage = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kFirstEpiWarp) {
         // ===================== epilogue: two teams of 8 warps =====================
@@ -449,7 +508,12 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t bar_id = 1 + team;                         // named barrier of this team
         const float lo = prm.relu ? 0.0f : -128.0f;
         const bool int8_out = (prm.out_mode == LBC_OUT_INT8);
-        uint8_t* my_staging = staging + (size_t)team * kBlockM * prm.panel_bytes;
+        // staging: stage_bufs panels per team; with two, the TMA store of panel i reads its buffer while panel i+1
+        // is converted into the other one, and a buffer is only waited for two panels later
+        const uint32_t panel_smem = (uint32_t)(kBlockM * prm.panel_bytes);
+        uint8_t* team_staging = staging + (size_t)team * prm.stage_bufs * panel_smem;
+        const bool two_bufs = prm.stage_bufs == 2;
+        uint32_t sbuf = 0;
         float* sc = ctl->scale[team];
         int32_t* bi = ctl->bias[team];
         // columns of a panel handled by this warp: [pc_begin, pc_end), multiples of 16
@@ -474,10 +538,12 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
         const uint32_t row_off = et.srow * (uint32_t)prm.panel_bytes;     // byte offset of this lane's staging row
         const uint32_t swz_mask = (1u << prm.panel_swz_bits) - 1u;
-        uint32_t acc_phase = 0;
         int32_t cur_nblk = -1;
-        for (int32_t tile = blockIdx.x + (int32_t)team * gridDim.x; tile < num_tiles; tile += kTeams * gridDim.x) {
-            const TileCoord tc = decode_tile(prm, tile);
+        TileIter it;
+        it.init(prm, (int32_t)(blockIdx.x + team * gridDim.x));
+        for (; it.tile < num_tiles; it.next(prm), it.next(prm)) {
+            const int32_t tile = it.local + (int32_t)team;   // CTA-local tile index (the iterator advances two CTA strides per loop)
+            struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.img, it.p0(prm), it.q0(prm), it.m0()};
             const int32_t col0 = tc.n_blk * prm.bn;
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
             if (tc.n_blk != cur_nblk) {
@@ -485,14 +551,16 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 for (int32_t c = (int32_t)tt_id; c < prm.bn; c += kTeamThreads) {
                     const int32_t kc = col0 + c;
                     const bool in = kc < prm.k_out;
-                    sc[c] = (in && scale) ? __ldg(scale + kc) : 0.0f;
-                    bi[c] = (in && bias) ? __ldg(bias + kc) : 0;
+                    const int32_t kp = prm.k_mod ? kc % prm.k_mod : kc;
+                    sc[c] = (in && scale) ? __ldg(scale + kp) : 0.0f;
+                    bi[c] = (in && bias) ? __ldg(bias + kp) : 0;
                 }
                 cur_nblk = tc.n_blk;
             }
-            // accumulator ready?
-            ptx::mbar_wait(&ctl->tmem_full[team], acc_phase, tflag);
-            acc_phase ^= 1;
+            // accumulator ready?  CTA-local tile L lives in TMEM stage L % n_acc, on that stage's (L / n_acc)-th use
+            const uint32_t acc = (uint32_t)tile & (uint32_t)(prm.n_acc - 1);
+            const uint32_t acc_phase = ((uint32_t)tile >> (prm.n_acc == 4 ? 2 : 1)) & 1u;
+            ptx::mbar_wait(&ctl->tmem_full[acc], acc_phase, tflag);
             ptx::tc_fence_after();
             if (issuer) trace_ev(prm, tile, EV_E_START);
 
@@ -502,17 +570,21 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     const int32_t pp = tc.p0 + et.wrow, qq = tc.q0 + et.wcol;
                     if (et.valid && pp < prm.p && qq < prm.q) out_row = ((int64_t)tc.img * prm.p + pp) * prm.q + qq;
                 } else {
-                    const int64_t r = tc.m0 + lane_row;
+                    const int64_t r = (int64_t)tc.m0 + lane_row;
                     if (r < prm.m_total) out_row = r;
                 }
             }
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + team * (uint32_t)prm.bn;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (uint32_t)prm.bn;
             int32_t* y32 = reinterpret_cast<int32_t*>(y);
 
             for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
                 const int32_t pbase = pnl * pcols;
-                // staging panel free (previous store has read it) + parameters visible
-                if (issuer && int8_out) ptx::tma_store_wait_read<0>();
+                // staging panel free (the store that last used it has read it) + parameters visible
+                uint8_t* my_staging = team_staging + sbuf * panel_smem;
+                if (issuer && int8_out) {
+                    if (two_bufs) ptx::tma_store_wait_read<1>();
+                    else ptx::tma_store_wait_read<0>();
+                }
                 ptx::named_bar_sync(bar_id, kTeamThreads);
                 if (int8_out)
                     epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
@@ -524,7 +596,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[team]);
+                    if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);
                     if (issuer) trace_ev(prm, tile, EV_E_DRAINED);
                 }
                 if (int8_out) {
@@ -541,6 +613,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         ptx::tma_store_commit();
                         if (pnl == n_panels - 1) trace_ev(prm, tile, EV_E_STORED);
                     }
+                    if (two_bufs) sbuf ^= 1;
                 }
             }
         }
@@ -631,11 +704,10 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
 {
     const lbc_conv_desc& d = g.d;
     IgemmConfig c{};
-    // ---- N tile: the whole K_out when it fits one 256-wide tile, else the largest of 256/128 dividing it
-    if (d.k <= 256) c.bn = d.k;
-    else if (d.k % 256 == 0) c.bn = 256;
-    else if (d.k % 128 == 0) c.bn = 128;
-    else c.bn = 256;   // tail tile handled by TMA zero-fill (loads) and clipping (stores)
+    // ---- N tile: the whole K_out when it fits one 256-wide tile, else an even split into the fewest tiles
+    // (multiples of 16; a ragged last tile is handled by TMA zero-fill on loads and clipping on stores)
+    c.tiles_n = (d.k + 255) / 256;
+    c.bn = ((d.k + c.tiles_n - 1) / c.tiles_n + 15) / 16 * 16;
     c.tiles_n = (d.k + c.bn - 1) / c.bn;
 
     // ---- A mode
@@ -690,24 +762,28 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     else c.panel_bytes = c.bn;                      // unswizzled single panel (rare channel counts)
     c.n_panels = c.bn / c.panel_bytes;
     c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
-    const uint32_t stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(kTeams * kBlockM * c.panel_bytes), 1024) : 0;
 
-    // ---- smem carve-up
+    // ---- smem carve-up: [A ring | window ring][B ring][output staging][control]
+    // Prefetch depth is what hides the ~2 us loaded HBM latency, so the A side (ring stages, or windows) gets every
+    // byte left over after two or three B stages (B comes from L2 and needs little run-ahead) and the staging panels.
     const uint32_t ctl_bytes = round_up((uint32_t)sizeof(Ctl), 256);
-    const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
     c.a_block_bytes = (c.mode == A_WINDOW) ? 0 : (uint32_t)(kBlockM * c.bkc);
     c.b_block_bytes = (uint32_t)(c.bn * c.bkb);
+    // tuning knobs (development aids; the defaults are what ships)
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+    const uint32_t tps_cap = (uint32_t)env_int("LBC_TPS_KB", 48) * 1024u;
+    const int max_win = std::min(kMaxWinStages, env_int("LBC_MAX_WIN", kMaxWinStages));
+    const int max_stages = std::min(kMaxStages, env_int("LBC_MAX_STAGES", kMaxStages));
+    const int max_bufs = std::min(2, env_int("LBC_STAGE_BUFS", 2));
     // blocks per ring stage: group small B blocks (window mode) so one mbarrier round trip feeds several MMAs
     c.tps = 1;
     if (c.mode == A_WINDOW) {
         for (int t = c.inner; t >= 1; --t)
-            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= 48u * 1024u) { c.tps = t; break; }
+            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= tps_cap) { c.tps = t; break; }
     }
     c.a_stage_bytes = c.tps * c.a_block_bytes;
     c.b_stage_bytes = c.tps * c.b_block_bytes;
     c.win_stage_bytes = c.win_tx_bytes = 0;
-    c.win_stages = 0;
-    uint32_t win_total = 0;
     if (c.mode == A_WINDOW) {
         const int s_eff = c.s_pad;
         const int ext_w = (s_eff - 1) * d.dil_w, ext_h = (d.r - 1) * d.dil_h;
@@ -715,22 +791,85 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         const uint32_t reach = (uint32_t)((kBlockM + ext_h * c.wt + ext_w + 1) * c.bkc);   // furthest row an MMA reads
         c.win_tx_bytes = box_bytes;
         c.win_stage_bytes = round_up(std::max(box_bytes, reach), 1024);
-        c.win_stages = std::min(kMaxWinStages, std::max(2, c.cblocks > 1 ? 3 : 2));
-        win_total = c.win_stages * c.win_stage_bytes;
-        LBC_REQUIRE(win_total + 2 * c.b_stage_bytes <= budget, LBC_ERR_UNSUPPORTED, "igemm: window does not fit in smem");
     }
-    const uint32_t ring_stage = c.a_stage_bytes + c.b_stage_bytes;
-    int stages = (int)std::min<uint32_t>(kMaxStages, (budget - win_total) / ring_stage);
-    stages = std::max(2, std::min(stages, std::max(2, c.k_blocks / c.tps * 2)));
-    c.stages = stages;
-    c.off_b = (c.mode == A_WINDOW) ? win_total : (uint32_t)stages * c.a_stage_bytes;
-    c.off_stage = c.off_b + (uint32_t)stages * c.b_stage_bytes;
-    c.off_ctl = c.off_stage + stage_bytes;
-    c.smem_bytes = c.off_ctl + ctl_bytes;
-    LBC_REQUIRE(c.smem_bytes <= 227 * 1024, LBC_ERR_UNSUPPORTED, "igemm: smem %zu too large", c.smem_bytes);
+    // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
+    // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
+    c.b_total_bytes = (uint32_t)c.k_blocks * c.b_block_bytes;
+    const bool res_b_ok = c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
+    uint32_t stage_bytes = 0;
+    bool fits = false;
+    for (int pass = 0; pass < 2 && !fits; ++pass)
+    for (int bufs = max_bufs; bufs >= 1 && !fits; --bufs) {   // two staging panels per team when they fit, else one
+        c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
+        if (pass == 0 && !res_b_ok) break;
+        c.stage_bufs = bufs;
+        stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(kTeams * bufs * kBlockM * c.panel_bytes), 1024) : 0;
+        if (stage_bytes + ctl_bytes >= 227u * 1024u) continue;
+        const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
+        uint32_t win_total = 0;
+        int stages;
+        uint32_t b_region;
+        if (c.res_b) {
+            if (c.b_total_bytes + 2 * std::max(c.win_stage_bytes, c.a_stage_bytes) > budget) continue;
+            b_region = round_up(c.b_total_bytes, 1024);
+            if (c.mode == A_WINDOW) {
+                stages = 0;   // no ring
+                c.win_stages = (int)std::min<uint32_t>(max_win, (budget - b_region) / c.win_stage_bytes);
+                if (c.win_stages < 2) continue;
+                win_total = c.win_stages * c.win_stage_bytes;
+            } else {
+                c.win_stages = 0;
+                stages = (int)std::min<uint32_t>(max_stages, (budget - b_region) / c.a_stage_bytes);
+                if (stages < 3) continue;
+            }
+        } else if (c.mode == A_WINDOW) {
+            if (2 * c.win_stage_bytes + 2 * c.b_stage_bytes > budget) continue;
+            stages = ((budget - 2 * c.win_stage_bytes) / c.b_stage_bytes >= 3 && max_stages >= 3) ? 3 : 2;
+            c.win_stages = (int)std::min<uint32_t>(max_win, (budget - stages * c.b_stage_bytes) / c.win_stage_bytes);
+            win_total = c.win_stages * c.win_stage_bytes;
+            b_region = (uint32_t)stages * c.b_stage_bytes;
+        } else {
+            c.win_stages = 0;
+            stages = (int)std::min<uint32_t>(max_stages, budget / (c.a_stage_bytes + c.b_stage_bytes));
+            if (stages < 2 || (stages < 3 && bufs == 2 && max_stages >= 3)) continue;
+            b_region = (uint32_t)stages * c.b_stage_bytes;
+        }
+        c.stages = stages;
+        c.off_b = (c.mode == A_WINDOW) ? win_total : (uint32_t)stages * c.a_stage_bytes;
+        c.off_stage = c.off_b + b_region;
+        c.off_ctl = c.off_stage + stage_bytes;
+        c.smem_bytes = c.off_ctl + ctl_bytes;
+        fits = c.smem_bytes <= 227 * 1024;
+    }
+    LBC_REQUIRE(fits, LBC_ERR_UNSUPPORTED, "igemm: operand rings do not fit in shared memory");
 
+    // ---- MMA issue table (A-descriptor offsets in 16-byte units, one channel chunk)
+    {
+        const int ks = c.bkb / 32;
+        if (c.mode != A_WINDOW) {
+            c.n_tab = ks;
+            for (int k = 0; k < ks; ++k) c.a_tab[k] = (uint16_t)(2 * k);
+        } else {
+            c.n_tab = c.inner * ks;
+            LBC_REQUIRE(c.n_tab <= (int)(sizeof(c.a_tab) / sizeof(c.a_tab[0])), LBC_ERR_UNSUPPORTED,
+                        "igemm: %d MMAs per channel chunk exceed the issue table", c.n_tab);
+            const uint32_t s_step16 = (uint32_t)(d.dil_w * c.bkc) >> 4;            // next tap in the filter row
+            const uint32_t r_step16 = (uint32_t)(d.dil_h * c.wt * c.bkc) >> 4;     // next filter row
+            for (int t = 0; t < c.inner; ++t)
+                for (int k = 0; k < ks; ++k) {
+                    uint32_t off;
+                    if (c.bkc == 16) off = (uint32_t)t * r_step16 + (uint32_t)k * 2u * s_step16;   // block = filter row, K-step = two taps
+                    else off = (uint32_t)(t / d.s) * r_step16 + (uint32_t)(t % d.s) * s_step16 + 2u * (uint32_t)k;
+                    const uint32_t boff = (uint32_t)t * (c.b_block_bytes >> 4) + 2u * (uint32_t)k;
+                    LBC_REQUIRE(off < 65536u && boff < 65536u, LBC_ERR_UNSUPPORTED, "igemm: window too large for the issue table");
+                    c.a_tab[t * ks + k] = (uint16_t)off;
+                    c.b_tab[t * ks + k] = (uint16_t)boff;
+                }
+        }
+    }
+    c.n_acc = (4 * c.bn <= 512 && !getenv("LBC_TWO_ACC")) ? 4 : 2;
     uint32_t cols = 32;
-    while (cols < 2u * (uint32_t)c.bn) cols <<= 1;
+    while (cols < (uint32_t)(c.n_acc * c.bn)) cols <<= 1;
     c.tmem_cols = cols;
     c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
     *cfg = c;
@@ -839,8 +978,22 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.wt = c.wt; prm.rows_per_tile = c.rows_per_tile; prm.cols_per_tile = c.cols_per_tile;
     prm.row_tiles = c.row_tiles; prm.col_tiles = c.col_tiles;
     prm.relu = ep.relu; prm.out_mode = ep.out_mode;
-    prm.tmem_cols = c.tmem_cols;
+    prm.tmem_cols = c.tmem_cols; prm.n_acc = c.n_acc;
     prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
+    prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod;
+    prm.n_tab = c.n_tab;
+    for (int i = 0; i < c.n_tab; ++i) { prm.a_tab[i] = c.a_tab[i]; prm.b_tab[i] = c.b_tab[i]; }
+    prm.res_b = c.res_b; prm.b_total_bytes = c.b_total_bytes;
+    // digits of the CTA stride in the (img | rt | ct | n_blk) tile numbering
+    prm.it_cols = c.mode == A_WINDOW ? c.col_tiles : 1;
+    prm.it_rows = c.mode == A_WINDOW ? c.row_tiles : 1;
+    {
+        int32_t v = c.grid;
+        prm.step_nb = v % c.tiles_n; v /= c.tiles_n;
+        prm.step_ct = v % prm.it_cols; v /= prm.it_cols;
+        prm.step_rt = v % prm.it_rows; v /= prm.it_rows;
+        prm.step_img = v;
+    }
     prm.off_b = c.off_b; prm.off_stage = c.off_stage; prm.off_ctl = c.off_ctl;
     prm.trace = g_trace_buf; prm.trace_tiles = g_trace_tiles;
     // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one
@@ -851,20 +1004,25 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     const int ks = c.bkb / 32;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams, const int32_t*,
                               const float*, void*);
-    static const KernelFn table[4][3] = {
-        {igemm_i8_kernel<0, 1>, igemm_i8_kernel<0, 2>, igemm_i8_kernel<0, 4>},
-        {igemm_i8_kernel<1, 1>, igemm_i8_kernel<1, 2>, igemm_i8_kernel<1, 4>},
-        {igemm_i8_kernel<2, 1>, igemm_i8_kernel<2, 2>, igemm_i8_kernel<2, 4>},
-        {igemm_i8_kernel<3, 1>, igemm_i8_kernel<3, 2>, igemm_i8_kernel<3, 4>},
+    static const KernelFn table[4][3][2] = {
+        {{igemm_i8_kernel<0, 1, false>, igemm_i8_kernel<0, 1, true>}, {igemm_i8_kernel<0, 2, false>, igemm_i8_kernel<0, 2, true>},
+         {igemm_i8_kernel<0, 4, false>, igemm_i8_kernel<0, 4, true>}},
+        {{igemm_i8_kernel<1, 1, false>, igemm_i8_kernel<1, 1, true>}, {igemm_i8_kernel<1, 2, false>, igemm_i8_kernel<1, 2, true>},
+         {igemm_i8_kernel<1, 4, false>, igemm_i8_kernel<1, 4, true>}},
+        {{igemm_i8_kernel<2, 1, false>, igemm_i8_kernel<2, 1, true>}, {igemm_i8_kernel<2, 2, false>, igemm_i8_kernel<2, 2, true>},
+         {igemm_i8_kernel<2, 4, false>, igemm_i8_kernel<2, 4, true>}},
+        {{igemm_i8_kernel<3, 1, false>, igemm_i8_kernel<3, 1, true>}, {igemm_i8_kernel<3, 2, false>, igemm_i8_kernel<3, 2, true>},
+         {igemm_i8_kernel<3, 4, false>, igemm_i8_kernel<3, 4, true>}},
     };
     LBC_REQUIRE(ks == 1 || ks == 2 || ks == 4, LBC_ERR_UNSUPPORTED, "igemm: unsupported K block of %d bytes", c.bkb);
-    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1];
+    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.res_b ? 1 : 0];
     {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (!g_attr_set) {
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 3; ++j)
-                    LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    for (int r = 0; r < 2; ++r)
+                        LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             g_attr_set = true;
         }
     }

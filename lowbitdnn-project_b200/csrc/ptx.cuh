@@ -252,6 +252,25 @@ __device__ __forceinline__ void mma_i8_ss_pred(uint32_t tmem_d, uint64_t desc_a,
         : "memory");
 }
 
+// Same with the descriptors given as {low, high} 32-bit halves: the issue loop only ever adds to the low word (the
+// 14-bit smem address field), which keeps its arithmetic 32-bit and uniform.
+__device__ __forceinline__ void mma_i8_ss_pred32(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                 uint32_t idesc, uint32_t accumulate, uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+
 __device__ __forceinline__ void mma_commit_pred(uint64_t* bar, uint32_t leader)
 {
     asm volatile(
