@@ -37,11 +37,9 @@ namespace lbc {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kTeams = 2;                              // epilogue teams; team t drains TMEM accumulator stage t
-constexpr int kTeamWarps = 8;
-constexpr int kTeamThreads = kTeamWarps * 32;
+constexpr int kEpiWarps = 16;                          // epilogue warps: 2 teams of 8 or 4 teams of 4
 constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA + TMEM alloc, 2: window TMA, 3: idle
-constexpr int kNumThreads = (kFirstEpiWarp + kTeams * kTeamWarps) * 32;   // 640
+constexpr int kNumThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 640
 constexpr int kMaxStages = 8;
 constexpr int kMaxWinStages = 6;
 constexpr int kMaxTab = 192;                           // A-descriptor offsets per channel chunk (taps x K-steps)
@@ -75,7 +73,8 @@ struct IgemmParams {
     uint32_t tmem_cols;
     int32_t n_acc;                // TMEM accumulator stages (2 or 4): how far the MMA warp may run ahead of the epilogue
     int32_t panel_bytes, panel_swz_bits, n_panels;
-    int32_t stage_bufs;           // staging panels per epilogue team (2 = a TMA store drains while the next panel fills)
+    int32_t stage_bufs;           // staging panels per epilogue team (2 or 3: TMA stores drain while later panels fill)
+    int32_t team_warps;           // 8: two epilogue teams (wide N tiles); 4: four teams (N tile <= 64 columns)
     int32_t k_mod;                // bias/scale index = channel % k_mod (pixel-group rewrite replicates them), 0 = plain
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
@@ -116,8 +115,8 @@ struct Ctl {
     uint64_t bfull;               // resident filter matrix has landed
     uint32_t tmem_base;
     uint32_t pad_[1];
-    alignas(16) float scale[kTeams][256];
-    alignas(16) int32_t bias[kTeams][256];
+    alignas(16) float scale[4][256];     // [team][column of the N tile] (4 teams only exist for N tiles <= 64)
+    alignas(16) int32_t bias[4][256];
 };
 
 // Persistent tile walk without divisions in the loop: the digits are decoded once (init) and then advanced by the
@@ -276,7 +275,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         for (int i = 0; i < prm.n_acc; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
-            ptx::mbar_init(&ctl->tmem_empty[i], kTeamWarps);
+            ptx::mbar_init(&ctl->tmem_empty[i], (uint32_t)prm.team_warps);
         }
         ptx::mbar_init(&ctl->bfull, 1);
         ptx::fence_barrier_init();
@@ -436,8 +435,19 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     ptx::tc_fence_after();
                     const uint32_t a_base = da_lo + ws * a_stage16;
                     if (cb == 0 && leader) trace_ev(prm, local, EV_M_WIN);
-#pragma unroll 4
-                    for (int32_t j = 0; j < n_tab; ++j) {
+                    // unrolled by the length of a filter row's worth of MMAs so the table loads and descriptor adds of one
+                    // batch overlap (the uniform datapath has long latencies and the loop's fixed cost is ~25 instructions)
+                    constexpr int kBatch = (KM == 3) ? 8 : 9;
+                    int32_t j = 0;
+                    for (; j + kBatch <= n_tab; j += kBatch) {
+#pragma unroll
+                        for (int u = 0; u < kBatch; ++u) {
+                            ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j + u], da_hi, b_base + (uint32_t)prm.b_tab[j + u],
+                                                  db_hi, idesc, accumulate, leader);
+                            accumulate = 1;
+                        }
+                    }
+                    for (; j < n_tab; ++j) {
                         ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j], da_hi, b_base + (uint32_t)prm.b_tab[j], db_hi,
                                               idesc, accumulate, leader);
                         accumulate = 1;
@@ -492,33 +502,38 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (++acc_stage == (uint32_t)prm.n_acc) { acc_stage = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kFirstEpiWarp) {
-        // ===================== epilogue: two teams of 8 warps =====================
-        // Team t owns TMEM accumulator stage t, i.e. every second tile of this CTA, and its own one-panel staging
-        // buffer; while one team waits (TMA-store read-out, accumulator not ready, barrier) the other converts.
-        // Per tile a team walks the N tile panel by panel (<= 128 columns): drain + requantise into the swizzled
-        // staging panel, then one thread issues the TMA store of that panel.
+        // ===================== epilogue: 16 warps in 2 teams of 8 or 4 teams of 4 =====================
+        // A team owns every n_teams-th tile of this CTA (CTA-local tile L sits in TMEM accumulator stage L % n_acc) and a
+        // ring of staging panels.  Wide N tiles use 2 x 8 warps (the two warp sets of a team split a panel's columns);
+        // N tiles of <= 64 columns use 4 x 4 warps, so a warp converts a whole row of the tile and the per-tile fixed
+        // cost (barrier, waits, address set-up) is paid half as often per output.
+        // Per panel (<= 128 columns): drain TMEM + requantise into the swizzled staging panel, ONE team barrier, then
+        // one thread issues the TMA store.  With 3 staging buffers no second barrier is needed: before the barrier of
+        // panel p the issuer has waited until the store of panel p-2 has read its buffer, which is the buffer panel
+        // p+1 will be written to.
         // Control flow is uniform across a team (named barriers): a watchdog trip only stops the waiting.
         const uint32_t e = warp - kFirstEpiWarp;                  // 0..15
-        const uint32_t team = e / kTeamWarps;
-        const uint32_t tw = e % kTeamWarps;                       // warp inside the team
+        const bool small_teams = prm.team_warps == 4;
+        const uint32_t team = small_teams ? (e >> 2) : (e >> 3);
+        const uint32_t tw = small_teams ? (e & 3) : (e & 7);      // warp inside the team
+        const uint32_t n_teams = small_teams ? 4 : 2;
+        const uint32_t team_threads = small_teams ? 128 : 256;
         const uint32_t quarter = warp & 3;                        // TMEM lanes [32*quarter, +32) for this warp
-        const uint32_t half = tw >> 2;                            // which half of a panel's columns
-        const uint32_t tt_id = (tw << 5) | lane;                  // thread inside the team, 0..255
+        const uint32_t half = tw >> 2;                            // which half of a panel's columns (8-warp teams)
+        const uint32_t tt_id = (tw << 5) | lane;                  // thread inside the team
         const bool issuer = (tt_id == 0);
         const uint32_t bar_id = 1 + team;                         // named barrier of this team
         const float lo = prm.relu ? 0.0f : -128.0f;
         const bool int8_out = (prm.out_mode == LBC_OUT_INT8);
-        // staging: stage_bufs panels per team; with two, the TMA store of panel i reads its buffer while panel i+1
-        // is converted into the other one, and a buffer is only waited for two panels later
         const uint32_t panel_smem = (uint32_t)(kBlockM * prm.panel_bytes);
-        uint8_t* team_staging = staging + (size_t)team * prm.stage_bufs * panel_smem;
-        const bool two_bufs = prm.stage_bufs == 2;
+        const uint32_t nbufs = (uint32_t)prm.stage_bufs;
+        uint8_t* team_staging = staging + (size_t)team * nbufs * panel_smem;
         uint32_t sbuf = 0;
         float* sc = ctl->scale[team];
         int32_t* bi = ctl->bias[team];
         // columns of a panel handled by this warp: [pc_begin, pc_end), multiples of 16
         const int32_t pcols = int8_out ? prm.panel_bytes : prm.bn;   // int32 mode: the whole N tile is one "panel"
-        const int32_t psplit = ((pcols / 16 + 1) / 2) * 16;
+        const int32_t psplit = small_teams ? pcols : ((pcols / 16 + 1) / 2) * 16;
         const int32_t pc_begin = half ? psplit : 0;
         const int32_t pc_end = half ? pcols : psplit;
         const int32_t n_panels = int8_out ? prm.n_panels : 1;
@@ -538,17 +553,18 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
         const uint32_t row_off = et.srow * (uint32_t)prm.panel_bytes;     // byte offset of this lane's staging row
         const uint32_t swz_mask = (1u << prm.panel_swz_bits) - 1u;
+        const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
         int32_t cur_nblk = -1;
         TileIter it;
         it.init(prm, (int32_t)(blockIdx.x + team * gridDim.x));
-        for (; it.tile < num_tiles; it.next(prm), it.next(prm)) {
-            const int32_t tile = it.local + (int32_t)team;   // CTA-local tile index (the iterator advances two CTA strides per loop)
+        for (; it.tile < num_tiles;) {
+            const int32_t tile = it.local + (int32_t)team;   // CTA-local tile index (it.local advances n_teams per loop)
             struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.img, it.p0(prm), it.q0(prm), it.m0()};
             const int32_t col0 = tc.n_blk * prm.bn;
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
             if (tc.n_blk != cur_nblk) {
-                ptx::named_bar_sync(bar_id, kTeamThreads);       // everyone done with the previous parameters
-                for (int32_t c = (int32_t)tt_id; c < prm.bn; c += kTeamThreads) {
+                ptx::named_bar_sync(bar_id, team_threads);       // everyone done with the previous parameters
+                for (int32_t c = (int32_t)tt_id; c < prm.bn; c += (int32_t)team_threads) {
                     const int32_t kc = col0 + c;
                     const bool in = kc < prm.k_out;
                     const int32_t kp = prm.k_mod ? kc % prm.k_mod : kc;
@@ -556,10 +572,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     bi[c] = (in && bias) ? __ldg(bias + kp) : 0;
                 }
                 cur_nblk = tc.n_blk;
+                ptx::named_bar_sync(bar_id, team_threads);       // parameters visible to the whole team
             }
             // accumulator ready?  CTA-local tile L lives in TMEM stage L % n_acc, on that stage's (L / n_acc)-th use
-            const uint32_t acc = (uint32_t)tile & (uint32_t)(prm.n_acc - 1);
-            const uint32_t acc_phase = ((uint32_t)tile >> (prm.n_acc == 4 ? 2 : 1)) & 1u;
+            const uint32_t acc = (uint32_t)tile & acc_mask;
+            const uint32_t acc_phase = ((uint32_t)tile >> acc_shift) & 1u;
             ptx::mbar_wait(&ctl->tmem_full[acc], acc_phase, tflag);
             ptx::tc_fence_after();
             if (issuer) trace_ev(prm, tile, EV_E_START);
@@ -579,13 +596,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
             for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
                 const int32_t pbase = pnl * pcols;
-                // staging panel free (the store that last used it has read it) + parameters visible
                 uint8_t* my_staging = team_staging + sbuf * panel_smem;
-                if (issuer && int8_out) {
-                    if (two_bufs) ptx::tma_store_wait_read<1>();
-                    else ptx::tma_store_wait_read<0>();
-                }
-                ptx::named_bar_sync(bar_id, kTeamThreads);
                 if (int8_out)
                     epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
                                     swz_mask, lo, y32, out_row, col0);
@@ -601,21 +612,28 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
                 if (int8_out) {
                     ptx::fence_proxy_async();
-                    ptx::named_bar_sync(bar_id, kTeamThreads);
+                    // the buffer the NEXT panel goes to must have been read out by its last store before anyone
+                    // passes the barrier below: with nbufs buffers that is the store issued nbufs-1 panels ago
+                    if (issuer) {
+                        if (nbufs >= 3) ptx::tma_store_wait_read<1>();
+                        else ptx::tma_store_wait_read<0>();
+                    }
+                    ptx::named_bar_sync(bar_id, team_threads);
                     if (issuer) {
                         const int32_t cbyte = col0 + pbase;
                         if (cbyte < prm.k_out) {
                             if (prm.mode == A_WINDOW)
                                 ptx::tma_store_4d(&tm_out, my_staging, cbyte, tc.q0, tc.p0, tc.img);
                             else
-                                ptx::tma_store_2d(&tm_out, my_staging, cbyte, (int32_t)tc.m0);
+                                ptx::tma_store_2d(&tm_out, my_staging, cbyte, tc.m0);
                         }
                         ptx::tma_store_commit();
                         if (pnl == n_panels - 1) trace_ev(prm, tile, EV_E_STORED);
                     }
-                    if (two_bufs) sbuf ^= 1;
+                    if (++sbuf == nbufs) sbuf = 0;
                 }
             }
+            for (uint32_t i = 0; i < n_teams; ++i) it.next(prm);
         }
         if (issuer && int8_out) ptx::tma_store_wait<0>();
     }
@@ -763,6 +781,11 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     c.n_panels = c.bn / c.panel_bytes;
     c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
 
+    // ---- accumulator stages and epilogue teams
+    c.n_acc = (4 * c.bn <= 512 && !getenv("LBC_TWO_ACC")) ? 4 : 2;
+    c.team_warps = (c.n_acc == 4 && c.bn <= 64 && !getenv("LBC_BIG_TEAMS")) ? 4 : 8;
+    const int n_teams = kEpiWarps / c.team_warps;
+
     // ---- smem carve-up: [A ring | window ring][B ring][output staging][control]
     // Prefetch depth is what hides the ~2 us loaded HBM latency, so the A side (ring stages, or windows) gets every
     // byte left over after two or three B stages (B comes from L2 and needs little run-ahead) and the staging panels.
@@ -774,7 +797,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     const uint32_t tps_cap = (uint32_t)env_int("LBC_TPS_KB", 48) * 1024u;
     const int max_win = std::min(kMaxWinStages, env_int("LBC_MAX_WIN", kMaxWinStages));
     const int max_stages = std::min(kMaxStages, env_int("LBC_MAX_STAGES", kMaxStages));
-    const int max_bufs = std::min(2, env_int("LBC_STAGE_BUFS", 2));
+    const int max_bufs = std::max(2, std::min(3, env_int("LBC_STAGE_BUFS", 3)));
     // blocks per ring stage: group small B blocks (window mode) so one mbarrier round trip feeds several MMAs
     c.tps = 1;
     if (c.mode == A_WINDOW) {
@@ -799,11 +822,11 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     uint32_t stage_bytes = 0;
     bool fits = false;
     for (int pass = 0; pass < 2 && !fits; ++pass)
-    for (int bufs = max_bufs; bufs >= 1 && !fits; --bufs) {   // two staging panels per team when they fit, else one
+    for (int bufs = max_bufs; bufs >= 2 && !fits; --bufs) {   // three staging panels per team when they fit, else two
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
         if (pass == 0 && !res_b_ok) break;
         c.stage_bufs = bufs;
-        stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(kTeams * bufs * kBlockM * c.panel_bytes), 1024) : 0;
+        stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(n_teams * bufs * kBlockM * c.panel_bytes), 1024) : 0;
         if (stage_bytes + ctl_bytes >= 227u * 1024u) continue;
         const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
         uint32_t win_total = 0;
@@ -812,16 +835,19 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         if (c.res_b) {
             if (c.b_total_bytes + 2 * std::max(c.win_stage_bytes, c.a_stage_bytes) > budget) continue;
             b_region = round_up(c.b_total_bytes, 1024);
+            // a third staging panel only pays where the epilogue is the bottleneck and must not cost A-side depth
             if (c.mode == A_WINDOW) {
                 stages = 0;   // no ring
                 c.win_stages = (int)std::min<uint32_t>(max_win, (budget - b_region) / c.win_stage_bytes);
-                if (c.win_stages < 2) continue;
+                if (c.win_stages < (bufs == 3 ? 4 : 2)) continue;
                 win_total = c.win_stages * c.win_stage_bytes;
             } else {
                 c.win_stages = 0;
                 stages = (int)std::min<uint32_t>(max_stages, (budget - b_region) / c.a_stage_bytes);
-                if (stages < 3) continue;
+                if (stages < (bufs == 3 ? 5 : 3)) continue;
             }
+        } else if (bufs == 3) {
+            continue;   // streaming B: operand depth matters more than a third staging panel
         } else if (c.mode == A_WINDOW) {
             if (2 * c.win_stage_bytes + 2 * c.b_stage_bytes > budget) continue;
             stages = ((budget - 2 * c.win_stage_bytes) / c.b_stage_bytes >= 3 && max_stages >= 3) ? 3 : 2;
@@ -831,7 +857,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         } else {
             c.win_stages = 0;
             stages = (int)std::min<uint32_t>(max_stages, budget / (c.a_stage_bytes + c.b_stage_bytes));
-            if (stages < 2 || (stages < 3 && bufs == 2 && max_stages >= 3)) continue;
+            if (stages < 2) continue;
             b_region = (uint32_t)stages * c.b_stage_bytes;
         }
         c.stages = stages;
@@ -867,7 +893,6 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
                 }
         }
     }
-    c.n_acc = (4 * c.bn <= 512 && !getenv("LBC_TWO_ACC")) ? 4 : 2;
     uint32_t cols = 32;
     while (cols < (uint32_t)(c.n_acc * c.bn)) cols <<= 1;
     c.tmem_cols = cols;
@@ -980,7 +1005,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.relu = ep.relu; prm.out_mode = ep.out_mode;
     prm.tmem_cols = c.tmem_cols; prm.n_acc = c.n_acc;
     prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
-    prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod;
+    prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps;
     prm.n_tab = c.n_tab;
     for (int i = 0; i < c.n_tab; ++i) { prm.a_tab[i] = c.a_tab[i]; prm.b_tab[i] = c.b_tab[i]; }
     prm.res_b = c.res_b; prm.b_total_bytes = c.b_total_bytes;
