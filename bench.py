@@ -294,14 +294,10 @@ def main():
     checksum = zlib.crc32(y_host.numpy().tobytes())
 
     # ---- gather (NCCL): max over ranks; checksums ------------------------------------------------------------
-    stats = torch.tensor([ms_total, e2e_ms, float(checksum)], dtype=torch.float64, device=dev)
-    if world > 1:
-        allst = [torch.zeros_like(stats) for _ in range(world)]
-        dist.all_gather(allst, stats)
-        ms_total = max(float(s[0]) for s in allst)
-        e2e_ms = max(float(s[1]) for s in allst)
+    job = lbc.shard.gather(lbc.shard.RankStats(ms_total, e2e_ms, checksum, args.batch), world, device=dev)
+    ms_total, e2e_ms = job.ms_total, job.e2e_ms
     ms_per_step = ms_total / args.steps
-    images_per_step = args.batch * world
+    images_per_step = job.images
 
     if rank == 0:
         peaks = read_peaks()
@@ -358,7 +354,7 @@ def main():
                     "note": "lbc_net_run_host: pinned host input -> H2D -> all layers -> D2H of the last layer's output"},
             "gpu_launches": int(args.steps * net.launches),
             "roofline": roofline,
-            "output_crc32": checksum,
+            "output_crc32": job.checksums,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -11,9 +11,10 @@ from .conv import (ConvDesc, ConvPlan, conv2DForward3x3, from_vect_c, nchw_to_nh
                    to_vect_c, vect_c_to_nhwc)
 from .net import Net
 from . import networks
+from . import shard
 
 __all__ = [
-    "ConvDesc", "ConvPlan", "Net", "networks", "LbcError", "load_library",
+    "ConvDesc", "ConvPlan", "Net", "networks", "shard", "LbcError", "load_library",
     "conv2DForward3x3", "to_vect_c", "from_vect_c", "nhwc_to_vect_c", "vect_c_to_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
     "OUT_INT8", "OUT_INT32", "W_KRSC", "W_OIHW", "KERNEL_AUTO", "KERNEL_DIRECT", "KERNEL_IGEMM_TC", "KERNEL_DEPTHWISE",
 ]

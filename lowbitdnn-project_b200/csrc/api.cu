@@ -98,8 +98,13 @@ struct lbc_plan {
     int32_t kind;
     IgemmConfig cfg;
     DeviceInfo dev;
-    // LBC_KERNEL_STEM_TC: the rewritten stride-1 / 16-channel problem the tcgen05 kernel actually runs
+    // LBC_KERNEL_STEM_TC, and LBC_KERNEL_IGEMM_TC with pw_factor > 1: the rewritten problem the tcgen05 kernel runs
     ConvGeom g_inner;
+    // Pixel-group rewrite of a pointwise (1x1, stride 1) layer whose C or K is not a multiple of 16 (MobileNetV2's
+    // 24-channel tensors): f consecutive pixels form one GEMM row of f*C channels against the block-diagonal
+    // [f*K][f*C] filter, so every TMA stride is a multiple of 16 bytes again and the [M/f][f*K] result IS the NHWC
+    // output.  The MMA does f times the useful work, which is free on these HBM-bound layers.
+    int32_t pw_factor = 1;
     int32_t stem_sh = 1, stem_sw = 1;
     void* stem_x = nullptr;     // [N][Hs][Ws][16] transformed input, owned by the plan
     // scratch for lbc_conv_run_host
@@ -119,7 +124,7 @@ size_t packed_weight_bytes(const lbc_plan* p)
     const lbc_conv_desc& d = p->g.d;
     switch (p->kind) {
         case LBC_KERNEL_IGEMM_TC:
-        case LBC_KERNEL_STEM_TC: return (size_t)d.k * p->cfg.packed_row_bytes;
+        case LBC_KERNEL_STEM_TC: return (size_t)d.k * p->pw_factor * p->cfg.packed_row_bytes;
         case LBC_KERNEL_DEPTHWISE: return (size_t)d.r * d.s * d.c;
         default: return (size_t)d.k * d.r * d.s * p->g.cg;
     }
@@ -150,7 +155,7 @@ lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const i
     out->ep.relu = plan->g.d.relu;
     out->ep.out_mode = plan->g.d.out_mode;
     if (plan->kind == LBC_KERNEL_IGEMM_TC)
-        return igemm_encode(plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, y, &out->ig);
+        return igemm_encode(plan->pw_factor > 1 ? plan->g_inner : plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, y, &out->ig);
     if (plan->kind == LBC_KERNEL_STEM_TC)
         return igemm_encode(plan->g_inner, plan->cfg, plan->dev, (const int8_t*)plan->stem_x, (const int8_t*)w, y, &out->ig);
     return LBC_OK;
@@ -160,7 +165,7 @@ lbc_status launch(const ResolvedLaunch& l, cudaStream_t stream)
 {
     const lbc_plan* p = l.plan;
     switch (p->kind) {
-        case LBC_KERNEL_IGEMM_TC: return igemm_launch(p->g, l.ig, l.ep, l.y, stream);
+        case LBC_KERNEL_IGEMM_TC: return igemm_launch(p->pw_factor > 1 ? p->g_inner : p->g, l.ig, l.ep, l.y, stream);
         case LBC_KERNEL_STEM_TC: {
             const lbc_conv_desc& d = p->g.d;
             lbc_status st = launch_stem_xform(l.x, p->stem_x, d.n, d.h, d.w, d.c, p->g_inner.d.h, p->g_inner.d.w, p->stem_sh,
@@ -268,11 +273,29 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
         stem_ok = make_geom(&di, &gi) == LBC_OK && gi.p == g.p && gi.q == g.q && igemm_supported(gi, nullptr) &&
                   igemm_make_config(gi, dev, &stem_cfg) == LBC_OK && stem_cfg.mode == 2 && stem_cfg.bkc == 16;
     }
+    // pixel-group rewrite for pointwise layers the tensor-core path cannot tile directly
+    ConvGeom gp{};
+    IgemmConfig pw_cfg{};
+    int32_t pw_factor = 1;
+    if (!tc_ok && d->groups == 1 && d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
+        d->pad_w == 0) {
+        for (int32_t f = 2; f <= 16 && pw_factor == 1; f *= 2) {
+            if ((f * d->c) % 16 || (f * d->k) % 16 || g.m_total % f || (int64_t)f * d->c > 4096) continue;
+            lbc_conv_desc di = *d;
+            di.n = 1; di.h = 1; di.w = (int32_t)(g.m_total / f); di.c = f * d->c; di.k = f * d->k;
+            if (g.m_total / f >= (1ll << 31)) continue;
+            if (make_geom(&di, &gp) == LBC_OK && igemm_supported(gp, nullptr) && igemm_make_config(gp, dev, &pw_cfg) == LBC_OK) {
+                pw_factor = f;
+                pw_cfg.k_mod = d->k;
+            }
+        }
+    }
+    const bool pw_ok = pw_factor > 1;
     int32_t kind = force;
     if (force == LBC_KERNEL_AUTO) {
         // Tile/layout planner: tensor cores for dense contractions, CUDA cores where they do not pay.
         if (dw_ok) kind = LBC_KERNEL_DEPTHWISE;
-        else if (tc_ok) kind = LBC_KERNEL_IGEMM_TC;
+        else if (tc_ok || pw_ok) kind = LBC_KERNEL_IGEMM_TC;
         else if (stem_ok) kind = LBC_KERNEL_STEM_TC;
         else kind = LBC_KERNEL_DIRECT;
     }
@@ -281,8 +304,8 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
                 LBC_ERR_UNSUPPORTED, "kernel kind %d is not available", kind);
     LBC_REQUIRE(kind != LBC_KERNEL_STEM_TC || stem_ok, LBC_ERR_UNSUPPORTED,
                 "small-C tensor-core path needs groups 1, C*stride^2 <= 16, stride 1 or 2, dilation 1, K %% 16 == 0");
-    LBC_REQUIRE(kind != LBC_KERNEL_IGEMM_TC || tc_ok, LBC_ERR_UNSUPPORTED, "tcgen05 implicit GEMM cannot run this shape: %s",
-                why.c_str());
+    LBC_REQUIRE(kind != LBC_KERNEL_IGEMM_TC || tc_ok || pw_ok, LBC_ERR_UNSUPPORTED,
+                "tcgen05 implicit GEMM cannot run this shape: %s", why.c_str());
     LBC_REQUIRE(kind != LBC_KERNEL_DEPTHWISE || dw_ok, LBC_ERR_UNSUPPORTED,
                 "depthwise kernel needs groups == C == K and C %% 4 == 0");
 
@@ -291,7 +314,11 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
     p->g = g;
     p->kind = kind;
     p->dev = dev;
-    if (kind == LBC_KERNEL_IGEMM_TC) {
+    if (kind == LBC_KERNEL_IGEMM_TC && !tc_ok) {
+        p->pw_factor = pw_factor;
+        p->g_inner = gp;
+        p->cfg = pw_cfg;
+    } else if (kind == LBC_KERNEL_IGEMM_TC) {
         st = igemm_make_config(g, dev, &p->cfg);
         if (st != LBC_OK) {
             delete p;
@@ -342,7 +369,8 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
         snprintf(buf, buf_len,
                  "%s N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %dx%d+%dw b=%s "
                  "a=%s(%dx%d px/tile) tiles %dx%d grid %d smem %zu tmem %u",
-                 plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : "igemm_tc", d.n, d.h, d.w, d.c, d.k, d.r, d.s,
+                 plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : plan->pw_factor > 1 ? "igemm_tc(pixel-groups)" : "igemm_tc",
+                 d.n, d.h, d.w, d.c, d.k, d.r, d.s,
                  d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.tps, c.win_stages,
                  c.res_b ? "resident" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols);
@@ -377,6 +405,18 @@ lbc_status lbc_conv_prepack_weights(const lbc_plan* plan, const int8_t* w_dev, i
     cudaStream_t s = (cudaStream_t)stream;
     switch (plan->kind) {
         case LBC_KERNEL_IGEMM_TC:
+            if (plan->pw_factor > 1) {
+                // [K][C] (KRSC and OIHW coincide for 1x1) -> block-diagonal [f*K][f*C] -> the kernel's filter matrix
+                const int32_t f = plan->pw_factor;
+                int8_t* tmp = nullptr;
+                LBC_CUDA_TRY(cudaMallocAsync((void**)&tmp, (size_t)f * d.k * f * d.c, s));
+                lbc_status st = launch_blockdiag(w_dev, tmp, d.k, d.c, f, s);
+                if (st == LBC_OK)
+                    st = launch_prepack_igemm(tmp, LBC_W_KRSC, (int8_t*)dst_dev, f * d.k, 1, 1, f * d.c, 1, plan->cfg.bkc,
+                                              plan->cfg.cblocks, 0, s);
+                cudaFreeAsync(tmp, s);
+                return st;
+            }
             return launch_prepack_igemm(w_dev, layout, (int8_t*)dst_dev, d.k, d.r, d.s, plan->g.cg, plan->cfg.s_pad,
                                         plan->cfg.bkc, plan->cfg.cblocks, plan->cfg.mode == 2, s);
         case LBC_KERNEL_STEM_TC:

@@ -125,6 +125,8 @@ lbc_status launch_stem_xform(const int8_t* x, void* out, int32_t n, int32_t h, i
                              int32_t ws, int32_t sh, int32_t sw, int32_t pad_h, int32_t pad_w, cudaStream_t stream);
 lbc_status launch_prepack_stem(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
                                int32_t c, int32_t sh, int32_t sw, int32_t r2, int32_t s_pad, cudaStream_t stream);
+// pixel-group rewrite of pointwise layers: [K][C] -> block-diagonal [f*K][f*C]
+lbc_status launch_blockdiag(const int8_t* src, int8_t* dst, int32_t k, int32_t c, int32_t f, cudaStream_t stream);
 lbc_status launch_prepack_depthwise(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t c, int32_t r,
                                     int32_t s, cudaStream_t stream);                         // -> [R][S][C]
 lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,

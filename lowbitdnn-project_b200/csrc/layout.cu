@@ -80,6 +80,21 @@ __global__ void __launch_bounds__(256) prepack_igemm_kernel(const int8_t* __rest
     }
 }
 
+// Pixel-group rewrite of a pointwise convolution (see api.cu): the [K][C] filter becomes the block-diagonal
+// [f*K][f*C] matrix  W'[j*K + k][i*C + c] = (i == j) ? W[k][c] : 0, so that f consecutive pixels, seen as ONE GEMM row
+// of f*C channels, produce their f*K outputs side by side - which is exactly the NHWC order of the f pixels.
+__global__ void __launch_bounds__(256) blockdiag_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, int32_t k,
+                                                        int32_t c, int32_t f)
+{
+    const int64_t total = (int64_t)f * k * f * c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t col = (int32_t)(i % ((int64_t)f * c));
+        const int32_t row = (int32_t)(i / ((int64_t)f * c));
+        const int32_t jb = row / k, kk = row - jb * k, ib = col / c, cc = col - ib * c;
+        dst[i] = (ib == jb) ? src[(int64_t)kk * c + cc] : (int8_t)0;
+    }
+}
+
 // Small-C ("stem") path.  A conv with C*sh*sw <= 16 input channels and stride (sh, sw) in {1, 2} is rewritten as a
 // stride-1, pad-0 conv over 16-channel pixels: the input is zero-padded and (for stride 2) space-to-depth'd,
 //   X'[n][hs][ws][(dr*sw + ds)*C + c] = Xpad[n][hs*sh + dr][ws*sw + ds][c],
@@ -179,6 +194,13 @@ lbc_status launch_prepack_igemm(const int8_t* src, int32_t src_layout, int8_t* d
     const int64_t total = (int64_t)k * r * s_pad * cblocks * bkc;
     prepack_igemm_kernel<<<grid_for(total), 256, 0, stream>>>(src, src_layout == LBC_W_OIHW, dst, k, r, s, cg, s_pad,
                                                               bkc, cblocks, chunk_outer);
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
+
+lbc_status launch_blockdiag(const int8_t* src, int8_t* dst, int32_t k, int32_t c, int32_t f, cudaStream_t stream)
+{
+    blockdiag_kernel<<<grid_for((int64_t)f * k * f * c), 256, 0, stream>>>(src, dst, k, c, f);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

@@ -101,6 +101,28 @@ def test_igemm_tc_kernel(d, out_mode):
     assert _check(D(**{**d.__dict__, "out_mode": out_mode}), force=IGEMM) == "igemm_tc"
 
 
+# pointwise layers whose C or K is not a multiple of 16: pixel-group rewrite (f pixels per GEMM row, block-diagonal filter)
+PIXEL_GROUP_CASES = [
+    D(n=2, h=14, w=14, c=24, k=144, r=1, s=1, relu=1),      # MobileNetV2 expand 24 -> 144 (f = 2, N tiles 2 x 144)
+    D(n=2, h=14, w=14, c=144, k=24, r=1, s=1),              # project 144 -> 24
+    D(n=1, h=56, w=56, c=96, k=24, r=1, s=1),               # project 96 -> 24
+    D(n=1, h=10, w=10, c=24, k=24, r=1, s=1, relu=1),
+    D(n=1, h=6, w=10, c=12, k=20, r=1, s=1, relu=1),        # f = 4
+    D(n=3, h=4, w=4, c=40, k=8, r=1, s=1),                  # f = 2, K' = 16
+]
+
+
+@pytest.mark.parametrize("d", PIXEL_GROUP_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}")
+@pytest.mark.parametrize("out_mode", [1, 0])
+def test_igemm_pixel_group_rewrite(d, out_mode):
+    assert _check(D(**{**d.__dict__, "out_mode": out_mode})) == "igemm_tc"
+
+
+def test_pixel_group_rewrite_needs_divisible_pixels():
+    """An odd pixel count cannot be grouped in pairs: the planner falls back to the CUDA-core kernel."""
+    assert _check(D(n=1, h=5, w=5, c=24, k=24, r=1, s=1, relu=1)) == "direct"
+
+
 @pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.stride_h == 1 and c.r > 1][:6],
                          ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}")
 def test_igemm_im2col_path_on_stride1_shapes(d, monkeypatch):
