@@ -277,10 +277,17 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
     ConvGeom gp{};
     IgemmConfig pw_cfg{};
     int32_t pw_factor = 1;
-    if (!tc_ok && d->groups == 1 && d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 &&
-        d->pad_w == 0) {
+    // ... and for narrow pointwise layers it CAN tile: a 128 x 16 output tile pays the per-tile costs (barriers, waits,
+    // TMA issue) for 2048 outputs; grouping f pixels makes the tile 128 x 16f over the same bytes.
+    const bool pointwise = d->groups == 1 && d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 &&
+                           d->pad_h == 0 && d->pad_w == 0;
+    const bool narrow = tc_ok && pointwise && (d->k < 64 || d->c < 32) && !getenv("LBC_NO_PIXEL_GROUPS");
+    if (pointwise && (!tc_ok || narrow)) {
         for (int32_t f = 2; f <= 16 && pw_factor == 1; f *= 2) {
             if ((f * d->c) % 16 || (f * d->k) % 16 || g.m_total % f || (int64_t)f * d->c > 4096) continue;
+            if (narrow && (f * d->k > 256 || f * d->c > 512)) break;
+            if (narrow && (f * d->k < 64 || f * d->c < 32) && 2 * f * d->k <= 256 && 2 * f * d->c <= 512 && g.m_total % (2 * f) == 0)
+                continue;   // a larger group still fits: keep growing
             lbc_conv_desc di = *d;
             di.n = 1; di.h = 1; di.w = (int32_t)(g.m_total / f); di.c = f * d->c; di.k = f * d->k;
             if (g.m_total / f >= (1ll << 31)) continue;
@@ -291,6 +298,7 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
         }
     }
     const bool pw_ok = pw_factor > 1;
+    bool use_pw = pw_ok && !tc_ok;   // a forced igemm_tc on a shape it tiles directly stays un-grouped
     int32_t kind = force;
     if (force == LBC_KERNEL_AUTO) {
         // Tile/layout planner: tensor cores for dense contractions, CUDA cores where they do not pay.
@@ -298,6 +306,7 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
         else if (tc_ok || pw_ok) kind = LBC_KERNEL_IGEMM_TC;
         else if (stem_ok) kind = LBC_KERNEL_STEM_TC;
         else kind = LBC_KERNEL_DIRECT;
+        use_pw = pw_ok;
     }
     LBC_REQUIRE(kind == LBC_KERNEL_DIRECT || kind == LBC_KERNEL_IGEMM_TC || kind == LBC_KERNEL_DEPTHWISE ||
                     kind == LBC_KERNEL_STEM_TC,
@@ -314,7 +323,7 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
     p->g = g;
     p->kind = kind;
     p->dev = dev;
-    if (kind == LBC_KERNEL_IGEMM_TC && !tc_ok) {
+    if (kind == LBC_KERNEL_IGEMM_TC && use_pw) {
         p->pw_factor = pw_factor;
         p->g_inner = gp;
         p->cfg = pw_cfg;
