@@ -165,6 +165,13 @@ lbc_status  lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_d
 lbc_status  lbc_net_run(lbc_net* net, const int8_t* x_dev, lbc_stream stream, float* per_layer_ms, float* total_ms);
 /* End to end: x_host -> (H2D) -> all layers -> (D2H) -> y_host (the last layer's output). */
 lbc_status  lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lbc_stream stream, float* total_ms);
+/* Pipelined end to end: enqueue H2D(x_host) -> all layers -> D2H(y_host) and return without waiting.  The copies
+ * run on the network's own copy streams and the network input is double-buffered, so the upload of step i+1 and the
+ * download of step i overlap the layers of the neighbouring steps (a serving loop's steady state).  x_host / y_host
+ * must stay valid - and be pinned for the copies to overlap - until lbc_net_sync_host() returns, which waits for
+ * everything submitted and reports the device time from the first submit to the last download. */
+lbc_status  lbc_net_submit_host(lbc_net* net, const int8_t* x_host, void* y_host, lbc_stream stream);
+lbc_status  lbc_net_sync_host(lbc_net* net, float* elapsed_ms);
 lbc_status  lbc_net_launches(const lbc_net* net, int32_t* launches);
 
 /* ---- measurement helpers (cpp/libbenchmark role) ---------------------------------------------- */

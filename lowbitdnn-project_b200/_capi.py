@@ -60,6 +60,8 @@ _PROTOS = {
     "lbc_net_layer_io": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "lbc_net_run": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "lbc_net_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "lbc_net_submit_host": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "lbc_net_sync_host": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "lbc_net_launches": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "lbc_probe_int8_mma_peak": (ctypes.c_int, [_i32, ctypes.POINTER(ctypes.c_double), _vp]),
     "lbc_probe_hbm_copy": (ctypes.c_int, [ctypes.c_size_t, _i32, ctypes.POINTER(ctypes.c_double), _vp]),

@@ -381,7 +381,7 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
                  plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : plan->pw_factor > 1 ? "igemm_tc(pixel-groups)" : "igemm_tc",
                  d.n, d.h, d.w, d.c, d.k, d.r, d.s,
                  d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.tps, c.win_stages,
-                 c.res_b ? "resident" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
+                 c.res_b ? (c.n_mma == 2 ? "resident,2mma" : "resident") : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols);
     } else {
         snprintf(buf, buf_len, "%s N%d %dx%dx%d->%d %dx%d s%d p%d g%d | M=%lld",
@@ -591,6 +591,16 @@ struct lbc_net {
     std::vector<Layer> layers;
     std::vector<cudaEvent_t> events;   // n_layers + 1
     std::mutex mu;
+    // pipelined host path (lbc_net_submit_host): copy streams, second input buffer, hand-over events
+    struct Pipe {
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        void* x_buf[2] = {nullptr, nullptr};          // [0] aliases layer 0's resident input buffer
+        cudaEvent_t up_done[2] = {nullptr, nullptr};  // upload into x_buf[i] finished
+        cudaEvent_t x_used[2] = {nullptr, nullptr};   // layer 0 has consumed x_buf[i]
+        cudaEvent_t comp_done = nullptr, d2h_done = nullptr, t_first = nullptr, t_last = nullptr;
+        uint64_t submitted = 0;
+        bool ready = false;
+    } pipe;
 };
 
 namespace {
@@ -641,6 +651,14 @@ lbc_status lbc_net_destroy(lbc_net* net)
         lbc_conv_plan_destroy(L.plan);
     }
     for (auto e : net->events) cudaEventDestroy(e);
+    {
+        lbc_net::Pipe& pp = net->pipe;
+        if (pp.h2d) cudaStreamDestroy(pp.h2d);
+        if (pp.d2h) cudaStreamDestroy(pp.d2h);
+        if (pp.x_buf[1]) cudaFree(pp.x_buf[1]);
+        for (cudaEvent_t e : {pp.up_done[0], pp.up_done[1], pp.x_used[0], pp.x_used[1], pp.comp_done, pp.d2h_done, pp.t_first, pp.t_last})
+            if (e) cudaEventDestroy(e);
+    }
     delete net;
     return LBC_OK;
 }
@@ -794,6 +812,80 @@ lbc_status lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lb
     LBC_CUDA_TRY(cudaEventRecord(net->events[n], s));
     LBC_CUDA_TRY(cudaEventSynchronize(net->events[n]));
     if (total_ms) LBC_CUDA_TRY(cudaEventElapsedTime(total_ms, net->events[0], net->events[n]));
+    return igemm_check_timeout();
+}
+
+static lbc_status pipe_init(lbc_net* net)
+{
+    lbc_net::Pipe& pp = net->pipe;
+    if (pp.ready) return LBC_OK;
+    lbc_net::Layer& first = net->layers[0];
+    LBC_REQUIRE(first.x_own, LBC_ERR_INVALID_ARG, "layer 0 must take the network input");
+    LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
+    LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking));
+    pp.x_buf[0] = first.x_own;
+    if (cudaMalloc(&pp.x_buf[1], in_bytes(first.plan->g)) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("lbc_net_submit_host: cannot allocate the second input buffer");
+        return LBC_ERR_ALLOC;
+    }
+    for (cudaEvent_t* e : {&pp.up_done[0], &pp.up_done[1], &pp.x_used[0], &pp.x_used[1], &pp.comp_done, &pp.d2h_done})
+        LBC_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    LBC_CUDA_TRY(cudaEventCreate(&pp.t_first));
+    LBC_CUDA_TRY(cudaEventCreate(&pp.t_last));
+    pp.ready = true;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_submit_host(lbc_net* net, const int8_t* x_host, void* y_host, lbc_stream stream)
+{
+    LBC_REQUIRE(net && x_host && y_host, LBC_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(net->mu);
+    lbc_status st = pipe_init(net);
+    if (st != LBC_OK) return st;
+    lbc_net::Pipe& pp = net->pipe;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = (int)net->layers.size();
+    const int b = (int)(pp.submitted & 1);
+    lbc_net::Layer& first = net->layers[0];
+    lbc_net::Layer& last = net->layers[n - 1];
+    // upload: the buffer is free once layer 0 of the step two submissions ago has run
+    if (pp.submitted == 0) LBC_CUDA_TRY(cudaEventRecord(pp.t_first, pp.h2d));
+    if (pp.submitted >= 2) LBC_CUDA_TRY(cudaStreamWaitEvent(pp.h2d, pp.x_used[b], 0));
+    LBC_CUDA_TRY(cudaMemcpyAsync(pp.x_buf[b], x_host, in_bytes(first.plan->g), cudaMemcpyHostToDevice, pp.h2d));
+    LBC_CUDA_TRY(cudaEventRecord(pp.up_done[b], pp.h2d));
+    // compute: layer 0 waits for its upload; the last layer waits until the previous result has been downloaded
+    LBC_CUDA_TRY(cudaStreamWaitEvent(s, pp.up_done[b], 0));
+    for (int i = 0; i < n; ++i) {
+        st = net_resolve(net, i, i == 0 ? (const int8_t*)pp.x_buf[b] : nullptr);
+        if (st != LBC_OK) return st;
+        if (i == n - 1 && pp.submitted >= 1) LBC_CUDA_TRY(cudaStreamWaitEvent(s, pp.d2h_done, 0));
+        st = launch(net->layers[i].rl, s);
+        if (st != LBC_OK) return st;
+        if (i == 0) LBC_CUDA_TRY(cudaEventRecord(pp.x_used[b], s));
+    }
+    LBC_CUDA_TRY(cudaEventRecord(pp.comp_done, s));
+    // download
+    LBC_CUDA_TRY(cudaStreamWaitEvent(pp.d2h, pp.comp_done, 0));
+    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, last.y, out_bytes(last.plan->g), cudaMemcpyDeviceToHost, pp.d2h));
+    LBC_CUDA_TRY(cudaEventRecord(pp.d2h_done, pp.d2h));
+    ++pp.submitted;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_sync_host(lbc_net* net, float* elapsed_ms)
+{
+    LBC_REQUIRE(net, LBC_ERR_INVALID_ARG, "null net");
+    std::lock_guard<std::mutex> lk(net->mu);
+    lbc_net::Pipe& pp = net->pipe;
+    if (elapsed_ms) *elapsed_ms = 0.f;
+    if (!pp.ready || pp.submitted == 0) return LBC_OK;
+    LBC_CUDA_TRY(cudaEventRecord(pp.t_last, pp.d2h));
+    LBC_CUDA_TRY(cudaEventSynchronize(pp.t_last));
+    if (elapsed_ms) LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, pp.t_first, pp.t_last));
+    pp.submitted = 0;
+    // layer 0 goes back to its resident buffer for lbc_net_run
+    net->layers[0].resolved = false;
     return igemm_check_timeout();
 }
 

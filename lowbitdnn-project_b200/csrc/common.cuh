@@ -90,6 +90,7 @@ struct IgemmConfig {
     uint16_t a_tab[192];
     uint16_t b_tab[192]; // resident-B window mode: matching B-descriptor offsets
     int32_t res_b;       // filter matrix resident in shared memory (loaded once per CTA)
+    int32_t n_mma;       // MMA-issuing warps (1 or 2)
     uint32_t b_total_bytes;
     uint32_t off_b, off_stage, off_ctl;
     int32_t grid;        // persistent CTAs

@@ -38,7 +38,7 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 16;                          // epilogue warps: 2 teams of 8 or 4 teams of 4
-constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA + TMEM alloc, 2: window TMA, 3: idle
+constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA (even tiles) + TMEM alloc, 2: window TMA, 3: MMA (odd tiles)
 constexpr int kNumThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 640
 constexpr int kMaxStages = 8;
 constexpr int kMaxWinStages = 6;
@@ -84,6 +84,8 @@ struct IgemmParams {
     uint16_t a_tab[kMaxTab];
     uint16_t b_tab[kMaxTab];      // resident-B window mode: B-descriptor offsets of the same MMAs (relative to the chunk)
     int32_t res_b;                // 1: the whole filter matrix stays in shared memory (loaded once per CTA)
+    int32_t n_mma;                // MMA-issuing warps (1 or 2); CTA-local tile L belongs to warp L % n_mma and to the
+                                  // L % n_mma-th sub-ring of the A ring / window ring (stages / n_mma stages each)
     uint32_t b_total_bytes;       // resident B: bytes of the filter matrix
     // division-free tile iteration: a tile index is the mixed-radix number (img | rt | ct | n_blk) with radices
     // (it_rows, it_cols, tiles_n); step_* are the digits of gridDim.x in that system
@@ -195,7 +197,9 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
         const int32_t cc = c + 16 * g;
         if (OUT8) {
             const uint4 r = requant16(v + 16 * g, sc + cc, bi + cc, lo);
-            if (et.valid) *reinterpret_cast<uint4*>(staging + swz(row_off + (uint32_t)(pc + 16 * g), swz_mask)) = r;
+            // swizzle: the XOR term depends only on the staging row (a panel row never crosses a 128-byte line), so
+            // `swz_mask` arrives here already as this thread's ((row_off >> 7) & mask) << 4
+            if (et.valid) *reinterpret_cast<uint4*>(staging + ((row_off + (uint32_t)(pc + 16 * g)) ^ swz_mask)) = r;
         } else if (out_row >= 0 && col0 + cc < prm.k_out) {
             int32_t* yo = y32 + out_row * prm.k_out + col0 + cc;
 #pragma unroll
@@ -312,10 +316,13 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             __syncwarp();
         }
         if (kRing) {
-            uint32_t stage = 0, phase = 0;
+            // one (stage, phase) cursor per sub-ring: with two MMA warps, even tiles flow through the first half of
+            // the ring and odd tiles through the second, so each consumer sees its stages strictly in phase order
+            const uint32_t sub_len = (uint32_t)prm.stages / (uint32_t)prm.n_mma;
+            uint32_t stage_e = 0, phase_e = 0, stage_o = 0, phase_o = 0;   // cursors of the even / odd sub-ring
             const uint32_t tx_bytes = (RESB ? 0u : prm.b_stage_bytes) + (kWindow ? 0u : prm.a_stage_bytes);
             const int32_t stages_per_tile = prm.cblocks * prm.inner / prm.tps;
-            const int32_t tps = prm.tps, nstages = prm.stages, cblocks = prm.cblocks;
+            const int32_t tps = prm.tps, cblocks = prm.cblocks;
             const int32_t bkb = prm.bkb, bkc = prm.bkc, s_taps = prm.s_taps;
             const int32_t dil_w = prm.dil_w, dil_h = prm.dil_h;
             const uint32_t a_block = prm.a_block_bytes, b_block = prm.b_block_bytes;
@@ -335,6 +342,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     h_base = p0 * prm.stride_h - prm.pad_h;
                 }
                 const int32_t brow = it.n_blk * prm.bn;
+                const uint32_t sub = (uint32_t)it.local & (uint32_t)(prm.n_mma - 1);
+                const uint32_t sub_base = sub * sub_len;
+                uint32_t stage = sub_base + (sub ? stage_o : stage_e), phase = sub ? phase_o : phase_e;
                 // ring modes walk K as [tap][channel chunk]: (off_h, off_w) filter tap offset, c0 channel offset
                 int32_t c0 = 0, cbi = 0, off_w = 0, off_h = 0, fs = 0, bcol = 0;
                 for (int32_t st = 0; st < stages_per_tile; ++st) {
@@ -365,20 +375,26 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                             }
                         }
                     }
-                    if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+                    if (++stage == sub_base + sub_len) { stage = sub_base; phase ^= 1; }
                 }
+                if (sub) { stage_o = stage - sub_base; phase_o = phase; }
+                else { stage_e = stage - sub_base; phase_e = phase; }
                 if (leader) trace_ev(prm, it.local, EV_P_DONE);
             }
         }
     } else if (warp == 2) {
         // ===================== window producer (WINDOW modes only) =====================
         if (kWindow) {
-            uint32_t ws = 0, wphase = 0;
+            const uint32_t sub_len = (uint32_t)prm.win_stages / (uint32_t)prm.n_mma;
+            uint32_t ws_e = 0, wphase_e = 0, ws_o = 0, wphase_o = 0;
             const bool leader = ptx::elect_one();
             bool ok = true;
             TileIter it;
             for (it.init(prm, blockIdx.x); it.tile < num_tiles && ok; it.next(prm)) {
                 const int32_t wq = it.q0(prm) - prm.pad_w, wp = it.p0(prm) - prm.pad_h;
+                const uint32_t sub = (uint32_t)it.local & (uint32_t)(prm.n_mma - 1);
+                const uint32_t sub_base = sub * sub_len;
+                uint32_t ws = sub_base + (sub ? ws_o : ws_e), wphase = sub ? wphase_o : wphase_e;
                 int32_t c0 = 0;
                 for (int32_t cb = 0; cb < prm.cblocks; ++cb, c0 += prm.bkc) {
                     ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
@@ -388,19 +404,27 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
                         ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
                     }
-                    if (++ws == (uint32_t)prm.win_stages) { ws = 0; wphase ^= 1; }
+                    if (++ws == sub_base + sub_len) { ws = sub_base; wphase ^= 1; }
                 }
+                if (sub) { ws_o = ws - sub_base; wphase_o = wphase; }
+                else { ws_e = ws - sub_base; wphase_e = wphase; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 3) {
+        // ===================== MMA issuers (two warps, alternating tiles) =====================
         // Convergent, exit-free loops (a watchdog trip only makes the waits return early).  One tcgen05.mma of
-        // M=128 x N<=128 takes 48-64 cycles (tools/exp/mma_rates.cu), so the issue loop has to stay well below that
-        // per MMA: the descriptor offsets of a channel chunk come from tables in the kernel-parameter bank, only the
-        // low 32 bits of the descriptors are ever touched (the smem address field cannot carry into the LBO field),
-        // and with a resident filter matrix there is no per-block handshake at all.
-        uint32_t stage = 0, phase = 0, ws = 0, wphase = 0;
-        uint32_t acc_stage = 0, acc_phase = 0;
+        // M=128 x N<=128 takes 48-64 cycles (tools/exp/mma_rates.cu) but a single warp needs ~75 cycles of scalar /
+        // uniform-datapath work to issue one (traces, r01), so layers with narrow N tiles were issue-bound.  Two
+        // warps may therefore issue for alternate tiles of the CTA (n_mma == 2): tile L (CTA-local) belongs to warp
+        // L % n_mma, uses TMEM accumulator stage L % n_acc and flows through that warp's half of the A-side ring (the
+        // producers fill the two sub-rings alternately, so every consumer sees its stages strictly in phase order - a
+        // shared ring would alias mbarrier parities between the two consumers).  Different tiles accumulate into
+        // different TMEM columns, so the interleaving of the two instruction streams in the tensor pipe is irrelevant.
+        // Descriptor offsets of a channel chunk come from tables in the kernel-parameter bank, only the low 32 bits
+        // of the descriptors are ever touched (the smem address field cannot carry into the LBO field), and with a
+        // resident filter matrix there is no per-block handshake at all.
+        const uint32_t which = warp >> 1;                              // 0 (warp 1) or 1 (warp 3)
+        const uint32_t n_mma = (uint32_t)prm.n_mma;
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
         const uint64_t db_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_b), (uint32_t)prm.bkb);
@@ -414,14 +438,23 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t b_chunk16 = b_block16 * (uint32_t)prm.inner;          // resident B: one channel chunk of blocks
         const int32_t inner_stages = prm.mma_inner / prm.tps;
         const int32_t tps = prm.tps, mma_outer = prm.mma_outer, n_tab = prm.n_tab;
-        const uint32_t nstages = (uint32_t)prm.stages, nwin = (uint32_t)prm.win_stages;
+        // this warp's sub-ring: stages [ring_lo, ring_hi) of the A/B ring and [win_lo, win_hi) of the window ring
+        const uint32_t ring_len = (uint32_t)prm.stages / n_mma, win_len = (uint32_t)prm.win_stages / n_mma;
+        const uint32_t ring_lo = which * ring_len, ring_hi = ring_lo + ring_len;
+        const uint32_t win_lo = which * win_len, win_hi = win_lo + win_len;
         const uint32_t bn = (uint32_t)prm.bn;
-
-        bool ready = kRing ? ptx::mbar_test(&ctl->full[0], 0) : true;
-        bool wready = kWindow ? ptx::mbar_test(&ctl->wfull[0], 0) : true;
-        if (RESB) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
-        int32_t local = 0;
-        for (int32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
+        uint32_t stage = ring_lo, phase = 0, ws = win_lo, wphase = 0;
+        const bool active = which < n_mma;
+        bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
+        bool wready = (kWindow && active) ? ptx::mbar_test(&ctl->wfull[ws], wphase) : true;
+        if (RESB && active) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
+        int32_t local = (int32_t)which;
+        const int32_t tile_step = (int32_t)(n_mma * gridDim.x);
+        for (int32_t tile = active ? (int32_t)(blockIdx.x + which * gridDim.x) : num_tiles; tile < num_tiles;
+             tile += tile_step, local += (int32_t)n_mma) {
+            const uint32_t acc_stage = (uint32_t)local & acc_mask;
+            const uint32_t acc_phase = ((uint32_t)local >> acc_shift) & 1u;
             ptx::mbar_wait_soft(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
             ptx::tc_fence_after();
             if (leader) trace_ev(prm, local, EV_M_START);
@@ -453,7 +486,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         accumulate = 1;
                     }
                     ptx::mma_commit_pred(&ctl->wempty[ws], leader);
-                    if (++ws == nwin) { ws = 0; wphase ^= 1; }
+                    if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
                     wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
                 }
             } else {
@@ -472,7 +505,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         if (st == 0 && cb == 0 && leader) trace_ev(prm, local, EV_M_FULL);
                         // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
                         uint32_t nstage = stage + 1, nphase = phase;
-                        if (nstage == nstages) { nstage = 0; nphase ^= 1; }
+                        if (nstage == ring_hi) { nstage = ring_lo; nphase ^= 1; }
                         const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
                         if (!kWindow) a_base = da_lo + stage * a_stage16;
                         uint32_t b_lo = RESB ? b_res : db_lo + stage * b_stage16;
@@ -492,14 +525,13 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     }
                     if (kWindow) {
                         ptx::mma_commit_pred(&ctl->wempty[ws], leader);
-                        if (++ws == nwin) { ws = 0; wphase ^= 1; }
+                        if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
                         wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
                     }
                 }
             }
             ptx::mma_commit_pred(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue
             if (leader) trace_ev(prm, local, EV_M_DONE);
-            if (++acc_stage == (uint32_t)prm.n_acc) { acc_stage = 0; acc_phase ^= 1; }
         }
     } else if (warp >= kFirstEpiWarp) {
         // ===================== epilogue: 16 warps in 2 teams of 8 or 4 teams of 4 =====================
@@ -552,7 +584,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
 
         const uint32_t row_off = et.srow * (uint32_t)prm.panel_bytes;     // byte offset of this lane's staging row
-        const uint32_t swz_mask = (1u << prm.panel_swz_bits) - 1u;
+        // per-thread XOR term of the staging swizzle (see epi_consume)
+        const uint32_t swz_mask = ((row_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
         int32_t cur_nblk = -1;
         TileIter it;
@@ -868,6 +901,17 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         fits = c.smem_bytes <= 227 * 1024;
     }
     LBC_REQUIRE(fits, LBC_ERR_UNSUPPORTED, "igemm: operand rings do not fit in shared memory");
+    // Two MMA-issuing warps (alternate tiles, half of the A-side ring each) where a single warp's issue rate is the
+    // bound: narrow N tiles with a resident filter matrix.  Wide tiles (128 cycles per MMA) gain nothing.
+    c.n_mma = 1;
+    // issue-bound test: ~75 cycles per MMA for one warp (traces) against the tile's share of HBM time (22.5 B/clk/SM)
+    const double issue_cycles = 450.0 + 75.0 * c.k_blocks * (c.bkb / 32);   // + per-tile fixed cost of the issuing warp
+    const double a_bytes = c.mode == A_WINDOW ? (double)c.win_tx_bytes * c.cblocks : (double)kBlockM * c.c_pad * (c.mode == A_TILED ? 1 : d.r * d.s);
+    const double hbm_cycles = (a_bytes + (double)kBlockM * c.bn) / 22.5;
+    if (c.res_b && c.bn <= 128 && issue_cycles > hbm_cycles && !getenv("LBC_ONE_MMA")) {
+        if (c.mode == A_WINDOW && c.win_stages >= 4) { c.n_mma = 2; c.win_stages &= ~1; }
+        else if (c.mode != A_WINDOW && c.stages >= 4) { c.n_mma = 2; c.stages &= ~1; }
+    }
 
     // ---- MMA issue table (A-descriptor offsets in 16-byte units, one channel chunk)
     {
@@ -897,6 +941,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     while (cols < (uint32_t)(c.n_acc * c.bn)) cols <<= 1;
     c.tmem_cols = cols;
     c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
+    if (const char* v = getenv("LBC_MAX_GRID")) c.grid = std::max(1, std::min(c.grid, atoi(v)));   // tests: many tiles per CTA
     *cfg = c;
     return LBC_OK;
 }
@@ -1008,7 +1053,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps;
     prm.n_tab = c.n_tab;
     for (int i = 0; i < c.n_tab; ++i) { prm.a_tab[i] = c.a_tab[i]; prm.b_tab[i] = c.b_tab[i]; }
-    prm.res_b = c.res_b; prm.b_total_bytes = c.b_total_bytes;
+    prm.res_b = c.res_b; prm.b_total_bytes = c.b_total_bytes; prm.n_mma = c.n_mma;
     // digits of the CTA stride in the (img | rt | ct | n_blk) tile numbering
     prm.it_cols = c.mode == A_WINDOW ? c.col_tiles : 1;
     prm.it_rows = c.mode == A_WINDOW ? c.row_tiles : 1;

@@ -82,6 +82,16 @@ class Net:
         check(self._lib.lbc_net_run(self._h, _ptr(x_dev), _stream_ptr(stream), per, ctypes.byref(tot)))
         return list(per), tot.value
 
+    def submit_host(self, x_host, y_host, stream=None) -> None:
+        """Pipelined end to end: enqueue H2D -> all layers -> D2H and return; see sync_host()."""
+        check(self._lib.lbc_net_submit_host(self._h, _ptr(x_host), _ptr(y_host), _stream_ptr(stream)))
+
+    def sync_host(self) -> float:
+        """Wait for every submit_host(); device ms from the first upload to the last download."""
+        tot = ctypes.c_float()
+        check(self._lib.lbc_net_sync_host(self._h, ctypes.byref(tot)))
+        return tot.value
+
     def run_host(self, x_host, y_host, stream=None) -> float:
         tot = ctypes.c_float()
         check(self._lib.lbc_net_run_host(self._h, _ptr(x_host), _ptr(y_host), _stream_ptr(stream), ctypes.byref(tot)))

@@ -40,3 +40,42 @@ def test_reference_signature_operator():
     out, ms = lbc.conv2DForward3x3(xv, wv)
     assert ms > 0
     assert np.array_equal(out.cpu().numpy(), oracle.to_vect_c(want, 16))
+
+
+def test_pipelined_host_path_matches_blocking_path():
+    """lbc_net_submit_host (double-buffered input, copy streams) == lbc_net_run_host == oracle, step after step."""
+    import numpy as np
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    from oracle import oracle
+    from oracle.oracle import ConvDesc as OD
+    n = 4
+    layers = [("a", lbc.ConvDesc(n=n, h=20, w=20, c=3, k=32, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1), None),
+              ("b", lbc.ConvDesc(n=n, h=10, w=10, c=32, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1), "a"),
+              ("c", lbc.ConvDesc(n=n, h=10, w=10, c=64, k=32, r=1, s=1), "b")]
+    net = lbc.Net(layers)
+    params = []
+    for i, (_, d, _) in enumerate(layers):
+        od = OD(**d.__dict__)
+        _, w, b, s = oracle.synth(od, layer=i)
+        net.set_params(i, w, b, s)
+        params.append((od, w, b, s))
+    rng = np.random.default_rng(5)
+    xs = [rng.integers(-128, 128, size=(n, 20, 20, 3), dtype=np.int8) for _ in range(5)]
+    want = []
+    for x in xs:
+        t = x
+        for od, w, b, s in params:
+            t = oracle.conv_nhwc(od, t, w, b, s)
+        want.append(t)
+    xh = [torch.from_numpy(x).pin_memory() for x in xs]
+    yh = [torch.empty((n, 10, 10, 32), dtype=torch.int8).pin_memory() for _ in xs]
+    for x, y in zip(xh, yh):
+        net.submit_host(x, y)
+    assert net.sync_host() > 0
+    for y, w in zip(yh, want):
+        assert np.array_equal(y.numpy(), w)
+    yb = torch.empty_like(yh[0])
+    net.run_host(xh[2], yb)
+    assert np.array_equal(yb.numpy(), want[2])
+    net.close()

@@ -131,6 +131,27 @@ def test_igemm_im2col_path_on_stride1_shapes(d, monkeypatch):
     assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
 
 
+MULTI_TILE_CASES = [
+    D(n=4, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # window, resident B, two MMA warps
+    D(n=2, h=28, w=28, c=64, k=256, r=1, s=1, relu=1),                         # tiled, resident B, 256-wide tile
+    D(n=2, h=28, w=28, c=256, k=64, r=1, s=1, relu=1),                         # tiled, resident B, two MMA warps
+    D(n=2, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # window, streaming B, 2 channel chunks
+    D(n=2, h=14, w=14, c=512, k=1024, r=1, s=1),                               # tiled, streaming B, 4 N tiles
+    D(n=2, h=28, w=28, c=128, k=128, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),   # im2col
+    D(n=2, h=40, w=40, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),      # stem
+    D(n=2, h=28, w=28, c=24, k=144, r=1, s=1, relu=1),                         # pixel groups, 2 N tiles
+]
+
+
+@pytest.mark.parametrize("grid", [1, 3])
+@pytest.mark.parametrize("d", MULTI_TILE_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_many_tiles_per_cta(d, grid, monkeypatch):
+    """Cap the persistent grid so every CTA walks many tiles: ring/window phases, TMEM accumulator reuse, the
+    alternating MMA warps and the staging ring all wrap several times (a full-size layer does this on 148 SMs)."""
+    monkeypatch.setenv("LBC_MAX_GRID", str(grid))
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+
+
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
 STEM_CASES = [
     D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),    # ResNet stem
