@@ -342,6 +342,19 @@ def main():
         else:
             roofline = {"bound": "tensor", "achieved": tops, "peak": tc_peak / 1e12, "unit": "TFLOP/s",
                         "frac": tops / (tc_peak / 1e12), "traffic": None}
+        # DRAM traffic per launch of the dominant kernel: from the committed ncu launch list of this same command
+        # (profiles/*_traffic.json, written by tools/make_profile_summary.py); only valid for the default workload
+        try:
+            tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+            if tfiles and args.network == "resnet50" and args.batch == nets.DEFAULT_BATCH["resnet50"] and dom == "igemm_tc":
+                with open(os.path.join(ROOT, "profiles", tfiles[-1])) as fh:
+                    tr = json.load(fh)
+                roofline["traffic"] = tr["dram_bytes_per_launch"] / 1e9 if roofline["unit"] == "GB/s" else tr["dram_bytes_per_launch"]
+                roofline["traffic_unit"] = "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the kernel's launches of one step)"
+                roofline["traffic_source"] = "profiles/" + tfiles[-1]
+                roofline["algorithmic_gb_per_launch"] = dom_bytes / len(sel) / 1e9
+        except Exception as e:  # noqa: BLE001
+            log("traffic file unreadable:", e)
         roofline.update({
             "kernel": {"igemm_tc": "igemm_i8_kernel", "direct": "direct_conv_kernel", "depthwise": "depthwise_kernel"}[dom],
             "launches_per_step": len(sel), "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / float(per_layer.sum()),
