@@ -91,6 +91,13 @@ struct IgemmParams {
     // (it_rows, it_cols, tiles_n); step_* are the digits of gridDim.x in that system
     int32_t it_cols, it_rows;
     int32_t step_nb, step_ct, step_rt, step_img;
+    int32_t tile_stride;          // tile indices one CTA advances per step: gridDim.x, or 2 * gridDim.x in pair mode
+    // Pair mode (window A, streaming B): a CTA works on TWO consecutive M tiles at once - two windows per window stage,
+    // two TMEM accumulators - and every B block fetched from L2 feeds the MMAs of both, halving the bytes per MMA that
+    // bound wide 3x3 layers.  Tiles are then numbered N-tile-major (n_blk | img | rt | ct) so the two tiles of a pair
+    // are the consecutive indices 2q, 2q + 1; it_imgs is the (padded, so the count is even) image radix.
+    int32_t pair, it_imgs;
+    uint32_t win_sub_bytes;       // pair mode: bytes of one of the two windows of a stage
     // optional pipeline trace (development aid): CTA 0 writes clock64 stamps, 16 slots per local tile
     long long* trace;
     int32_t trace_tiles;
@@ -129,23 +136,48 @@ struct TileIter {
     {
         tile = t0;
         local = 0;
-        n_blk = t0 % prm.tiles_n;
-        const int32_t mt = t0 / prm.tiles_n;
+        int32_t mt;
+        if (prm.pair) {   // N-tile-major numbering
+            const int32_t per_n = prm.it_cols * prm.it_rows * prm.it_imgs;
+            n_blk = t0 / per_n;
+            mt = t0 - n_blk * per_n;
+        } else {
+            n_blk = t0 % prm.tiles_n;
+            mt = t0 / prm.tiles_n;
+        }
         ct = mt % prm.it_cols;
         rt = (mt / prm.it_cols) % prm.it_rows;
         img = mt / (prm.it_cols * prm.it_rows);
     }
     __device__ __forceinline__ void next(const IgemmParams& prm)
     {
-        tile += (int32_t)gridDim.x;
+        tile += prm.tile_stride;
         ++local;
-        n_blk += prm.step_nb;
-        if (n_blk >= prm.tiles_n) { n_blk -= prm.tiles_n; ++ct; }
-        ct += prm.step_ct;
-        if (ct >= prm.it_cols) { ct -= prm.it_cols; ++rt; }
-        rt += prm.step_rt;
-        if (rt >= prm.it_rows) { rt -= prm.it_rows; ++img; }
-        img += prm.step_img;
+        if (prm.pair) {
+            ct += prm.step_ct;
+            if (ct >= prm.it_cols) { ct -= prm.it_cols; ++rt; }
+            rt += prm.step_rt;
+            if (rt >= prm.it_rows) { rt -= prm.it_rows; ++img; }
+            img += prm.step_img;
+            if (img >= prm.it_imgs) { img -= prm.it_imgs; ++n_blk; }
+            n_blk += prm.step_nb;
+        } else {
+            n_blk += prm.step_nb;
+            if (n_blk >= prm.tiles_n) { n_blk -= prm.tiles_n; ++ct; }
+            ct += prm.step_ct;
+            if (ct >= prm.it_cols) { ct -= prm.it_cols; ++rt; }
+            rt += prm.step_rt;
+            if (rt >= prm.it_rows) { rt -= prm.it_rows; ++img; }
+            img += prm.step_img;
+        }
+    }
+    // the M tile right after this one (pair mode: the second tile of the pair; same n_blk because the count is even)
+    __device__ __forceinline__ TileIter succ(const IgemmParams& prm) const
+    {
+        TileIter t = *this;
+        ++t.tile;
+        if (++t.ct >= prm.it_cols) { t.ct = 0; if (++t.rt >= prm.it_rows) { t.rt = 0; ++t.img; } }
+        return t;
     }
     // WINDOW: first output row / column of the tile; ring modes: first GEMM row
     __device__ __forceinline__ int32_t p0(const IgemmParams& prm) const { return rt * prm.rows_per_tile; }
@@ -265,17 +297,19 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         return;
     }
 
+    ptx::griddep_launch_dependents();   // the next layer's CTAs may take this SM as soon as this CTA has left it
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_b);
         ptx::prefetch_tensormap(&tm_out);
+        const uint32_t consumers = prm.pair ? 2u : 1u;   // pair mode: both MMA warps read every stage
         for (int i = 0; i < prm.stages; ++i) {
             ptx::mbar_init(&ctl->full[i], 1);
-            ptx::mbar_init(&ctl->empty[i], 1);
+            ptx::mbar_init(&ctl->empty[i], consumers);
         }
         for (int i = 0; i < prm.win_stages; ++i) {
             ptx::mbar_init(&ctl->wfull[i], 1);
-            ptx::mbar_init(&ctl->wempty[i], 1);
+            ptx::mbar_init(&ctl->wempty[i], consumers);
         }
         for (int i = 0; i < prm.n_acc; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
@@ -291,8 +325,14 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    // Programmatic dependent launch: everything above is on-chip set-up (barriers, TMEM, descriptor prefetch) and may
+    // overlap the tail of the previous kernel in the stream; from here on global memory is read and written.
+    ptx::griddep_wait();
+    if (prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
-    const int32_t num_tiles = prm.tiles_m * prm.tiles_n;
+    // pair mode counts the padded tile space (dummy tiles of the padding image load zeros and store nothing)
+    const int32_t num_tiles = prm.pair ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
+    const int32_t first_tile = prm.pair ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
 
     // The three issue roles below run with ALL 32 lanes of their warp executing the (warp-uniform) loops; only
     // the TMA / MMA / commit instructions themselves are predicated on one elected lane.  Keeping the loops
@@ -329,7 +369,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t a_stage = prm.a_stage_bytes, b_stage = prm.b_stage_bytes;
             bool ok = true;
             TileIter it;
-            for (it.init(prm, blockIdx.x); it.tile < num_tiles && ok; it.next(prm)) {
+            for (it.init(prm, first_tile); it.tile < num_tiles && ok; it.next(prm)) {
                 const int32_t m0 = it.m0();
                 int32_t w_base = 0, h_base = 0, n0 = 0;
                 if (KM == A_IM2COL) {
@@ -390,8 +430,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const bool leader = ptx::elect_one();
             bool ok = true;
             TileIter it;
-            for (it.init(prm, blockIdx.x); it.tile < num_tiles && ok; it.next(prm)) {
+            for (it.init(prm, first_tile); it.tile < num_tiles && ok; it.next(prm)) {
                 const int32_t wq = it.q0(prm) - prm.pad_w, wp = it.p0(prm) - prm.pad_h;
+                const TileIter it1 = it.succ(prm);                      // pair mode: the second tile of the pair
+                const int32_t wq1 = it1.q0(prm) - prm.pad_w, wp1 = it1.p0(prm) - prm.pad_h;
                 const uint32_t sub = (uint32_t)it.local & (uint32_t)(prm.n_mma - 1);
                 const uint32_t sub_base = sub * sub_len;
                 uint32_t ws = sub_base + (sub ? ws_o : ws_e), wphase = sub ? wphase_o : wphase_e;
@@ -401,8 +443,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (!ok) break;
                     if (leader) {
                         if (cb == 0) trace_ev(prm, it.local, EV_W_ISSUE);
-                        ptx::mbar_expect_tx(&ctl->wfull[ws], prm.win_tx_bytes);
+                        ptx::mbar_expect_tx(&ctl->wfull[ws], prm.pair ? 2u * prm.win_tx_bytes : prm.win_tx_bytes);
                         ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
+                        if (prm.pair)
+                            ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes + prm.win_sub_bytes, &tm_a, &ctl->wfull[ws], c0, wq1,
+                                             wp1, it1.img);
                     }
                     if (++ws == sub_base + sub_len) { ws = sub_base; wphase ^= 1; }
                 }
@@ -440,15 +485,64 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int32_t tps = prm.tps, mma_outer = prm.mma_outer, n_tab = prm.n_tab;
         // this warp's sub-ring: stages [ring_lo, ring_hi) of the A/B ring and [win_lo, win_hi) of the window ring
         const uint32_t ring_len = (uint32_t)prm.stages / n_mma, win_len = (uint32_t)prm.win_stages / n_mma;
-        const uint32_t ring_lo = which * ring_len, ring_hi = ring_lo + ring_len;
-        const uint32_t win_lo = which * win_len, win_hi = win_lo + win_len;
+        const uint32_t sub_ring = prm.pair ? 0u : which;   // pair mode: both warps walk the whole (single) ring
+        const uint32_t ring_lo = sub_ring * ring_len, ring_hi = ring_lo + ring_len;
+        const uint32_t win_lo = sub_ring * win_len, win_hi = win_lo + win_len;
         const uint32_t bn = (uint32_t)prm.bn;
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
         uint32_t stage = ring_lo, phase = 0, ws = win_lo, wphase = 0;
-        const bool active = which < n_mma;
+        const bool active = which < n_mma || prm.pair;
         bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
         bool wready = (kWindow && active) ? ptx::mbar_test(&ctl->wfull[ws], wphase) : true;
         if (RESB && active) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
+        if (kWindow && !RESB && prm.pair) {
+            // ---- pair mode: two M tiles per step share every B block (see IgemmParams::pair).  Warp `which` issues
+            // the MMAs of the which-th tile of the pair: both read the same B stage and the same window stage (one
+            // window each), so those stages are released by TWO commits (their empty barriers count 2).
+            const uint32_t win_sub16 = prm.win_sub_bytes >> 4;
+            int32_t lp = 0;   // CTA-local pair index; its tiles are CTA-local tiles 2*lp and 2*lp + 1
+            for (int32_t tile = first_tile; tile < num_tiles; tile += prm.tile_stride, ++lp) {
+                const uint32_t acc = ((uint32_t)(2 * lp) & acc_mask) + which;
+                const uint32_t acc_phase = ((uint32_t)(2 * lp) >> acc_shift) & 1u;
+                ptx::mbar_wait_soft(&ctl->tmem_empty[acc], acc_phase ^ 1, tflag);
+                ptx::tc_fence_after();
+                if (leader && which == 0) trace_ev(prm, lp, EV_M_START);
+                const uint32_t tmem_d = tmem_base + acc * bn;
+                uint32_t accumulate = 0;
+                for (int32_t cb = 0; cb < mma_outer; ++cb) {
+                    if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
+                    const uint32_t a_base = da_lo + ws * a_stage16 + which * win_sub16;
+                    if (cb == 0 && leader && which == 0) trace_ev(prm, lp, EV_M_WIN);
+                    int32_t j = 0;
+                    for (int32_t st = 0; st < inner_stages; ++st) {
+                        if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
+                        ptx::tc_fence_after();
+                        if (st == 0 && cb == 0 && leader && which == 0) trace_ev(prm, lp, EV_M_FULL);
+                        uint32_t nstage = stage + 1, nphase = phase;
+                        if (nstage == ring_hi) { nstage = ring_lo; nphase ^= 1; }
+                        const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
+                        uint32_t b_lo = db_lo + stage * b_stage16;
+                        for (int32_t t = 0; t < tps; ++t) {
+#pragma unroll
+                            for (int k = 0; k < KS; ++k) {
+                                ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j + k], da_hi, b_lo + 2u * k, db_hi, idesc,
+                                                      accumulate, leader);
+                                accumulate = 1;
+                            }
+                            j += KS;
+                            b_lo += b_block16;
+                        }
+                        ptx::mma_commit_pred(&ctl->empty[stage], leader);
+                        stage = nstage; phase = nphase; ready = ready_next;
+                    }
+                    ptx::mma_commit_pred(&ctl->wempty[ws], leader);
+                    if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
+                    wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
+                }
+                ptx::mma_commit_pred(&ctl->tmem_full[acc], leader);
+                if (leader && which == 0) trace_ev(prm, lp, EV_M_DONE);
+            }
+        } else {
         int32_t local = (int32_t)which;
         const int32_t tile_step = (int32_t)(n_mma * gridDim.x);
         for (int32_t tile = active ? (int32_t)(blockIdx.x + which * gridDim.x) : num_tiles; tile < num_tiles;
@@ -533,6 +627,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             ptx::mma_commit_pred(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue
             if (leader) trace_ev(prm, local, EV_M_DONE);
         }
+        }
     } else if (warp >= kFirstEpiWarp) {
         // ===================== epilogue: 16 warps in 2 teams of 8 or 4 teams of 4 =====================
         // A team owns every n_teams-th tile of this CTA (CTA-local tile L sits in TMEM accumulator stage L % n_acc) and a
@@ -589,9 +684,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
         int32_t cur_nblk = -1;
         TileIter it;
-        it.init(prm, (int32_t)(blockIdx.x + team * gridDim.x));
+        // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
+        it.init(prm, prm.pair ? first_tile + (int32_t)team : (int32_t)(blockIdx.x + team * gridDim.x));
         for (; it.tile < num_tiles;) {
-            const int32_t tile = it.local + (int32_t)team;   // CTA-local tile index (it.local advances n_teams per loop)
+            // CTA-local tile index (it.local advances once per pair / n_teams times per loop)
+            const int32_t tile = prm.pair ? 2 * it.local + (int32_t)team : it.local + (int32_t)team;
             struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.img, it.p0(prm), it.q0(prm), it.m0()};
             const int32_t col0 = tc.n_blk * prm.bn;
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
@@ -618,7 +715,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (!int8_out) {
                 if (prm.mode == A_WINDOW) {
                     const int32_t pp = tc.p0 + et.wrow, qq = tc.q0 + et.wcol;
-                    if (et.valid && pp < prm.p && qq < prm.q) out_row = ((int64_t)tc.img * prm.p + pp) * prm.q + qq;
+                    if (et.valid && pp < prm.p && qq < prm.q && tc.img < prm.n_img) out_row = ((int64_t)tc.img * prm.p + pp) * prm.q + qq;
                 } else {
                     const int64_t r = (int64_t)tc.m0 + lane_row;
                     if (r < prm.m_total) out_row = r;
@@ -655,8 +752,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (issuer) {
                         const int32_t cbyte = col0 + pbase;
                         if (cbyte < prm.k_out) {
-                            if (prm.mode == A_WINDOW)
-                                ptx::tma_store_4d(&tm_out, my_staging, cbyte, tc.q0, tc.p0, tc.img);
+                            if (prm.mode == A_WINDOW) {
+                                if (tc.img < prm.n_img)   // pair mode pads the tile space with dummy tiles
+                                    ptx::tma_store_4d(&tm_out, my_staging, cbyte, tc.q0, tc.p0, tc.img);
+                            }
                             else
                                 ptx::tma_store_2d(&tm_out, my_staging, cbyte, tc.m0);
                         }
@@ -666,7 +765,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (++sbuf == nbufs) sbuf = 0;
                 }
             }
-            for (uint32_t i = 0; i < n_teams; ++i) it.next(prm);
+            if (prm.pair) it.next(prm);
+            else
+                for (uint32_t i = 0; i < n_teams; ++i) it.next(prm);
         }
         if (issuer && int8_out) ptx::tma_store_wait<0>();
     }
@@ -674,6 +775,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // ---- teardown ----
     ptx::tc_fence_before();
     __syncthreads();
+    // trace mode: every CTA also leaves its own start / end time (its SM's cycle counter) behind the per-tile stamps
+    if (prm.trace != nullptr && threadIdx.x == 0) {
+        long long* cta_times = prm.trace + (size_t)prm.trace_tiles * 16;
+        cta_times[2 * blockIdx.x + 1] = clock64();
+    }
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, prm.tmem_cols);
@@ -803,6 +909,16 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     c.k_blocks = c.cblocks * c.inner;
     c.packed_row_bytes = (size_t)c.k_blocks * c.bkb;
 
+    // ---- pair mode (see IgemmParams::pair): window layers whose filter matrix is too large to stay resident.
+    // N tiles of <= 128 columns leave TMEM room for the two accumulators of a pair, double-buffered.
+    c.pair = 0;
+    if (c.mode == A_WINDOW && !c16 && (size_t)d.k * c.packed_row_bytes > 80u * 1024u && (d.k <= 128 || d.k % 128 == 0) &&
+        d.n * c.row_tiles * c.col_tiles >= 2 && !getenv("LBC_NO_PAIR")) {
+        c.pair = 1;
+        c.bn = d.k <= 128 ? d.k : 128;
+        c.tiles_n = d.k / c.bn;
+    }
+
     // ---- M tiles
     if (c.mode == A_WINDOW) c.tiles_m = d.n * c.row_tiles * c.col_tiles;
     else c.tiles_m = (int32_t)((g.m_total + kBlockM - 1) / kBlockM);
@@ -815,7 +931,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
 
     // ---- accumulator stages and epilogue teams
-    c.n_acc = (4 * c.bn <= 512 && !getenv("LBC_TWO_ACC")) ? 4 : 2;
+    c.n_acc = (4 * c.bn <= 512 && (c.pair || !getenv("LBC_TWO_ACC"))) ? 4 : 2;
     c.team_warps = (c.n_acc == 4 && c.bn <= 64 && !getenv("LBC_BIG_TEAMS")) ? 4 : 8;
     const int n_teams = kEpiWarps / c.team_warps;
 
@@ -834,8 +950,9 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     // blocks per ring stage: group small B blocks (window mode) so one mbarrier round trip feeds several MMAs
     c.tps = 1;
     if (c.mode == A_WINDOW) {
+        const uint32_t cap = c.pair ? 16u * 1024u : tps_cap;   // a pair issues twice the MMAs per block: small stages, deep ring
         for (int t = c.inner; t >= 1; --t)
-            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= tps_cap) { c.tps = t; break; }
+            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= cap) { c.tps = t; break; }
     }
     c.a_stage_bytes = c.tps * c.a_block_bytes;
     c.b_stage_bytes = c.tps * c.b_block_bytes;
@@ -846,12 +963,13 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         const uint32_t box_bytes = (uint32_t)(c.wt * (c.rows_per_tile + ext_h) * c.bkc);
         const uint32_t reach = (uint32_t)((kBlockM + ext_h * c.wt + ext_w + 1) * c.bkc);   // furthest row an MMA reads
         c.win_tx_bytes = box_bytes;
-        c.win_stage_bytes = round_up(std::max(box_bytes, reach), 1024);
+        c.win_sub_bytes = round_up(std::max(box_bytes, reach), 1024);
+        c.win_stage_bytes = c.pair ? 2 * c.win_sub_bytes : c.win_sub_bytes;
     }
     // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.k_blocks * c.b_block_bytes;
-    const bool res_b_ok = c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
+    const bool res_b_ok = !c.pair && c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
     uint32_t stage_bytes = 0;
     bool fits = false;
     for (int pass = 0; pass < 2 && !fits; ++pass)
@@ -884,6 +1002,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         } else if (c.mode == A_WINDOW) {
             if (2 * c.win_stage_bytes + 2 * c.b_stage_bytes > budget) continue;
             stages = ((budget - 2 * c.win_stage_bytes) / c.b_stage_bytes >= 3 && max_stages >= 3) ? 3 : 2;
+            if (c.pair) stages = (int)std::min<uint32_t>(std::min(max_stages, 6), (budget - 2 * c.win_stage_bytes) / c.b_stage_bytes);
             c.win_stages = (int)std::min<uint32_t>(max_win, (budget - stages * c.b_stage_bytes) / c.win_stage_bytes);
             win_total = c.win_stages * c.win_stage_bytes;
             b_region = (uint32_t)stages * c.b_stage_bytes;
@@ -941,6 +1060,13 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     while (cols < (uint32_t)(c.n_acc * c.bn)) cols <<= 1;
     c.tmem_cols = cols;
     c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
+    c.it_imgs = d.n;
+    if (c.pair) {
+        // pad the image radix so that the tiles of one N tile come in whole pairs; CTAs walk pairs
+        if ((c.row_tiles * c.col_tiles * c.it_imgs) & 1) ++c.it_imgs;
+        const int32_t pairs = c.row_tiles * c.col_tiles * c.it_imgs / 2 * c.tiles_n;
+        c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, pairs);
+    }
     if (const char* v = getenv("LBC_MAX_GRID")) c.grid = std::max(1, std::min(c.grid, atoi(v)));   // tests: many tiles per CTA
     *cfg = c;
     return LBC_OK;
@@ -1057,7 +1183,15 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     // digits of the CTA stride in the (img | rt | ct | n_blk) tile numbering
     prm.it_cols = c.mode == A_WINDOW ? c.col_tiles : 1;
     prm.it_rows = c.mode == A_WINDOW ? c.row_tiles : 1;
-    {
+    prm.pair = c.pair; prm.it_imgs = c.it_imgs; prm.win_sub_bytes = c.win_sub_bytes;
+    prm.tile_stride = c.pair ? 2 * c.grid : c.grid;
+    if (c.pair) {   // (n_blk | img | rt | ct), CTA stride = 2 * grid tiles
+        int32_t v = prm.tile_stride;
+        prm.step_ct = v % prm.it_cols; v /= prm.it_cols;
+        prm.step_rt = v % prm.it_rows; v /= prm.it_rows;
+        prm.step_img = v % prm.it_imgs; v /= prm.it_imgs;
+        prm.step_nb = v;
+    } else {
         int32_t v = c.grid;
         prm.step_nb = v % c.tiles_n; v /= c.tiles_n;
         prm.step_ct = v % prm.it_cols; v /= prm.it_cols;
@@ -1096,7 +1230,21 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
             g_attr_set = true;
         }
     }
-    fn<<<c.grid, kNumThreads, c.smem_bytes, stream>>>(l.tm_a, l.tm_b, l.tm_out, prm, ep.bias, ep.scale, y);
+    // programmatic stream serialisation: this kernel's on-chip prologue may overlap the previous kernel's tail; its
+    // griddepcontrol.wait orders every global access after the previous grid (see the kernel)
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)c.grid);
+    lc.blockDim = dim3(kNumThreads);
+    lc.dynamicSmemBytes = c.smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = getenv("LBC_NO_PDL") ? 0 : 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    const int32_t* bias_p = ep.bias;
+    const float* scale_p = ep.scale;
+    LBC_CUDA_TRY(cudaLaunchKernelEx(&lc, fn, l.tm_a, l.tm_b, l.tm_out, prm, bias_p, scale_p, y));
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

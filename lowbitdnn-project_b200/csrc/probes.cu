@@ -16,7 +16,7 @@ constexpr int kProbeThreads = 128;
 __device__ int g_probe_timeout = 0;
 
 // Every CTA: 128x256x128-byte operand tiles in smem (zeros), one thread issues `iters` x 4 MMAs
-// (M=128, N=256, K=32 int8 each) back to back into one TMEM accumulator.  No loads, no epilogue.
+// (M=128, N=256, K=32 int8 each) back to back into one TMEM accumulator (pseudo-random operands).  No loads, no epilogue.
 __global__ void __launch_bounds__(kProbeThreads, 1) mma_i8_peak_kernel(int32_t iters)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -26,8 +26,17 @@ __global__ void __launch_bounds__(kProbeThreads, 1) mma_i8_peak_kernel(int32_t i
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_base_s;
 
-    for (int i = threadIdx.x; i < (128 + kProbeN) * 128 / 16; i += blockDim.x)
-        reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
+    // pseudo-random operand bytes: all-zero operands draw far less power than real data and would let the clocks sit
+    // at boost, overstating what a kernel working on real activations can reach
+    for (int i = threadIdx.x; i < (128 + kProbeN) * 128 / 16; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u + 12345u;
+        int4 v;
+        h ^= h >> 15; h *= 2246822519u; v.x = (int)h;
+        h ^= h >> 13; h *= 3266489917u; v.y = (int)h;
+        h ^= h >> 16; h *= 668265263u;  v.z = (int)h;
+        h ^= h >> 15; h *= 374761393u;  v.w = (int)h;
+        reinterpret_cast<int4*>(smem)[i] = v;
+    }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         ptx::mbar_init(&done_bar, 1);

@@ -397,6 +397,13 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_i8(uint32_t m, uint32_t 
     return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------
+// launch_dependents: the next kernel in the stream (launched with programmatic stream serialisation) may start
+// occupying SMs as they become free.  wait: block until the previous grid has completed and its memory is visible;
+// nothing that touches global memory may come before it.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- misc ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads)
 {

@@ -140,6 +140,9 @@ MULTI_TILE_CASES = [
     D(n=2, h=28, w=28, c=128, k=128, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),   # im2col
     D(n=2, h=40, w=40, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),      # stem
     D(n=2, h=28, w=28, c=24, k=144, r=1, s=1, relu=1),                         # pixel groups, 2 N tiles
+    D(n=3, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # paired tiles, odd tile count (padding image)
+    D(n=3, h=7, w=7, c=64, k=512, r=3, s=3, pad_h=1, pad_w=1),                 # paired tiles, 4 N tiles, 1 tile per image
+    D(n=5, h=14, w=14, c=512, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # paired tiles, 4 channel chunks
 ]
 
 
@@ -150,6 +153,8 @@ def test_many_tiles_per_cta(d, grid, monkeypatch):
     alternating MMA warps and the staging ring all wrap several times (a full-size layer does this on 148 SMs)."""
     monkeypatch.setenv("LBC_MAX_GRID", str(grid))
     assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    if grid == 1 and d.r == 3 and d.c >= 64:
+        assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"    # raw accumulators through the same walk
 
 
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------

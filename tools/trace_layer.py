@@ -39,11 +39,19 @@ def main():
         for _ in range(2):
             plan.run(x, wp, bias, scale, out=y)
         ntile = a.tiles + a.skip
-        buf = torch.zeros(ntile * 16, dtype=torch.int64, device=dev)
+        buf = torch.zeros(ntile * 16 + 2 * 148, dtype=torch.int64, device=dev)
         _capi.check(lib.lbc_debug_set_trace(ctypes.c_void_p(buf.data_ptr()), ntile))
         _, ms = plan.run(x, wp, bias, scale, out=y, timed=True)
         _capi.check(lib.lbc_debug_set_trace(None, 0))
-        t = buf.cpu().numpy().reshape(ntile, 16)
+        raw = buf.cpu().numpy()
+        t = raw[:ntile * 16].reshape(ntile, 16)
+        cta = raw[ntile * 16:].reshape(148, 2)
+        cta = cta[cta[:, 0] > 0]
+        if len(cta):
+            dur = (cta[:, 1] - cta[:, 0]) / 1965.0          # SM cycles -> us at the 1965 MHz boost clock
+            order = np.argsort(dur)
+            print(f"   per-CTA duration (us @1965 MHz): min {dur.min():.1f} median {np.median(dur):.1f} max {dur.max():.1f}; "
+                  f"slowest {[(int(i), round(float(dur[i]), 1)) for i in order[-4:]]} fastest {[(int(i), round(float(dur[i]), 1)) for i in order[:3]]}")
         t0 = t[a.skip][t[a.skip] > 0].min()
         print(f"== {name}: {ms * 1e3:.1f} us | {plan.describe()}")
         print("tile " + " ".join(f"{e:>8s}" for e in EV) + "   | dM(start->done) dE(start->drain) tile-to-tile(M_DONE)")
