@@ -105,6 +105,9 @@ lbc_status  lbc_conv_work(const lbc_conv_desc* d, double* ops, double* bytes);
  * choice, or a specific kind (fails with LBC_ERR_UNSUPPORTED if that kernel cannot run the shape). */
 lbc_status  lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan);
 lbc_status  lbc_conv_plan_destroy(lbc_plan* plan);
+/* Dry run of the planner for a B200 with `sm_count` SMs (0 = 148): no CUDA call, usable without a GPU.  Reports the
+ * kernel kind and the planner's description (tile, K chunk, stages, modes, shared memory) or the reason it refuses. */
+lbc_status  lbc_conv_plan_dry(const lbc_conv_desc* d, int32_t force, int32_t sm_count, int32_t* kind, char* buf, size_t buf_len);
 lbc_status  lbc_conv_plan_kernel(const lbc_plan* plan, int32_t* kind);           /* lbc_kernel_kind   */
 lbc_status  lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_len); /* human-readable */
 /* Number of kernels one lbc_conv_run() launches (for launch accounting in the harness). */

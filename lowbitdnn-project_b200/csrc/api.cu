@@ -240,15 +240,14 @@ lbc_status lbc_conv_work(const lbc_conv_desc* d, double* ops, double* bytes)
     return LBC_OK;
 }
 
-lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan)
+// The planner proper: pure host logic for a given device description.  `dry` plans without touching CUDA (no scratch
+// allocation): lbc_conv_plan_dry() uses it to make every tiling decision checkable on a machine without a GPU.
+static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const DeviceInfo& dev, bool dry, lbc_plan** plan)
 {
     LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan out-pointer");
     *plan = nullptr;
     ConvGeom g;
     lbc_status st = make_geom(d, &g);
-    if (st != LBC_OK) return st;
-    DeviceInfo dev;
-    st = current_device(&dev);
     if (st != LBC_OK) return st;
 
     std::string why;
@@ -340,7 +339,7 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
         p->stem_sh = d->stride_h;
         p->stem_sw = d->stride_w;
         const size_t bytes = (size_t)gi.d.n * gi.d.h * gi.d.w * 16;
-        if (cudaMalloc(&p->stem_x, bytes) != cudaSuccess) {
+        if (!dry && cudaMalloc(&p->stem_x, bytes) != cudaSuccess) {
             cudaGetLastError();
             delete p;
             set_error("small-C path: cannot allocate the %zu-byte transformed input", bytes);
@@ -349,6 +348,34 @@ lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan*
     }
     *plan = p;
     return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan)
+{
+    LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan out-pointer");
+    *plan = nullptr;
+    DeviceInfo dev;
+    lbc_status st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    return plan_build(d, force, dev, false, plan);
+}
+
+lbc_status lbc_conv_plan_dry(const lbc_conv_desc* d, int32_t force, int32_t sm_count, int32_t* kind, char* buf, size_t buf_len)
+{
+    DeviceInfo dev;
+    dev.device = 0;
+    dev.sm_count = sm_count > 0 ? sm_count : 148;
+    dev.cc_major = 10;
+    dev.cc_minor = 0;
+    dev.hbm_bytes = (size_t)180 << 30;
+    dev.driver_version = 13000;
+    lbc_plan* p = nullptr;
+    lbc_status st = plan_build(d, force, dev, true, &p);
+    if (st != LBC_OK) return st;
+    if (kind) *kind = p->kind;
+    if (buf && buf_len) st = lbc_conv_plan_describe(p, buf, buf_len);
+    delete p;
+    return st;
 }
 
 lbc_status lbc_conv_plan_destroy(lbc_plan* plan)

@@ -727,6 +727,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
                 const int32_t pbase = pnl * pcols;
                 uint8_t* my_staging = team_staging + sbuf * panel_smem;
+                if (nbufs == 1 && int8_out) {
+                    // a single staging panel (shared memory is tight): its previous store must have read it out
+                    if (issuer) ptx::tma_store_wait_read<0>();
+                    ptx::named_bar_sync(bar_id, team_threads);
+                }
                 if (int8_out)
                     epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
                                     swz_mask, lo, y32, out_row, col0);
@@ -746,7 +751,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     // passes the barrier below: with nbufs buffers that is the store issued nbufs-1 panels ago
                     if (issuer) {
                         if (nbufs >= 3) ptx::tma_store_wait_read<1>();
-                        else ptx::tma_store_wait_read<0>();
+                        else if (nbufs == 2) ptx::tma_store_wait_read<0>();
                     }
                     ptx::named_bar_sync(bar_id, team_threads);
                     if (issuer) {
@@ -857,7 +862,16 @@ bool igemm_supported(const ConvGeom& g, std::string* why)
     return true;
 }
 
+static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, bool allow_pair, IgemmConfig* cfg);
+
 lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConfig* cfg)
+{
+    // pair mode doubles the window footprint: where that does not fit (very wide rows), plan without it
+    if (make_config_impl(g, dev, true, cfg) == LBC_OK) return LBC_OK;
+    return make_config_impl(g, dev, false, cfg);
+}
+
+static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, bool allow_pair, IgemmConfig* cfg)
 {
     const lbc_conv_desc& d = g.d;
     IgemmConfig c{};
@@ -913,7 +927,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     // N tiles of <= 128 columns leave TMEM room for the two accumulators of a pair, double-buffered.
     c.pair = 0;
     if (c.mode == A_WINDOW && !c16 && (size_t)d.k * c.packed_row_bytes > 80u * 1024u && (d.k <= 128 || d.k % 128 == 0) &&
-        d.n * c.row_tiles * c.col_tiles >= 2 && !getenv("LBC_NO_PAIR")) {
+        d.n * c.row_tiles * c.col_tiles >= 2 && allow_pair && getenv("LBC_PAIR")) {   // opt-in: measured gains are marginal (r01)
         c.pair = 1;
         c.bn = d.k <= 128 ? d.k : 128;
         c.tiles_n = d.k / c.bn;
@@ -946,13 +960,18 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     const uint32_t tps_cap = (uint32_t)env_int("LBC_TPS_KB", 48) * 1024u;
     const int max_win = std::min(kMaxWinStages, env_int("LBC_MAX_WIN", kMaxWinStages));
     const int max_stages = std::min(kMaxStages, env_int("LBC_MAX_STAGES", kMaxStages));
-    const int max_bufs = std::max(2, std::min(3, env_int("LBC_STAGE_BUFS", 3)));
+    const int max_bufs = std::max(1, std::min(3, env_int("LBC_STAGE_BUFS", 3)));
     // blocks per ring stage: group small B blocks (window mode) so one mbarrier round trip feeds several MMAs
+    bool fits = false;
+    uint32_t stage_bytes = 0;
+    // a pair issues twice the MMAs per block: small stages, deep ring; otherwise try the large grouping first and fall
+    // back to single blocks when shared memory is tight (wide windows)
+    const uint32_t caps[2] = {c.pair ? 16u * 1024u : tps_cap, 16u * 1024u};
+    for (int ci = 0; ci < 2 && !fits; ++ci) {
     c.tps = 1;
     if (c.mode == A_WINDOW) {
-        const uint32_t cap = c.pair ? 16u * 1024u : tps_cap;   // a pair issues twice the MMAs per block: small stages, deep ring
         for (int t = c.inner; t >= 1; --t)
-            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= cap) { c.tps = t; break; }
+            if (c.inner % t == 0 && (uint32_t)t * c.b_block_bytes <= caps[ci]) { c.tps = t; break; }
     }
     c.a_stage_bytes = c.tps * c.a_block_bytes;
     c.b_stage_bytes = c.tps * c.b_block_bytes;
@@ -970,10 +989,8 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.k_blocks * c.b_block_bytes;
     const bool res_b_ok = !c.pair && c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
-    uint32_t stage_bytes = 0;
-    bool fits = false;
     for (int pass = 0; pass < 2 && !fits; ++pass)
-    for (int bufs = max_bufs; bufs >= 2 && !fits; --bufs) {   // three staging panels per team when they fit, else two
+    for (int bufs = max_bufs; bufs >= 1 && !fits; --bufs) {   // three staging panels per team when they fit, else two, else one
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
         if (pass == 0 && !res_b_ok) break;
         c.stage_bufs = bufs;
@@ -997,8 +1014,8 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
                 stages = (int)std::min<uint32_t>(max_stages, (budget - b_region) / c.a_stage_bytes);
                 if (stages < (bufs == 3 ? 5 : 3)) continue;
             }
-        } else if (bufs == 3) {
-            continue;   // streaming B: operand depth matters more than a third staging panel
+        } else if (bufs == 3 || (bufs == 2 && c.bn > 128 && c.k_blocks > 8 && !c.pair)) {
+            continue;   // streaming B with a long K loop: operand depth matters more than extra staging panels
         } else if (c.mode == A_WINDOW) {
             if (2 * c.win_stage_bytes + 2 * c.b_stage_bytes > budget) continue;
             stages = ((budget - 2 * c.win_stage_bytes) / c.b_stage_bytes >= 3 && max_stages >= 3) ? 3 : 2;
@@ -1019,6 +1036,7 @@ lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConf
         c.smem_bytes = c.off_ctl + ctl_bytes;
         fits = c.smem_bytes <= 227 * 1024;
     }
+    }   // tps candidates
     LBC_REQUIRE(fits, LBC_ERR_UNSUPPORTED, "igemm: operand rings do not fit in shared memory");
     // Two MMA-issuing warps (alternate tiles, half of the A-side ring each) where a single warp's issue rate is the
     // bound: narrow N tiles with a resident filter matrix.  Wide tiles (128 cycles per MMA) gain nothing.

@@ -78,3 +78,27 @@ def test_product_path_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(root, f)).read()
                 assert not pat.search(src), f"{os.path.join(root, f)} reaches into oracle/"
+
+
+def test_planner_dry_run_covers_every_benchmark_layer(lbc):
+    """Every layer of the five benchmark configurations gets a plan (tile, stages, shared memory all fit) and the kernel
+    family the design assigns to it - checked through the host-only dry planner, no GPU needed."""
+    import ctypes
+    from collections import Counter
+    lib = lbc.load_library()
+    want = {"resnet50": {"igemm_tc": 52, "stem_tc": 1}, "resnet18": {"igemm_tc": 19, "stem_tc": 1},
+            "vgg16": {"igemm_tc": 12, "stem_tc": 1}, "mobilenet_v2": {"igemm_tc": 34, "depthwise": 17, "stem_tc": 1},
+            "single_3x3": {"igemm_tc": 1}}
+    for net, kinds in want.items():
+        got = Counter()
+        for name, d, _ in lbc.networks.NETWORKS[net](lbc.networks.DEFAULT_BATCH[net]):
+            kind = ctypes.c_int32()
+            buf = ctypes.create_string_buffer(512)
+            cd = d.c_struct()
+            st = lib.lbc_conv_plan_dry(ctypes.byref(cd), 0, 148, ctypes.byref(kind), buf, 512)
+            assert st == 0, (net, name, lib.lbc_last_error_string().decode())
+            got[lbc._capi.KERNEL_NAMES[kind.value]] += 1
+            text = buf.value.decode()
+            if "smem" in text:
+                assert int(text.split("smem ")[1].split()[0]) <= 227 * 1024, text
+        assert dict(got) == kinds, (net, dict(got))

@@ -92,6 +92,7 @@ IGEMM_CASES = [
     D(n=2, h=33, w=115, c=16, k=64, r=4, s=4, relu=1),                         # the space-to-depth'd 7x7 stem shape
     D(n=2, h=20, w=57, c=16, k=32, r=2, s=2),
     D(n=1, h=8, w=40, c=64, k=64, r=1, s=3, pad_h=0, pad_w=1),
+    D(n=1, h=6, w=112, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1),     # VGG conv2_2 rows: windows too wide for pair mode
 ]
 
 
@@ -152,6 +153,9 @@ def test_many_tiles_per_cta(d, grid, monkeypatch):
     """Cap the persistent grid so every CTA walks many tiles: ring/window phases, TMEM accumulator reuse, the
     alternating MMA warps and the staging ring all wrap several times (a full-size layer does this on 148 SMs)."""
     monkeypatch.setenv("LBC_MAX_GRID", str(grid))
+    monkeypatch.setenv("LBC_PAIR", "1")      # the opt-in paired-tile mode stays covered (cases marked "paired tiles")
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    monkeypatch.delenv("LBC_PAIR")
     assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
     if grid == 1 and d.r == 3 and d.c >= 64:
         assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"    # raw accumulators through the same walk
