@@ -103,29 +103,71 @@ struct StemXformParams {
     int32_t n, h, w, c, hs, ws, sh, sw, pad_h, pad_w;
 };
 
-__global__ void __launch_bounds__(256) stem_xform_kernel(StemXformParams p, const int8_t* __restrict__ x,
+// grid (ceil(Ws / 128), ceil(Hs / kXformRows), N): one thread = one column of kXformRows 16-byte output pixels; no
+// divisions, and the loads of several output rows are in flight together (a one-pixel-per-thread version was bound by
+// block turnover: every block was a single load -> store dependency chain).  A warp reads sw*C*32 consecutive bytes
+// of each input row it needs (192 for the 7x7/stride-2 RGB stem) and writes 512 consecutive bytes per output row.
+constexpr int kXformRows = 8;
+
+// C, SH, SW > 0: compile-time channel count and strides (every loop unrolls, every byte slot is a constant: ~50
+// instructions per output pixel instead of ~470 with run-time bounds); C == 0: generic run-time version.
+template <int C, int SH, int SW>
+__global__ void __launch_bounds__(128) stem_xform_kernel(StemXformParams p, const int8_t* __restrict__ x,
                                                          uint4* __restrict__ out)
 {
-    const int64_t total = (int64_t)p.n * p.hs * p.ws;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t ws = (int32_t)(i % p.ws);
-        const int32_t hs = (int32_t)((i / p.ws) % p.hs);
-        const int32_t n = (int32_t)(i / ((int64_t)p.ws * p.hs));
-        uint32_t v[4] = {0, 0, 0, 0};
-        int slot = 0;
-        for (int dr = 0; dr < p.sh; ++dr) {
-            const int32_t ih = hs * p.sh + dr - p.pad_h;
-            for (int ds = 0; ds < p.sw; ++ds) {
-                const int32_t iw = ws * p.sw + ds - p.pad_w;
-                const bool in = ih >= 0 && ih < p.h && iw >= 0 && iw < p.w;
-                const int8_t* src = x + (((int64_t)n * p.h + ih) * p.w + iw) * p.c;
-                for (int c = 0; c < p.c; ++c, ++slot) {
-                    const uint32_t b = in ? (uint32_t)(uint8_t)src[c] : 0u;
-                    v[slot >> 2] |= b << (8 * (slot & 3));
+    const int32_t ws = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (ws >= p.ws) return;
+    const int32_t hs0 = (int32_t)blockIdx.y * kXformRows, n = (int32_t)blockIdx.z;
+    const int32_t pc = C ? C : p.c, psh = C ? SH : p.sh, psw = C ? SW : p.sw;
+    const int32_t iw0 = ws * psw - p.pad_w;
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(x) + (int64_t)n * p.h * p.w * pc;
+    uint4* dst = out + ((int64_t)n * p.hs + hs0) * p.ws + ws;
+#pragma unroll 4
+    for (int j = 0; j < kXformRows; ++j) {
+        const int32_t hs = hs0 + j;
+        if (hs >= p.hs) break;
+        if (C) {
+            uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int dr = 0; dr < (C ? SH : 1); ++dr) {
+                const int32_t ih = hs * SH + dr - p.pad_h;
+                const bool row_in = ih >= 0 && ih < p.h;
+                const uint8_t* row = img + (row_in ? ih : 0) * (p.w * C);
+#pragma unroll
+                for (int ds = 0; ds < (C ? SW : 1); ++ds) {
+                    const int32_t iw = iw0 + ds;
+                    const bool in = row_in && iw >= 0 && iw < p.w;
+                    const uint8_t* src = row + (in ? iw : 0) * C;
+#pragma unroll
+                    for (int c = 0; c < (C ? C : 1); ++c) {
+                        const int slot = (dr * SW + ds) * C + c;
+                        const uint32_t b = in ? (uint32_t)__ldg(src + c) : 0u;
+                        v[slot >> 2] |= b << (8 * (slot & 3));
+                    }
                 }
             }
+            dst[(int64_t)j * p.ws] = make_uint4(v[0], v[1], v[2], v[3]);
+        } else {
+            // the 16 output bytes are assembled in two 64-bit registers (an indexed array would live in local memory)
+            uint64_t lo = 0, hi = 0;
+            int slot = 0;
+            for (int dr = 0; dr < psh; ++dr) {
+                const int32_t ih = hs * psh + dr - p.pad_h;
+                const bool row_in = ih >= 0 && ih < p.h;
+                const uint8_t* row = img + (row_in ? ih : 0) * (p.w * pc);
+                for (int ds = 0; ds < psw; ++ds) {
+                    const int32_t iw = iw0 + ds;
+                    const bool in = row_in && iw >= 0 && iw < p.w;
+                    const uint8_t* src = row + (in ? iw : 0) * pc;
+                    for (int c = 0; c < pc; ++c, ++slot) {
+                        const uint64_t b = in ? (uint64_t)__ldg(src + c) : 0ull;
+                        if (slot < 8) lo |= b << (8 * slot);
+                        else hi |= b << (8 * (slot - 8));
+                    }
+                }
+            }
+            dst[(int64_t)j * p.ws] = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
         }
-        out[i] = make_uint4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -209,7 +251,14 @@ lbc_status launch_stem_xform(const int8_t* x, void* out, int32_t n, int32_t h, i
                              int32_t ws, int32_t sh, int32_t sw, int32_t pad_h, int32_t pad_w, cudaStream_t stream)
 {
     StemXformParams p{n, h, w, c, hs, ws, sh, sw, pad_h, pad_w};
-    stem_xform_kernel<<<grid_for((int64_t)n * hs * ws), 256, 0, stream>>>(p, x, reinterpret_cast<uint4*>(out));
+    LBC_REQUIRE(hs <= 65535 && n <= 65535, LBC_ERR_UNSUPPORTED, "small-C path: image height / batch beyond the grid limits");
+    const dim3 grid((unsigned)((ws + 127) / 128), (unsigned)((hs + kXformRows - 1) / kXformRows), (unsigned)n);
+    uint4* o = reinterpret_cast<uint4*>(out);
+    if (c == 3 && sh == 2 && sw == 2) stem_xform_kernel<3, 2, 2><<<grid, 128, 0, stream>>>(p, x, o);
+    else if (c == 3 && sh == 1 && sw == 1) stem_xform_kernel<3, 1, 1><<<grid, 128, 0, stream>>>(p, x, o);
+    else if (c == 4 && sh == 2 && sw == 2) stem_xform_kernel<4, 2, 2><<<grid, 128, 0, stream>>>(p, x, o);
+    else if (c == 1 && sh == 1 && sw == 1) stem_xform_kernel<1, 1, 1><<<grid, 128, 0, stream>>>(p, x, o);
+    else stem_xform_kernel<0, 0, 0><<<grid, 128, 0, stream>>>(p, x, o);
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }
