@@ -138,6 +138,7 @@ struct ResolvedLaunch {
     EpilogueParams ep{};
     void* y = nullptr;
     IgemmLaunch ig{};
+    DwLaunch dw{};
 };
 
 lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const int32_t* bias, const float* scale,
@@ -158,6 +159,7 @@ lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const i
         return igemm_encode(plan->pw_factor > 1 ? plan->g_inner : plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, y, &out->ig);
     if (plan->kind == LBC_KERNEL_STEM_TC)
         return igemm_encode(plan->g_inner, plan->cfg, plan->dev, (const int8_t*)plan->stem_x, (const int8_t*)w, y, &out->ig);
+    if (plan->kind == LBC_KERNEL_DEPTHWISE) return depthwise_encode(plan->g, x, &out->dw);
     return LBC_OK;
 }
 
@@ -173,7 +175,7 @@ lbc_status launch(const ResolvedLaunch& l, cudaStream_t stream)
             if (st != LBC_OK) return st;
             return igemm_launch(p->g_inner, l.ig, l.ep, l.y, stream);
         }
-        case LBC_KERNEL_DEPTHWISE: return launch_depthwise(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
+        case LBC_KERNEL_DEPTHWISE: return launch_depthwise(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, &l.dw, stream);
         case LBC_KERNEL_DIRECT: return launch_direct_conv(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
         default: set_error("plan has unknown kernel kind %d", p->kind); return LBC_ERR_UNSUPPORTED;
     }

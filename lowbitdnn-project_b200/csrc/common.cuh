@@ -64,8 +64,18 @@ lbc_status launch_direct_conv(const ConvGeom& g, const int8_t* x, const int8_t* 
                               void* y, cudaStream_t stream);
 
 // depthwise.cu — groups == C == K; weights packed [R][S][C].
+// The 3x3 kernel stages input tiles in shared memory with TMA when the shape allows it (DwLaunch::tiled); the launch
+// descriptor (tensor map over x) is built once per (plan, x) by depthwise_encode.
+struct DwLaunch {
+    int32_t tiled = 0;           // 1: TMA-staged tile kernel, 0: direct global-memory kernel
+    CUtensorMap tm_x;
+    int32_t cc, th, tq, nb, tw, in_h, in_w, tiles_c, tiles_q, tiles_p, tiles_n;
+    uint32_t tile_bytes;
+};
+lbc_status depthwise_encode(const ConvGeom& g, const int8_t* x, DwLaunch* out);
 lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
-                            void* y, cudaStream_t stream);
+                            void* y, const DwLaunch* dw, cudaStream_t stream);
+lbc_status encode_tiled_u8_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4]);
 
 // igemm_tc.cu — tcgen05 implicit GEMM.
 struct IgemmConfig {

@@ -20,6 +20,9 @@
 // Replaces nothing in the reference (it has no depthwise path: `groups` is accepted but never forwarded,
 // python/qtorch/cpp/conv2d.cuh:96,140); the shape family comes from BASELINE.json config 5 (MobileNetV2).
 #include "common.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
 
 namespace lbc {
 
@@ -225,6 +228,156 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, con
     }
 }
 
+// ---- TMA-staged 3x3 kernel ---------------------------------------------------------------------------------
+// The direct kernel above is latency-bound (ncu, r01: 48 % issue utilisation, every loop iteration waits on its own
+// global loads).  Here a CTA stages one input tile - nb images x (th*S+2) rows x (tq*S+2) columns x cc channels - in
+// shared memory with ONE rank-4 TMA load (out-of-image elements arrive as zeros, so there is no padding logic at all),
+// several CTAs per SM keep ~100 KB of loads in flight, and the arithmetic is the same row-packed dp4a scheme reading
+// shared memory with constant offsets.
+struct DwTiledParams {
+    int32_t n, p, q, cq_total;     // output extents, C / 4
+    int32_t cc, ccq;               // channels of a tile, / 4
+    int32_t th, tq, nb, tw;        // output rows / cols / images per tile, strip width
+    int32_t in_h, in_w;            // input rows / cols of a tile
+    int32_t tiles_c, tiles_q, tiles_p;
+    int32_t pad_h, pad_w;
+    int32_t strips, row_groups;    // per tile
+    int32_t relu, out_mode;
+    uint32_t tile_bytes;
+};
+
+__device__ int g_dw_timeout = 0;
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) depthwise3x3_tiled_kernel(const __grid_constant__ CUtensorMap tm_x, const DwTiledParams g,
+                                                                 const int8_t* __restrict__ w_rsc,
+                                                                 const int32_t* __restrict__ bias,
+                                                                 const float* __restrict__ scale, void* __restrict__ y)
+{
+    constexpr int ROWS = (STRIDE == 1) ? 2 : 1;
+    constexpr int IN_ROWS = (STRIDE == 1) ? 4 : 3;
+    extern __shared__ __align__(128) uint8_t tile[];
+    __shared__ uint64_t bar;
+
+    // tile coordinates
+    uint32_t t = blockIdx.x;
+    const int32_t tc = (int32_t)(t % (uint32_t)g.tiles_c); t /= (uint32_t)g.tiles_c;
+    const int32_t tq_i = (int32_t)(t % (uint32_t)g.tiles_q); t /= (uint32_t)g.tiles_q;
+    const int32_t tp_i = (int32_t)(t % (uint32_t)g.tiles_p); t /= (uint32_t)g.tiles_p;
+    const int32_t n0 = (int32_t)t * g.nb, p0 = tp_i * g.th, q0 = tq_i * g.tq, c0 = tc * g.cc;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&bar, 1);
+        ptx::fence_barrier_init();
+        ptx::mbar_expect_tx(&bar, g.tile_bytes);
+        ptx::tma_load_4d(tile, &tm_x, &bar, c0, q0 * STRIDE - g.pad_w, p0 * STRIDE - g.pad_h, n0);
+    }
+    __syncthreads();
+    ptx::mbar_wait(&bar, 0, &g_dw_timeout);
+
+    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+    const float lo = g.relu ? 0.0f : -128.0f;
+    uint32_t* y8 = reinterpret_cast<uint32_t*>(y);
+    int4* y32 = reinterpret_cast<int4*>(y);
+    const int32_t items = g.nb * g.row_groups * g.strips * g.ccq;
+    for (int32_t item = (int32_t)threadIdx.x; item < items; item += (int32_t)blockDim.x) {
+        uint32_t r = (uint32_t)item;
+        const int32_t cqi = (int32_t)(r % (uint32_t)g.ccq); r /= (uint32_t)g.ccq;
+        const int32_t strip = (int32_t)(r % (uint32_t)g.strips); r /= (uint32_t)g.strips;
+        const int32_t rg = (int32_t)(r % (uint32_t)g.row_groups);
+        const int32_t img = (int32_t)(r / (uint32_t)g.row_groups);
+        const int32_t n = n0 + img, pl = rg * ROWS, ql0 = strip * g.tw;
+        const int32_t pg = p0 + pl;                       // global output row of the (first) row of this item
+        if (n >= g.n || pg >= g.p || q0 + ql0 >= g.q) continue;
+        const int32_t cg4 = tc * g.ccq + cqi;             // global channel quad
+        const int32_t ch0 = cg4 * 4;
+
+        // filter columns (see depthwise3x3_kernel); reloaded per item: keeping them across items (a thread bound to
+        // one channel quad) measured slower on the stride-2 layers (r01)
+        uint32_t wa[3][4], wb[3][4];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (0 * 3 + s) * (g.cq_total * 4) + ch0));
+            const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (1 * 3 + s) * (g.cq_total * 4) + ch0));
+            const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(w_rsc + (2 * 3 + s) * (g.cq_total * 4) + ch0));
+            rows_to_channels<false>(a, b, c, 0u, wa[s]);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                wa[s][ch] &= 0x00ffffffu;
+                wb[s][ch] = wa[s][ch] << 8;
+            }
+        }
+        int32_t bi[4] = {0, 0, 0, 0};
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias) {
+            const int4 b = __ldg(reinterpret_cast<const int4*>(bias + ch0));
+            bi[0] = b.x; bi[1] = b.y; bi[2] = b.z; bi[3] = b.w;
+        }
+        if (g.out_mode == LBC_OUT_INT8) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + ch0));
+            sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
+        }
+        // shared-memory word offset of (img, input row pl*S, input col ql0*S, this channel quad)
+        const uint32_t row_words = (uint32_t)(g.in_w * g.ccq);
+        const uint32_t base = ((uint32_t)(img * g.in_h + pl * STRIDE) * (uint32_t)g.in_w + (uint32_t)(ql0 * STRIDE)) * (uint32_t)g.ccq + (uint32_t)cqi;
+        auto load_col = [&](int32_t col, uint32_t(&v)[4]) {
+            const uint32_t o = base + (uint32_t)col * (uint32_t)g.ccq;
+            uint32_t rw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int rr = 0; rr < IN_ROWS; ++rr) rw[rr] = tile32[o + (uint32_t)rr * row_words];
+            rows_to_channels<(IN_ROWS == 4)>(rw[0], rw[1], rw[2], rw[3], v);
+        };
+        const bool row1 = (ROWS == 2) && (pg + 1 < g.p) && (pl + 1 < g.th);
+        const uint32_t yoff0 = ((uint32_t)(n * g.p + pg) * (uint32_t)g.q + (uint32_t)(q0 + ql0)) * (uint32_t)g.cq_total + (uint32_t)cg4;
+        const uint32_t yoff1 = yoff0 + (uint32_t)g.q * (uint32_t)g.cq_total;
+        auto emit = [&](const int32_t(&acc)[4], uint32_t o) {
+            if (g.out_mode == LBC_OUT_INT32) y32[o] = make_int4(acc[0], acc[1], acc[2], acc[3]);
+            else y8[o] = pack4_sat_s8(requant_s32(acc[0], 0, sc[0], lo), requant_s32(acc[1], 0, sc[1], lo),
+                                      requant_s32(acc[2], 0, sc[2], lo), requant_s32(acc[3], 0, sc[3], lo));
+        };
+        auto compute = [&](const uint32_t(&va)[4], const uint32_t(&vb)[4], const uint32_t(&vc)[4], int32_t j) {
+            int32_t a0[4], a1[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                a0[ch] = __dp4a((int32_t)va[ch], (int32_t)wa[0][ch], bi[ch]);
+                a0[ch] = __dp4a((int32_t)vb[ch], (int32_t)wa[1][ch], a0[ch]);
+                a0[ch] = __dp4a((int32_t)vc[ch], (int32_t)wa[2][ch], a0[ch]);
+                if (ROWS == 2) {
+                    a1[ch] = __dp4a((int32_t)va[ch], (int32_t)wb[0][ch], bi[ch]);
+                    a1[ch] = __dp4a((int32_t)vb[ch], (int32_t)wb[1][ch], a1[ch]);
+                    a1[ch] = __dp4a((int32_t)vc[ch], (int32_t)wb[2][ch], a1[ch]);
+                }
+            }
+            const uint32_t qo = (uint32_t)j * (uint32_t)g.cq_total;
+            emit(a0, yoff0 + qo);
+            if (ROWS == 2 && row1) emit(a1, yoff1 + qo);
+        };
+        const int32_t jn = min(g.tw, g.q - (q0 + ql0));     // output columns of this strip inside the image
+        uint32_t v0[4], v1[4], v2[4];
+        load_col(0, v0);
+        if (STRIDE == 1) {
+            load_col(1, v1);
+            for (int32_t j = 0; j < jn; j += 3) {
+                load_col(j + 2, v2);
+                compute(v0, v1, v2, j);
+                if (j + 1 < jn) { load_col(j + 3, v0); compute(v1, v2, v0, j + 1); }
+                if (j + 2 < jn) { load_col(j + 4, v1); compute(v2, v0, v1, j + 2); }
+            }
+        } else {
+            for (int32_t j = 0; j < jn; j += 2) {
+                load_col(2 * j + 1, v1);
+                load_col(2 * j + 2, v2);
+                compute(v0, v1, v2, j);
+                if (j + 1 < jn) {
+                    load_col(2 * j + 3, v1);
+                    load_col(2 * j + 4, v0);
+                    compute(v2, v1, v0, j + 1);
+                }
+            }
+        }
+    }
+}
+
 // ---- generic depthwise (any R, S, stride, dilation): one thread = one output pixel x 4 channels ------------
 struct DwGenericParams {
     int32_t n, h, w, c, r, s, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, p, q, cq;
@@ -288,10 +441,93 @@ int32_t pick_strip(int32_t q)
 
 }  // namespace
 
-lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
-                            void* y, cudaStream_t stream)
+// Tile geometry of the TMA-staged kernel; tiled == 0 when the shape does not qualify.
+lbc_status depthwise_encode(const ConvGeom& g, const int8_t* x, DwLaunch* out)
 {
     const lbc_conv_desc& d = g.d;
+    *out = DwLaunch{};
+    const bool fast = d.r == 3 && d.s == 3 && d.dil_h == 1 && d.dil_w == 1 && d.stride_h == d.stride_w &&
+                      (d.stride_h == 1 || d.stride_h == 2) && d.c % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                      (int64_t)d.n * d.h * d.w * d.c < (1ll << 32) && g.m_total * d.c < (1ll << 32) && !getenv("LBC_DW_DIRECT");
+    if (!fast) return LBC_OK;
+    const int S = d.stride_h, rows = S == 1 ? 2 : 1;
+    DwLaunch l{};
+    // channels per tile: the largest multiple of 16 that divides C, up to 128
+    l.cc = 16;
+    for (int c = 128; c >= 16; c -= 16)
+        if (d.c % c == 0) { l.cc = c; break; }
+    const int ccq = l.cc / 4;
+    // strips of 7 or 8 output columns, up to 4 strips (28..32 columns) per tile
+    l.tw = (g.q % 7 == 0) ? 7 : (g.q < 8 ? g.q : 8);
+    const int strips = std::min(4, (g.q + l.tw - 1) / l.tw);
+    l.tq = strips * l.tw;
+    // row groups: aim at ~3 passes of the 256 threads over the tile's work items, within the image
+    const int rg_img = (g.p + rows - 1) / rows;
+    int rg = std::max(1, std::min(rg_img, 768 / (strips * ccq)));
+    l.th = rg * rows;
+    l.in_w = (l.tq - 1) * S + 3;
+    l.in_h = (l.th - 1) * S + 3;
+    // small images: several images per tile so that the CTA has work for all its threads
+    l.nb = 1;
+    if (rg >= rg_img && strips * l.tw >= g.q) {
+        const int items = rg * strips * ccq;
+        l.nb = std::max(1, std::min(std::min(d.n, 8), 512 / std::max(1, items)));
+    }
+    while (l.nb > 1 && (size_t)l.nb * l.in_h * l.in_w * l.cc > 96u * 1024u) --l.nb;
+    while (rg > 1 && (size_t)l.nb * l.in_h * l.in_w * l.cc > 96u * 1024u) {
+        --rg;
+        l.th = rg * rows;
+        l.in_h = (l.th - 1) * S + 3;
+    }
+    l.tile_bytes = (uint32_t)((size_t)l.nb * l.in_h * l.in_w * l.cc);
+    if (l.tile_bytes > 96u * 1024u || l.in_w > 256 || l.in_h > 256) return LBC_OK;   // direct kernel
+    l.tiles_c = d.c / l.cc;
+    l.tiles_q = (g.q + l.tq - 1) / l.tq;
+    l.tiles_p = (g.p + l.th - 1) / l.th;
+    l.tiles_n = (d.n + l.nb - 1) / l.nb;
+    if ((int64_t)l.tiles_c * l.tiles_q * l.tiles_p * l.tiles_n >= (1ll << 31)) return LBC_OK;
+    const uint64_t dims[4] = {(uint64_t)d.c, (uint64_t)d.w, (uint64_t)d.h, (uint64_t)d.n};
+    const uint32_t box[4] = {(uint32_t)l.cc, (uint32_t)l.in_w, (uint32_t)l.in_h, (uint32_t)l.nb};
+    lbc_status st = encode_tiled_u8_4d(&l.tm_x, x, dims, box);
+    if (st != LBC_OK) return st;
+    l.tiled = 1;
+    *out = l;
+    return LBC_OK;
+}
+
+lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
+                            void* y, const DwLaunch* dw, cudaStream_t stream)
+{
+    const lbc_conv_desc& d = g.d;
+    if (dw && dw->tiled) {
+        LBC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_rsc) & 3) == 0, LBC_ERR_INVALID_ARG,
+                    "depthwise: w must be 4-byte aligned and y 16-byte aligned");
+        DwTiledParams p{};
+        p.n = d.n; p.p = g.p; p.q = g.q; p.cq_total = d.c / 4;
+        p.cc = dw->cc; p.ccq = dw->cc / 4;
+        p.th = dw->th; p.tq = dw->tq; p.nb = dw->nb; p.tw = dw->tw; p.in_h = dw->in_h; p.in_w = dw->in_w;
+        p.tiles_c = dw->tiles_c; p.tiles_q = dw->tiles_q; p.tiles_p = dw->tiles_p;
+        p.pad_h = d.pad_h; p.pad_w = d.pad_w;
+        p.strips = dw->tq / dw->tw;
+        p.row_groups = dw->th / (d.stride_h == 1 ? 2 : 1);
+        p.relu = ep.relu; p.out_mode = ep.out_mode;
+        p.tile_bytes = dw->tile_bytes;
+        const unsigned grid = (unsigned)(dw->tiles_c * dw->tiles_q * dw->tiles_p * dw->tiles_n);
+        const size_t smem = dw->tile_bytes;
+        const unsigned block = 256;
+        static bool attr_set = false;
+        if (!attr_set) {
+            LBC_CUDA_TRY(cudaFuncSetAttribute(depthwise3x3_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            LBC_CUDA_TRY(cudaFuncSetAttribute(depthwise3x3_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = true;
+        }
+        if (d.stride_h == 1)
+            depthwise3x3_tiled_kernel<1><<<grid, block, smem, stream>>>(dw->tm_x, p, w_rsc, ep.bias, ep.scale, y);
+        else
+            depthwise3x3_tiled_kernel<2><<<grid, block, smem, stream>>>(dw->tm_x, p, w_rsc, ep.bias, ep.scale, y);
+        LBC_CUDA_TRY(cudaGetLastError());
+        return LBC_OK;
+    }
     LBC_REQUIRE(d.groups == d.c && d.k == d.c && (d.c % 4) == 0, LBC_ERR_UNSUPPORTED,
                 "depthwise kernel needs groups == C == K and C %% 4 == 0");
     LBC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&

@@ -848,6 +848,22 @@ uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+// rank-4 (C, W, H, N) uint8 tiled map without swizzle, out-of-bounds elements read as zero (used by depthwise.cu)
+lbc_status encode_tiled_u8_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4])
+{
+    lbc_status st = resolve_driver_entry_points();
+    if (st != LBC_OK) return st;
+    const cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+    const cuuint64_t strides[3] = {dims[0], dims[0] * dims[1], dims[0] * dims[1] * dims[2]};
+    const cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), d, strides, b, ones,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(rank 4) failed: %d", (int)r);
+    return LBC_OK;
+}
+
 bool igemm_supported(const ConvGeom& g, std::string* why)
 {
     const lbc_conv_desc& d = g.d;
