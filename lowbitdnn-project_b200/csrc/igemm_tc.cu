@@ -14,15 +14,21 @@
 //             computed and dropped (87.5% of the MMA rows are useful for 56/28/112/224-wide layers).
 //             For C == 16 (space-to-depth'd stems) pixel rows are 16 bytes, unswizzled, and one K=32 MMA covers
 //             two horizontally adjacent taps through the descriptor's leading-dimension offset.
-//   B operand:  TMA 2-D loads of the pre-packed filter matrix, one [bn][<=128 B] block per stage.
-//   MMA      :  tcgen05.mma.cta_group::1.kind::i8, M=128 x N=bn x K=32 per instruction, issued by one thread.
-//   Epilogue :  8 warps drain the TMEM accumulator (tcgen05.ld 32x32b, software-pipelined), fuse bias +
-//               per-channel fp32 scale + round-to-nearest-even + ReLU/saturate, pack to int8, stage the tile in
-//               swizzled shared memory and write it with TMA stores (full 128-byte lines).  int32 output mode
-//               writes 16-byte vectors directly.
-//   Schedule :  persistent CTAs (one per SM), static round-robin over tiles, mbarrier rings between the TMA
-//               warps and the MMA warp, two TMEM accumulator stages so the epilogue of tile i overlaps the main
-//               loop of tile i+1.
+//   B operand:  the pre-packed filter matrix, either streamed through the mbarrier ring ([bn][<=128 B] blocks, TMA
+//               2-D loads) or - one N tile, <= 80 KB - RESIDENT in shared memory: loaded once per CTA, no per-block
+//               handshake and no L2 re-fetch per tile (stems, ResNet stage 1, MobileNetV2 pointwise layers).
+//   MMA      :  tcgen05.mma.cta_group::1.kind::i8, M=128 x N=bn x K=32 per instruction.  Issue loop: descriptor
+//               offsets from a table in the kernel-parameter bank, 32-bit arithmetic on the descriptor low word,
+//               batches of one filter row; two issuing warps on alternate tiles (each with its own half of the A-side
+//               ring) where one warp's ~75 cycles per issue would be the bound.
+//   Epilogue :  16 warps (2 teams x 8, or 4 x 4 for N tiles <= 64) drain the TMEM accumulators (tcgen05.ld 32x32b.x32),
+//               fuse bias + per-channel fp32 scale + round-to-nearest-even + ReLU/saturate, pack to int8 (F2IP), stage
+//               the tile in swizzled shared memory (ring of up to 3 panels, one named barrier per panel) and write it
+//               with TMA stores (full 128-byte lines).  int32 output mode writes 16-byte vectors directly.
+//   Schedule :  persistent CTAs (one per SM), division-free strided walk over tiles (TileIter), mbarrier rings between
+//               the TMA warps and the MMA warps, 2 or 4 TMEM accumulator stages so the epilogue of tile i overlaps
+//               the main loops of the following tiles; programmatic dependent launch hides the prologue behind the
+//               previous layer's tail.
 //
 // Replaces CUDAConv2DForward3x3TensorCoures (cpp/int8conv/conv2DForward3x3TensorCores.cuh:537-693: wmma
 // m32n8k16, single-buffered 34x34x16 halo tile in smem, int32 stores, 3x3/stride-1/VALID only).
@@ -191,11 +197,6 @@ __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, vol
     return ptx::mbar_wait(bar, parity, flag);
 }
 
-__device__ __forceinline__ uint32_t swz(uint32_t off, uint32_t mask)
-{
-    return off ^ (((off >> 7) & mask) << 4);
-}
-
 // One 16-column group of one output pixel: requantise (bias/scale from smem) and return 16 packed int8.
 __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi, float lo)
 {
@@ -265,12 +266,6 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
         epi_consume<1, OUT8>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
     }
 }
-
-// Opaque copy: keeps a loop-invariant in a register instead of letting the compiler re-read it from the constant
-// bank (LDCU, ~25 cycles of latency) inside the single-warp issue loops.
-__device__ __forceinline__ uint32_t keep(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
-__device__ __forceinline__ int32_t keep(int32_t v) { asm volatile("" : "+r"(v)); return v; }
-__device__ __forceinline__ uint64_t keep(uint64_t v) { asm volatile("" : "+l"(v)); return v; }
 
 // KM: 0 tiled A, 1 im2col A, 2 window A (>= 32-byte pixels), 3 window A with 16-byte pixels (paired taps)
 // KS: MMA K-steps (32 bytes each) per B block = bkb / 32
