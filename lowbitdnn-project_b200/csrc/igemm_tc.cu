@@ -222,7 +222,7 @@ struct EpiThread {
 template <int NG, bool OUT8>
 __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
                                             const uint32_t* v, int32_t c, int32_t pc, const EpiThread& et,
-                                            uint8_t* staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32,
+                                            uint32_t staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32,
                                             int64_t out_row, int32_t col0)
 {
 #pragma unroll
@@ -232,7 +232,8 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
             const uint4 r = requant16(v + 16 * g, sc + cc, bi + cc, lo);
             // swizzle: the XOR term depends only on the staging row (a panel row never crosses a 128-byte line), so
             // `swz_mask` arrives here already as this thread's ((row_off >> 7) & mask) << 4
-            if (et.valid) *reinterpret_cast<uint4*>(staging + ((row_off + (uint32_t)(pc + 16 * g)) ^ swz_mask)) = r;
+            // `staging` arrives as a 32-bit shared-window address (one conversion per panel, not one per store)
+            if (et.valid) ptx::st_shared_v4(staging + ((row_off + (uint32_t)(pc + 16 * g)) ^ swz_mask), r.x, r.y, r.z, r.w);
         } else if (out_row >= 0 && col0 + cc < prm.k_out) {
             int32_t* yo = y32 + out_row * prm.k_out + col0 + cc;
 #pragma unroll
@@ -248,7 +249,7 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
 // Drain this warp's share [c0, c1) of one panel out of TMEM.
 template <bool OUT8>
 __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* sc, const int32_t* bi, uint32_t taddr,
-                                          int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint8_t* staging,
+                                          int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint32_t staging,
                                           uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
                                           int32_t col0)
 {
@@ -727,11 +728,12 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (issuer) ptx::tma_store_wait_read<0>();
                     ptx::named_bar_sync(bar_id, team_threads);
                 }
+                const uint32_t staging_s = ptx::smem_u32(my_staging);
                 if (int8_out)
-                    epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
+                    epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
                                     swz_mask, lo, y32, out_row, col0);
                 else
-                    epi_drain<false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, my_staging, row_off,
+                    epi_drain<false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
                                      swz_mask, lo, y32, out_row, col0);
                 if (pnl == n_panels - 1) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
