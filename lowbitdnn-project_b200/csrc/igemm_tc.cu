@@ -198,6 +198,10 @@ __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, vol
 }
 
 // One 16-column group of one output pixel: requantise (bias/scale from smem) and return 16 packed int8.
+// RELU: the clamp at zero is applied to the PACKED bytes (sign-replicating PRMT + AND: 2 instructions per 4 outputs
+// instead of 4 FMNMX).  Rounding then clamping at an integer equals clamping then rounding, and a NaN product converts to
+// 0 either way, so the bytes are identical to requant_s32 with lo = 0.
+template <bool RELU>
 __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi, float lo)
 {
     uint32_t w[4];
@@ -205,8 +209,19 @@ __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, c
     for (int t = 0; t < 4; ++t) {
         const float4 f = *reinterpret_cast<const float4*>(sc + 4 * t);
         const int4 b = *reinterpret_cast<const int4*>(bi + 4 * t);
-        w[t] = pack4_sat_s8(requant_s32((int32_t)v[4 * t + 0], b.x, f.x, lo), requant_s32((int32_t)v[4 * t + 1], b.y, f.y, lo),
-                            requant_s32((int32_t)v[4 * t + 2], b.z, f.z, lo), requant_s32((int32_t)v[4 * t + 3], b.w, f.w, lo));
+        if (RELU) {
+            const int32_t q0 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 0] + b.x), f.x));
+            const int32_t q1 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 1] + b.y), f.y));
+            const int32_t q2 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 2] + b.z), f.z));
+            const int32_t q3 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 3] + b.w), f.w));
+            const uint32_t r = pack4_sat_s8(q0, q1, q2, q3);
+            uint32_t neg;
+            asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(neg) : "r"(r));     // 0xff in every byte whose sign bit is set
+            w[t] = r & ~neg;
+        } else {
+            w[t] = pack4_sat_s8(requant_s32((int32_t)v[4 * t + 0], b.x, f.x, lo), requant_s32((int32_t)v[4 * t + 1], b.y, f.y, lo),
+                                requant_s32((int32_t)v[4 * t + 2], b.z, f.z, lo), requant_s32((int32_t)v[4 * t + 3], b.w, f.w, lo));
+        }
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -219,7 +234,7 @@ struct EpiThread {
 
 // Process NG 16-column groups held in v[]: tile columns [c, c + 16*NG), which are staging-panel columns
 // [pc, pc + 16*NG).  OUT8 selects the fused int8 path (requantise -> swizzled staging panel) or raw int32 stores.
-template <int NG, bool OUT8>
+template <int NG, bool OUT8, bool RELU>
 __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
                                             const uint32_t* v, int32_t c, int32_t pc, const EpiThread& et,
                                             uint32_t staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32,
@@ -229,7 +244,7 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
     for (int g = 0; g < NG; ++g) {
         const int32_t cc = c + 16 * g;
         if (OUT8) {
-            const uint4 r = requant16(v + 16 * g, sc + cc, bi + cc, lo);
+            const uint4 r = requant16<RELU>(v + 16 * g, sc + cc, bi + cc, lo);
             // swizzle: the XOR term depends only on the staging row (a panel row never crosses a 128-byte line), so
             // `swz_mask` arrives here already as this thread's ((row_off >> 7) & mask) << 4
             // `staging` arrives as a 32-bit shared-window address (one conversion per panel, not one per store)
@@ -247,7 +262,7 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
 }
 
 // Drain this warp's share [c0, c1) of one panel out of TMEM.
-template <bool OUT8>
+template <bool OUT8, bool RELU>
 __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* sc, const int32_t* bi, uint32_t taddr,
                                           int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint32_t staging,
                                           uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
@@ -258,13 +273,13 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         ptx::tmem_ld_wait_dep(v);
-        epi_consume<2, OUT8>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+        epi_consume<2, OUT8, RELU>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
     }
     if (c + 16 <= c1) {
         uint32_t v16[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
         ptx::tmem_ld_wait_dep16(v16);
-        epi_consume<1, OUT8>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+        epi_consume<1, OUT8, RELU>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
     }
 }
 
@@ -729,12 +744,15 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     ptx::named_bar_sync(bar_id, team_threads);
                 }
                 const uint32_t staging_s = ptx::smem_u32(my_staging);
-                if (int8_out)
-                    epi_drain<true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
-                                    swz_mask, lo, y32, out_row, col0);
+                if (int8_out && prm.relu)
+                    epi_drain<true, true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
+                                          swz_mask, lo, y32, out_row, col0);
+                else if (int8_out)
+                    epi_drain<true, false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
+                                           swz_mask, lo, y32, out_row, col0);
                 else
-                    epi_drain<false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
-                                     swz_mask, lo, y32, out_row, col0);
+                    epi_drain<false, false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
+                                            swz_mask, lo, y32, out_row, col0);
                 if (pnl == n_panels - 1) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
