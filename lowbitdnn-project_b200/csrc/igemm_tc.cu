@@ -138,56 +138,64 @@ struct Ctl {
 // digits of gridDim.x with carries (next).  In the ring modes it_cols == it_rows == 1 and `img` is the M-tile index.
 struct TileIter {
     int32_t tile, n_blk, ct, rt, img, local;
+    // loop constants, copied into registers once: the producer roles are single warps whose per-tile instruction count
+    // (not the TMA engine) paces the rings - every constant-bank reload in next() showed up in the traces
+    int32_t stride, tiles_n, cols, rows, imgs, s_nb, s_ct, s_rt, s_img, rpt, cpt;
+    bool pair;
     __device__ __forceinline__ void init(const IgemmParams& prm, int32_t t0)
     {
+        stride = prm.tile_stride; tiles_n = prm.tiles_n; cols = prm.it_cols; rows = prm.it_rows; imgs = prm.it_imgs;
+        s_nb = prm.step_nb; s_ct = prm.step_ct; s_rt = prm.step_rt; s_img = prm.step_img;
+        rpt = prm.rows_per_tile; cpt = prm.cols_per_tile;
+        pair = prm.pair != 0;
         tile = t0;
         local = 0;
         int32_t mt;
-        if (prm.pair) {   // N-tile-major numbering
-            const int32_t per_n = prm.it_cols * prm.it_rows * prm.it_imgs;
+        if (pair) {   // N-tile-major numbering
+            const int32_t per_n = cols * rows * imgs;
             n_blk = t0 / per_n;
             mt = t0 - n_blk * per_n;
         } else {
-            n_blk = t0 % prm.tiles_n;
-            mt = t0 / prm.tiles_n;
+            n_blk = t0 % tiles_n;
+            mt = t0 / tiles_n;
         }
-        ct = mt % prm.it_cols;
-        rt = (mt / prm.it_cols) % prm.it_rows;
-        img = mt / (prm.it_cols * prm.it_rows);
+        ct = mt % cols;
+        rt = (mt / cols) % rows;
+        img = mt / (cols * rows);
     }
-    __device__ __forceinline__ void next(const IgemmParams& prm)
+    __device__ __forceinline__ void next(const IgemmParams&)
     {
-        tile += prm.tile_stride;
+        tile += stride;
         ++local;
-        if (prm.pair) {
-            ct += prm.step_ct;
-            if (ct >= prm.it_cols) { ct -= prm.it_cols; ++rt; }
-            rt += prm.step_rt;
-            if (rt >= prm.it_rows) { rt -= prm.it_rows; ++img; }
-            img += prm.step_img;
-            if (img >= prm.it_imgs) { img -= prm.it_imgs; ++n_blk; }
-            n_blk += prm.step_nb;
+        if (pair) {
+            ct += s_ct;
+            if (ct >= cols) { ct -= cols; ++rt; }
+            rt += s_rt;
+            if (rt >= rows) { rt -= rows; ++img; }
+            img += s_img;
+            if (img >= imgs) { img -= imgs; ++n_blk; }
+            n_blk += s_nb;
         } else {
-            n_blk += prm.step_nb;
-            if (n_blk >= prm.tiles_n) { n_blk -= prm.tiles_n; ++ct; }
-            ct += prm.step_ct;
-            if (ct >= prm.it_cols) { ct -= prm.it_cols; ++rt; }
-            rt += prm.step_rt;
-            if (rt >= prm.it_rows) { rt -= prm.it_rows; ++img; }
-            img += prm.step_img;
+            n_blk += s_nb;
+            if (n_blk >= tiles_n) { n_blk -= tiles_n; ++ct; }
+            ct += s_ct;
+            if (ct >= cols) { ct -= cols; ++rt; }
+            rt += s_rt;
+            if (rt >= rows) { rt -= rows; ++img; }
+            img += s_img;
         }
     }
     // the M tile right after this one (pair mode: the second tile of the pair; same n_blk because the count is even)
-    __device__ __forceinline__ TileIter succ(const IgemmParams& prm) const
+    __device__ __forceinline__ TileIter succ(const IgemmParams&) const
     {
         TileIter t = *this;
         ++t.tile;
-        if (++t.ct >= prm.it_cols) { t.ct = 0; if (++t.rt >= prm.it_rows) { t.rt = 0; ++t.img; } }
+        if (++t.ct >= cols) { t.ct = 0; if (++t.rt >= rows) { t.rt = 0; ++t.img; } }
         return t;
     }
     // WINDOW: first output row / column of the tile; ring modes: first GEMM row
-    __device__ __forceinline__ int32_t p0(const IgemmParams& prm) const { return rt * prm.rows_per_tile; }
-    __device__ __forceinline__ int32_t q0(const IgemmParams& prm) const { return ct * prm.cols_per_tile; }
+    __device__ __forceinline__ int32_t p0(const IgemmParams&) const { return rt * rpt; }
+    __device__ __forceinline__ int32_t q0(const IgemmParams&) const { return ct * cpt; }
     __device__ __forceinline__ int32_t m0() const { return img * kBlockM; }
 };
 
@@ -440,25 +448,32 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             uint32_t ws_e = 0, wphase_e = 0, ws_o = 0, wphase_o = 0;
             const bool leader = ptx::elect_one();
             bool ok = true;
+            const int32_t pad_w = prm.pad_w, pad_h = prm.pad_h, cblocks = prm.cblocks, bkc = prm.bkc;
+            const uint32_t n_mma_mask = (uint32_t)(prm.n_mma - 1), win_stage_bytes = prm.win_stage_bytes;
+            const uint32_t win_sub_bytes = prm.win_sub_bytes;
+            const bool pair = prm.pair != 0;
+            const uint32_t win_tx = pair ? 2u * prm.win_tx_bytes : prm.win_tx_bytes;
             TileIter it;
             for (it.init(prm, first_tile); it.tile < num_tiles && ok; it.next(prm)) {
-                const int32_t wq = it.q0(prm) - prm.pad_w, wp = it.p0(prm) - prm.pad_h;
-                const TileIter it1 = it.succ(prm);                      // pair mode: the second tile of the pair
-                const int32_t wq1 = it1.q0(prm) - prm.pad_w, wp1 = it1.p0(prm) - prm.pad_h;
-                const uint32_t sub = (uint32_t)it.local & (uint32_t)(prm.n_mma - 1);
+                const int32_t wq = it.q0(prm) - pad_w, wp = it.p0(prm) - pad_h;
+                int32_t wq1 = 0, wp1 = 0, img1 = 0;
+                if (pair) {                                             // the second tile of the pair
+                    const TileIter it1 = it.succ(prm);
+                    wq1 = it1.q0(prm) - pad_w; wp1 = it1.p0(prm) - pad_h; img1 = it1.img;
+                }
+                const uint32_t sub = (uint32_t)it.local & n_mma_mask;
                 const uint32_t sub_base = sub * sub_len;
                 uint32_t ws = sub_base + (sub ? ws_o : ws_e), wphase = sub ? wphase_o : wphase_e;
                 int32_t c0 = 0;
-                for (int32_t cb = 0; cb < prm.cblocks; ++cb, c0 += prm.bkc) {
+                for (int32_t cb = 0; cb < cblocks; ++cb, c0 += bkc) {
                     ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
                     if (!ok) break;
                     if (leader) {
                         if (cb == 0) trace_ev(prm, it.local, EV_W_ISSUE);
-                        ptx::mbar_expect_tx(&ctl->wfull[ws], prm.pair ? 2u * prm.win_tx_bytes : prm.win_tx_bytes);
-                        ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
-                        if (prm.pair)
-                            ptx::tma_load_4d(smem_a + ws * prm.win_stage_bytes + prm.win_sub_bytes, &tm_a, &ctl->wfull[ws], c0, wq1,
-                                             wp1, it1.img);
+                        ptx::mbar_expect_tx(&ctl->wfull[ws], win_tx);
+                        ptx::tma_load_4d(smem_a + ws * win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
+                        if (pair)
+                            ptx::tma_load_4d(smem_a + ws * win_stage_bytes + win_sub_bytes, &tm_a, &ctl->wfull[ws], c0, wq1, wp1, img1);
                     }
                     if (++ws == sub_base + sub_len) { ws = sub_base; wphase ^= 1; }
                 }
