@@ -103,6 +103,11 @@ struct IgemmParams {
     // bound wide 3x3 layers.  Tiles are then numbered N-tile-major (n_blk | img | rt | ct) so the two tiles of a pair
     // are the consecutive indices 2q, 2q + 1; it_imgs is the (padded, so the count is even) image radix.
     int32_t pair, it_imgs;
+    // CTA-pair mode (cta_group::2, streaming B): CTAs 2c and 2c+1 form a cluster and work on the consecutive M tiles
+    // 2q, 2q+1 of one N tile (same N-tile-major numbering, tile space padded to an even count).  Each CTA loads its own
+    // A tile / window and HALF of the B rows; the leader (even) CTA issues M=256 MMAs that read both halves, so the
+    // shared-memory fill and operand-read traffic per MMA of each SM drops from A + B to A + B/2.
+    int32_t cta2, n_major;
     uint32_t win_sub_bytes;       // pair mode: bytes of one of the two windows of a stage
     // optional pipeline trace (development aid): CTA 0 writes clock64 stamps, 16 slots per local tile
     long long* trace;
@@ -147,7 +152,7 @@ struct TileIter {
         stride = prm.tile_stride; tiles_n = prm.tiles_n; cols = prm.it_cols; rows = prm.it_rows; imgs = prm.it_imgs;
         s_nb = prm.step_nb; s_ct = prm.step_ct; s_rt = prm.step_rt; s_img = prm.step_img;
         rpt = prm.rows_per_tile; cpt = prm.cols_per_tile;
-        pair = prm.pair != 0;
+        pair = prm.n_major != 0;
         tile = t0;
         local = 0;
         int32_t mt;
@@ -295,7 +300,23 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
 // KS: MMA K-steps (32 bytes each) per B block = bkb / 32
 // RESB: the filter matrix is resident in shared memory (one N tile, loaded once per CTA); the ring then carries
 //       only A blocks (tiled / im2col) or does not exist at all (window modes)
-template <int KM, int KS, bool RESB>
+template <bool CTA2>
+__device__ __forceinline__ void mma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t leader)
+{
+    if (CTA2) ptx::mma_i8_ss_pred32_2cta(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate, leader);
+    else ptx::mma_i8_ss_pred32(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate, leader);
+}
+
+template <bool CTA2>
+__device__ __forceinline__ void mma_commit(uint64_t* bar, uint32_t leader)
+{
+    if (CTA2) ptx::mma_commit_2cta_pred(bar, leader);     // arrives on the barrier at this offset in BOTH CTAs
+    else ptx::mma_commit_pred(bar, leader);
+}
+
+// CTA2: CTA-pair mode (see IgemmParams::cta2); only instantiated with RESB == false
+template <int KM, int KS, bool RESB, bool CTA2>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
@@ -310,6 +331,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
     volatile int* tflag = &g_timeout_flag;
+    const uint32_t cta_rank = CTA2 ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
 
     if ((ptx::smem_u32(smem) & 1023u) != 0) {       // swizzle atoms need a 1024-byte aligned base
         if (threadIdx.x == 0) *tflag = 2;
@@ -332,17 +354,23 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         for (int i = 0; i < prm.n_acc; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
-            ptx::mbar_init(&ctl->tmem_empty[i], (uint32_t)prm.team_warps);
+            ptx::mbar_init(&ctl->tmem_empty[i], (uint32_t)prm.team_warps * (CTA2 ? 2u : 1u));   // pair: both CTAs' teams
         }
         ptx::mbar_init(&ctl->bfull, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(&ctl->tmem_base, prm.tmem_cols);
-        ptx::tmem_relinquish();
+        if (CTA2) {
+            ptx::tmem_alloc_2cta(&ctl->tmem_base, prm.tmem_cols);
+            ptx::tmem_relinquish_2cta();
+        } else {
+            ptx::tmem_alloc(&ctl->tmem_base, prm.tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync();     // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     // Programmatic dependent launch: everything above is on-chip set-up (barriers, TMEM, descriptor prefetch) and may
     // overlap the tail of the previous kernel in the stream; from here on global memory is read and written.
@@ -350,7 +378,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
     // pair mode counts the padded tile space (dummy tiles of the padding image load zeros and store nothing)
-    const int32_t num_tiles = prm.pair ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
+    const int32_t num_tiles = prm.n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
     const int32_t first_tile = prm.pair ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
 
     // The three issue roles below run with ALL 32 lanes of their warp executing the (warp-uniform) loops; only
@@ -379,7 +407,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             // the ring and odd tiles through the second, so each consumer sees its stages strictly in phase order
             const uint32_t sub_len = (uint32_t)prm.stages / (uint32_t)prm.n_mma;
             uint32_t stage_e = 0, phase_e = 0, stage_o = 0, phase_o = 0;   // cursors of the even / odd sub-ring
-            const uint32_t tx_bytes = (RESB ? 0u : prm.b_stage_bytes) + (kWindow ? 0u : prm.a_stage_bytes);
+            // pair mode: the leader's full barrier collects the bytes of both CTAs' loads
+            const uint32_t tx_bytes = ((RESB ? 0u : prm.b_stage_bytes) + (kWindow ? 0u : prm.a_stage_bytes)) * (CTA2 ? 2u : 1u);
+            const uint32_t full0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->full[0]), 0) : 0u;
+            const int32_t brow_off = CTA2 ? (int32_t)cta_rank * (prm.bn >> 1) : 0;
             const int32_t stages_per_tile = prm.cblocks * prm.inner / prm.tps;
             const int32_t tps = prm.tps, cblocks = prm.cblocks;
             const int32_t bkb = prm.bkb, bkc = prm.bkc, s_taps = prm.s_taps;
@@ -400,7 +431,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     w_base = q0 * prm.stride_w - prm.pad_w;
                     h_base = p0 * prm.stride_h - prm.pad_h;
                 }
-                const int32_t brow = it.n_blk * prm.bn;
+                const int32_t brow = it.n_blk * prm.bn + brow_off;
                 const uint32_t sub = (uint32_t)it.local & (uint32_t)(prm.n_mma - 1);
                 const uint32_t sub_base = sub * sub_len;
                 uint32_t stage = sub_base + (sub ? stage_o : stage_e), phase = sub ? phase_o : phase_e;
@@ -410,11 +441,20 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
                     if (!ok) break;
                     if (st == 0 && leader) trace_ev(prm, it.local, EV_P_ISSUE);
-                    if (leader) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
+                    if (leader && cta_rank == 0) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
                     uint8_t* dst_a = smem_a + stage * a_stage;
                     uint8_t* dst_b = smem_b + stage * b_stage;
                     for (int32_t t = 0; t < tps; ++t) {
-                        if (leader) {
+                        if (CTA2) {
+                            if (leader) {
+                                const uint32_t fbar = full0 + stage * 8u;
+                                if (KM == A_IM2COL)
+                                    ptx::tma_load_im2col_4d_2sm(dst_a, &tm_a, fbar, c0, w_base, h_base, n0, (uint16_t)off_w, (uint16_t)off_h);
+                                else if (KM == A_TILED)
+                                    ptx::tma_load_2d_2sm(dst_a, &tm_a, fbar, c0, m0);
+                                ptx::tma_load_2d_2sm(dst_b, &tm_b, fbar, bcol, brow);
+                            }
+                        } else if (leader) {
                             if (KM == A_IM2COL)
                                 ptx::tma_load_im2col_4d(dst_a, &tm_a, &ctl->full[stage], c0, w_base, h_base, n0, (uint16_t)off_w,
                                                         (uint16_t)off_h);
@@ -452,7 +492,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t n_mma_mask = (uint32_t)(prm.n_mma - 1), win_stage_bytes = prm.win_stage_bytes;
             const uint32_t win_sub_bytes = prm.win_sub_bytes;
             const bool pair = prm.pair != 0;
-            const uint32_t win_tx = pair ? 2u * prm.win_tx_bytes : prm.win_tx_bytes;
+            const uint32_t win_tx = (pair || CTA2) ? 2u * prm.win_tx_bytes : prm.win_tx_bytes;
+            const uint32_t wfull0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->wfull[0]), 0) : 0u;
             TileIter it;
             for (it.init(prm, first_tile); it.tile < num_tiles && ok; it.next(prm)) {
                 const int32_t wq = it.q0(prm) - pad_w, wp = it.p0(prm) - pad_h;
@@ -470,8 +511,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (!ok) break;
                     if (leader) {
                         if (cb == 0) trace_ev(prm, it.local, EV_W_ISSUE);
-                        ptx::mbar_expect_tx(&ctl->wfull[ws], win_tx);
-                        ptx::tma_load_4d(smem_a + ws * win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
+                        if (cta_rank == 0) ptx::mbar_expect_tx(&ctl->wfull[ws], win_tx);
+                        if (CTA2) ptx::tma_load_4d_2sm(smem_a + ws * win_stage_bytes, &tm_a, wfull0 + ws * 8u, c0, wq, wp, it.img);
+                        else ptx::tma_load_4d(smem_a + ws * win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
                         if (pair)
                             ptx::tma_load_4d(smem_a + ws * win_stage_bytes + win_sub_bytes, &tm_a, &ctl->wfull[ws], c0, wq1, wp1, img1);
                     }
@@ -497,7 +539,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t which = warp >> 1;                              // 0 (warp 1) or 1 (warp 3)
         const uint32_t n_mma = (uint32_t)prm.n_mma;
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
-        const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
+        const uint32_t idesc = ptx::make_idesc_i8(CTA2 ? 2 * kBlockM : kBlockM, (uint32_t)prm.bn);
         const uint64_t db_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_b), (uint32_t)prm.bkb);
         const uint64_t da_base = (KM != 3) ? ptx::make_kmajor_desc(ptx::smem_u32(smem_a), (uint32_t)prm.bkc)
                                            : ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem_a), (uint32_t)prm.dil_w * 16u, 128u);
@@ -517,11 +559,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t bn = (uint32_t)prm.bn;
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
         uint32_t stage = ring_lo, phase = 0, ws = win_lo, wphase = 0;
-        const bool active = which < n_mma || prm.pair;
+        const bool active = (which < n_mma || prm.pair) && cta_rank == 0;   // CTA pairs: only the leader issues
         bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
         bool wready = (kWindow && active) ? ptx::mbar_test(&ctl->wfull[ws], wphase) : true;
         if (RESB && active) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
-        if (kWindow && !RESB && prm.pair) {
+        if (kWindow && !RESB && !CTA2 && prm.pair) {
             // ---- pair mode: two M tiles per step share every B block (see IgemmParams::pair).  Warp `which` issues
             // the MMAs of the which-th tile of the pair: both read the same B stage and the same window stage (one
             // window each), so those stages are released by TWO commits (their empty barriers count 2).
@@ -571,6 +613,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         } else {
         int32_t local = (int32_t)which;
         const int32_t tile_step = (int32_t)(n_mma * gridDim.x);
+        // (a pair leader counts its own tiles; the peer's tile of each step shares the MMAs)
         for (int32_t tile = active ? (int32_t)(blockIdx.x + which * gridDim.x) : num_tiles; tile < num_tiles;
              tile += tile_step, local += (int32_t)n_mma) {
             const uint32_t acc_stage = (uint32_t)local & acc_mask;
@@ -633,24 +676,24 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
                             for (int k = 0; k < KS; ++k) {
                                 const uint32_t a_lo = a_base + (uint32_t)prm.a_tab[kWindow ? j + k : k];
-                                ptx::mma_i8_ss_pred32(tmem_d, a_lo, da_hi, b_lo + 2u * k, db_hi, idesc, accumulate, leader);
+                                mma_issue<CTA2>(tmem_d, a_lo, da_hi, b_lo + 2u * k, db_hi, idesc, accumulate, leader);
                                 accumulate = 1;
                             }
                             j += KS;
                             b_lo += b_block16;
                         }
                         if (RESB) b_res = b_lo;
-                        ptx::mma_commit_pred(&ctl->empty[stage], leader);     // slot reusable once these MMAs retire
+                        mma_commit<CTA2>(&ctl->empty[stage], leader);     // slot reusable once these MMAs retire
                         stage = nstage; phase = nphase; ready = ready_next;
                     }
                     if (kWindow) {
-                        ptx::mma_commit_pred(&ctl->wempty[ws], leader);
+                        mma_commit<CTA2>(&ctl->wempty[ws], leader);
                         if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
                         wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
                     }
                 }
             }
-            ptx::mma_commit_pred(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue
+            mma_commit<CTA2>(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue (of both CTAs)
             if (leader) trace_ev(prm, local, EV_M_DONE);
         }
         }
@@ -709,6 +752,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t swz_mask = ((row_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
         int32_t cur_nblk = -1;
+        const uint32_t tmem_empty0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->tmem_empty[0]), 0) : 0u;   // the leader's barriers
         TileIter it;
         // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
         it.init(prm, prm.pair ? first_tile + (int32_t)team : (int32_t)(blockIdx.x + team * gridDim.x));
@@ -772,7 +816,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+                    if (lane == 0) {
+                        if (CTA2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8u);
+                        else ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+                    }
                     if (issuer) trace_ev(prm, tile, EV_E_DRAINED);
                 }
                 if (int8_out) {
@@ -788,7 +835,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         const int32_t cbyte = col0 + pbase;
                         if (cbyte < prm.k_out) {
                             if (prm.mode == A_WINDOW) {
-                                if (tc.img < prm.n_img)   // pair mode pads the tile space with dummy tiles
+                                if (tc.img < prm.n_img)   // the pair modes pad the tile space with dummy tiles
                                     ptx::tma_store_4d(&tm_out, my_staging, cbyte, tc.q0, tc.p0, tc.img);
                             }
                             else
@@ -809,7 +856,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
     // ---- teardown ----
     ptx::tc_fence_before();
-    __syncthreads();
+    if (CTA2) ptx::cluster_sync();     // neither CTA may leave while its peer still reads its operands / signals its barriers
+    else __syncthreads();
     // trace mode: every CTA also leaves its own start / end time (its SM's cycle counter) behind the per-tile stamps
     if (prm.trace != nullptr && threadIdx.x == 0) {
         long long* cta_times = prm.trace + (size_t)prm.trace_tiles * 16;
@@ -817,7 +865,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, prm.tmem_cols);
+        if (CTA2) ptx::tmem_dealloc_2cta(tmem_base, prm.tmem_cols);
+        else ptx::tmem_dealloc(tmem_base, prm.tmem_cols);
     }
 }
 
@@ -983,6 +1032,24 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     if (c.mode == A_WINDOW) c.tiles_m = d.n * c.row_tiles * c.col_tiles;
     else c.tiles_m = (int32_t)((g.m_total + kBlockM - 1) / kBlockM);
 
+    // ---- CTA-pair mode (see IgemmParams::cta2): layers whose filter matrix streams through the ring (too large to stay
+    // resident, or several N tiles).  Their MMAs run at 128 operand bytes per cycle out of shared memory while TMA fills
+    // the same banks, and ~80% tensor-pipe utilisation was the measured ceiling (profiles/r01_*); sharing B between
+    // the two SMs of a TPC removes a third of that traffic.
+    {
+        const size_t full_b = (size_t)c.k_blocks * c.bn * c.bkb;
+        const bool streams = !(c.tiles_n == 1 && full_b <= 80u * 1024u) || getenv("LBC_NO_RESB");
+        const bool possible = !c.pair && !c16 && streams && c.bn % 32 == 0 && c.tiles_m >= 2;
+        // Pairing couples the two CTAs' pipelines (one MMA stream waits for both producers and both epilogues), which
+        // costs where the epilogue is the bound: short K loops (1x1 channel expansions) measured 10-15% slower in pairs,
+        // long ones (3x3, wide 1x1 reductions) 5-25% faster.  Cross-over: MMA time per tile (128 cycles per N=256
+        // instruction) against ~16 cycles per output column of epilogue.
+        const int mma_cycles = c.k_blocks * (c.bkb / 32) * (c.bn / 2);
+        bool want = mma_cycles >= 16 * c.bn;
+        if (const char* v = getenv("LBC_CTA2")) want = atoi(v) != 0;       // development / test override
+        c.cta2 = (possible && want) ? 1 : 0;
+    }
+
     // ---- output staging (int8 mode): panels of <= 128 bytes per row
     if (c.bn % 128 == 0) c.panel_bytes = 128;
     else if (c.bn == 64 || c.bn == 32) c.panel_bytes = c.bn;
@@ -1000,7 +1067,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // byte left over after two or three B stages (B comes from L2 and needs little run-ahead) and the staging panels.
     const uint32_t ctl_bytes = round_up((uint32_t)sizeof(Ctl), 256);
     c.a_block_bytes = (c.mode == A_WINDOW) ? 0 : (uint32_t)(kBlockM * c.bkc);
-    c.b_block_bytes = (uint32_t)(c.bn * c.bkb);
+    c.b_block_bytes = (uint32_t)((c.cta2 ? c.bn / 2 : c.bn) * c.bkb);     // a pair's CTAs hold half of the B rows each
     // tuning knobs (development aids; the defaults are what ships)
     auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
     const uint32_t tps_cap = (uint32_t)env_int("LBC_TPS_KB", 48) * 1024u;
@@ -1034,7 +1101,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.k_blocks * c.b_block_bytes;
-    const bool res_b_ok = !c.pair && c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
+    const bool res_b_ok = !c.pair && !c.cta2 && c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
     for (int pass = 0; pass < 2 && !fits; ++pass)
     for (int bufs = max_bufs; bufs >= 1 && !fits; --bufs) {   // three staging panels per team when they fit, else two, else one
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
@@ -1125,6 +1192,14 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     c.tmem_cols = cols;
     c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
     c.it_imgs = d.n;
+    if (c.cta2) {
+        // the two CTAs of a cluster take the consecutive tiles 2q, 2q+1 of an N tile: pad the M-tile space to an even count
+        c.it_imgs = c.mode == A_WINDOW ? d.n : c.tiles_m;
+        const int32_t per_img = c.mode == A_WINDOW ? c.row_tiles * c.col_tiles : 1;
+        if ((per_img * c.it_imgs) & 1) ++c.it_imgs;
+        const int32_t sms = (dev.sm_count > 0 ? dev.sm_count : 148) & ~1;
+        c.grid = std::min(sms, per_img * c.it_imgs * c.tiles_n);
+    }
     if (c.pair) {
         // pad the image radix so that the tiles of one N tile come in whole pairs; CTAs walk pairs
         if ((c.row_tiles * c.col_tiles * c.it_imgs) & 1) ++c.it_imgs;
@@ -1132,6 +1207,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, pairs);
     }
     if (const char* v = getenv("LBC_MAX_GRID")) c.grid = std::max(1, std::min(c.grid, atoi(v)));   // tests: many tiles per CTA
+    if (c.cta2) c.grid = std::max(2, c.grid & ~1);
     *cfg = c;
     return LBC_OK;
 }
@@ -1153,7 +1229,7 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
     {
         const cuuint64_t dims[2] = {(cuuint64_t)cfg.packed_row_bytes, (cuuint64_t)d.k};
         const cuuint64_t strides[1] = {(cuuint64_t)cfg.packed_row_bytes};
-        const cuuint32_t box[2] = {(cuuint32_t)cfg.bkb, (cuuint32_t)cfg.bn};
+        const cuuint32_t box[2] = {(cuuint32_t)cfg.bkb, (cuuint32_t)(cfg.cta2 ? cfg.bn / 2 : cfg.bn)};
         CUresult r = g_encode_tiled(&out->tm_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)w_packed, dims, strides, box,
                                     ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(cfg.bkb), promo,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1248,8 +1324,9 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.it_cols = c.mode == A_WINDOW ? c.col_tiles : 1;
     prm.it_rows = c.mode == A_WINDOW ? c.row_tiles : 1;
     prm.pair = c.pair; prm.it_imgs = c.it_imgs; prm.win_sub_bytes = c.win_sub_bytes;
+    prm.cta2 = c.cta2; prm.n_major = (c.pair || c.cta2) ? 1 : 0;
     prm.tile_stride = c.pair ? 2 * c.grid : c.grid;
-    if (c.pair) {   // (n_blk | img | rt | ct), CTA stride = 2 * grid tiles
+    if (prm.n_major) {   // (n_blk | img | rt | ct), CTA stride = 2 * grid tiles (pair) or grid tiles (CTA pairs)
         int32_t v = prm.tile_stride;
         prm.step_ct = v % prm.it_cols; v /= prm.it_cols;
         prm.step_rt = v % prm.it_rows; v /= prm.it_rows;
@@ -1272,25 +1349,27 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     const int ks = c.bkb / 32;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams, const int32_t*,
                               const float*, void*);
-    static const KernelFn table[4][3][2] = {
-        {{igemm_i8_kernel<0, 1, false>, igemm_i8_kernel<0, 1, true>}, {igemm_i8_kernel<0, 2, false>, igemm_i8_kernel<0, 2, true>},
-         {igemm_i8_kernel<0, 4, false>, igemm_i8_kernel<0, 4, true>}},
-        {{igemm_i8_kernel<1, 1, false>, igemm_i8_kernel<1, 1, true>}, {igemm_i8_kernel<1, 2, false>, igemm_i8_kernel<1, 2, true>},
-         {igemm_i8_kernel<1, 4, false>, igemm_i8_kernel<1, 4, true>}},
-        {{igemm_i8_kernel<2, 1, false>, igemm_i8_kernel<2, 1, true>}, {igemm_i8_kernel<2, 2, false>, igemm_i8_kernel<2, 2, true>},
-         {igemm_i8_kernel<2, 4, false>, igemm_i8_kernel<2, 4, true>}},
-        {{igemm_i8_kernel<3, 1, false>, igemm_i8_kernel<3, 1, true>}, {igemm_i8_kernel<3, 2, false>, igemm_i8_kernel<3, 2, true>},
-         {igemm_i8_kernel<3, 4, false>, igemm_i8_kernel<3, 4, true>}},
+    // last index: 0 streaming B, 1 resident B, 2 streaming B in CTA pairs (not for 16-byte pixels)
+#define LBC_KERNELS(KM_, KS_) {igemm_i8_kernel<KM_, KS_, false, false>, igemm_i8_kernel<KM_, KS_, true, false>, \
+                               (KM_ == 3 ? (KernelFn) nullptr : (KernelFn)igemm_i8_kernel<(KM_ == 3 ? 2 : KM_), KS_, false, true>)}
+    static const KernelFn table[4][3][3] = {
+        {LBC_KERNELS(0, 1), LBC_KERNELS(0, 2), LBC_KERNELS(0, 4)},
+        {LBC_KERNELS(1, 1), LBC_KERNELS(1, 2), LBC_KERNELS(1, 4)},
+        {LBC_KERNELS(2, 1), LBC_KERNELS(2, 2), LBC_KERNELS(2, 4)},
+        {LBC_KERNELS(3, 1), LBC_KERNELS(3, 2), LBC_KERNELS(3, 4)},
     };
+#undef LBC_KERNELS
     LBC_REQUIRE(ks == 1 || ks == 2 || ks == 4, LBC_ERR_UNSUPPORTED, "igemm: unsupported K block of %d bytes", c.bkb);
-    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.res_b ? 1 : 0];
+    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.cta2 ? 2 : c.res_b ? 1 : 0];
+    LBC_REQUIRE(fn != nullptr, LBC_ERR_UNSUPPORTED, "igemm: no kernel for this configuration");
     {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (!g_attr_set) {
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 3; ++j)
-                    for (int r = 0; r < 2; ++r)
-                        LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    for (int r = 0; r < 3; ++r)
+                        if (table[i][j][r])
+                            LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             g_attr_set = true;
         }
     }
@@ -1301,11 +1380,16 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     lc.blockDim = dim3(kNumThreads);
     lc.dynamicSmemBytes = c.smem_bytes;
     lc.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = getenv("LBC_NO_PDL") ? 0 : 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
+    if (c.cta2) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+        lc.numAttrs = 2;
+    }
     const int32_t* bias_p = ep.bias;
     const float* scale_p = ep.scale;
     LBC_CUDA_TRY(cudaLaunchKernelEx(&lc, fn, l.tm_a, l.tm_b, l.tm_out, prm, bias_p, scale_p, y));

@@ -397,6 +397,117 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_i8(uint32_t m, uint32_t 
     return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- thread-block clusters / CTA pairs (cta_group::2) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void cluster_sync()   // all threads of both CTAs
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// shared::cluster address of `local_smem_addr` (a shared::cta address) in the CTA with rank `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+
+// arrive (count 1) on an mbarrier of another CTA of the cluster, given its shared::cluster address
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// arrive + expect_tx on an mbarrier given by its shared::cluster address (used on the pair leader's barriers)
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+                 : "memory");
+}
+
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the bytes are signalled on an mbarrier that may
+// live in the peer (leader) CTA - `bar_cluster_addr` is a shared::cluster address.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int32_t c0,
+                                                int32_t c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int32_t c0,
+                                                int32_t c1, int32_t c2, int32_t c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int32_t c,
+                                                       int32_t w, int32_t h, int32_t n, uint16_t off_w, uint16_t off_h)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(off_w), "h"(off_h)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_out, uint32_t ncols)  // one warp in EACH CTA of the pair
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 2-CTA MMA (M = 256: 128 rows per CTA, each CTA supplies its own A tile and half of the B rows), issued by the leader
+__device__ __forceinline__ void mma_i8_ss_pred32_2cta(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                      uint32_t idesc, uint32_t accumulate, uint32_t leader)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.ne.b32 q, %7, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+
+// commit of a 2-CTA MMA stream: arrives on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_2cta_pred(uint64_t* bar, uint32_t leader, uint16_t mask = 3)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(leader), "h"(mask)
+        : "memory");
+}
+
 // ---- programmatic dependent launch ----------------------------------------------------------------
 // launch_dependents: the next kernel in the stream (launched with programmatic stream serialisation) may start
 // occupying SMs as they become free.  wait: block until the previous grid has completed and its memory is visible;

@@ -132,6 +132,16 @@ def test_igemm_im2col_path_on_stride1_shapes(d, monkeypatch):
     assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
 
 
+@pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.c >= 32], ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_igemm_cta_pairs_forced(d, monkeypatch):
+    """Every igemm shape that can run in CTA pairs (two-CTA clusters, cta_group::2 MMAs, half of the filter rows per CTA)
+    does so here regardless of the planner's preference, with the resident-filter variant switched off so that small
+    filter matrices stream too."""
+    monkeypatch.setenv("LBC_CTA2", "1")
+    monkeypatch.setenv("LBC_NO_RESB", "1")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
+
+
 MULTI_TILE_CASES = [
     D(n=4, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # window, resident B, two MMA warps
     D(n=2, h=28, w=28, c=64, k=256, r=1, s=1, relu=1),                         # tiled, resident B, 256-wide tile
@@ -144,6 +154,9 @@ MULTI_TILE_CASES = [
     D(n=3, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # paired tiles, odd tile count (padding image)
     D(n=3, h=7, w=7, c=64, k=512, r=3, s=3, pad_h=1, pad_w=1),                 # paired tiles, 4 N tiles, 1 tile per image
     D(n=5, h=14, w=14, c=512, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # paired tiles, 4 channel chunks
+    D(n=3, h=14, w=14, c=256, k=320, r=1, s=1, relu=1),                        # CTA pairs: odd M tile count, 160-wide N tiles
+    D(n=3, h=15, w=15, c=128, k=96, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1),   # CTA pairs: im2col, M tail, 48 B rows per CTA
+    D(n=1, h=9, w=9, c=2048, k=512, r=1, s=1, relu=1),                         # CTA pairs: one real M tile + its padding twin
 ]
 
 
@@ -157,6 +170,15 @@ def test_many_tiles_per_cta(d, grid, monkeypatch):
     assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
     monkeypatch.delenv("LBC_PAIR")
     assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    # CTA pairs (cta_group::2) forced on wherever the layer streams its filter matrix, then forced off: the planner's own
+    # choice between the two only depends on the K-loop length
+    monkeypatch.setenv("LBC_CTA2", "1")
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    if d.r == 3 and d.c >= 128:
+        assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"
+    monkeypatch.setenv("LBC_CTA2", "0")
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    monkeypatch.delenv("LBC_CTA2")
     if grid == 1 and d.r == 3 and d.c >= 64:
         assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"    # raw accumulators through the same walk
 
