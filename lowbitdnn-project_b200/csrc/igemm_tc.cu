@@ -81,6 +81,7 @@ struct IgemmParams {
     int32_t panel_bytes, panel_swz_bits, n_panels;
     int32_t stage_bufs;           // staging panels per epilogue team (2 or 3: TMA stores drain while later panels fill)
     int32_t team_warps;           // 8: two epilogue teams (wide N tiles); 4: four teams (N tile <= 64 columns)
+    int32_t warp_store;           // 1: each epilogue warp owns a 32-row staging buffer and issues its own TMA stores
     int32_t k_mod;                // bias/scale index = channel % k_mod (pixel-group rewrite replicates them), 0 = plain
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
@@ -794,6 +795,43 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (uint32_t)prm.bn;
             int32_t* y32 = reinterpret_cast<int32_t*>(y);
 
+            if (prm.warp_store) {
+                // ---- ring modes, int8 output: no team barrier at all.  The warp converts whole panels (its 32 rows x
+                // <= 128 columns, panels dealt round-robin to the two warp sets of an 8-warp team) into its OWN swizzled
+                // staging buffer and stores them with its own TMA store; lane 0 tracks the buffer through its bulk group.
+                const uint32_t wbuf = ptx::smem_u32(staging) + e * (32u * (uint32_t)prm.panel_bytes);
+                const uint32_t wrow_off = lane * (uint32_t)prm.panel_bytes;
+                const uint32_t wswz = ((wrow_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
+                const int32_t n_halves = small_teams ? 1 : 2;
+                EpiThread wt = et;
+                wt.valid = true;
+                for (int32_t pnl = (int32_t)half; pnl < n_panels; pnl += n_halves) {
+                    const int32_t pbase = pnl * pcols;
+                    if (lane == 0) ptx::tma_store_wait_read<0>();      // the previous store has read this buffer out
+                    __syncwarp();
+                    if (prm.relu)
+                        epi_drain<true, true>(prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, lo, y32, -1, col0);
+                    else
+                        epi_drain<true, false>(prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, lo, y32, -1, col0);
+                    if (pnl + n_halves >= n_panels) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CTA2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8u);
+                            else ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+                        }
+                        if (issuer) trace_ev(prm, tile, EV_E_DRAINED);
+                    }
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int32_t cbyte = col0 + pbase;
+                        if (cbyte < prm.k_out) ptx::tma_store_2d_s(&tm_out, wbuf, cbyte, tc.m0 + (int32_t)(quarter * 32u));
+                        ptx::tma_store_commit();
+                    }
+                }
+                if (issuer) trace_ev(prm, tile, EV_E_STORED);
+            } else
             for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
                 const int32_t pbase = pnl * pcols;
                 uint8_t* my_staging = team_staging + sbuf * panel_smem;
@@ -851,7 +889,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             else
                 for (uint32_t i = 0; i < n_teams; ++i) it.next(prm);
         }
-        if (issuer && int8_out) ptx::tma_store_wait<0>();
+        if ((issuer || (prm.warp_store && lane == 0)) && int8_out) ptx::tma_store_wait<0>();
     }
 
     // ---- teardown ----
@@ -1054,6 +1092,19 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     if (c.bn % 128 == 0) c.panel_bytes = 128;
     else if (c.bn == 64 || c.bn == 32) c.panel_bytes = c.bn;
     else c.panel_bytes = c.bn;                      // unswizzled single panel (rare channel counts)
+    // ring modes with int8 output: per-warp staging and stores (see the kernel's epilogue) wherever the N tile splits into
+    // whole panels per warp - 256 -> 2 x 128 B, 128 -> 2 x 64 B for the two warp sets of a team, <= 64 -> one panel
+    // Measured (r01): +5-10% on 256-wide tiles with a short K loop (the 1x1 channel expansions, whose epilogue is the
+    // bound); a loss where the extra staging bytes cost ring depth (long K loops) and on narrow tiles (2 KB stores).
+    c.warp_store = 0;
+    {
+        bool want = c.bn == 256 && !c.cta2 && c.k_blocks * (c.bkb / 32) <= 8;
+        if (const char* v = getenv("LBC_WARP_STORE")) want = atoi(v) != 0;     // development / test override
+        if (c.mode != A_WINDOW && d.out_mode == LBC_OUT_INT8 && want && (c.bn == 256 || c.bn == 128 || c.bn == 64 || c.bn == 32)) {
+            c.warp_store = 1;
+            if (c.bn == 128) c.panel_bytes = 64;
+        }
+    }
     c.n_panels = c.bn / c.panel_bytes;
     c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
 
@@ -1103,11 +1154,12 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     c.b_total_bytes = (uint32_t)c.k_blocks * c.b_block_bytes;
     const bool res_b_ok = !c.pair && !c.cta2 && c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
     for (int pass = 0; pass < 2 && !fits; ++pass)
-    for (int bufs = max_bufs; bufs >= 1 && !fits; --bufs) {   // three staging panels per team when they fit, else two, else one
+    for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs) {   // three staging panels per team when they fit, else two, else one
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
         if (pass == 0 && !res_b_ok) break;
         c.stage_bufs = bufs;
         stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(n_teams * bufs * kBlockM * c.panel_bytes), 1024) : 0;
+        if (c.warp_store) stage_bytes = (uint32_t)(kEpiWarps * 32 * c.panel_bytes);   // one 32-row panel per epilogue warp
         if (stage_bytes + ctl_bytes >= 227u * 1024u) continue;
         const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
         uint32_t win_total = 0;
@@ -1283,7 +1335,7 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
         } else {
             const cuuint64_t dims[2] = {(cuuint64_t)d.k, (cuuint64_t)g.m_total};
             const cuuint64_t strides[1] = {(cuuint64_t)d.k};
-            const cuuint32_t box[2] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)kBlockM};
+            const cuuint32_t box[2] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)(cfg.warp_store ? 32 : kBlockM)};
             r = g_encode_tiled(&out->tm_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, y, dims, strides, box, ones,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1316,7 +1368,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.relu = ep.relu; prm.out_mode = ep.out_mode;
     prm.tmem_cols = c.tmem_cols; prm.n_acc = c.n_acc;
     prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
-    prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps;
+    prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps; prm.warp_store = c.warp_store;
     prm.n_tab = c.n_tab;
     for (int i = 0; i < c.n_tab; ++i) { prm.a_tab[i] = c.a_tab[i]; prm.b_tab[i] = c.b_tab[i]; }
     prm.res_b = c.res_b; prm.b_total_bytes = c.b_total_bytes; prm.n_mma = c.n_mma;

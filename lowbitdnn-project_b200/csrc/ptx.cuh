@@ -178,6 +178,15 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
                  : "memory");
 }
 
+// same, the source given as a 32-bit shared-window address
+__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1,
                                              int32_t c2, int32_t c3)
 {

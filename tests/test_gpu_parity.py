@@ -142,6 +142,17 @@ def test_igemm_cta_pairs_forced(d, monkeypatch):
     assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
 
 
+@pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.r == 1 or c.stride_h > 1],
+                         ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_igemm_per_warp_stores_forced(d, monkeypatch):
+    """Ring-mode layers with the per-warp epilogue (own 32-row staging buffer and TMA store per warp, no team barrier)
+    forced on for every N tile it supports (256 / 128 / 64 / 32 columns), and forced off."""
+    monkeypatch.setenv("LBC_WARP_STORE", "1")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
+    monkeypatch.setenv("LBC_WARP_STORE", "0")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
+
+
 MULTI_TILE_CASES = [
     D(n=4, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # window, resident B, two MMA warps
     D(n=2, h=28, w=28, c=64, k=256, r=1, s=1, relu=1),                         # tiled, resident B, 256-wide tile
@@ -177,8 +188,12 @@ def test_many_tiles_per_cta(d, grid, monkeypatch):
     if d.r == 3 and d.c >= 128:
         assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"
     monkeypatch.setenv("LBC_CTA2", "0")
+    monkeypatch.setenv("LBC_WARP_STORE", "1")    # ... and the per-warp epilogue with and without CTA pairs
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    monkeypatch.setenv("LBC_CTA2", "1")
     assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
     monkeypatch.delenv("LBC_CTA2")
+    monkeypatch.delenv("LBC_WARP_STORE")
     if grid == 1 and d.r == 3 and d.c >= 64:
         assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"    # raw accumulators through the same walk
 
