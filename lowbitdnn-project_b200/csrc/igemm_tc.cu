@@ -99,6 +99,8 @@ struct IgemmParams {
     int32_t it_cols, it_rows;
     int32_t step_nb, step_ct, step_rt, step_img;
     int32_t tile_stride;          // tile indices one CTA advances per step: gridDim.x, or 2 * gridDim.x in pair mode
+    // the same for an epilogue team, which takes every n_teams-th tile of its CTA: digits of n_teams * tile_stride
+    int32_t team_stride, tstep_nb, tstep_ct, tstep_rt, tstep_img;
     // Pair mode (window A, streaming B): a CTA works on TWO consecutive M tiles at once - two windows per window stage,
     // two TMEM accumulators - and every B block fetched from L2 feeds the MMAs of both, halving the bytes per MMA that
     // bound wide 3x3 layers.  Tiles are then numbered N-tile-major (n_blk | img | rt | ct) so the two tiles of a pair
@@ -148,10 +150,15 @@ struct TileIter {
     // (not the TMA engine) paces the rings - every constant-bank reload in next() showed up in the traces
     int32_t stride, tiles_n, cols, rows, imgs, s_nb, s_ct, s_rt, s_img, rpt, cpt;
     bool pair;
-    __device__ __forceinline__ void init(const IgemmParams& prm, int32_t t0)
+    // team_steps: advance by an epilogue team's stride (n_teams tiles of the CTA's sequence) per next()
+    __device__ __forceinline__ void init(const IgemmParams& prm, int32_t t0, bool team_steps = false)
     {
         stride = prm.tile_stride; tiles_n = prm.tiles_n; cols = prm.it_cols; rows = prm.it_rows; imgs = prm.it_imgs;
         s_nb = prm.step_nb; s_ct = prm.step_ct; s_rt = prm.step_rt; s_img = prm.step_img;
+        if (team_steps) {
+            stride = prm.team_stride;
+            s_nb = prm.tstep_nb; s_ct = prm.tstep_ct; s_rt = prm.tstep_rt; s_img = prm.tstep_img;
+        }
         rpt = prm.rows_per_tile; cpt = prm.cols_per_tile;
         pair = prm.n_major != 0;
         tile = t0;
@@ -756,10 +763,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t tmem_empty0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->tmem_empty[0]), 0) : 0u;   // the leader's barriers
         TileIter it;
         // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
-        it.init(prm, prm.pair ? first_tile + (int32_t)team : (int32_t)(blockIdx.x + team * gridDim.x));
+        it.init(prm, prm.pair ? first_tile + (int32_t)team : (int32_t)(blockIdx.x + team * gridDim.x), !prm.pair);
         for (; it.tile < num_tiles;) {
-            // CTA-local tile index (it.local advances once per pair / n_teams times per loop)
-            const int32_t tile = prm.pair ? 2 * it.local + (int32_t)team : it.local + (int32_t)team;
+            // CTA-local tile index (it.local counts pairs / team steps)
+            const int32_t tile = prm.pair ? 2 * it.local + (int32_t)team : it.local * (int32_t)n_teams + (int32_t)team;
             struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.img, it.p0(prm), it.q0(prm), it.m0()};
             const int32_t col0 = tc.n_blk * prm.bn;
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
@@ -885,9 +892,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (++sbuf == nbufs) sbuf = 0;
                 }
             }
-            if (prm.pair) it.next(prm);
-            else
-                for (uint32_t i = 0; i < n_teams; ++i) it.next(prm);
+            it.next(prm);
         }
         if ((issuer || (prm.warp_store && lane == 0)) && int8_out) ptx::tma_store_wait<0>();
     }
@@ -1390,6 +1395,21 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
         prm.step_ct = v % prm.it_cols; v /= prm.it_cols;
         prm.step_rt = v % prm.it_rows; v /= prm.it_rows;
         prm.step_img = v;
+    }
+    {   // an epilogue team's stride through the same numbering
+        const int32_t n_teams = kEpiWarps / c.team_warps;
+        int32_t v = prm.team_stride = n_teams * prm.tile_stride;
+        if (prm.n_major) {
+            prm.tstep_ct = v % prm.it_cols; v /= prm.it_cols;
+            prm.tstep_rt = v % prm.it_rows; v /= prm.it_rows;
+            prm.tstep_img = v % prm.it_imgs; v /= prm.it_imgs;
+            prm.tstep_nb = v;
+        } else {
+            prm.tstep_nb = v % c.tiles_n; v /= c.tiles_n;
+            prm.tstep_ct = v % prm.it_cols; v /= prm.it_cols;
+            prm.tstep_rt = v % prm.it_rows; v /= prm.it_rows;
+            prm.tstep_img = v;
+        }
     }
     prm.off_b = c.off_b; prm.off_stage = c.off_stage; prm.off_ctl = c.off_ctl;
     prm.trace = g_trace_buf; prm.trace_tiles = g_trace_tiles;
