@@ -121,9 +121,11 @@ enum : int { EV_P_ISSUE = 0, EV_W_ISSUE, EV_M_START, EV_M_WIN, EV_M_FULL, EV_M_D
              EV_P_DONE };
 
 // `local` = index of the tile in this CTA's own sequence (0, 1, 2, ...)
-__device__ __forceinline__ void trace_ev(const IgemmParams& prm, int32_t local, int ev)
+// `tracing` is the CTA-uniform "trace buffer attached and this is CTA 0", evaluated once per role: the per-call cost
+// in a normal run is one predicated branch
+__device__ __forceinline__ void trace_ev(const IgemmParams& prm, bool tracing, int32_t local, int ev)
 {
-    if (prm.trace != nullptr && blockIdx.x == 0 && local < prm.trace_tiles) prm.trace[local * 16 + ev] = clock64();
+    if (tracing && local < prm.trace_tiles) prm.trace[local * 16 + ev] = clock64();
 }
 
 __device__ int g_timeout_flag = 0;
@@ -340,6 +342,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t lane = threadIdx.x & 31;
     volatile int* tflag = &g_timeout_flag;
     const uint32_t cta_rank = CTA2 ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
+    const bool tracing = prm.trace != nullptr && blockIdx.x == 0;
 
     if ((ptx::smem_u32(smem) & 1023u) != 0) {       // swizzle atoms need a 1024-byte aligned base
         if (threadIdx.x == 0) *tflag = 2;
@@ -448,7 +451,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 for (int32_t st = 0; st < stages_per_tile; ++st) {
                     ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
                     if (!ok) break;
-                    if (st == 0 && leader) trace_ev(prm, it.local, EV_P_ISSUE);
+                    if (st == 0 && leader) trace_ev(prm, tracing, it.local, EV_P_ISSUE);
                     if (leader && cta_rank == 0) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
                     uint8_t* dst_a = smem_a + stage * a_stage;
                     uint8_t* dst_b = smem_b + stage * b_stage;
@@ -486,7 +489,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
                 if (sub) { stage_o = stage - sub_base; phase_o = phase; }
                 else { stage_e = stage - sub_base; phase_e = phase; }
-                if (leader) trace_ev(prm, it.local, EV_P_DONE);
+                if (leader) trace_ev(prm, tracing, it.local, EV_P_DONE);
             }
         }
     } else if (warp == 2) {
@@ -518,7 +521,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
                     if (!ok) break;
                     if (leader) {
-                        if (cb == 0) trace_ev(prm, it.local, EV_W_ISSUE);
+                        if (cb == 0) trace_ev(prm, tracing, it.local, EV_W_ISSUE);
                         if (cta_rank == 0) ptx::mbar_expect_tx(&ctl->wfull[ws], win_tx);
                         if (CTA2) ptx::tma_load_4d_2sm(smem_a + ws * win_stage_bytes, &tm_a, wfull0 + ws * 8u, c0, wq, wp, it.img);
                         else ptx::tma_load_4d(smem_a + ws * win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.img);
@@ -582,18 +585,18 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t acc_phase = ((uint32_t)(2 * lp) >> acc_shift) & 1u;
                 ptx::mbar_wait_soft(&ctl->tmem_empty[acc], acc_phase ^ 1, tflag);
                 ptx::tc_fence_after();
-                if (leader && which == 0) trace_ev(prm, lp, EV_M_START);
+                if (leader && which == 0) trace_ev(prm, tracing, lp, EV_M_START);
                 const uint32_t tmem_d = tmem_base + acc * bn;
                 uint32_t accumulate = 0;
                 for (int32_t cb = 0; cb < mma_outer; ++cb) {
                     if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
                     const uint32_t a_base = da_lo + ws * a_stage16 + which * win_sub16;
-                    if (cb == 0 && leader && which == 0) trace_ev(prm, lp, EV_M_WIN);
+                    if (cb == 0 && leader && which == 0) trace_ev(prm, tracing, lp, EV_M_WIN);
                     int32_t j = 0;
                     for (int32_t st = 0; st < inner_stages; ++st) {
                         if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
                         ptx::tc_fence_after();
-                        if (st == 0 && cb == 0 && leader && which == 0) trace_ev(prm, lp, EV_M_FULL);
+                        if (st == 0 && cb == 0 && leader && which == 0) trace_ev(prm, tracing, lp, EV_M_FULL);
                         uint32_t nstage = stage + 1, nphase = phase;
                         if (nstage == ring_hi) { nstage = ring_lo; nphase ^= 1; }
                         const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
@@ -616,7 +619,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
                 }
                 ptx::mma_commit_pred(&ctl->tmem_full[acc], leader);
-                if (leader && which == 0) trace_ev(prm, lp, EV_M_DONE);
+                if (leader && which == 0) trace_ev(prm, tracing, lp, EV_M_DONE);
             }
         } else {
         int32_t local = (int32_t)which;
@@ -628,7 +631,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t acc_phase = ((uint32_t)local >> acc_shift) & 1u;
             ptx::mbar_wait_soft(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
             ptx::tc_fence_after();
-            if (leader) trace_ev(prm, local, EV_M_START);
+            if (leader) trace_ev(prm, tracing, local, EV_M_START);
             const uint32_t tmem_d = tmem_base + acc_stage * bn;
             uint32_t accumulate = 0;
             if (kWindow && RESB) {
@@ -638,7 +641,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
                     ptx::tc_fence_after();
                     const uint32_t a_base = da_lo + ws * a_stage16;
-                    if (cb == 0 && leader) trace_ev(prm, local, EV_M_WIN);
+                    if (cb == 0 && leader) trace_ev(prm, tracing, local, EV_M_WIN);
                     // unrolled by the length of a filter row's worth of MMAs so the table loads and descriptor adds of one
                     // batch overlap (the uniform datapath has long latencies and the loop's fixed cost is ~25 instructions)
                     constexpr int kBatch = (KM == 3) ? 8 : 9;
@@ -667,13 +670,13 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (kWindow) {
                         if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
                         a_base = da_lo + ws * a_stage16;
-                        if (cb == 0 && leader) trace_ev(prm, local, EV_M_WIN);
+                        if (cb == 0 && leader) trace_ev(prm, tracing, local, EV_M_WIN);
                     }
                     int32_t j = 0;   // index into the chunk's A-offset table
                     for (int32_t st = 0; st < inner_stages; ++st) {
                         if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
                         ptx::tc_fence_after();
-                        if (st == 0 && cb == 0 && leader) trace_ev(prm, local, EV_M_FULL);
+                        if (st == 0 && cb == 0 && leader) trace_ev(prm, tracing, local, EV_M_FULL);
                         // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
                         uint32_t nstage = stage + 1, nphase = phase;
                         if (nstage == ring_hi) { nstage = ring_lo; nphase ^= 1; }
@@ -702,7 +705,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
             }
             mma_commit<CTA2>(&ctl->tmem_full[acc_stage], leader);     // accumulator complete -> epilogue (of both CTAs)
-            if (leader) trace_ev(prm, local, EV_M_DONE);
+            if (leader) trace_ev(prm, tracing, local, EV_M_DONE);
         }
         }
     } else if (warp >= kFirstEpiWarp) {
@@ -727,11 +730,24 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t tt_id = (tw << 5) | lane;                  // thread inside the team
         const bool issuer = (tt_id == 0);
         const uint32_t bar_id = 1 + team;                         // named barrier of this team
+        // the per-panel barrier, with immediate operands where the team shape is the common one (BAR.SYNC imm, imm)
+        auto team_sync = [&]() {
+            if (!small_teams) {
+                if (team == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+                else asm volatile("bar.sync 2, 256;" ::: "memory");
+            } else {
+                ptx::named_bar_sync(bar_id, team_threads);
+            }
+        };
         const float lo = prm.relu ? 0.0f : -128.0f;
         const bool int8_out = (prm.out_mode == LBC_OUT_INT8);
         const uint32_t panel_smem = (uint32_t)(kBlockM * prm.panel_bytes);
         const uint32_t nbufs = (uint32_t)prm.stage_bufs;
-        uint8_t* team_staging = staging + (size_t)team * nbufs * panel_smem;
+        const uint32_t team_staging_s = ptx::smem_u32(staging) + team * nbufs * panel_smem;   // 32-bit shared-window address
+        const uint32_t tmem_lane_base = tmem_base + ((quarter * 32u) << 16);
+        const uint32_t tmem_empty_s = ptx::smem_u32(&ctl->tmem_empty[0]);
+        const uint32_t tmem_full_s = ptx::smem_u32(&ctl->tmem_full[0]);
+        const uint32_t bn_u = (uint32_t)prm.bn;
         uint32_t sbuf = 0;
         float* sc = ctl->scale[team];
         int32_t* bi = ctl->bias[team];
@@ -785,9 +801,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             // accumulator ready?  CTA-local tile L lives in TMEM stage L % n_acc, on that stage's (L / n_acc)-th use
             const uint32_t acc = (uint32_t)tile & acc_mask;
             const uint32_t acc_phase = ((uint32_t)tile >> acc_shift) & 1u;
-            ptx::mbar_wait(&ctl->tmem_full[acc], acc_phase, tflag);
+            ptx::mbar_wait_s(tmem_full_s + acc * 8u, acc_phase, tflag);
             ptx::tc_fence_after();
-            if (issuer) trace_ev(prm, tile, EV_E_START);
+            if (issuer) trace_ev(prm, tracing, tile, EV_E_START);
 
             int64_t out_row = -1;   // int32 mode: global output row of this lane
             if (!int8_out) {
@@ -799,7 +815,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (r < prm.m_total) out_row = r;
                 }
             }
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * (uint32_t)prm.bn;
+            const uint32_t taddr = tmem_lane_base + acc * bn_u;
             int32_t* y32 = reinterpret_cast<int32_t*>(y);
 
             if (prm.warp_store) {
@@ -825,9 +841,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         __syncwarp();
                         if (lane == 0) {
                             if (CTA2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8u);
-                            else ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+                            else ptx::mbar_arrive_s(tmem_empty_s + acc * 8u);
                         }
-                        if (issuer) trace_ev(prm, tile, EV_E_DRAINED);
+                        if (issuer) trace_ev(prm, tracing, tile, EV_E_DRAINED);
                     }
                     ptx::fence_proxy_async();
                     __syncwarp();
@@ -837,17 +853,16 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         ptx::tma_store_commit();
                     }
                 }
-                if (issuer) trace_ev(prm, tile, EV_E_STORED);
+                if (issuer) trace_ev(prm, tracing, tile, EV_E_STORED);
             } else
             for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
                 const int32_t pbase = pnl * pcols;
-                uint8_t* my_staging = team_staging + sbuf * panel_smem;
                 if (nbufs == 1 && int8_out) {
                     // a single staging panel (shared memory is tight): its previous store must have read it out
                     if (issuer) ptx::tma_store_wait_read<0>();
-                    ptx::named_bar_sync(bar_id, team_threads);
+                    team_sync();
                 }
-                const uint32_t staging_s = ptx::smem_u32(my_staging);
+                const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
                 if (int8_out && prm.relu)
                     epi_drain<true, true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
                                           swz_mask, lo, y32, out_row, col0);
@@ -863,9 +878,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     __syncwarp();
                     if (lane == 0) {
                         if (CTA2) ptx::mbar_arrive_cluster(tmem_empty0 + acc * 8u);
-                        else ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+                        else ptx::mbar_arrive_s(tmem_empty_s + acc * 8u);
                     }
-                    if (issuer) trace_ev(prm, tile, EV_E_DRAINED);
+                    if (issuer) trace_ev(prm, tracing, tile, EV_E_DRAINED);
                 }
                 if (int8_out) {
                     ptx::fence_proxy_async();
@@ -875,19 +890,19 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         if (nbufs >= 3) ptx::tma_store_wait_read<1>();
                         else if (nbufs == 2) ptx::tma_store_wait_read<0>();
                     }
-                    ptx::named_bar_sync(bar_id, team_threads);
+                    team_sync();
                     if (issuer) {
                         const int32_t cbyte = col0 + pbase;
                         if (cbyte < prm.k_out) {
                             if (prm.mode == A_WINDOW) {
                                 if (tc.img < prm.n_img)   // the pair modes pad the tile space with dummy tiles
-                                    ptx::tma_store_4d(&tm_out, my_staging, cbyte, tc.q0, tc.p0, tc.img);
+                                    ptx::tma_store_4d_s(&tm_out, staging_s, cbyte, tc.q0, tc.p0, tc.img);
                             }
                             else
-                                ptx::tma_store_2d(&tm_out, my_staging, cbyte, tc.m0);
+                                ptx::tma_store_2d_s(&tm_out, staging_s, cbyte, tc.m0);
                         }
                         ptx::tma_store_commit();
-                        if (pnl == n_panels - 1) trace_ev(prm, tile, EV_E_STORED);
+                        if (pnl == n_panels - 1) trace_ev(prm, tracing, tile, EV_E_STORED);
                     }
                     if (++sbuf == nbufs) sbuf = 0;
                 }

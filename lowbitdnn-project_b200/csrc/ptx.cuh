@@ -67,6 +67,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar_smem_addr)     // barrier given as a 32-bit shared-window address
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_smem_addr) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar_smem_addr, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_smem_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
@@ -108,6 +128,26 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
     const uint64_t t0 = globaltimer_ns();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0) {
+            if (*timeout_flag != 0) return false;
+            if (globaltimer_ns() - t0 > budget_ns) {
+                *timeout_flag = 1;
+                __threadfence();
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+// mbar_wait with the barrier given as a 32-bit shared-window address (hot loops: no generic->shared conversion per call)
+__device__ __forceinline__ bool mbar_wait_s(uint32_t bar_smem_addr, uint32_t parity, volatile int* timeout_flag,
+                                            uint64_t budget_ns = 2000000000ull)
+{
+    if (mbar_try_wait_s(bar_smem_addr, parity)) return true;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_s(bar_smem_addr, parity)) {
         if ((++spins & 0x3ff) == 0) {
             if (*timeout_flag != 0) return false;
             if (globaltimer_ns() - t0 > budget_ns) {
@@ -184,6 +224,15 @@ __device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* tm, uint32_t s
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(tm)),
                  "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_4d_s(const CUtensorMap* tm, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                               int32_t c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 
