@@ -77,7 +77,8 @@ struct IgemmParams {
     // epilogue
     int32_t relu, out_mode;
     uint32_t tmem_cols;
-    int32_t n_acc;                // TMEM accumulator stages (2 or 4): how far the MMA warp may run ahead of the epilogue
+    int32_t n_acc;                // TMEM accumulator stages (2, 4 or 8): how far the MMA warp may run ahead of the epilogue
+    int32_t tpi;                  // tiles an epilogue team takes per iteration (2 for N tiles <= 64 columns with 8 stages)
     int32_t panel_bytes, panel_swz_bits, n_panels;
     int32_t stage_bufs;           // staging panels per epilogue team (2 or 3: TMA stores drain while later panels fill)
     int32_t team_warps;           // 8: two epilogue teams (wide N tiles); 4: four teams (N tile <= 64 columns)
@@ -135,8 +136,8 @@ struct Ctl {
     uint64_t empty[kMaxStages];
     uint64_t wfull[kMaxWinStages];
     uint64_t wempty[kMaxWinStages];
-    uint64_t tmem_full[4];
-    uint64_t tmem_empty[4];
+    uint64_t tmem_full[8];
+    uint64_t tmem_empty[8];
     uint64_t bfull;               // resident filter matrix has landed
     uint32_t tmem_base;
     uint32_t pad_[1];
@@ -568,7 +569,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t ring_lo = sub_ring * ring_len, ring_hi = ring_lo + ring_len;
         const uint32_t win_lo = sub_ring * win_len, win_hi = win_lo + win_len;
         const uint32_t bn = (uint32_t)prm.bn;
-        const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
+        const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 8 ? 3u : prm.n_acc == 4 ? 2u : 1u;
         uint32_t stage = ring_lo, phase = 0, ws = win_lo, wphase = 0;
         const bool active = (which < n_mma || prm.pair) && cta_rank == 0;   // CTA pairs: only the leader issues
         bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
@@ -774,9 +775,86 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t row_off = et.srow * (uint32_t)prm.panel_bytes;     // byte offset of this lane's staging row
         // per-thread XOR term of the staging swizzle (see epi_consume)
         const uint32_t swz_mask = ((row_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
-        const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 4 ? 2u : 1u;
+        const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 8 ? 3u : prm.n_acc == 4 ? 2u : 1u;
         int32_t cur_nblk = -1;
         const uint32_t tmem_empty0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->tmem_empty[0]), 0) : 0u;   // the leader's barriers
+        if (!CTA2 && prm.tpi == 2) {
+            // ---- narrow N tiles (<= 64 columns, one N tile, 8 accumulator stages): a 4-warp team takes TWO consecutive
+            // CTA-local tiles per iteration - adjacent TMEM stages, one staging panel each - so the per-iteration
+            // bookkeeping (iterator, barriers, waits, store issue), which is a third of this role's instructions on
+            // 64-column tiles, is paid once per two tiles.
+            TileIter ia, ib;
+            ia.init(prm, (int32_t)(blockIdx.x + (2u * team) * gridDim.x), true);
+            ib.init(prm, (int32_t)(blockIdx.x + (2u * team + 1u) * gridDim.x), true);
+            // per-channel parameters: a single N tile, loaded once
+            for (int32_t c = (int32_t)tt_id; c < prm.bn; c += (int32_t)team_threads) {
+                const bool in = c < prm.k_out;
+                const int32_t kp = prm.k_mod ? c % prm.k_mod : c;
+                sc[c] = (in && scale) ? __ldg(scale + kp) : 0.0f;
+                bi[c] = (in && bias) ? __ldg(bias + kp) : 0;
+            }
+            ptx::named_bar_sync(bar_id, team_threads);
+            int32_t* y32 = reinterpret_cast<int32_t*>(y);
+            for (; ia.tile < num_tiles; ia.next(prm), ib.next(prm)) {
+                const int32_t tile0 = ia.local * 8 + 2 * (int32_t)team;        // CTA-local index of the first tile
+                const uint32_t acc0 = (uint32_t)tile0 & 7u, acc_phase = ((uint32_t)tile0 >> 3) & 1u;
+                const bool have_b = ib.tile < num_tiles;
+#pragma unroll 1
+                for (uint32_t sub = 0; sub < 2; ++sub) {
+                    if (sub == 1 && !have_b) break;
+                    const TileIter& it2 = sub ? ib : ia;
+                    const uint32_t acc = acc0 + sub;
+                    ptx::mbar_wait_s(tmem_full_s + acc * 8u, acc_phase, tflag);
+                    ptx::tc_fence_after();
+                    if (issuer) trace_ev(prm, tracing, tile0 + (int32_t)sub, EV_E_START);
+                    int64_t out_row = -1;
+                    if (!int8_out) {
+                        if (prm.mode == A_WINDOW) {
+                            const int32_t pp = it2.p0(prm) + et.wrow, qq = it2.q0(prm) + et.wcol;
+                            if (et.valid && pp < prm.p && qq < prm.q && it2.img < prm.n_img) out_row = ((int64_t)it2.img * prm.p + pp) * prm.q + qq;
+                        } else {
+                            const int64_t r = (int64_t)it2.m0() + lane_row;
+                            if (r < prm.m_total) out_row = r;
+                        }
+                    }
+                    const uint32_t taddr = tmem_lane_base + acc * bn_u;
+                    const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
+                    if (nbufs == 1 && int8_out) {
+                        if (issuer) ptx::tma_store_wait_read<0>();
+                        ptx::named_bar_sync(bar_id, team_threads);
+                    }
+                    if (int8_out && prm.relu)
+                        epi_drain<true, true>(prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32, out_row, 0);
+                    else if (int8_out)
+                        epi_drain<true, false>(prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32, out_row, 0);
+                    else
+                        epi_drain<false, false>(prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32, out_row, 0);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_s(tmem_empty_s + acc * 8u);
+                    if (issuer) trace_ev(prm, tracing, tile0 + (int32_t)sub, EV_E_DRAINED);
+                    if (int8_out) {   // same staging-ring protocol as the general path below: one barrier per panel
+                        ptx::fence_proxy_async();
+                        if (issuer) {
+                            if (nbufs >= 3) ptx::tma_store_wait_read<1>();
+                            else if (nbufs == 2) ptx::tma_store_wait_read<0>();
+                        }
+                        ptx::named_bar_sync(bar_id, team_threads);
+                        if (issuer) {
+                            if (prm.mode == A_WINDOW) {
+                                if (it2.img < prm.n_img) ptx::tma_store_4d_s(&tm_out, staging_s, 0, it2.q0(prm), it2.p0(prm), it2.img);
+                            } else {
+                                ptx::tma_store_2d_s(&tm_out, staging_s, 0, it2.m0());
+                            }
+                            ptx::tma_store_commit();
+                            trace_ev(prm, tracing, tile0 + (int32_t)sub, EV_E_STORED);
+                        }
+                        if (++sbuf == nbufs) sbuf = 0;
+                    }
+                }
+            }
+            if (issuer && int8_out) ptx::tma_store_wait<0>();
+        } else {
         TileIter it;
         // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
         it.init(prm, prm.pair ? first_tile + (int32_t)team : (int32_t)(blockIdx.x + team * gridDim.x), !prm.pair);
@@ -910,6 +988,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             it.next(prm);
         }
         if ((issuer || (prm.warp_store && lane == 0)) && int8_out) ptx::tma_store_wait<0>();
+        }
     }
 
     // ---- teardown ----
@@ -1058,6 +1137,17 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
             c.s_pad = s_eff;
             c.rows_per_tile = rows; c.cols_per_tile = cols; c.row_tiles = row_tiles; c.col_tiles = col_tiles; c.wt = wt;
         }
+        // Wide layers that will run in CTA pairs (256-wide N tiles, >= 256 channels): a 128-cycle MMA consumes 4 KB of A,
+        // which L2 sustains even with every tap fetched separately, so the im2col mode's fully used M tiles (no halo rows,
+        // no ragged last row tile: 100% against 77-88% of the MMA rows) win - measured 4% (14x14x256), 10% (28x28x512)
+        // and 17% (14x14x512) with pairs, while 128-wide tiles (64-cycle MMAs) stay 25% faster with windows.
+        const char* pairs_env = getenv("LBC_CTA2");
+        if (c.mode == A_WINDOW && c.bn == 256 && d.c >= 256 && d.c % 128 == 0 && !(pairs_env && atoi(pairs_env) == 0) &&
+            !getenv("LBC_KEEP_WINDOW")) {
+            c.mode = A_IM2COL;
+            c.s_pad = d.s;
+            c.rows_per_tile = c.cols_per_tile = c.row_tiles = c.col_tiles = c.wt = 0;
+        }
     }
 
     // ---- K chunking
@@ -1131,6 +1221,12 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // ---- accumulator stages and epilogue teams
     c.n_acc = (4 * c.bn <= 512 && (c.pair || !getenv("LBC_TWO_ACC"))) ? 4 : 2;
     c.team_warps = (c.n_acc == 4 && c.bn <= 64 && !getenv("LBC_BIG_TEAMS")) ? 4 : 8;
+    // narrow tiles: 8 accumulator stages and two tiles per epilogue iteration (see the kernel's tpi == 2 path)
+    c.tpi = 1;
+    if (c.team_warps == 4 && c.tiles_n == 1 && !c.pair && !c.cta2 && !c.warp_store && c.bn == c.panel_bytes && !getenv("LBC_TPI1")) {
+        c.tpi = 2;
+        c.n_acc = 8;
+    }
     const int n_teams = kEpiWarps / c.team_warps;
 
     // ---- smem carve-up: [A ring | window ring][B ring][output staging][control]
@@ -1386,7 +1482,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.wt = c.wt; prm.rows_per_tile = c.rows_per_tile; prm.cols_per_tile = c.cols_per_tile;
     prm.row_tiles = c.row_tiles; prm.col_tiles = c.col_tiles;
     prm.relu = ep.relu; prm.out_mode = ep.out_mode;
-    prm.tmem_cols = c.tmem_cols; prm.n_acc = c.n_acc;
+    prm.tmem_cols = c.tmem_cols; prm.n_acc = c.n_acc; prm.tpi = c.tpi;
     prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
     prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps; prm.warp_store = c.warp_store;
     prm.n_tab = c.n_tab;
@@ -1413,7 +1509,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     }
     {   // an epilogue team's stride through the same numbering
         const int32_t n_teams = kEpiWarps / c.team_warps;
-        int32_t v = prm.team_stride = n_teams * prm.tile_stride;
+        int32_t v = prm.team_stride = n_teams * c.tpi * prm.tile_stride;
         if (prm.n_major) {
             prm.tstep_ct = v % prm.it_cols; v /= prm.it_cols;
             prm.tstep_rt = v % prm.it_rows; v /= prm.it_rows;
