@@ -163,7 +163,7 @@ def reference_arm(args, layers):
     """The reference's own CPU path (refConv2DForward.hpp, unmodified, oracle/_ref) on a bounded sample."""
     from oracle import oracle
     if not oracle.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_conv.so missing (built only where /root/reference exists)"}))
+        emit_json({"impl": "reference", "unavailable": "oracle/_ref/libref_conv.so missing (built only where /root/reference exists)"})
         return
     b, ic, ih, iw, oc, oh, ow, kh, kw = REF_SAMPLE
     rng = np.random.default_rng(99)
@@ -194,7 +194,20 @@ def reference_arm(args, layers):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit_json(out)
+
+
+_JSON_FD = None
+
+
+def emit_json(obj):
+    """The one JSON line of the contract, on the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -214,6 +227,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
 
     import lowbitdnn_project_b200 as lbc   # raises if liblowbit_cnn.so is missing — no fallback
     nets = lbc.networks
@@ -406,7 +424,7 @@ def main():
             with open(args.layer_report, "w") as fh:
                 json.dump({"network": args.network, "batch": args.batch, "int8_peak_tops": int8_peak,
                            "hbm_gbs": peaks["hbm_gbs"], "layers": rep}, fh, indent=1)
-        print(json.dumps(out))
+        emit_json(out)
     net.close()
     if world > 1:
         dist.destroy_process_group()
