@@ -412,7 +412,10 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
                  d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.tps, c.win_stages,
                  c.res_b ? (c.n_mma == 2 ? "resident,2mma" : "resident") : c.pair ? "ring,paired-tiles" : c.cta2 ? "ring,cta-pair" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols,
-                 d.out_mode != LBC_OUT_INT8 ? "int32" : c.warp_store ? "warp-stores" : c.team_warps == 4 ? "4x4-warp-teams" : "2x8-warp-teams");
+                 d.out_mode != LBC_OUT_INT8 ? (c.fold ? "int32,bias-in-mma" : "int32")
+                 : c.warp_store ? (c.fold ? "warp-stores,bias-in-mma" : "warp-stores")
+                 : c.team_warps == 4 ? (c.fold ? "4x4-warp-teams,bias-in-mma" : "4x4-warp-teams")
+                                     : (c.fold ? "2x8-warp-teams,bias-in-mma" : "2x8-warp-teams"));
     } else {
         snprintf(buf, buf_len, "%s N%d %dx%dx%d->%d %dx%d s%d p%d g%d | M=%lld",
                  plan->kind == LBC_KERNEL_DEPTHWISE ? "depthwise" : "direct", d.n, d.h, d.w, d.c, d.k, d.r, d.s,

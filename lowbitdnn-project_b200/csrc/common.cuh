@@ -104,6 +104,8 @@ struct IgemmConfig {
     int32_t n_mma;       // MMA-issuing warps (1 or 2)
     int32_t pair;        // two M tiles per CTA step share every B block (window A, streaming B)
     int32_t it_imgs;     // pair modes: image (ring modes: M tile) radix of the tile numbering, padded so tiles come in pairs
+    int32_t fold;        // bias folded into the first MMA of every tile (resident filter matrix); off_fold = its operand blocks
+    uint32_t off_fold;
     int32_t tpi;         // tiles per epilogue-team iteration (2: narrow N tiles with 8 accumulator stages)
     int32_t cta2;        // CTA-pair mode: clusters of two CTAs, cta_group::2 MMAs, half of the B rows per CTA
     uint32_t win_sub_bytes;   // bytes of one window (a pair-mode stage holds two)

@@ -36,6 +36,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <mutex>
 
 namespace lbc {
@@ -83,6 +84,13 @@ struct IgemmParams {
     int32_t stage_bufs;           // staging panels per epilogue team (2 or 3: TMA stores drain while later panels fill)
     int32_t team_warps;           // 8: two epilogue teams (wide N tiles); 4: four teams (N tile <= 64 columns)
     int32_t warp_store;           // 1: each epilogue warp owns a 32-row staging buffer and issues its own TMA stores
+    // Bias folded into the MMA (resident-filter kernels): the first MMA of every tile multiplies a constant A block (every
+    // row = 31 x 127, 1) with a B block of per-channel bias digits (bias = 127 * sum(d_0..d_30) + d_31), so the
+    // accumulator starts at the bias and the epilogue skips its add and the bias fetch (1.25 of its 4.75 instructions
+    // per output).  Both blocks live at off_fold, written once per CTA by the epilogue warps; biases beyond +-500000 turn
+    // the fold off for the launch (ctl->fold_ok).
+    int32_t fold;
+    uint32_t off_fold;
     int32_t k_mod;                // bias/scale index = channel % k_mod (pixel-group rewrite replicates them), 0 = plain
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
@@ -139,8 +147,9 @@ struct Ctl {
     uint64_t tmem_full[8];
     uint64_t tmem_empty[8];
     uint64_t bfull;               // resident filter matrix has landed
+    uint64_t bias_ready;          // bias-digit block written (one arrival per epilogue warp)
     uint32_t tmem_base;
-    uint32_t pad_[1];
+    uint32_t fold_ok;             // 0: some |bias| is out of the digit range - the epilogue adds the bias as usual
     alignas(16) float scale[4][256];     // [team][column of the N tile] (4 teams only exist for N tiles <= 64)
     alignas(16) int32_t bias[4][256];
 };
@@ -225,14 +234,15 @@ __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, vol
 // RELU: the clamp at zero is applied to the PACKED bytes (sign-replicating PRMT + AND: 2 instructions per 4 outputs
 // instead of 4 FMNMX).  Rounding then clamping at an integer equals clamping then rounding, and a NaN product converts to
 // 0 either way, so the bytes are identical to requant_s32 with lo = 0.
-template <bool RELU>
+// FOLD: the accumulator already contains the bias (see IgemmParams::fold)
+template <bool RELU, bool FOLD>
 __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi, float lo)
 {
     uint32_t w[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const float4 f = *reinterpret_cast<const float4*>(sc + 4 * t);
-        const int4 b = *reinterpret_cast<const int4*>(bi + 4 * t);
+        const int4 b = FOLD ? make_int4(0, 0, 0, 0) : *reinterpret_cast<const int4*>(bi + 4 * t);
         if (RELU) {
             const int32_t q0 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 0] + b.x), f.x));
             const int32_t q1 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 1] + b.y), f.y));
@@ -258,7 +268,7 @@ struct EpiThread {
 
 // Process NG 16-column groups held in v[]: tile columns [c, c + 16*NG), which are staging-panel columns
 // [pc, pc + 16*NG).  OUT8 selects the fused int8 path (requantise -> swizzled staging panel) or raw int32 stores.
-template <int NG, bool OUT8, bool RELU>
+template <int NG, bool OUT8, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
                                             const uint32_t* v, int32_t c, int32_t pc, const EpiThread& et,
                                             uint32_t staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32,
@@ -268,16 +278,17 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
     for (int g = 0; g < NG; ++g) {
         const int32_t cc = c + 16 * g;
         if (OUT8) {
-            const uint4 r = requant16<RELU>(v + 16 * g, sc + cc, bi + cc, lo);
+            const uint4 r = requant16<RELU, FOLD>(v + 16 * g, sc + cc, bi + cc, lo);
             // swizzle: the XOR term depends only on the staging row (a panel row never crosses a 128-byte line), so
             // `swz_mask` arrives here already as this thread's ((row_off >> 7) & mask) << 4
             // `staging` arrives as a 32-bit shared-window address (one conversion per panel, not one per store)
             if (et.valid) ptx::st_shared_v4(staging + ((row_off + (uint32_t)(pc + 16 * g)) ^ swz_mask), r.x, r.y, r.z, r.w);
+            if (FOLD) asm volatile("" ::: "memory");   // keep the next group's parameter loads behind this store (register cap)
         } else if (out_row >= 0 && col0 + cc < prm.k_out) {
             int32_t* yo = y32 + out_row * prm.k_out + col0 + cc;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                const int4 b = *reinterpret_cast<const int4*>(bi + cc + j);
+                const int4 b = FOLD ? make_int4(0, 0, 0, 0) : *reinterpret_cast<const int4*>(bi + cc + j);
                 ptx::st_global_v4(yo + j, v[16 * g + j] + (uint32_t)b.x, v[16 * g + j + 1] + (uint32_t)b.y,
                                   v[16 * g + j + 2] + (uint32_t)b.z, v[16 * g + j + 3] + (uint32_t)b.w);
             }
@@ -286,7 +297,7 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
 }
 
 // Drain this warp's share [c0, c1) of one panel out of TMEM.
-template <bool OUT8, bool RELU>
+template <bool OUT8, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* sc, const int32_t* bi, uint32_t taddr,
                                           int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint32_t staging,
                                           uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
@@ -297,14 +308,75 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         ptx::tmem_ld_wait_dep(v);
-        epi_consume<2, OUT8, RELU>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+        epi_consume<2, OUT8, RELU, FOLD>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
     }
     if (c + 16 <= c1) {
         uint32_t v16[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
         ptx::tmem_ld_wait_dep16(v16);
-        epi_consume<1, OUT8, RELU>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
     }
+}
+
+// One-time set-up of the bias-fold operand blocks (see IgemmParams::fold), by the 512 epilogue threads.
+// Called before the role computes its per-thread constants, so its temporaries do not overlap their live ranges.
+__device__ __forceinline__ void write_fold_blocks(uint8_t* fold_base, uint32_t etid, int32_t bn, int32_t k_out, int32_t k_mod,
+                                               const int32_t* __restrict__ bias, uint32_t* fold_ok)
+{
+    // [A': 4 KB][B': bn x 32 B], both as 8-row x 16-byte core matrices (K chunks 128 B apart, 8-row groups 256 B apart)
+    // A': every row = 31 x 127, then 1.  16-byte piece i sits at i * 16 and belongs to K chunk (i >> 3) & 1.
+    for (uint32_t i = etid; i < 256u; i += kEpiWarps * 32u) {
+        const uint32_t last = ((i >> 3) & 1u) ? 0x017f7f7fu : 0x7f7f7f7fu;
+        *reinterpret_cast<uint4*>(fold_base + i * 16u) = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, last);
+    }
+    // B': one thread per output channel
+    bool ok = true;
+    for (uint32_t c = etid; c < (uint32_t)bn; c += kEpiWarps * 32u) {
+        const bool in = (int32_t)c < k_out;
+        const int32_t kp = k_mod ? (int32_t)c % k_mod : (int32_t)c;
+        int32_t b = (in && bias) ? __ldg(bias + kp) : 0;
+        if (b > 500000 || b < -500000) { ok = false; b = 0; }
+        int32_t q = (b + (b >= 0 ? 63 : -63)) / 127;          // bias = 127 * q + r0, |r0| <= 63
+        const int32_t r0 = b - 127 * q;
+        uint32_t wds[8];
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int bj = 0; bj < 4; ++bj) {
+                int32_t dgt;
+                if (wi == 7 && bj == 3) dgt = r0;
+                else { dgt = max(-127, min(127, q)); q -= dgt; }
+                wv |= ((uint32_t)dgt & 0xffu) << (8 * bj);
+            }
+            wds[wi] = wv;
+        }
+        uint8_t* dst = fold_base + 4096u + (c >> 3) * 256u + (c & 7u) * 16u;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        *reinterpret_cast<uint4*>(dst + 128) = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+    }
+    if (!ok) *reinterpret_cast<volatile uint32_t*>(fold_ok) = 0u;
+}
+
+// Selects the epilogue instantiation for the (warp-uniform) run-time switches.  MAY_FOLD is false in kernels that never
+// fold the bias (streaming filter matrix), so they carry no second copy of the conversion code.
+template <bool MAY_FOLD>
+__device__ __forceinline__ void epi_run(bool int8_out, bool relu, bool fold, const IgemmParams& prm, const float* sc,
+                                        const int32_t* bi, uint32_t taddr, int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et,
+                                        uint32_t staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
+                                        int32_t col0)
+{
+#define LBC_EPI(O8, RL, FD) epi_drain<O8, RL, FD>(prm, sc, bi, taddr, pbase, c0, c1, et, staging, row_off, swz_mask, lo, y32, out_row, col0)
+    if (MAY_FOLD && fold) {
+        if (int8_out && relu) LBC_EPI(true, true, true);
+        else if (int8_out) LBC_EPI(true, false, true);
+        else LBC_EPI(false, false, true);
+    } else {
+        if (int8_out && relu) LBC_EPI(true, true, false);
+        else if (int8_out) LBC_EPI(true, false, false);
+        else LBC_EPI(false, false, false);
+    }
+#undef LBC_EPI
 }
 
 // KM: 0 tiled A, 1 im2col A, 2 window A (>= 32-byte pixels), 3 window A with 16-byte pixels (paired taps)
@@ -327,7 +399,10 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar, uint32_t leader)
 }
 
 // CTA2: CTA-pair mode (see IgemmParams::cta2); only instantiated with RESB == false
-template <int KM, int KS, bool RESB, bool CTA2>
+// MAYFOLD: the launch may fold the bias into the MMA (see IgemmParams::fold); only with RESB.  A separate instantiation,
+// because carrying the folded copy of the tile loops costs the narrow-tile kernels registers (spills: +4-7% time on
+// 64-column tiles, measured), so kernels that never fold are compiled without it.
+template <int KM, int KS, bool RESB, bool CTA2, bool MAYFOLD>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
@@ -369,6 +444,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             ptx::mbar_init(&ctl->tmem_empty[i], (uint32_t)prm.team_warps * (CTA2 ? 2u : 1u));   // pair: both CTAs' teams
         }
         ptx::mbar_init(&ctl->bfull, 1);
+        ptx::mbar_init(&ctl->bias_ready, kEpiWarps);
+        ctl->fold_ok = 1;
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -575,6 +652,16 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
         bool wready = (kWindow && active) ? ptx::mbar_test(&ctl->wfull[ws], wphase) : true;
         if (RESB && active) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
+        // bias folded into the MMA: the epilogue warps write the constant A block and the bias-digit B block first
+        bool fold = false;
+        uint32_t fa_lo = 0, fa_hi = 0, fb_lo = 0, fb_hi = 0;
+        if (MAYFOLD && prm.fold && active) {
+            ptx::mbar_wait_soft(&ctl->bias_ready, 0, tflag);
+            fold = *reinterpret_cast<volatile uint32_t*>(&ctl->fold_ok) != 0;
+            const uint64_t dfa = ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem + prm.off_fold), 128u, 256u);
+            const uint64_t dfb = ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem + prm.off_fold) + 4096u, 128u, 256u);
+            fa_lo = (uint32_t)dfa; fa_hi = (uint32_t)(dfa >> 32); fb_lo = (uint32_t)dfb; fb_hi = (uint32_t)(dfb >> 32);
+        }
         if (kWindow && !RESB && !CTA2 && prm.pair) {
             // ---- pair mode: two M tiles per step share every B block (see IgemmParams::pair).  Warp `which` issues
             // the MMAs of the which-th tile of the pair: both read the same B stage and the same window stage (one
@@ -635,6 +722,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (leader) trace_ev(prm, tracing, local, EV_M_START);
             const uint32_t tmem_d = tmem_base + acc_stage * bn;
             uint32_t accumulate = 0;
+            if (MAYFOLD && fold) {      // D = ones-block x bias digits: the accumulator starts at the bias
+                ptx::mma_i8_ss_pred32(tmem_d, fa_lo, fa_hi, fb_lo, fb_hi, idesc, 0u, leader);
+                accumulate = 1;
+            }
             if (kWindow && RESB) {
                 // ---- window A, resident B: per channel chunk one wait, then a flat run of table-driven MMAs
                 uint32_t b_base = db_lo;
@@ -721,6 +812,16 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // p+1 will be written to.
         // Control flow is uniform across a team (named barriers): a watchdog trip only stops the waiting.
         const uint32_t e = warp - kFirstEpiWarp;                  // 0..15
+        // (first thing in the role, while nothing else is live: its temporaries must not cost the tile loops registers)
+        bool fold = false;
+        if (MAYFOLD && prm.fold) {
+            write_fold_blocks(smem + prm.off_fold, e * 32u + lane, prm.bn, prm.k_out, prm.k_mod, bias, &ctl->fold_ok);
+            ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ctl->bias_ready);
+            ptx::mbar_wait(&ctl->bias_ready, 0, tflag);
+            fold = *reinterpret_cast<volatile uint32_t*>(&ctl->fold_ok) != 0;
+        }
         const bool small_teams = prm.team_warps == 4;
         const uint32_t team = small_teams ? (e >> 2) : (e >> 3);
         const uint32_t tw = small_teams ? (e & 3) : (e & 7);      // warp inside the team
@@ -776,6 +877,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // per-thread XOR term of the staging swizzle (see epi_consume)
         const uint32_t swz_mask = ((row_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 8 ? 3u : prm.n_acc == 4 ? 2u : 1u;
+        // The tile loops exist once per value of the (launch-wide) fold switch: inside a copy the switch is a compile-time
+        // constant, so it costs no register in loops that already run at the 96-register cap.
+        auto epilogue_tiles = [&](auto fold_tag) __attribute__((always_inline)) {
+        constexpr bool kFold = decltype(fold_tag)::value;
         int32_t cur_nblk = -1;
         const uint32_t tmem_empty0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->tmem_empty[0]), 0) : 0u;   // the leader's barriers
         if (!CTA2 && prm.tpi == 2) {
@@ -823,12 +928,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         if (issuer) ptx::tma_store_wait_read<0>();
                         ptx::named_bar_sync(bar_id, team_threads);
                     }
-                    if (int8_out && prm.relu)
-                        epi_drain<true, true>(prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32, out_row, 0);
-                    else if (int8_out)
-                        epi_drain<true, false>(prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32, out_row, 0);
-                    else
-                        epi_drain<false, false>(prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32, out_row, 0);
+                    epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32,
+                                  out_row, 0);
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_s(tmem_empty_s + acc * 8u);
@@ -910,10 +1011,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     const int32_t pbase = pnl * pcols;
                     if (lane == 0) ptx::tma_store_wait_read<0>();      // the previous store has read this buffer out
                     __syncwarp();
-                    if (prm.relu)
-                        epi_drain<true, true>(prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, lo, y32, -1, col0);
-                    else
-                        epi_drain<true, false>(prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, lo, y32, -1, col0);
+                    epi_run<kFold>(true, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, lo,
+                                  y32, -1, col0);
                     if (pnl + n_halves >= n_panels) {
                         ptx::tc_fence_before();
                         __syncwarp();
@@ -941,15 +1040,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     team_sync();
                 }
                 const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
-                if (int8_out && prm.relu)
-                    epi_drain<true, true>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
-                                          swz_mask, lo, y32, out_row, col0);
-                else if (int8_out)
-                    epi_drain<true, false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
-                                           swz_mask, lo, y32, out_row, col0);
-                else
-                    epi_drain<false, false>(prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s, row_off,
-                                            swz_mask, lo, y32, out_row, col0);
+                epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s,
+                              row_off, swz_mask, lo, y32, out_row, col0);
                 if (pnl == n_panels - 1) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
@@ -989,6 +1081,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         if ((issuer || (prm.warp_store && lane == 0)) && int8_out) ptx::tma_store_wait<0>();
         }
+        };   // epilogue_tiles
+        if (MAYFOLD && fold) epilogue_tiles(std::true_type{});
+        else epilogue_tiles(std::false_type{});
     }
 
     // ---- teardown ----
@@ -1276,8 +1371,17 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         c.stage_bufs = bufs;
         stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(n_teams * bufs * kBlockM * c.panel_bytes), 1024) : 0;
         if (c.warp_store) stage_bytes = (uint32_t)(kEpiWarps * 32 * c.panel_bytes);   // one 32-row panel per epilogue warp
-        if (stage_bytes + ctl_bytes >= 227u * 1024u) continue;
-        const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes;
+        // bias folded into the MMA (resident filter matrix only): a 4 KB constant A block + bn x 32 B of bias digits
+        // Enabled for N tiles >= 128 columns: -11% time on the 64->256 expansions, -2% on 128-wide tiles; narrow tiles
+        // gain nothing (their per-tile bookkeeping dominates) and pay for the extra MMA per tile.  LBC_FOLD=0/1 overrides.
+        {
+            bool want = c.bn >= 128;
+            if (const char* v = getenv("LBC_FOLD")) want = atoi(v) != 0;
+            c.fold = (c.res_b && want) ? 1 : 0;
+        }
+        const uint32_t fold_bytes = c.fold ? round_up(4096u + (uint32_t)c.bn * 32u, 1024) : 0u;
+        if (stage_bytes + ctl_bytes + fold_bytes >= 227u * 1024u) continue;
+        const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes - fold_bytes;
         uint32_t win_total = 0;
         int stages;
         uint32_t b_region;
@@ -1313,7 +1417,8 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         c.stages = stages;
         c.off_b = (c.mode == A_WINDOW) ? win_total : (uint32_t)stages * c.a_stage_bytes;
         c.off_stage = c.off_b + b_region;
-        c.off_ctl = c.off_stage + stage_bytes;
+        c.off_fold = c.off_stage + stage_bytes;
+        c.off_ctl = c.off_fold + fold_bytes;
         c.smem_bytes = c.off_ctl + ctl_bytes;
         fits = c.smem_bytes <= 227 * 1024;
     }
@@ -1523,6 +1628,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
         }
     }
     prm.off_b = c.off_b; prm.off_stage = c.off_stage; prm.off_ctl = c.off_ctl;
+    prm.fold = c.fold; prm.off_fold = c.off_fold;
     prm.trace = g_trace_buf; prm.trace_tiles = g_trace_tiles;
     // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one
     // "channel chunk" of cblocks*inner blocks.
@@ -1532,10 +1638,12 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     const int ks = c.bkb / 32;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams, const int32_t*,
                               const float*, void*);
-    // last index: 0 streaming B, 1 resident B, 2 streaming B in CTA pairs (not for 16-byte pixels)
-#define LBC_KERNELS(KM_, KS_) {igemm_i8_kernel<KM_, KS_, false, false>, igemm_i8_kernel<KM_, KS_, true, false>, \
-                               (KM_ == 3 ? (KernelFn) nullptr : (KernelFn)igemm_i8_kernel<(KM_ == 3 ? 2 : KM_), KS_, false, true>)}
-    static const KernelFn table[4][3][3] = {
+    // last index: 0 streaming B, 1 resident B, 2 streaming B in CTA pairs (not for 16-byte pixels), 3 resident B with the
+    // bias-fold variant of the tile loops
+#define LBC_KERNELS(KM_, KS_) {igemm_i8_kernel<KM_, KS_, false, false, false>, igemm_i8_kernel<KM_, KS_, true, false, false>, \
+                               (KM_ == 3 ? (KernelFn) nullptr : (KernelFn)igemm_i8_kernel<(KM_ == 3 ? 2 : KM_), KS_, false, true, false>), \
+                               igemm_i8_kernel<KM_, KS_, true, false, true>}
+    static const KernelFn table[4][3][4] = {
         {LBC_KERNELS(0, 1), LBC_KERNELS(0, 2), LBC_KERNELS(0, 4)},
         {LBC_KERNELS(1, 1), LBC_KERNELS(1, 2), LBC_KERNELS(1, 4)},
         {LBC_KERNELS(2, 1), LBC_KERNELS(2, 2), LBC_KERNELS(2, 4)},
@@ -1543,14 +1651,14 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     };
 #undef LBC_KERNELS
     LBC_REQUIRE(ks == 1 || ks == 2 || ks == 4, LBC_ERR_UNSUPPORTED, "igemm: unsupported K block of %d bytes", c.bkb);
-    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.cta2 ? 2 : c.res_b ? 1 : 0];
+    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.cta2 ? 2 : c.res_b ? (c.fold ? 3 : 1) : 0];
     LBC_REQUIRE(fn != nullptr, LBC_ERR_UNSUPPORTED, "igemm: no kernel for this configuration");
     {
         std::lock_guard<std::mutex> lk(g_attr_mu);
         if (!g_attr_set) {
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 3; ++j)
-                    for (int r = 0; r < 3; ++r)
+                    for (int r = 0; r < 4; ++r)
                         if (table[i][j][r])
                             LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             g_attr_set = true;

@@ -34,9 +34,12 @@ def run_gpu(od: ODesc, x, w, bias, scale, force=0, w_layout="krsc"):
     return out, name, ms
 
 
-def check_case(od: ODesc, layer=0, style="full", force=0, use_bias=True, w_layout="krsc"):
-    """Runs GPU and oracle on identical seeded inputs; returns (mismatches, total, kernel, detail)."""
+def check_case(od: ODesc, layer=0, style="full", force=0, use_bias=True, w_layout="krsc", bias_range=None):
+    """Runs GPU and oracle on identical seeded inputs; returns (mismatches, total, kernel, detail).
+    bias_range: replace the synthetic biases by uniform int32 values in [-bias_range, bias_range]."""
     x, w, bias, scale = oracle.synth(od, layer=layer, style=style)
+    if bias_range is not None:
+        bias = np.random.default_rng(99 + layer).integers(-bias_range, bias_range + 1, size=bias.shape).astype(np.int32)
     if not use_bias:
         bias = None
     want = oracle.conv_nhwc(od, x, w, bias, scale)

@@ -153,6 +153,29 @@ def test_igemm_per_warp_stores_forced(d, monkeypatch):
     assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
 
 
+FOLD_EXTRA_CASES = [
+    D(n=2, h=28, w=28, c=64, k=256, r=1, s=1, relu=1),                         # the 64->256 expansion (per-warp stores)
+    D(n=2, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # window, two MMA warps, two tiles per iteration
+    D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),   # stem (16-byte pixels)
+    D(n=2, h=28, w=28, c=24, k=144, r=1, s=1, relu=1),                         # pixel groups: bias index = channel % 144
+    D(n=1, h=14, w=14, c=128, k=80, r=1, s=1),                                 # ragged N tile (80 of 80... unswizzled panel)
+]
+
+
+@pytest.mark.parametrize("d", IGEMM_CASES + FOLD_EXTRA_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_igemm_bias_folded_into_mma(d, monkeypatch):
+    """Resident-filter layers with the bias fed through the first MMA of every tile (constant A block x bias digits)
+    instead of the epilogue's add, forced on for every N tile width, int8 and raw int32 outputs.  _check's biases are a few
+    thousand; the second call uses biases beyond the digit range, which the kernel must detect and add the classic way."""
+    monkeypatch.setenv("LBC_FOLD", "1")
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 1})) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 1}), bias_range=3_000_000) in ("igemm_tc", "stem_tc")
+    monkeypatch.setenv("LBC_FOLD", "0")
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+
+
 MULTI_TILE_CASES = [
     D(n=4, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # window, resident B, two MMA warps
     D(n=2, h=28, w=28, c=64, k=256, r=1, s=1, relu=1),                         # tiled, resident B, 256-wide tile
