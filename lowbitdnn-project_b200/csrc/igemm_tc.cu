@@ -480,14 +480,16 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // ===================== ring producer: B blocks (+ A blocks in TILED / IM2COL) =====================
         const bool leader = ptx::elect_one();
         if (RESB) {
-            // the whole filter matrix, once: k_blocks boxes of [bn][bkb] side by side
+            // the whole filter matrix, once: per N tile, k_blocks boxes of [bn][bkb] side by side
             if (leader) {
                 ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes);
                 const int32_t nblk = prm.cblocks * prm.inner;
                 uint8_t* dst = smem_b;
-                int32_t bcol = 0;
-                for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb)
-                    ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, 0);
+                for (int32_t nt = 0; nt < prm.tiles_n; ++nt) {
+                    int32_t bcol = 0;
+                    for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb)
+                        ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, nt * prm.bn);
+                }
             }
             __syncwarp();
         }
@@ -712,6 +714,12 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         } else {
         int32_t local = (int32_t)which;
         const int32_t tile_step = (int32_t)(n_mma * gridDim.x);
+        // resident B with several N tiles: the tile's N index (fastest digit of the tile number), advanced without division
+        const uint32_t tiles_n_u = (uint32_t)prm.tiles_n;
+        const uint32_t nb_step = RESB ? (uint32_t)tile_step % tiles_n_u : 0u;
+        uint32_t n_blk = RESB ? (blockIdx.x + which * gridDim.x) % tiles_n_u : 0u;
+        const uint32_t b_tile16 = b_block16 * (uint32_t)(prm.cblocks * prm.inner);      // one N tile of the resident matrix
+        const uint32_t fold_tile16 = (bn * 32u) >> 4;
         // (a pair leader counts its own tiles; the peer's tile of each step shares the MMAs)
         for (int32_t tile = active ? (int32_t)(blockIdx.x + which * gridDim.x) : num_tiles; tile < num_tiles;
              tile += tile_step, local += (int32_t)n_mma) {
@@ -722,13 +730,15 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (leader) trace_ev(prm, tracing, local, EV_M_START);
             const uint32_t tmem_d = tmem_base + acc_stage * bn;
             uint32_t accumulate = 0;
+            const uint32_t db_n = RESB ? db_lo + n_blk * b_tile16 : db_lo;
             if (MAYFOLD && fold) {      // D = ones-block x bias digits: the accumulator starts at the bias
-                ptx::mma_i8_ss_pred32(tmem_d, fa_lo, fa_hi, fb_lo, fb_hi, idesc, 0u, leader);
+                ptx::mma_i8_ss_pred32(tmem_d, fa_lo, fa_hi, fb_lo + n_blk * fold_tile16, fb_hi, idesc, 0u, leader);
                 accumulate = 1;
             }
+            if (RESB) { n_blk += nb_step; if (n_blk >= tiles_n_u) n_blk -= tiles_n_u; }
             if (kWindow && RESB) {
                 // ---- window A, resident B: per channel chunk one wait, then a flat run of table-driven MMAs
-                uint32_t b_base = db_lo;
+                uint32_t b_base = db_n;
                 for (int32_t cb = 0; cb < mma_outer; ++cb, b_base += b_chunk16) {
                     if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
                     ptx::tc_fence_after();
@@ -756,7 +766,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
                 }
             } else {
-                uint32_t b_res = db_lo;   // resident B (ring modes): walks the blocks of the tile in order
+                uint32_t b_res = db_n;    // resident B (ring modes): walks the blocks of the tile in order
                 for (int32_t cb = 0; cb < mma_outer; ++cb) {
                     uint32_t a_base = da_lo;
                     if (kWindow) {
@@ -815,7 +825,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // (first thing in the role, while nothing else is live: its temporaries must not cost the tile loops registers)
         bool fold = false;
         if (MAYFOLD && prm.fold) {
-            write_fold_blocks(smem + prm.off_fold, e * 32u + lane, prm.bn, prm.k_out, prm.k_mod, bias, &ctl->fold_ok);
+            write_fold_blocks(smem + prm.off_fold, e * 32u + lane, prm.bn * prm.tiles_n, prm.k_out, prm.k_mod, bias, &ctl->fold_ok);
             ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->bias_ready);
@@ -1281,7 +1291,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // the two SMs of a TPC removes a third of that traffic.
     {
         const size_t full_b = (size_t)c.k_blocks * c.bn * c.bkb;
-        const bool streams = !(c.tiles_n == 1 && full_b <= 80u * 1024u) || getenv("LBC_NO_RESB");
+        const bool streams = !((size_t)c.tiles_n * full_b <= 80u * 1024u) || getenv("LBC_NO_RESB");
         const bool possible = !c.pair && !c16 && streams && c.bn % 32 == 0 && c.tiles_m >= 2;
         // Pairing couples the two CTAs' pipelines (one MMA stream waits for both producers and both epilogues), which
         // costs where the epilogue is the bound: short K loops (1x1 channel expansions) measured 10-15% slower in pairs,
@@ -1362,8 +1372,9 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     }
     // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
-    c.b_total_bytes = (uint32_t)c.k_blocks * c.b_block_bytes;
-    const bool res_b_ok = !c.pair && !c.cta2 && c.tiles_n == 1 && c.b_total_bytes <= 80u * 1024u && !getenv("LBC_NO_RESB");
+    c.b_total_bytes = (uint32_t)c.tiles_n * c.k_blocks * c.b_block_bytes;      // all N tiles
+    const bool res_b_ok = !c.pair && !c.cta2 && (c.tiles_n == 1 || !getenv("LBC_RESB_ONE_TILE")) && c.b_total_bytes <= 80u * 1024u &&
+                          !getenv("LBC_NO_RESB");
     for (int pass = 0; pass < 2 && !fits; ++pass)
     for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs) {   // three staging panels per team when they fit, else two, else one
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
@@ -1379,7 +1390,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
             if (const char* v = getenv("LBC_FOLD")) want = atoi(v) != 0;
             c.fold = (c.res_b && want) ? 1 : 0;
         }
-        const uint32_t fold_bytes = c.fold ? round_up(4096u + (uint32_t)c.bn * 32u, 1024) : 0u;
+        const uint32_t fold_bytes = c.fold ? round_up(4096u + (uint32_t)(c.bn * c.tiles_n) * 32u, 1024) : 0u;
         if (stage_bytes + ctl_bytes + fold_bytes >= 227u * 1024u) continue;
         const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes - fold_bytes;
         uint32_t win_total = 0;

@@ -158,7 +158,11 @@ FOLD_EXTRA_CASES = [
     D(n=2, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # window, two MMA warps, two tiles per iteration
     D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),   # stem (16-byte pixels)
     D(n=2, h=28, w=28, c=24, k=144, r=1, s=1, relu=1),                         # pixel groups: bias index = channel % 144
-    D(n=1, h=14, w=14, c=128, k=80, r=1, s=1),                                 # ragged N tile (80 of 80... unswizzled panel)
+    D(n=1, h=14, w=14, c=128, k=80, r=1, s=1),                                 # 80-column tile: unswizzled staging panel
+    D(n=2, h=28, w=28, c=128, k=512, r=1, s=1, relu=1),                        # resident filter matrix, 2 N tiles (128->512)
+    D(n=2, h=14, w=14, c=64, k=384, r=1, s=1, relu=1),                         # resident, 2 N tiles of 192
+    D(n=3, h=14, w=14, c=32, k=600, r=1, s=1),                                 # resident, 3 N tiles, ragged last tile (600 of 624)
+    D(n=1, h=20, w=20, c=16, k=320, r=3, s=3, pad_h=1, pad_w=1, relu=1),       # 16-byte pixels, resident, 2 N tiles
 ]
 
 
@@ -191,6 +195,8 @@ MULTI_TILE_CASES = [
     D(n=3, h=14, w=14, c=256, k=320, r=1, s=1, relu=1),                        # CTA pairs: odd M tile count, 160-wide N tiles
     D(n=3, h=15, w=15, c=128, k=96, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1),   # CTA pairs: im2col, M tail, 48 B rows per CTA
     D(n=1, h=9, w=9, c=2048, k=512, r=1, s=1, relu=1),                         # CTA pairs: one real M tile + its padding twin
+    D(n=2, h=28, w=28, c=128, k=512, r=1, s=1, relu=1),                        # resident filter matrix with 2 N tiles
+    D(n=3, h=14, w=14, c=32, k=600, r=1, s=1),                                 # resident, 3 N tiles, ragged last tile
 ]
 
 
