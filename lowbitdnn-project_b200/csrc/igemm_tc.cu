@@ -1214,7 +1214,8 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     IgemmConfig c{};
     // ---- N tile: the whole K_out when it fits one 256-wide tile, else an even split into the fewest tiles
     // (multiples of 16; a ragged last tile is handled by TMA zero-fill on loads and clipping on stores)
-    c.tiles_n = (d.k + 255) / 256;
+    const int max_bn = getenv("LBC_MAX_BN") ? std::max(16, std::min(256, atoi(getenv("LBC_MAX_BN")))) : 256;   // development aid
+    c.tiles_n = (d.k + max_bn - 1) / max_bn;
     c.bn = ((d.k + c.tiles_n - 1) / c.tiles_n + 15) / 16 * 16;
     c.tiles_n = (d.k + c.bn - 1) / c.bn;
 
@@ -1373,10 +1374,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.tiles_n * c.k_blocks * c.b_block_bytes;      // all N tiles
-    const bool res_b_ok = !c.pair && !c.cta2 && (c.tiles_n == 1 || !getenv("LBC_RESB_ONE_TILE")) && c.b_total_bytes <= 80u * 1024u &&
+    const bool res_b_ok = !c.pair && !c.cta2 && (c.tiles_n == 1 || !getenv("LBC_RESB_ONE_TILE")) && c.b_total_bytes <= (uint32_t)env_int("LBC_RESB_KB", 80) * 1024u &&
                           !getenv("LBC_NO_RESB");
     for (int pass = 0; pass < 2 && !fits; ++pass)
-    for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs) {   // three staging panels per team when they fit, else two, else one
+    for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs)
+    for (int fold_try = 1; fold_try >= 0 && !fits; --fold_try) {     // with the bias-fold blocks if they fit, else without   // three staging panels per team when they fit, else two, else one
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
         if (pass == 0 && !res_b_ok) break;
         c.stage_bufs = bufs;
@@ -1388,7 +1390,8 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         {
             bool want = c.bn >= 128;
             if (const char* v = getenv("LBC_FOLD")) want = atoi(v) != 0;
-            c.fold = (c.res_b && want) ? 1 : 0;
+            c.fold = (c.res_b && want && fold_try) ? 1 : 0;
+            if (!fold_try && !(c.res_b && want)) continue;      // nothing to drop: this variant was already tried
         }
         const uint32_t fold_bytes = c.fold ? round_up(4096u + (uint32_t)(c.bn * c.tiles_n) * 32u, 1024) : 0u;
         if (stage_bytes + ctl_bytes + fold_bytes >= 227u * 1024u) continue;
