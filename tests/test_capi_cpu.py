@@ -102,3 +102,41 @@ def test_planner_dry_run_covers_every_benchmark_layer(lbc):
             if "smem" in text:
                 assert int(text.split("smem ")[1].split()[0]) <= 227 * 1024, text
         assert dict(got) == kinds, (net, dict(got))
+
+
+def test_planner_choices_on_resnet50(lbc):
+    """The planner's per-layer decisions that DESIGN.md section 4.1 describes, pinned through the host-only dry planner:
+    which layers run in CTA pairs, which keep their filter matrix resident (also across two N tiles), where the bias is
+    folded into the MMA, where warps store their own rows, and which A mode the 3x3 layers use."""
+    import ctypes
+    lib = lbc.load_library()
+    plans = {}
+    for name, d, _ in lbc.networks.NETWORKS["resnet50"](512):
+        kind = ctypes.c_int32()
+        buf = ctypes.create_string_buffer(512)
+        cd = d.c_struct()
+        assert lib.lbc_conv_plan_dry(ctypes.byref(cd), 0, 148, ctypes.byref(kind), buf, 512) == 0
+        plans[name] = buf.value.decode()
+    expect = {
+        "conv1": ["stem_tc", "b=resident,2mma", "a=window", "4x4-warp-teams"],
+        "l1.0.conv2": ["b=resident,2mma", "a=window(2x56", "tmem 512", "4x4-warp-teams"],            # 8 stages of 64 columns
+        "l1.0.conv3": ["b=resident", "a=tiled", "warp-stores,bias-in-mma"],                          # 64 -> 256
+        "l1.1.conv1": ["b=resident", "a=tiled", "tile 128x64"],                                      # 256 -> 64
+        "l2.0.conv1": ["b=resident", "bias-in-mma", "tile 128x128"],                                 # 256 -> 128
+        "l2.0.conv3": ["b=resident", "tiles 3136x2", "warp-stores,bias-in-mma"],                     # 128 -> 512, two N tiles
+        "l2.1.conv2": ["b=ring,cta-pair", "a=window(4x28", "tile 128x128"],                          # 3x3, 128-wide: windows
+        "l3.0.conv3": ["b=ring ", "a=tiled", "tiles 784x4", "warp-stores"],                          # 256 -> 1024 streams
+        "l3.1.conv1": ["b=ring,cta-pair", "a=tiled"],                                                # 1024 -> 256: long K loop
+        "l3.1.conv2": ["b=ring,cta-pair", "a=im2col", "tile 128x256"],                               # wide 3x3 in pairs: im2col
+        "l3.0.conv2": ["b=ring,cta-pair", "a=im2col"],                                               # stride 2
+        "l4.1.conv2": ["b=ring,cta-pair", "a=im2col"],
+        "l4.0.conv3": ["b=ring ", "tiles 196x8", "2x8-warp-teams"],                                  # 512 -> 2048
+    }
+    for name, needles in expect.items():
+        for n in needles:
+            assert n in plans[name], (name, n, plans[name])
+    # every CTA-pair plan has an even grid; nothing exceeds the shared-memory or TMEM limits
+    for name, text in plans.items():
+        if "cta-pair" in text:
+            assert int(text.split("grid ")[1].split()[0]) % 2 == 0, text
+        assert int(text.split("tmem ")[1].split()[0]) <= 512, text
