@@ -313,3 +313,60 @@ def test_requant_extremes_on_device():
         for force in (DIRECT, IGEMM):
             got, _, _ = run_gpu(dd, x, w, bias, scale, force=force)
             assert np.array_equal(got, want), (relu, force)
+
+
+def test_folded_bias_digit_boundaries():
+    """The bias-in-MMA path on a layer where the planner enables it by default (resident filter matrix, 128-column tile):
+    biases at the edges of the digit decomposition (multiples of 127, +-63/64 remainders, the +-500000 range limit and
+    just beyond it, where the launch must fall back to the epilogue add) - raw int32 accumulators and requantised int8."""
+    from tests.parity_util import run_gpu
+    import lowbitdnn_project_b200 as lbc
+    base = D(n=2, h=8, w=8, c=32, k=128, r=1, s=1)
+    plan = lbc.ConvPlan(lbc.ConvDesc(**{**base.__dict__, "out_mode": 0}))
+    assert "bias-in-mma" in plan.describe(), plan.describe()
+    plan.close()
+    rng = np.random.default_rng(11)
+    x = rng.integers(-128, 128, size=(2, 8, 8, 32), dtype=np.int8)
+    w = rng.integers(-127, 128, size=(128, 1, 1, 32), dtype=np.int8)
+    edge = np.array([0, 1, -1, 63, 64, -63, -64, 126, 127, 128, -127, -128, 127 * 31, 127 * 31 + 63, 127 * 3937, 127 * 3937 + 63,
+                     -127 * 3937 - 63, 499999, 500000, -500000, 190, 191, -190, -191, 32767, -32768, 16129, -16129, 8001, -8001,
+                     254, -254], dtype=np.int32)
+    scale = np.full(128, 2.0**-9, dtype=np.float32)
+    for name, bias in (("in-range", np.resize(edge, 128)),
+                       ("beyond", np.where(np.arange(128) == 77, 500001, np.resize(edge, 128)).astype(np.int32)),
+                       ("int32-extremes", np.where(np.arange(128) % 2 == 0, 2**31 - 1, -2**31).astype(np.int32))):
+        for out_mode, relu in ((1, 0), (0, 0), (0, 1)):
+            dd = D(**{**base.__dict__, "out_mode": out_mode, "relu": relu})
+            want = oracle.conv_nhwc(dd, x, w, bias, scale)
+            got, kern, _ = run_gpu(dd, x, w, bias, scale if out_mode == 0 else None)
+            assert kern == "igemm_tc" and np.array_equal(got, want), (name, out_mode, relu)
+
+
+@pytest.mark.parametrize("d", [
+    D(n=4, h=28, w=28, c=64, k=256, r=1, s=1, relu=1),                         # resident, per-warp stores, folded bias
+    D(n=4, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # CTA pairs
+    D(n=4, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # two MMA warps, two tiles per epilogue iteration
+    D(n=4, h=28, w=28, c=128, k=512, r=1, s=1, relu=1),                        # resident filter matrix over two N tiles
+], ids=lambda d: f"c{d.c}k{d.k}r{d.r}")
+def test_repeated_launches_are_identical(d, monkeypatch):
+    """The same plan launched ten times back to back (no host synchronisation in between, so launches overlap through
+    programmatic dependent launch) on a grid capped to 8 CTAs: every run must reproduce the oracle bit for bit - a race in
+    the TMEM / staging / ring reuse or across the PDL boundary would show up as a run-to-run difference."""
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    from tests.parity_util import lbc_desc
+    monkeypatch.setenv("LBC_MAX_GRID", "8")
+    od = D(**{**d.__dict__, "out_mode": 0})
+    x, w, bias, scale = oracle.synth(od, layer=3)
+    want = oracle.conv_nhwc(od, x, w, bias, scale)
+    dev = torch.device("cuda:0")
+    plan = lbc.ConvPlan(lbc_desc(od))
+    wp = plan.prepack(torch.from_numpy(w).to(dev).reshape(-1), lbc.W_KRSC)
+    xt, bt, st = torch.from_numpy(x).to(dev), torch.from_numpy(bias).to(dev), torch.from_numpy(scale).to(dev)
+    outs = [plan.empty_output(dev) for _ in range(10)]
+    for y in outs:
+        plan.run(xt, wp, bt, st, out=y)
+    torch.cuda.synchronize()
+    for i, y in enumerate(outs):
+        assert np.array_equal(y.cpu().numpy(), want), f"launch {i} differs"
+    plan.close()
