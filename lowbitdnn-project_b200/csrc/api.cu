@@ -620,6 +620,9 @@ struct lbc_net {
         void* y = nullptr;
         ResolvedLaunch rl;
         bool resolved = false;
+        // tcgen05 layers alternate their traversal direction along producer -> consumer edges, so a consumer starts on
+        // the images its producer wrote last (still in L2) instead of on the ones written first (evicted)
+        bool reverse = false;
     };
     std::vector<Layer> layers;
     std::vector<cudaEvent_t> events;   // n_layers + 1
@@ -650,7 +653,10 @@ lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
     const int8_t* x = x_override ? x_override : (const int8_t*)layer_input(net, i);
     if (L.resolved && L.rl.x == x) return LBC_OK;
     lbc_status st = resolve(L.plan, x, L.w, L.bias, L.scale, L.y, &L.rl);
-    if (st == LBC_OK) L.resolved = true;
+    if (st == LBC_OK) {
+        L.resolved = true;
+        L.rl.ig.reverse = L.reverse ? 1 : 0;
+    }
     return st;
 }
 
@@ -723,6 +729,12 @@ lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, i
                 st = LBC_ERR_INVALID_ARG;
                 break;
             }
+        }
+        {
+            const bool tc = L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC;
+            const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
+            // a producer that ran forwards finished on the last images: start there; CUDA-core kernels always run forwards
+            L.reverse = tc && L.input_of >= 0 && !producer_rev && !getenv("LBC_NO_SNAKE");
         }
         const size_t wb = packed_weight_bytes(L.plan);
         bool ok = cudaMalloc(&L.w, wb) == cudaSuccess && cudaMalloc((void**)&L.bias, sizeof(int32_t) * g.d.k) == cudaSuccess &&

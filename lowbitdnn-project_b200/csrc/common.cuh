@@ -121,6 +121,7 @@ struct IgemmLaunch {
     CUtensorMap tm_b;
     CUtensorMap tm_out;
     IgemmConfig cfg;
+    int32_t reverse = 0;   // walk the M tiles / images last-to-first (L2 reuse of the producer's most recent output)
 };
 bool igemm_supported(const ConvGeom& g, std::string* why);
 lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConfig* cfg);
