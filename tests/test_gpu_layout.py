@@ -79,3 +79,45 @@ def test_pipelined_host_path_matches_blocking_path():
     net.run_host(xh[2], yb)
     assert np.array_equal(yb.numpy(), want[2])
     net.close()
+
+
+def test_network_runner_matches_oracle_with_branches():
+    """A bottleneck-shaped graph (one producer feeding two consumers, a stride-2 branch, an odd image count) through
+    lbc_net_run: the runner alternates the tile traversal direction along producer -> consumer edges, and every layer's
+    resident output must still equal the oracle's, image for image."""
+    import numpy as np
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    from oracle import oracle
+    from oracle.oracle import ConvDesc as OD
+    n = 5
+    layers = [("in", lbc.ConvDesc(n=n, h=28, w=28, c=64, k=64, r=1, s=1, relu=1), None),
+              ("conv1", lbc.ConvDesc(n=n, h=28, w=28, c=64, k=32, r=1, s=1, relu=1), "in"),
+              ("conv2", lbc.ConvDesc(n=n, h=28, w=28, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1, relu=1), "conv1"),
+              ("conv3", lbc.ConvDesc(n=n, h=28, w=28, c=32, k=128, r=1, s=1, relu=1), "conv2"),
+              ("down", lbc.ConvDesc(n=n, h=28, w=28, c=64, k=128, r=1, s=1, stride_h=2, stride_w=2), "in"),
+              ("next", lbc.ConvDesc(n=n, h=28, w=28, c=128, k=256, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1), "conv3")]
+    net = lbc.Net(layers)
+    names = [l[0] for l in layers]
+    rng = np.random.default_rng(17)
+    x = rng.integers(-128, 128, size=(n, 28, 28, 64), dtype=np.int8)
+    outs = {}
+    for i, (name, d, src) in enumerate(layers):
+        od = OD(**d.__dict__)
+        _, w, b, s = oracle.synth(od, layer=i)
+        net.set_params(i, w, b, s)
+        outs[name] = oracle.conv_nhwc(od, x if src is None else outs[src], w, b, s)
+    net.set_input(0, x)
+    for _ in range(2):
+        net.run()
+    torch.cuda.synchronize()
+    class _DevBuf:     # the layer's resident output buffer, viewed through the CUDA array interface
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|i1", "data": (ptr, False), "version": 3}
+
+    for i, name in enumerate(names):
+        _, y_ptr = net.layer_io(i)
+        want = outs[name]
+        got = torch.as_tensor(_DevBuf(y_ptr, want.shape), device="cuda:0").cpu().numpy()
+        assert np.array_equal(got, want), name
+    net.close()
