@@ -656,6 +656,7 @@ lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
     if (st == LBC_OK) {
         L.resolved = true;
         L.rl.ig.reverse = L.reverse ? 1 : 0;
+        L.rl.dw.reverse = (L.reverse && L.rl.dw.tiled) ? 1 : 0;
     }
     return st;
 }
@@ -731,7 +732,8 @@ lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, i
             }
         }
         {
-            const bool tc = L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC;
+            const bool tc = L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC ||
+                            L.plan->kind == LBC_KERNEL_DEPTHWISE;      // (the tiled depthwise kernel mirrors its tile index)
             const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
             // a producer that ran forwards finished on the last images: start there; CUDA-core kernels always run forwards
             L.reverse = tc && L.input_of >= 0 && !producer_rev && !getenv("LBC_NO_SNAKE");

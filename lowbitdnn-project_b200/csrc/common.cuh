@@ -71,6 +71,7 @@ struct DwLaunch {
     CUtensorMap tm_x;
     int32_t cc, th, tq, nb, tw, in_h, in_w, tiles_c, tiles_q, tiles_p, tiles_n;
     uint32_t tile_bytes;
+    int32_t reverse = 0;         // tiled kernel: walk the tiles last-to-first
 };
 lbc_status depthwise_encode(const ConvGeom& g, const int8_t* x, DwLaunch* out);
 lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,

@@ -244,6 +244,7 @@ struct DwTiledParams {
     int32_t strips, row_groups;    // per tile
     int32_t relu, out_mode;
     uint32_t tile_bytes;
+    int32_t reverse;               // visit the tiles last-to-first (see IgemmLaunch::reverse)
 };
 
 __device__ int g_dw_timeout = 0;
@@ -259,8 +260,8 @@ __global__ void __launch_bounds__(256) depthwise3x3_tiled_kernel(const __grid_co
     extern __shared__ __align__(128) uint8_t tile[];
     __shared__ uint64_t bar;
 
-    // tile coordinates
-    uint32_t t = blockIdx.x;
+    // tile coordinates (blocks are dispatched in index order, so mirroring the index mirrors the traversal)
+    uint32_t t = g.reverse ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
     const int32_t tc = (int32_t)(t % (uint32_t)g.tiles_c); t /= (uint32_t)g.tiles_c;
     const int32_t tq_i = (int32_t)(t % (uint32_t)g.tiles_q); t /= (uint32_t)g.tiles_q;
     const int32_t tp_i = (int32_t)(t % (uint32_t)g.tiles_p); t /= (uint32_t)g.tiles_p;
@@ -512,6 +513,7 @@ lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_
         p.row_groups = dw->th / (d.stride_h == 1 ? 2 : 1);
         p.relu = ep.relu; p.out_mode = ep.out_mode;
         p.tile_bytes = dw->tile_bytes;
+        p.reverse = (dw->reverse || getenv("LBC_SNAKE")) ? 1 : 0;
         const unsigned grid = (unsigned)(dw->tiles_c * dw->tiles_q * dw->tiles_p * dw->tiles_n);
         const size_t smem = dw->tile_bytes;
         const unsigned block = 256;
