@@ -38,7 +38,10 @@ def launches(path, layer_names, per_step):
         d = L.setdefault(int(r[0]), {"name": r[4]})
         d[r[12]] = float(r[14])
     ids = sorted(L)
-    step = [L[i] for i in ids[-per_step:]]          # the last captured step
+    # the last COMPLETE step of the capture: a step starts with the stem's space-to-depth launch
+    starts = [k for k, i in enumerate(ids) if "stem_xform" in L[i]["name"] and k + per_step <= len(ids)]
+    first = starts[-1] if starts else len(ids) - per_step
+    step = [L[i] for i in ids[first:first + per_step]]
     tot = sum(s["gpu__time_duration.sum"] for s in step)
     lines = ["| # | layer | kernel | ncu duration us (cold cache, serialised) | share of step | DRAM read MB | DRAM write MB |",
              "|---|---|---|---|---|---|---|"]
