@@ -15,7 +15,7 @@
 //             For C == 16 (space-to-depth'd stems) pixel rows are 16 bytes, unswizzled, and one K=32 MMA covers
 //             two horizontally adjacent taps through the descriptor's leading-dimension offset.
 //   B operand:  the pre-packed filter matrix, either streamed through the mbarrier ring ([bn][<=128 B] blocks, TMA
-//               2-D loads) or - one N tile, <= 80 KB - RESIDENT in shared memory: loaded once per CTA, no per-block
+//               2-D loads) or - all N tiles together <= 80 KB - RESIDENT in shared memory: loaded once per CTA, no per-block
 //               handshake and no L2 re-fetch per tile (stems, ResNet stage 1, MobileNetV2 pointwise layers).
 //   MMA      :  tcgen05.mma.cta_group::1.kind::i8, M=128 x N=bn x K=32 per instruction.  Issue loop: descriptor
 //               offsets from a table in the kernel-parameter bank, 32-bit arithmetic on the descriptor low word,
@@ -25,10 +25,17 @@
 //               fuse bias + per-channel fp32 scale + round-to-nearest-even + ReLU/saturate, pack to int8 (F2IP), stage
 //               the tile in swizzled shared memory (ring of up to 3 panels, one named barrier per panel) and write it
 //               with TMA stores (full 128-byte lines).  int32 output mode writes 16-byte vectors directly.
+//               Ring-mode 256-wide tiles with short K loops: every warp stages and TMA-stores its own 32 rows (no team
+//               barrier).  Resident-filter layers with >= 128-column tiles: the bias enters through the first MMA of each
+//               tile (constant A block x bias digits), so the epilogue skips its add and its bias fetch.
+//   CTA pairs:  layers that stream their filter matrix through a long K loop run as two-CTA clusters: each CTA loads its
+//               own A tile and half of the B rows, the leader issues tcgen05.mma.cta_group::2 (M = 256) and multicast
+//               commits; see IgemmParams::cta2.
 //   Schedule :  persistent CTAs (one per SM), division-free strided walk over tiles (TileIter), mbarrier rings between
 //               the TMA warps and the MMA warps, 2 or 4 TMEM accumulator stages so the epilogue of tile i overlaps
 //               the main loops of the following tiles; programmatic dependent launch hides the prologue behind the
-//               previous layer's tail.
+//               previous layer's tail.  A launch may walk its tiles last-to-first (IgemmLaunch::reverse) so that a
+//               consumer starts on what its producer wrote last (L2 reuse; the network runner alternates directions).
 //
 // Replaces CUDAConv2DForward3x3TensorCoures (cpp/int8conv/conv2DForward3x3TensorCores.cuh:537-693: wmma
 // m32n8k16, single-buffered 34x34x16 halo tile in smem, int32 stores, 3x3/stride-1/VALID only).
