@@ -52,11 +52,18 @@ def main():
             order = np.argsort(dur)
             print(f"   per-CTA duration (us @1965 MHz): min {dur.min():.1f} median {np.median(dur):.1f} max {dur.max():.1f}; "
                   f"slowest {[(int(i), round(float(dur[i]), 1)) for i in order[-4:]]} fastest {[(int(i), round(float(dur[i]), 1)) for i in order[:3]]}")
-        t0 = t[a.skip][t[a.skip] > 0].min()
+        have = [k for k in range(ntile) if (t[k] > 0).any()]       # CTA 0 may own fewer tiles than asked for
+        if not have:
+            print(f"== {name}: no tiles traced")
+            plan.close()
+            continue
+        skip = min(a.skip, max(0, len(have) - 4))
+        ntile = have[-1] + 1
+        t0 = t[skip][t[skip] > 0].min()
         print(f"== {name}: {ms * 1e3:.1f} us | {plan.describe()}")
         print("tile " + " ".join(f"{e:>8s}" for e in EV) + "   | dM(start->done) dE(start->drain) tile-to-tile(M_DONE)")
         prev = None
-        for k in range(a.skip, ntile):
+        for k in range(skip, ntile):
             row = t[k]
             cells = " ".join(f"{(int(row[e]) - int(t0)) if row[e] else -1:8d}" for e in range(len(EV)))
             dm = int(row[5] - row[2]) if row[5] and row[2] else -1
