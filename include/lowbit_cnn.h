@@ -70,7 +70,8 @@ typedef enum lbc_kernel_kind {
     LBC_KERNEL_DIRECT = 1,       /* CUDA-core direct convolution (any shape)                          */
     LBC_KERNEL_IGEMM_TC = 2,     /* tcgen05 implicit GEMM (TMA im2col + TMEM accumulators)            */
     LBC_KERNEL_DEPTHWISE = 3,    /* CUDA-core depthwise (groups == C == K)                            */
-    LBC_KERNEL_STEM_TC = 4       /* tcgen05 GEMM over an in-kernel im2col for tiny C (C <= 4)         */
+    LBC_KERNEL_STEM_TC = 4       /* tiny C (C*stride^2 <= 16): zero-pad + space-to-depth pre-pass into 16-channel
+                                    pixels at stride 1, then the tcgen05 kernel's 16-byte-pixel window mode      */
 } lbc_kernel_kind;
 
 /* Plain-old-data convolution descriptor.  All sizes in elements. */
@@ -85,7 +86,43 @@ typedef struct lbc_conv_desc {
     int32_t out_mode;            /* lbc_out_mode                                                      */
 } lbc_conv_desc;
 
-typedef struct lbc_plan lbc_plan;     /* opaque, immutable after creation, thread-safe to share      */
+/* Planner options.  Every field has a "planner decides" value, so a zero-initialised struct passed through
+ * lbc_plan_options_init() reproduces lbc_conv_plan_create().  They exist for the parity tests (which force every
+ * code path on every shape) and for tuning sweeps; the library reads NO environment variables.
+ * Tri-state fields: -1 = planner decides, 0 = off, 1 = on (where the mechanism is structurally possible).
+ * Limit fields: 0 = planner decides. */
+typedef struct lbc_plan_options {
+    int32_t struct_size;         /* sizeof(lbc_plan_options); set by lbc_plan_options_init                         */
+    int32_t cta_pairs;           /* two-CTA clusters, cta_group::2 MMAs, half of the filter rows per CTA           */
+    int32_t warp_store;          /* per-warp staging + TMA stores in the epilogue (ring modes)                      */
+    int32_t fold_bias;           /* bias through the first MMA of every tile (resident filter matrix)               */
+    int32_t paired_tiles;        /* two M tiles per CTA step share every B block (window A, streaming B); opt-in    */
+    int32_t resident_filter;     /* filter matrix kept in shared memory when it fits                                */
+    int32_t window;              /* shifted-window A operand for stride-1 RxS layers (0: TMA im2col instead)        */
+    int32_t keep_window;         /* 1: keep the window mode where the planner would prefer im2col + CTA pairs        */
+    int32_t force_im2col;        /* 1: TMA im2col A operand even for pure GEMMs                                     */
+    int32_t pixel_groups;        /* pixel-group rewrite of narrow pointwise layers                                  */
+    int32_t dw_tiled;            /* TMA-staged depthwise 3x3 kernel (0: direct global-memory kernel)                */
+    int32_t reverse;             /* 1: walk the tiles last-to-first (single-layer API; networks alternate)          */
+    int32_t pdl;                 /* programmatic dependent launch                                                   */
+    int32_t two_mma_warps;       /* 0: a single MMA-issuing warp                                                    */
+    int32_t tiles_per_iter2;     /* 0: one tile per epilogue-team iteration on narrow tiles                         */
+    int32_t small_teams;         /* 0: 2 x 8-warp epilogue teams even on narrow tiles                               */
+    int32_t four_acc;            /* 0: two TMEM accumulator stages where four would fit                             */
+    int32_t n_stationary;        /* CTAs keep one N tile of the filter matrix resident and walk M (multi-N-tile)    */
+    int32_t epi_pipeline;        /* software-pipelined TMEM drain (next chunk's tcgen05.ld under this chunk's ALU)  */
+    int32_t max_grid;            /* cap on persistent CTAs (tests: many tiles per CTA)                              */
+    int32_t max_bn;              /* cap on the N tile width                                                         */
+    int32_t max_stages;          /* cap on operand ring stages                                                      */
+    int32_t max_win_stages;      /* cap on window ring stages                                                       */
+    int32_t stage_bufs;          /* cap on output staging panels per epilogue team (1..3)                           */
+    int32_t tps_kb;              /* cap (KB) on the B bytes grouped into one ring stage in window mode              */
+    int32_t resident_kb;         /* largest filter matrix (KB) kept resident                                        */
+    int32_t reserved[8];
+} lbc_plan_options;
+
+typedef struct lbc_plan lbc_plan;     /* opaque; immutable after creation and safe to share between threads and
+                                         streams (per-run scratch is allocated stream-ordered per call)            */
 typedef struct lbc_net  lbc_net;      /* opaque: a fixed chain/list of planned convolutions           */
 typedef void* lbc_stream;             /* a cudaStream_t (NULL = legacy default stream)                */
 
@@ -104,10 +141,15 @@ lbc_status  lbc_conv_work(const lbc_conv_desc* d, double* ops, double* bytes);
 /* Chooses kernel + tiling for `d` on the current device.  `force` = LBC_KERNEL_AUTO for the planner's
  * choice, or a specific kind (fails with LBC_ERR_UNSUPPORTED if that kernel cannot run the shape). */
 lbc_status  lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan);
+/* The same with explicit planner options (NULL = defaults). */
+void        lbc_plan_options_init(lbc_plan_options* opt);
+lbc_status  lbc_conv_plan_create_ex(const lbc_conv_desc* d, int32_t force, const lbc_plan_options* opt, lbc_plan** plan);
 lbc_status  lbc_conv_plan_destroy(lbc_plan* plan);
 /* Dry run of the planner for a B200 with `sm_count` SMs (0 = 148): no CUDA call, usable without a GPU.  Reports the
  * kernel kind and the planner's description (tile, K chunk, stages, modes, shared memory) or the reason it refuses. */
 lbc_status  lbc_conv_plan_dry(const lbc_conv_desc* d, int32_t force, int32_t sm_count, int32_t* kind, char* buf, size_t buf_len);
+lbc_status  lbc_conv_plan_dry_ex(const lbc_conv_desc* d, int32_t force, const lbc_plan_options* opt, int32_t sm_count,
+                                 int32_t* kind, char* buf, size_t buf_len);
 lbc_status  lbc_conv_plan_kernel(const lbc_plan* plan, int32_t* kind);           /* lbc_kernel_kind   */
 lbc_status  lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_len); /* human-readable */
 /* Number of kernels one lbc_conv_run() launches (for launch accounting in the harness). */
@@ -126,6 +168,12 @@ lbc_status  lbc_conv_prepack_weights(const lbc_plan* plan, const int8_t* w_dev, 
 lbc_status  lbc_conv_run(const lbc_plan* plan, const int8_t* x_nhwc, const void* w_packed,
                          const int32_t* bias, const float* scale, void* y_nhwc,
                          lbc_stream stream, float* elapsed_ms);
+
+/* Device-side status of the asynchronous paths: every pipeline wait in the kernels is bounded by a watchdog; a trip
+ * sets the plan's (network's) device flag.  Call after synchronising the stream: reads and clears the flag and returns
+ * LBC_ERR_KERNEL_TIMEOUT if any launch of this plan since the last check gave up waiting.  The timed / _host entry
+ * points check it themselves. */
+lbc_status  lbc_conv_plan_check(const lbc_plan* plan);
 
 /* Same, but x / y are HOST buffers (pinned or pageable); H2D and D2H copies are issued on `stream`
  * around the kernel and the call returns after the result is in y_host.  w/bias/scale stay on device. */
@@ -154,6 +202,11 @@ lbc_status  lbc_nhwc_to_nchw(const void* src, void* dst, int32_t n, int32_t c, i
 /* `input_of[i]` = index of the layer whose OUTPUT feeds layer i, or -1 for the network input.  The
  * network owns its packed weights, bias, scale and activation buffers (synthetic or caller-loaded). */
 lbc_status  lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers, lbc_net** net);
+/* With planner options applied to every layer (NULL = defaults); opt->reverse == 0 switches the alternating traversal
+ * direction off. */
+lbc_status  lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers,
+                              const lbc_plan_options* opt, lbc_net** net);
+lbc_status  lbc_net_check(lbc_net* net);              /* as lbc_conv_plan_check, for every layer of the network */
 lbc_status  lbc_net_destroy(lbc_net* net);
 lbc_status  lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan** plan);
 /* Load parameters for one layer from HOST memory (weights in `layout`, bias int32[K], scale f32[K]). */
@@ -182,9 +235,10 @@ lbc_status  lbc_net_launches(const lbc_net* net, int32_t* launches);
 lbc_status  lbc_probe_int8_mma_peak(int32_t iters, double* tops, lbc_stream stream);
 /* Streaming-copy probe (int4 loads/stores), GB/s read+write. */
 lbc_status  lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stream stream);
-/* Development aid: when device_buf != NULL, CTA 0 of the tcgen05 kernel records clock64 stamps of its pipeline
- * events (16 int64 slots per local tile, `tiles` tiles) into it.  NULL switches tracing off. */
-lbc_status  lbc_debug_set_trace(void* device_buf, int32_t tiles);
+/* Development aid, per plan: when device_buf != NULL, CTA 0 of the plan's tcgen05 kernel records clock64 stamps of its
+ * pipeline events (16 int64 slots per local tile, `tiles` tiles, then 2 x grid CTA start/end stamps) into it.
+ * NULL switches tracing off.  Not thread-safe against concurrent runs of the same plan. */
+lbc_status  lbc_conv_plan_set_trace(lbc_plan* plan, void* device_buf, int32_t tiles);
 /* Writes `bytes` of zeros to an internal scratch buffer to evict L2 (timing hygiene). */
 lbc_status  lbc_flush_l2(lbc_stream stream);
 

@@ -29,6 +29,26 @@ class CConvDesc(ctypes.Structure):
         "dil_h", "dil_w", "groups", "relu", "out_mode")]
 
 
+class CPlanOptions(ctypes.Structure):
+    """lbc_plan_options (include/lowbit_cnn.h); build one with plan_options(**kw)."""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "struct_size", "cta_pairs", "warp_store", "fold_bias", "paired_tiles", "resident_filter", "window", "keep_window",
+        "force_im2col", "pixel_groups", "dw_tiled", "reverse", "pdl", "two_mma_warps", "tiles_per_iter2", "small_teams",
+        "four_acc", "n_stationary", "epi_pipeline", "max_grid", "max_bn", "max_stages", "max_win_stages", "stage_bufs",
+        "tps_kb", "resident_kb")] + [("reserved", ctypes.c_int32 * 8)]
+
+
+def plan_options(**kw) -> CPlanOptions:
+    """Planner options with the library's defaults, then the given fields (e.g. cta_pairs=1, max_grid=3)."""
+    o = CPlanOptions()
+    load_library().lbc_plan_options_init(ctypes.byref(o))
+    for k, v in kw.items():
+        if k not in dict(CPlanOptions._fields_) or k in ("struct_size", "reserved"):
+            raise KeyError(f"unknown planner option {k!r}")
+        setattr(o, k, int(v))
+    return o
+
+
 _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32
 _PROTOS = {
@@ -38,6 +58,12 @@ _PROTOS = {
     "lbc_conv_out_shape": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "lbc_conv_work": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "lbc_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _i32, ctypes.POINTER(_vp)]),
+    "lbc_plan_options_init": (None, [ctypes.POINTER(CPlanOptions)]),
+    "lbc_conv_plan_create_ex": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _i32, ctypes.POINTER(CPlanOptions), ctypes.POINTER(_vp)]),
+    "lbc_conv_plan_dry_ex": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _i32, ctypes.POINTER(CPlanOptions), _i32, ctypes.POINTER(_i32),
+                                            ctypes.c_char_p, ctypes.c_size_t]),
+    "lbc_conv_plan_set_trace": (ctypes.c_int, [_vp, _vp, _i32]),
+    "lbc_conv_plan_check": (ctypes.c_int, [_vp]),
     "lbc_conv_plan_destroy": (ctypes.c_int, [_vp]),
     "lbc_conv_plan_kernel": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "lbc_conv_plan_describe": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_size_t]),
@@ -54,6 +80,9 @@ _PROTOS = {
     "lbc_nhwc_to_nchw": (ctypes.c_int, [_vp, _vp] + [_i32] * 5 + [_vp]),
     "lbc_conv_plan_dry": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _i32, _i32, ctypes.POINTER(_i32), ctypes.c_char_p, ctypes.c_size_t]),
     "lbc_net_create": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), _i32, ctypes.POINTER(_vp)]),
+    "lbc_net_create_ex": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), _i32, ctypes.POINTER(CPlanOptions),
+                                         ctypes.POINTER(_vp)]),
+    "lbc_net_check": (ctypes.c_int, [_vp]),
     "lbc_net_destroy": (ctypes.c_int, [_vp]),
     "lbc_net_layer_plan": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp)]),
     "lbc_net_set_params_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
@@ -66,7 +95,6 @@ _PROTOS = {
     "lbc_net_launches": (ctypes.c_int, [_vp, ctypes.POINTER(_i32)]),
     "lbc_probe_int8_mma_peak": (ctypes.c_int, [_i32, ctypes.POINTER(ctypes.c_double), _vp]),
     "lbc_probe_hbm_copy": (ctypes.c_int, [ctypes.c_size_t, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
-    "lbc_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "lbc_flush_l2": (ctypes.c_int, [_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -74,12 +74,17 @@ def _ptr(t) -> ctypes.c_void_p:
 class ConvPlan:
     """An lbc_plan plus convenience methods on torch CUDA tensors."""
 
-    def __init__(self, desc: ConvDesc, force: int = _capi.KERNEL_AUTO):
+    def __init__(self, desc: ConvDesc, force: int = _capi.KERNEL_AUTO, options: dict | None = None):
+        """options: lbc_plan_options fields by name (tests / tuning), e.g. {"cta_pairs": 1, "max_grid": 3}."""
         self.desc = desc
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         st = desc.c_struct()
-        check(self._lib.lbc_conv_plan_create(ctypes.byref(st), force, ctypes.byref(self._h)))
+        if options:
+            opt = _capi.plan_options(**options)
+            check(self._lib.lbc_conv_plan_create_ex(ctypes.byref(st), force, ctypes.byref(opt), ctypes.byref(self._h)))
+        else:
+            check(self._lib.lbc_conv_plan_create(ctypes.byref(st), force, ctypes.byref(self._h)))
         self.p, self.q = desc.out_hw
 
     def close(self):
@@ -109,6 +114,14 @@ class ConvPlan:
         n = ctypes.c_int32()
         check(self._lib.lbc_conv_plan_launches(self._h, ctypes.byref(n)))
         return n.value
+
+    def set_trace(self, buf, tiles: int) -> None:
+        """Development aid: int64 CUDA tensor receiving CTA 0's pipeline time stamps (None switches it off)."""
+        check(self._lib.lbc_conv_plan_set_trace(self._h, _ptr(buf), tiles))
+
+    def check_status(self) -> None:
+        """Raises LbcError(LBC_ERR_KERNEL_TIMEOUT) if a launch of this plan tripped its device watchdog (sync first)."""
+        check(self._lib.lbc_conv_plan_check(self._h))
 
     @property
     def packed_weight_bytes(self) -> int:

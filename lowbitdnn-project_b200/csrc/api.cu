@@ -88,16 +88,55 @@ lbc_status current_device(DeviceInfo* info)
     return LBC_OK;
 }
 
+bool first_use_on_device(uint64_t (&mask)[4], int device)
+{
+    if (device < 0 || device >= 256) return true;      // out of the bitmap: set the attributes every time
+    const bool first = !((mask[device >> 6] >> (device & 63)) & 1ull);
+    mask[device >> 6] |= 1ull << (device & 63);
+    return first;
+}
+
+// planner defaults: every tri-state "planner decides", every limit "default"
+void default_options(lbc_plan_options* o)
+{
+    memset(o, 0, sizeof *o);
+    o->struct_size = (int32_t)sizeof *o;
+    o->cta_pairs = o->warp_store = o->fold_bias = o->resident_filter = o->window = o->pixel_groups = o->dw_tiled = -1;
+    o->paired_tiles = 0;
+    o->keep_window = o->force_im2col = 0;
+    o->reverse = -1;
+    o->pdl = o->two_mma_warps = o->tiles_per_iter2 = o->small_teams = o->four_acc = -1;
+    o->n_stationary = o->epi_pipeline = -1;
+}
+
 }  // namespace lbc
 
 using namespace lbc;
 
 // ---- opaque types ------------------------------------------------------------------------------------
+// A fully resolved launch: everything needed to put the layer on a stream.
+struct ResolvedLaunch {
+    const lbc_plan* plan = nullptr;
+    const int8_t* x = nullptr;
+    const void* w = nullptr;
+    EpilogueParams ep{};
+    void* y = nullptr;
+    IgemmLaunch ig{};
+    DwLaunch dw{};
+};
+
 struct lbc_plan {
     ConvGeom g;
     int32_t kind;
     IgemmConfig cfg;
     DeviceInfo dev;
+    lbc_plan_options opt;
+    // device watchdog word: owned by the plan, or borrowed from the network the plan belongs to
+    int* flag = nullptr;
+    bool own_flag = false;
+    // pipeline trace (development aid, lbc_conv_plan_set_trace)
+    long long* trace = nullptr;
+    int32_t trace_tiles = 0;
     // LBC_KERNEL_STEM_TC, and LBC_KERNEL_IGEMM_TC with pw_factor > 1: the rewritten problem the tcgen05 kernel runs
     ConvGeom g_inner;
     // Pixel-group rewrite of a pointwise (1x1, stride 1) layer whose C or K is not a multiple of 16 (MobileNetV2's
@@ -106,7 +145,17 @@ struct lbc_plan {
     // output.  The MMA does f times the useful work, which is free on these HBM-bound layers.
     int32_t pw_factor = 1;
     int32_t stem_sh = 1, stem_sw = 1;
-    void* stem_x = nullptr;     // [N][Hs][Ws][16] transformed input, owned by the plan
+    // [N][Hs][Ws][16] transformed input of the small-C path, owned by the plan.  It is the one piece of mutable state a
+    // run touches: runs of the same plan on different streams are ordered on the device through `stem_last` (the
+    // second stream waits for the first run's igemm before its transform overwrites the buffer); no host blocking.
+    void* stem_x = nullptr;
+    mutable std::mutex stem_mu;
+    mutable cudaEvent_t stem_last = nullptr;
+    mutable cudaStream_t stem_stream = nullptr;
+    mutable bool stem_used = false;
+    // encoded launches (three CUtensorMaps each) of the most recent (x, w, bias, scale, y) argument sets of lbc_conv_run
+    mutable std::mutex cache_mu;
+    mutable std::vector<ResolvedLaunch> cache;
     // scratch for lbc_conv_run_host
     mutable std::mutex mu;
     mutable void* x_dev = nullptr;
@@ -130,17 +179,6 @@ size_t packed_weight_bytes(const lbc_plan* p)
     }
 }
 
-// A fully resolved launch: everything needed to put the layer on a stream.
-struct ResolvedLaunch {
-    const lbc_plan* plan = nullptr;
-    const int8_t* x = nullptr;
-    const void* w = nullptr;
-    EpilogueParams ep{};
-    void* y = nullptr;
-    IgemmLaunch ig{};
-    DwLaunch dw{};
-};
-
 lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const int32_t* bias, const float* scale,
                    void* y, ResolvedLaunch* out)
 {
@@ -159,7 +197,52 @@ lbc_status resolve(const lbc_plan* plan, const int8_t* x, const void* w, const i
         return igemm_encode(plan->pw_factor > 1 ? plan->g_inner : plan->g, plan->cfg, plan->dev, x, (const int8_t*)w, y, &out->ig);
     if (plan->kind == LBC_KERNEL_STEM_TC)
         return igemm_encode(plan->g_inner, plan->cfg, plan->dev, (const int8_t*)plan->stem_x, (const int8_t*)w, y, &out->ig);
-    if (plan->kind == LBC_KERNEL_DEPTHWISE) return depthwise_encode(plan->g, x, &out->dw);
+    if (plan->kind == LBC_KERNEL_DEPTHWISE) return depthwise_encode(plan->g, plan->opt, x, &out->dw);
+    return LBC_OK;
+}
+
+// lbc_conv_run: the encoded launch for this argument set, from the plan's small cache when it has been seen before
+// (cuTensorMapEncode* costs a few microseconds per map; a serving loop calls with the same buffers every step)
+lbc_status resolve_cached(const lbc_plan* plan, const int8_t* x, const void* w, const int32_t* bias, const float* scale,
+                          void* y, ResolvedLaunch* out)
+{
+    {
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        for (const ResolvedLaunch& c : plan->cache)
+            if (c.x == x && c.w == w && c.y == y && c.ep.bias == bias && c.ep.scale == scale) {
+                *out = c;
+                return LBC_OK;
+            }
+    }
+    lbc_status st = resolve(plan, x, w, bias, scale, y, out);
+    if (st != LBC_OK) return st;
+    std::lock_guard<std::mutex> lk(plan->cache_mu);
+    if (plan->cache.size() >= 4) plan->cache.erase(plan->cache.begin());
+    plan->cache.push_back(*out);
+    return LBC_OK;
+}
+
+IgemmRuntime runtime_of(const lbc_plan* p)
+{
+    IgemmRuntime rt;
+    rt.flag = p->flag;
+    rt.trace = p->trace;
+    rt.trace_tiles = p->trace_tiles;
+    return rt;
+}
+
+// reads and clears a device watchdog word
+lbc_status check_flag(int* flag)
+{
+    if (!flag) return LBC_OK;
+    int v = 0;
+    LBC_CUDA_TRY(cudaMemcpy(&v, flag, sizeof v, cudaMemcpyDeviceToHost));
+    if (v) {
+        cudaMemset(flag, 0, sizeof v);
+        set_error(v == 2 ? "igemm: dynamic shared memory base is not 1024-byte aligned"
+                         : "device pipeline watchdog fired (a bounded mbarrier wait exceeded 2 s)");
+        return LBC_ERR_KERNEL_TIMEOUT;
+    }
     return LBC_OK;
 }
 
@@ -167,15 +250,23 @@ lbc_status launch(const ResolvedLaunch& l, cudaStream_t stream)
 {
     const lbc_plan* p = l.plan;
     switch (p->kind) {
-        case LBC_KERNEL_IGEMM_TC: return igemm_launch(p->pw_factor > 1 ? p->g_inner : p->g, l.ig, l.ep, l.y, stream);
+        case LBC_KERNEL_IGEMM_TC: return igemm_launch(p->pw_factor > 1 ? p->g_inner : p->g, l.ig, l.ep, l.y, runtime_of(p), stream);
         case LBC_KERNEL_STEM_TC: {
             const lbc_conv_desc& d = p->g.d;
+            // the transformed-input scratch is per plan: order this run after the previous one if that was on another stream
+            std::lock_guard<std::mutex> lk(p->stem_mu);
+            if (p->stem_used && p->stem_stream != stream) LBC_CUDA_TRY(cudaStreamWaitEvent(stream, p->stem_last, 0));
             lbc_status st = launch_stem_xform(l.x, p->stem_x, d.n, d.h, d.w, d.c, p->g_inner.d.h, p->g_inner.d.w, p->stem_sh,
                                               p->stem_sw, d.pad_h, d.pad_w, stream);
             if (st != LBC_OK) return st;
-            return igemm_launch(p->g_inner, l.ig, l.ep, l.y, stream);
+            st = igemm_launch(p->g_inner, l.ig, l.ep, l.y, runtime_of(p), stream);
+            if (st != LBC_OK) return st;
+            LBC_CUDA_TRY(cudaEventRecord(p->stem_last, stream));
+            p->stem_stream = stream;
+            p->stem_used = true;
+            return LBC_OK;
         }
-        case LBC_KERNEL_DEPTHWISE: return launch_depthwise(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, &l.dw, stream);
+        case LBC_KERNEL_DEPTHWISE: return launch_depthwise(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, &l.dw, p->flag, stream);
         case LBC_KERNEL_DIRECT: return launch_direct_conv(p->g, l.x, (const int8_t*)l.w, l.ep, l.y, stream);
         default: set_error("plan has unknown kernel kind %d", p->kind); return LBC_ERR_UNSUPPORTED;
     }
@@ -244,10 +335,19 @@ lbc_status lbc_conv_work(const lbc_conv_desc* d, double* ops, double* bytes)
 
 // The planner proper: pure host logic for a given device description.  `dry` plans without touching CUDA (no scratch
 // allocation): lbc_conv_plan_dry() uses it to make every tiling decision checkable on a machine without a GPU.
-static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const DeviceInfo& dev, bool dry, lbc_plan** plan)
+static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const DeviceInfo& dev, const lbc_plan_options* opt_in,
+                             bool dry, int* shared_flag, lbc_plan** plan)
 {
     LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan out-pointer");
     *plan = nullptr;
+    lbc_plan_options opt;
+    default_options(&opt);
+    if (opt_in) {
+        LBC_REQUIRE(opt_in->struct_size == (int32_t)sizeof(lbc_plan_options), LBC_ERR_INVALID_ARG,
+                    "lbc_plan_options.struct_size is %d, this library expects %d (call lbc_plan_options_init first)",
+                    opt_in->struct_size, (int)sizeof(lbc_plan_options));
+        opt = *opt_in;
+    }
     ConvGeom g;
     lbc_status st = make_geom(d, &g);
     if (st != LBC_OK) return st;
@@ -272,7 +372,7 @@ static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const Device
         di.stride_h = di.stride_w = 1;
         di.pad_h = di.pad_w = 0;
         stem_ok = make_geom(&di, &gi) == LBC_OK && gi.p == g.p && gi.q == g.q && igemm_supported(gi, nullptr) &&
-                  igemm_make_config(gi, dev, &stem_cfg) == LBC_OK && stem_cfg.mode == 2 && stem_cfg.bkc == 16;
+                  igemm_make_config(gi, dev, opt, &stem_cfg) == LBC_OK && stem_cfg.mode == 2 && stem_cfg.bkc == 16;
     }
     // pixel-group rewrite for pointwise layers the tensor-core path cannot tile directly
     ConvGeom gp{};
@@ -282,7 +382,7 @@ static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const Device
     // TMA issue) for 2048 outputs; grouping f pixels makes the tile 128 x 16f over the same bytes.
     const bool pointwise = d->groups == 1 && d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 &&
                            d->pad_h == 0 && d->pad_w == 0;
-    const bool narrow = tc_ok && pointwise && (d->k < 64 || d->c < 32) && !getenv("LBC_NO_PIXEL_GROUPS");
+    const bool narrow = tc_ok && pointwise && (d->k < 64 || d->c < 32) && opt.pixel_groups != 0;
     if (pointwise && (!tc_ok || narrow)) {
         for (int32_t f = 2; f <= 16 && pw_factor == 1; f *= 2) {
             if ((f * d->c) % 16 || (f * d->k) % 16 || g.m_total % f || (int64_t)f * d->c > 4096) continue;
@@ -292,7 +392,7 @@ static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const Device
             lbc_conv_desc di = *d;
             di.n = 1; di.h = 1; di.w = (int32_t)(g.m_total / f); di.c = f * d->c; di.k = f * d->k;
             if (g.m_total / f >= (1ll << 31)) continue;
-            if (make_geom(&di, &gp) == LBC_OK && igemm_supported(gp, nullptr) && igemm_make_config(gp, dev, &pw_cfg) == LBC_OK) {
+            if (make_geom(&di, &gp) == LBC_OK && igemm_supported(gp, nullptr) && igemm_make_config(gp, dev, opt, &pw_cfg) == LBC_OK) {
                 pw_factor = f;
                 pw_cfg.k_mod = d->k;
             }
@@ -324,14 +424,26 @@ static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const Device
     p->g = g;
     p->kind = kind;
     p->dev = dev;
+    p->opt = opt;
+    if (shared_flag) {
+        p->flag = shared_flag;
+    } else if (!dry) {
+        if (cudaMalloc((void**)&p->flag, sizeof(int)) != cudaSuccess || cudaMemset(p->flag, 0, sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            delete p;
+            set_error("cannot allocate the plan's device status word");
+            return LBC_ERR_ALLOC;
+        }
+        p->own_flag = true;
+    }
     if (kind == LBC_KERNEL_IGEMM_TC && use_pw) {
         p->pw_factor = pw_factor;
         p->g_inner = gp;
         p->cfg = pw_cfg;
     } else if (kind == LBC_KERNEL_IGEMM_TC) {
-        st = igemm_make_config(g, dev, &p->cfg);
+        st = igemm_make_config(g, dev, opt, &p->cfg);
         if (st != LBC_OK) {
-            delete p;
+            lbc_conv_plan_destroy(p);
             return st;
         }
     }
@@ -341,9 +453,10 @@ static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const Device
         p->stem_sh = d->stride_h;
         p->stem_sw = d->stride_w;
         const size_t bytes = (size_t)gi.d.n * gi.d.h * gi.d.w * 16;
-        if (!dry && cudaMalloc(&p->stem_x, bytes) != cudaSuccess) {
+        if (!dry && (cudaMalloc(&p->stem_x, bytes) != cudaSuccess ||
+                     cudaEventCreateWithFlags(&p->stem_last, cudaEventDisableTiming) != cudaSuccess)) {
             cudaGetLastError();
-            delete p;
+            lbc_conv_plan_destroy(p);
             set_error("small-C path: cannot allocate the %zu-byte transformed input", bytes);
             return LBC_ERR_ALLOC;
         }
@@ -352,17 +465,33 @@ static lbc_status plan_build(const lbc_conv_desc* d, int32_t force, const Device
     return LBC_OK;
 }
 
-lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan)
+void lbc_plan_options_init(lbc_plan_options* opt)
+{
+    if (opt) default_options(opt);
+}
+
+lbc_status lbc_conv_plan_create_ex(const lbc_conv_desc* d, int32_t force, const lbc_plan_options* opt, lbc_plan** plan)
 {
     LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan out-pointer");
     *plan = nullptr;
     DeviceInfo dev;
     lbc_status st = current_device(&dev);
     if (st != LBC_OK) return st;
-    return plan_build(d, force, dev, false, plan);
+    return plan_build(d, force, dev, opt, false, nullptr, plan);
+}
+
+lbc_status lbc_conv_plan_create(const lbc_conv_desc* d, int32_t force, lbc_plan** plan)
+{
+    return lbc_conv_plan_create_ex(d, force, nullptr, plan);
 }
 
 lbc_status lbc_conv_plan_dry(const lbc_conv_desc* d, int32_t force, int32_t sm_count, int32_t* kind, char* buf, size_t buf_len)
+{
+    return lbc_conv_plan_dry_ex(d, force, nullptr, sm_count, kind, buf, buf_len);
+}
+
+lbc_status lbc_conv_plan_dry_ex(const lbc_conv_desc* d, int32_t force, const lbc_plan_options* opt, int32_t sm_count,
+                                int32_t* kind, char* buf, size_t buf_len)
 {
     DeviceInfo dev;
     dev.device = 0;
@@ -372,7 +501,7 @@ lbc_status lbc_conv_plan_dry(const lbc_conv_desc* d, int32_t force, int32_t sm_c
     dev.hbm_bytes = (size_t)180 << 30;
     dev.driver_version = 13000;
     lbc_plan* p = nullptr;
-    lbc_status st = plan_build(d, force, dev, true, &p);
+    lbc_status st = plan_build(d, force, dev, opt, true, nullptr, &p);
     if (st != LBC_OK) return st;
     if (kind) *kind = p->kind;
     if (buf && buf_len) st = lbc_conv_plan_describe(p, buf, buf_len);
@@ -386,8 +515,24 @@ lbc_status lbc_conv_plan_destroy(lbc_plan* plan)
     if (plan->x_dev) cudaFree(plan->x_dev);
     if (plan->y_dev) cudaFree(plan->y_dev);
     if (plan->stem_x) cudaFree(plan->stem_x);
+    if (plan->stem_last) cudaEventDestroy(plan->stem_last);
+    if (plan->own_flag && plan->flag) cudaFree(plan->flag);
     delete plan;
     return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_set_trace(lbc_plan* plan, void* device_buf, int32_t tiles)
+{
+    LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan");
+    plan->trace = device_buf ? reinterpret_cast<long long*>(device_buf) : nullptr;
+    plan->trace_tiles = device_buf ? tiles : 0;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_plan_check(const lbc_plan* plan)
+{
+    LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan");
+    return check_flag(plan->flag);
 }
 
 lbc_status lbc_conv_plan_kernel(const lbc_plan* plan, int32_t* kind)
@@ -475,7 +620,7 @@ lbc_status lbc_conv_run(const lbc_plan* plan, const int8_t* x, const void* w_pac
                         const float* scale, void* y, lbc_stream stream, float* elapsed_ms)
 {
     ResolvedLaunch l;
-    lbc_status st = resolve(plan, x, w_packed, bias, scale, y, &l);
+    lbc_status st = resolve_cached(plan, x, w_packed, bias, scale, y, &l);
     if (st != LBC_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
     if (!elapsed_ms) return launch(l, s);
@@ -488,8 +633,7 @@ lbc_status lbc_conv_run(const lbc_plan* plan, const int8_t* x, const void* w_pac
     LBC_CUDA_TRY(cudaEventRecord(ev.b, s));
     LBC_CUDA_TRY(cudaEventSynchronize(ev.b));
     LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ev.a, ev.b));
-    if (plan->kind == LBC_KERNEL_IGEMM_TC || plan->kind == LBC_KERNEL_STEM_TC) return igemm_check_timeout();
-    return LBC_OK;
+    return check_flag(plan->flag);
 }
 
 lbc_status lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const void* w_packed, const int32_t* bias,
@@ -519,8 +663,7 @@ lbc_status lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const v
     LBC_CUDA_TRY(cudaEventRecord(ev.b, s));
     LBC_CUDA_TRY(cudaEventSynchronize(ev.b));
     if (elapsed_ms) LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ev.a, ev.b));
-    if (plan->kind == LBC_KERNEL_IGEMM_TC) return igemm_check_timeout();
-    return LBC_OK;
+    return check_flag(plan->flag);
 }
 
 // ---- layout converters -------------------------------------------------------------------------------
@@ -590,12 +733,6 @@ lbc_status lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stre
 {
     return probe_hbm_copy(bytes, iters, gbs, (cudaStream_t)stream);
 }
-lbc_status lbc_debug_set_trace(void* device_buf, int32_t tiles)
-{
-    igemm_set_trace(reinterpret_cast<long long*>(device_buf), tiles);
-    return LBC_OK;
-}
-
 lbc_status lbc_flush_l2(lbc_stream stream)
 {
     DeviceInfo dev;
@@ -627,6 +764,10 @@ struct lbc_net {
     std::vector<Layer> layers;
     std::vector<cudaEvent_t> events;   // n_layers + 1
     std::mutex mu;
+    int* flag = nullptr;               // device watchdog word shared by every layer's plan
+    // layer 0 resolved against each of the pipelined host path's two input buffers (see Pipe)
+    ResolvedLaunch first_rl[2];
+    bool first_rl_ok[2] = {false, false};
     // pipelined host path (lbc_net_submit_host): copy streams, second input buffer, hand-over events
     struct Pipe {
         cudaStream_t h2d = nullptr, d2h = nullptr;
@@ -690,7 +831,9 @@ lbc_status lbc_net_destroy(lbc_net* net)
         if (L.y) cudaFree(L.y);
         lbc_conv_plan_destroy(L.plan);
     }
-    for (auto e : net->events) cudaEventDestroy(e);
+    for (auto e : net->events)
+        if (e) cudaEventDestroy(e);
+    if (net->flag) cudaFree(net->flag);
     {
         lbc_net::Pipe& pp = net->pipe;
         if (pp.h2d) cudaStreamDestroy(pp.h2d);
@@ -705,12 +848,35 @@ lbc_status lbc_net_destroy(lbc_net* net)
 
 lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers, lbc_net** out)
 {
+    return lbc_net_create_ex(descs, input_of, n_layers, nullptr, out);
+}
+
+lbc_status lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers, const lbc_plan_options* opt_in,
+                             lbc_net** out)
+{
     LBC_REQUIRE(descs && out && n_layers > 0, LBC_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
+    DeviceInfo dev;
+    lbc_status st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    lbc_plan_options opt;
+    default_options(&opt);
+    if (opt_in) {
+        LBC_REQUIRE(opt_in->struct_size == (int32_t)sizeof(lbc_plan_options), LBC_ERR_INVALID_ARG,
+                    "lbc_plan_options.struct_size is %d, this library expects %d", opt_in->struct_size, (int)sizeof(lbc_plan_options));
+        opt = *opt_in;
+    }
+    const bool snake = opt.reverse != 0;     // the network sets every layer's direction itself
+    opt.reverse = -1;
     lbc_net* net = new (std::nothrow) lbc_net();
     LBC_REQUIRE(net, LBC_ERR_ALLOC, "out of host memory");
+    if (cudaMalloc((void**)&net->flag, sizeof(int)) != cudaSuccess || cudaMemset(net->flag, 0, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        delete net;
+        set_error("cannot allocate the network's device status word");
+        return LBC_ERR_ALLOC;
+    }
     net->layers.resize(n_layers);
-    lbc_status st = LBC_OK;
     for (int i = 0; i < n_layers && st == LBC_OK; ++i) {
         lbc_net::Layer& L = net->layers[i];
         L.input_of = input_of ? input_of[i] : (i == 0 ? -1 : i - 1);
@@ -719,7 +885,7 @@ lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, i
             st = LBC_ERR_INVALID_ARG;
             break;
         }
-        st = lbc_conv_plan_create(&descs[i], LBC_KERNEL_AUTO, &L.plan);
+        st = plan_build(&descs[i], LBC_KERNEL_AUTO, dev, &opt, false, net->flag, &L.plan);
         if (st != LBC_OK) break;
         const ConvGeom& g = L.plan->g;
         if (L.input_of >= 0) {
@@ -736,7 +902,7 @@ lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, i
                             L.plan->kind == LBC_KERNEL_DEPTHWISE;      // (the tiled depthwise kernel mirrors its tile index)
             const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
             // a producer that ran forwards finished on the last images: start there; CUDA-core kernels always run forwards
-            L.reverse = tc && L.input_of >= 0 && !producer_rev && !getenv("LBC_NO_SNAKE");
+            L.reverse = tc && L.input_of >= 0 && !producer_rev && snake;
         }
         const size_t wb = packed_weight_bytes(L.plan);
         bool ok = cudaMalloc(&L.w, wb) == cudaSuccess && cudaMalloc((void**)&L.bias, sizeof(int32_t) * g.d.k) == cudaSuccess &&
@@ -754,7 +920,7 @@ lbc_status lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, i
         if (L.x_own) cudaMemset(L.x_own, 0, in_bytes(g));
     }
     if (st == LBC_OK) {
-        net->events.resize(n_layers + 1);
+        net->events.assign(n_layers + 1, nullptr);
         for (auto& e : net->events)
             if (cudaEventCreate(&e) != cudaSuccess) {
                 e = nullptr;
@@ -839,7 +1005,7 @@ lbc_status lbc_net_run(lbc_net* net, const int8_t* x_dev, lbc_stream stream, flo
     if (per_layer_ms)
         for (int i = 0; i < n; ++i) LBC_CUDA_TRY(cudaEventElapsedTime(&per_layer_ms[i], net->events[i], net->events[i + 1]));
     if (total_ms) LBC_CUDA_TRY(cudaEventElapsedTime(total_ms, net->events[0], net->events[n]));
-    return igemm_check_timeout();
+    return check_flag(net->flag);
 }
 
 lbc_status lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lbc_stream stream, float* total_ms)
@@ -859,7 +1025,7 @@ lbc_status lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lb
     LBC_CUDA_TRY(cudaEventRecord(net->events[n], s));
     LBC_CUDA_TRY(cudaEventSynchronize(net->events[n]));
     if (total_ms) LBC_CUDA_TRY(cudaEventElapsedTime(total_ms, net->events[0], net->events[n]));
-    return igemm_check_timeout();
+    return check_flag(net->flag);
 }
 
 static lbc_status pipe_init(lbc_net* net)
@@ -868,18 +1034,21 @@ static lbc_status pipe_init(lbc_net* net)
     if (pp.ready) return LBC_OK;
     lbc_net::Layer& first = net->layers[0];
     LBC_REQUIRE(first.x_own, LBC_ERR_INVALID_ARG, "layer 0 must take the network input");
-    LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
-    LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking));
+    // every handle is created only if it is still null, so a call that failed half-way can simply be repeated
+    // (lbc_net_destroy releases whatever exists)
+    if (!pp.h2d) LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
+    if (!pp.d2h) LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking));
     pp.x_buf[0] = first.x_own;
-    if (cudaMalloc(&pp.x_buf[1], in_bytes(first.plan->g)) != cudaSuccess) {
+    if (!pp.x_buf[1] && cudaMalloc(&pp.x_buf[1], in_bytes(first.plan->g)) != cudaSuccess) {
         cudaGetLastError();
+        pp.x_buf[1] = nullptr;
         set_error("lbc_net_submit_host: cannot allocate the second input buffer");
         return LBC_ERR_ALLOC;
     }
     for (cudaEvent_t* e : {&pp.up_done[0], &pp.up_done[1], &pp.x_used[0], &pp.x_used[1], &pp.comp_done, &pp.d2h_done})
-        LBC_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    LBC_CUDA_TRY(cudaEventCreate(&pp.t_first));
-    LBC_CUDA_TRY(cudaEventCreate(&pp.t_last));
+        if (!*e) LBC_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    if (!pp.t_first) LBC_CUDA_TRY(cudaEventCreate(&pp.t_first));
+    if (!pp.t_last) LBC_CUDA_TRY(cudaEventCreate(&pp.t_last));
     pp.ready = true;
     return LBC_OK;
 }
@@ -904,10 +1073,24 @@ lbc_status lbc_net_submit_host(lbc_net* net, const int8_t* x_host, void* y_host,
     // compute: layer 0 waits for its upload; the last layer waits until the previous result has been downloaded
     LBC_CUDA_TRY(cudaStreamWaitEvent(s, pp.up_done[b], 0));
     for (int i = 0; i < n; ++i) {
-        st = net_resolve(net, i, i == 0 ? (const int8_t*)pp.x_buf[b] : nullptr);
-        if (st != LBC_OK) return st;
+        const ResolvedLaunch* rl = &net->layers[i].rl;
+        if (i == 0) {
+            // layer 0 alternates between the two input buffers: keep one encoded launch per buffer
+            if (!net->first_rl_ok[b]) {
+                lbc_net::Layer& L = net->layers[0];
+                st = resolve(L.plan, (const int8_t*)pp.x_buf[b], L.w, L.bias, L.scale, L.y, &net->first_rl[b]);
+                if (st != LBC_OK) return st;
+                net->first_rl[b].ig.reverse = L.reverse ? 1 : 0;
+                net->first_rl[b].dw.reverse = (L.reverse && net->first_rl[b].dw.tiled) ? 1 : 0;
+                net->first_rl_ok[b] = true;
+            }
+            rl = &net->first_rl[b];
+        } else {
+            st = net_resolve(net, i, nullptr);
+            if (st != LBC_OK) return st;
+        }
         if (i == n - 1 && pp.submitted >= 1) LBC_CUDA_TRY(cudaStreamWaitEvent(s, pp.d2h_done, 0));
-        st = launch(net->layers[i].rl, s);
+        st = launch(*rl, s);
         if (st != LBC_OK) return st;
         if (i == 0) LBC_CUDA_TRY(cudaEventRecord(pp.x_used[b], s));
     }
@@ -931,9 +1114,13 @@ lbc_status lbc_net_sync_host(lbc_net* net, float* elapsed_ms)
     LBC_CUDA_TRY(cudaEventSynchronize(pp.t_last));
     if (elapsed_ms) LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, pp.t_first, pp.t_last));
     pp.submitted = 0;
-    // layer 0 goes back to its resident buffer for lbc_net_run
-    net->layers[0].resolved = false;
-    return igemm_check_timeout();
+    return check_flag(net->flag);
+}
+
+lbc_status lbc_net_check(lbc_net* net)
+{
+    LBC_REQUIRE(net, LBC_ERR_INVALID_ARG, "null net");
+    return check_flag(net->flag);
 }
 
 lbc_status lbc_net_launches(const lbc_net* net, int32_t* launches)

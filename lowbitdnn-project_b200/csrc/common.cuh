@@ -73,9 +73,10 @@ struct DwLaunch {
     uint32_t tile_bytes;
     int32_t reverse = 0;         // tiled kernel: walk the tiles last-to-first
 };
-lbc_status depthwise_encode(const ConvGeom& g, const int8_t* x, DwLaunch* out);
+lbc_status depthwise_encode(const ConvGeom& g, const lbc_plan_options& opt, const int8_t* x, DwLaunch* out);
+// `flag`: the plan's device watchdog word (see IgemmRuntime)
 lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
-                            void* y, const DwLaunch* dw, cudaStream_t stream);
+                            void* y, const DwLaunch* dw, int* flag, cudaStream_t stream);
 lbc_status encode_tiled_u8_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4]);
 
 // igemm_tc.cu — tcgen05 implicit GEMM.
@@ -115,7 +116,15 @@ struct IgemmConfig {
     int32_t grid;        // persistent CTAs
     size_t smem_bytes;
     uint32_t tmem_cols;  // power of two >= n_acc*bn
-    int32_t n_acc;       // TMEM accumulator stages (2 or 4)
+    int32_t n_acc;       // TMEM accumulator stages (2, 4 or 8)
+    int32_t reverse;     // lbc_plan_options::reverse: walk the tiles last-to-first
+    int32_t pdl;         // programmatic dependent launch allowed
+};
+// per-launch state that belongs to the plan, not to the tiling
+struct IgemmRuntime {
+    int* flag = nullptr;            // device watchdog word of the plan (never null on a launch)
+    long long* trace = nullptr;     // optional pipeline trace buffer (development aid)
+    int32_t trace_tiles = 0;
 };
 struct IgemmLaunch {
     CUtensorMap tm_a;
@@ -125,13 +134,13 @@ struct IgemmLaunch {
     int32_t reverse = 0;   // walk the M tiles / images last-to-first (L2 reuse of the producer's most recent output)
 };
 bool igemm_supported(const ConvGeom& g, std::string* why);
-lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConfig* cfg);
+lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, const lbc_plan_options& opt, IgemmConfig* cfg);
 lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceInfo& dev, const int8_t* x,
                         const int8_t* w_packed, void* y, IgemmLaunch* out);
 lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
-                        cudaStream_t stream);
-void igemm_set_trace(long long* device_buf, int32_t tiles);   // development aid: CTA 0 pipeline time stamps
-lbc_status igemm_check_timeout();  // reads (and clears) the device watchdog flag; call after a sync
+                        const IgemmRuntime& rt, cudaStream_t stream);
+// per-device one-time kernel attributes: true the first time it is called for `device` under `mask`
+bool first_use_on_device(uint64_t (&mask)[4], int device);
 
 // layout.cu
 lbc_status launch_prepack_krsc(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t k, int32_t r, int32_t s,
@@ -159,16 +168,17 @@ lbc_status probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, cudaStream_t
 lbc_status flush_l2(cudaStream_t stream);
 
 // ---- the fused epilogue, shared by every kernel (bit-exact with oracle_requant) ----------------
-// t = acc + bias (int32 wraparound) ; f = float(t) RNE ; f *= scale (single multiply) ; f = fmaxf(f, lo)
-// (drops NaN to lo) ; q = cvt.rni.s32.f32(f) (round-half-to-even, saturating) ; the upper clamp to 127 (and the
-// lower one, already guaranteed by lo >= -128) is done by the saturating int32->int8 pack.
+// The reference's quantize() (cpp/int8conv/conv2DForward3x3WinogradFused.cuh:39-46): round FIRST, then clamp.
+// t = acc + bias (int32 wraparound) ; f = float(t) RNE ; f *= scale (single multiply) ; q = cvt.rni.s32.f32(f)
+// (round-half-to-even, saturating, NaN -> 0) ; q = max(q, lo) with lo = 0 (ReLU) or -128 ; the upper clamp to 127 is
+// done by the saturating int32->int8 pack.  Rounding then clamping at an integer bound equals clamping then rounding
+// for every finite value; the order only matters for NaN (-> 0, as in the reference).
 // Measured on B200 (tools/exp/epi_bench.cu): this F2I + cvt.pack.sat form is ~25% faster than a float clamp +
 // magic-number rounding + PRMT packing.
-__device__ __forceinline__ int32_t requant_s32(int32_t acc, int32_t bias, float scale, float lo)
+__device__ __forceinline__ int32_t requant_s32(int32_t acc, int32_t bias, float scale, int32_t lo)
 {
     const int32_t t = acc + bias;
-    const float f = fmaxf(__fmul_rn(__int2float_rn(t), scale), lo);
-    return __float2int_rn(f);
+    return max(__float2int_rn(__fmul_rn(__int2float_rn(t), scale)), lo);
 }
 
 // {a, b, c, d} (int32, already >= -128) -> four saturated int8 packed little-endian.
@@ -180,7 +190,7 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int32_t a, int32_t b, int32_t c
     return r;
 }
 
-__device__ __forceinline__ int8_t requant_s8(int32_t acc, int32_t bias, float scale, float lo)
+__device__ __forceinline__ int8_t requant_s8(int32_t acc, int32_t bias, float scale, int32_t lo)
 {
     return (int8_t)min(requant_s32(acc, bias, scale, lo), 127);
 }

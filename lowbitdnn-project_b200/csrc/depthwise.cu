@@ -23,6 +23,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <mutex>
 
 namespace lbc {
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, con
     }
 
     // ---- epilogue parameters of the 4 channels
-    const float lo = g.relu ? 0.0f : -128.0f;
+    const int32_t lo = g.relu ? 0 : -128;
     int32_t bi[4] = {0, 0, 0, 0};
     float sc[4] = {0.f, 0.f, 0.f, 0.f};
     if (bias) {
@@ -245,9 +246,8 @@ struct DwTiledParams {
     int32_t relu, out_mode;
     uint32_t tile_bytes;
     int32_t reverse;               // visit the tiles last-to-first (see IgemmLaunch::reverse)
+    int* flag;                     // the plan's device watchdog word
 };
-
-__device__ int g_dw_timeout = 0;
 
 template <int STRIDE>
 __global__ void __launch_bounds__(256) depthwise3x3_tiled_kernel(const __grid_constant__ CUtensorMap tm_x, const DwTiledParams g,
@@ -274,10 +274,11 @@ __global__ void __launch_bounds__(256) depthwise3x3_tiled_kernel(const __grid_co
         ptx::tma_load_4d(tile, &tm_x, &bar, c0, q0 * STRIDE - g.pad_w, p0 * STRIDE - g.pad_h, n0);
     }
     __syncthreads();
-    ptx::mbar_wait(&bar, 0, &g_dw_timeout);
+    // a watchdog trip (tile never landed) must not store results computed from unfilled shared memory
+    if (!ptx::mbar_wait(&bar, 0, g.flag)) return;
 
     const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
-    const float lo = g.relu ? 0.0f : -128.0f;
+    const int32_t lo = g.relu ? 0 : -128;
     uint32_t* y8 = reinterpret_cast<uint32_t*>(y);
     int4* y32 = reinterpret_cast<int4*>(y);
     const int32_t items = g.nb * g.row_groups * g.strips * g.ccq;
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(256) depthwise_generic_kernel(const DwGenericP
         }
     }
     const int64_t o = m * g.c + c0;
-    const float lo = g.relu ? 0.0f : -128.0f;
+    const int32_t lo = g.relu ? 0 : -128;
     if (g.out_mode == LBC_OUT_INT32) {
         int4 v;
         v.x = acc[0] + (bias ? bias[c0 + 0] : 0);
@@ -443,13 +444,13 @@ int32_t pick_strip(int32_t q)
 }  // namespace
 
 // Tile geometry of the TMA-staged kernel; tiled == 0 when the shape does not qualify.
-lbc_status depthwise_encode(const ConvGeom& g, const int8_t* x, DwLaunch* out)
+lbc_status depthwise_encode(const ConvGeom& g, const lbc_plan_options& opt, const int8_t* x, DwLaunch* out)
 {
     const lbc_conv_desc& d = g.d;
     *out = DwLaunch{};
     const bool fast = d.r == 3 && d.s == 3 && d.dil_h == 1 && d.dil_w == 1 && d.stride_h == d.stride_w &&
                       (d.stride_h == 1 || d.stride_h == 2) && d.c % 16 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-                      (int64_t)d.n * d.h * d.w * d.c < (1ll << 32) && g.m_total * d.c < (1ll << 32) && !getenv("LBC_DW_DIRECT");
+                      (int64_t)d.n * d.h * d.w * d.c < (1ll << 32) && g.m_total * d.c < (1ll << 32) && opt.dw_tiled != 0;
     if (!fast) return LBC_OK;
     const int S = d.stride_h, rows = S == 1 ? 2 : 1;
     DwLaunch l{};
@@ -497,7 +498,7 @@ lbc_status depthwise_encode(const ConvGeom& g, const int8_t* x, DwLaunch* out)
 }
 
 lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_rsc, const EpilogueParams& ep,
-                            void* y, const DwLaunch* dw, cudaStream_t stream)
+                            void* y, const DwLaunch* dw, int* flag, cudaStream_t stream)
 {
     const lbc_conv_desc& d = g.d;
     if (dw && dw->tiled) {
@@ -513,15 +514,21 @@ lbc_status launch_depthwise(const ConvGeom& g, const int8_t* x, const int8_t* w_
         p.row_groups = dw->th / (d.stride_h == 1 ? 2 : 1);
         p.relu = ep.relu; p.out_mode = ep.out_mode;
         p.tile_bytes = dw->tile_bytes;
-        p.reverse = (dw->reverse || getenv("LBC_SNAKE")) ? 1 : 0;
+        p.reverse = dw->reverse ? 1 : 0;
+        p.flag = flag;
         const unsigned grid = (unsigned)(dw->tiles_c * dw->tiles_q * dw->tiles_p * dw->tiles_n);
         const size_t smem = dw->tile_bytes;
         const unsigned block = 256;
-        static bool attr_set = false;
-        if (!attr_set) {
-            LBC_CUDA_TRY(cudaFuncSetAttribute(depthwise3x3_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            LBC_CUDA_TRY(cudaFuncSetAttribute(depthwise3x3_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
+        {   // the attribute is per device
+            static std::mutex mu;
+            static uint64_t done[4] = {0, 0, 0, 0};
+            int dev_ord = 0;
+            LBC_CUDA_TRY(cudaGetDevice(&dev_ord));
+            std::lock_guard<std::mutex> lk(mu);
+            if (first_use_on_device(done, dev_ord)) {
+                LBC_CUDA_TRY(cudaFuncSetAttribute(depthwise3x3_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                LBC_CUDA_TRY(cudaFuncSetAttribute(depthwise3x3_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            }
         }
         if (d.stride_h == 1)
             depthwise3x3_tiled_kernel<1><<<grid, block, smem, stream>>>(dw->tm_x, p, w_rsc, ep.bias, ep.scale, y);

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) direct_conv_kernel(DirectParams g, const 
     }
 
     const int64_t o = m * g.k + k0;
-    const float lo = g.relu ? 0.0f : -128.0f;
+    const int32_t lo = g.relu ? 0 : -128;
     if (g.out_mode == LBC_OUT_INT32) {
         int32_t* yo = reinterpret_cast<int32_t*>(y) + o;
 #pragma unroll

@@ -132,6 +132,7 @@ struct IgemmParams {
     // optional pipeline trace (development aid): CTA 0 writes clock64 stamps, 16 slots per local tile
     long long* trace;
     int32_t trace_tiles;
+    int* flag;                    // the plan's device watchdog word (1: a bounded wait gave up, 2: misaligned smem base)
 };
 
 enum : int { EV_P_ISSUE = 0, EV_W_ISSUE, EV_M_START, EV_M_WIN, EV_M_FULL, EV_M_DONE, EV_E_START, EV_E_DRAINED, EV_E_STORED,
@@ -144,8 +145,6 @@ __device__ __forceinline__ void trace_ev(const IgemmParams& prm, bool tracing, i
 {
     if (tracing && local < prm.trace_tiles) prm.trace[local * 16 + ev] = clock64();
 }
-
-__device__ int g_timeout_flag = 0;
 
 struct Ctl {
     uint64_t full[kMaxStages];
@@ -245,31 +244,29 @@ __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, vol
 }
 
 // One 16-column group of one output pixel: requantise (bias/scale from smem) and return 16 packed int8.
-// RELU: the clamp at zero is applied to the PACKED bytes (sign-replicating PRMT + AND: 2 instructions per 4 outputs
-// instead of 4 FMNMX).  Rounding then clamping at an integer equals clamping then rounding, and a NaN product converts to
-// 0 either way, so the bytes are identical to requant_s32 with lo = 0.
+// The rule is requant_s32's (round half-to-even with NaN -> 0, then clamp): cvt.rni.s32.f32 rounds and saturates to
+// int32, the saturating int32 -> int8 pack clamps to [-128, 127], and with RELU the clamp at zero is applied to the
+// PACKED bytes (sign-replicating PRMT + AND: 2 instructions per 4 outputs instead of 4 IMNMX).
 // FOLD: the accumulator already contains the bias (see IgemmParams::fold)
 template <bool RELU, bool FOLD>
-__device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi, float lo)
+__device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi)
 {
     uint32_t w[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const float4 f = *reinterpret_cast<const float4*>(sc + 4 * t);
         const int4 b = FOLD ? make_int4(0, 0, 0, 0) : *reinterpret_cast<const int4*>(bi + 4 * t);
+        const int32_t q0 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 0] + b.x), f.x));
+        const int32_t q1 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 1] + b.y), f.y));
+        const int32_t q2 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 2] + b.z), f.z));
+        const int32_t q3 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 3] + b.w), f.w));
+        uint32_t r = pack4_sat_s8(q0, q1, q2, q3);
         if (RELU) {
-            const int32_t q0 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 0] + b.x), f.x));
-            const int32_t q1 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 1] + b.y), f.y));
-            const int32_t q2 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 2] + b.z), f.z));
-            const int32_t q3 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 3] + b.w), f.w));
-            const uint32_t r = pack4_sat_s8(q0, q1, q2, q3);
             uint32_t neg;
             asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(neg) : "r"(r));     // 0xff in every byte whose sign bit is set
-            w[t] = r & ~neg;
-        } else {
-            w[t] = pack4_sat_s8(requant_s32((int32_t)v[4 * t + 0], b.x, f.x, lo), requant_s32((int32_t)v[4 * t + 1], b.y, f.y, lo),
-                                requant_s32((int32_t)v[4 * t + 2], b.z, f.z, lo), requant_s32((int32_t)v[4 * t + 3], b.w, f.w, lo));
+            r &= ~neg;
         }
+        w[t] = r;
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -285,14 +282,14 @@ struct EpiThread {
 template <int NG, bool OUT8, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
                                             const uint32_t* v, int32_t c, int32_t pc, const EpiThread& et,
-                                            uint32_t staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32,
+                                            uint32_t staging, uint32_t row_off, uint32_t swz_mask, int32_t* y32,
                                             int64_t out_row, int32_t col0)
 {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         const int32_t cc = c + 16 * g;
         if (OUT8) {
-            const uint4 r = requant16<RELU, FOLD>(v + 16 * g, sc + cc, bi + cc, lo);
+            const uint4 r = requant16<RELU, FOLD>(v + 16 * g, sc + cc, bi + cc);
             // swizzle: the XOR term depends only on the staging row (a panel row never crosses a 128-byte line), so
             // `swz_mask` arrives here already as this thread's ((row_off >> 7) & mask) << 4
             // `staging` arrives as a 32-bit shared-window address (one conversion per panel, not one per store)
@@ -314,7 +311,7 @@ __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float*
 template <bool OUT8, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* sc, const int32_t* bi, uint32_t taddr,
                                           int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint32_t staging,
-                                          uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
+                                          uint32_t row_off, uint32_t swz_mask, int32_t* y32, int64_t out_row,
                                           int32_t col0)
 {
     int32_t c = c0;
@@ -322,13 +319,13 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         ptx::tmem_ld_wait_dep(v);
-        epi_consume<2, OUT8, RELU, FOLD>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+        epi_consume<2, OUT8, RELU, FOLD>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
     }
     if (c + 16 <= c1) {
         uint32_t v16[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
         ptx::tmem_ld_wait_dep16(v16);
-        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, lo, y32, out_row, col0);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
     }
 }
 
@@ -377,10 +374,10 @@ __device__ __forceinline__ void write_fold_blocks(uint8_t* fold_base, uint32_t e
 template <bool MAY_FOLD>
 __device__ __forceinline__ void epi_run(bool int8_out, bool relu, bool fold, const IgemmParams& prm, const float* sc,
                                         const int32_t* bi, uint32_t taddr, int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et,
-                                        uint32_t staging, uint32_t row_off, uint32_t swz_mask, float lo, int32_t* y32, int64_t out_row,
+                                        uint32_t staging, uint32_t row_off, uint32_t swz_mask, int32_t* y32, int64_t out_row,
                                         int32_t col0)
 {
-#define LBC_EPI(O8, RL, FD) epi_drain<O8, RL, FD>(prm, sc, bi, taddr, pbase, c0, c1, et, staging, row_off, swz_mask, lo, y32, out_row, col0)
+#define LBC_EPI(O8, RL, FD) epi_drain<O8, RL, FD>(prm, sc, bi, taddr, pbase, c0, c1, et, staging, row_off, swz_mask, y32, out_row, col0)
     if (MAY_FOLD && fold) {
         if (int8_out && relu) LBC_EPI(true, true, true);
         else if (int8_out) LBC_EPI(true, false, true);
@@ -430,7 +427,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    volatile int* tflag = &g_timeout_flag;
+    volatile int* tflag = prm.flag;
     const uint32_t cta_rank = CTA2 ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
     const bool tracing = prm.trace != nullptr && blockIdx.x == 0;
 
@@ -865,7 +862,6 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 ptx::named_bar_sync(bar_id, team_threads);
             }
         };
-        const float lo = prm.relu ? 0.0f : -128.0f;
         const bool int8_out = (prm.out_mode == LBC_OUT_INT8);
         const uint32_t panel_smem = (uint32_t)(kBlockM * prm.panel_bytes);
         const uint32_t nbufs = (uint32_t)prm.stage_bufs;
@@ -952,7 +948,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         if (issuer) ptx::tma_store_wait_read<0>();
                         ptx::named_bar_sync(bar_id, team_threads);
                     }
-                    epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, lo, y32,
+                    epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, 0, 0, pcols, et, staging_s, row_off, swz_mask, y32,
                                   out_row, 0);
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -1035,7 +1031,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     const int32_t pbase = pnl * pcols;
                     if (lane == 0) ptx::tma_store_wait_read<0>();      // the previous store has read this buffer out
                     __syncwarp();
-                    epi_run<kFold>(true, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, lo,
+                    epi_run<kFold>(true, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz,
                                   y32, -1, col0);
                     if (pnl + n_halves >= n_panels) {
                         ptx::tc_fence_before();
@@ -1065,7 +1061,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
                 const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
                 epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s,
-                              row_off, swz_mask, lo, y32, out_row, col0);
+                              row_off, swz_mask, y32, out_row, col0);
                 if (pnl == n_panels - 1) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
@@ -1174,10 +1170,9 @@ void small_tensor_fixup(CUtensorMap* tm, size_t tensor_bytes, int driver_version
         reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
 }
 
-bool g_attr_set = false;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: one bit per device ordinal
 std::mutex g_attr_mu;
-long long* g_trace_buf = nullptr;   // development aid, see igemm_set_trace()
-int32_t g_trace_tiles = 0;
+uint64_t g_attr_devices[4] = {0, 0, 0, 0};
 
 uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
@@ -1213,22 +1208,26 @@ bool igemm_supported(const ConvGeom& g, std::string* why)
     return true;
 }
 
-static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, bool allow_pair, IgemmConfig* cfg);
+static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, const lbc_plan_options& o, bool allow_pair,
+                                   IgemmConfig* cfg);
 
-lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, IgemmConfig* cfg)
+lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, const lbc_plan_options& opt, IgemmConfig* cfg)
 {
     // pair mode doubles the window footprint: where that does not fit (very wide rows), plan without it
-    if (make_config_impl(g, dev, true, cfg) == LBC_OK) return LBC_OK;
-    return make_config_impl(g, dev, false, cfg);
+    if (make_config_impl(g, dev, opt, true, cfg) == LBC_OK) return LBC_OK;
+    return make_config_impl(g, dev, opt, false, cfg);
 }
 
-static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, bool allow_pair, IgemmConfig* cfg)
+// `o`: explicit planner options (include/lowbit_cnn.h); tri-states are -1 = planner decides / 0 / 1, limits 0 = default
+static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, const lbc_plan_options& o, bool allow_pair,
+                                   IgemmConfig* cfg)
 {
     const lbc_conv_desc& d = g.d;
     IgemmConfig c{};
+    auto limit = [](int32_t v, int dflt) { return v > 0 ? (int)v : dflt; };
     // ---- N tile: the whole K_out when it fits one 256-wide tile, else an even split into the fewest tiles
     // (multiples of 16; a ragged last tile is handled by TMA zero-fill on loads and clipping on stores)
-    const int max_bn = getenv("LBC_MAX_BN") ? std::max(16, std::min(256, atoi(getenv("LBC_MAX_BN")))) : 256;   // development aid
+    const int max_bn = std::max(16, std::min(256, limit(o.max_bn, 256)));
     c.tiles_n = (d.k + max_bn - 1) / max_bn;
     c.bn = ((d.k + c.tiles_n - 1) / c.tiles_n + 15) / 16 * 16;
     c.tiles_n = (d.k + c.bn - 1) / c.bn;
@@ -1236,11 +1235,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // ---- A mode
     const bool pure_gemm = d.r == 1 && d.s == 1 && d.stride_h == 1 && d.stride_w == 1 && d.pad_h == 0 && d.pad_w == 0;
     c.mode = pure_gemm ? A_TILED : A_IM2COL;
-    if (getenv("LBC_FORCE_IM2COL")) c.mode = A_IM2COL;   // debugging aid
+    if (o.force_im2col == 1) c.mode = A_IM2COL;
     const bool c16 = (d.c == 16);
     c.s_pad = d.s;
     c.rows_per_tile = c.cols_per_tile = c.row_tiles = c.col_tiles = c.wt = 0;
-    if (!pure_gemm && d.stride_h == 1 && d.stride_w == 1 && !getenv("LBC_FORCE_IM2COL") && !getenv("LBC_NO_WINDOW")) {
+    if (!pure_gemm && d.stride_h == 1 && d.stride_w == 1 && o.force_im2col != 1 && o.window != 0) {
         // 16-byte pixels: taps are consumed in pairs and a B block is one filter row of 32/64/128 bytes
         const int s_eff = !c16 ? d.s : (d.s <= 2 ? 2 : d.s <= 4 ? 4 : 8);
         const int ext_w = (s_eff - 1) * d.dil_w, ext_h = (d.r - 1) * d.dil_h;
@@ -1261,9 +1260,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         // which L2 sustains even with every tap fetched separately, so the im2col mode's fully used M tiles (no halo rows,
         // no ragged last row tile: 100% against 77-88% of the MMA rows) win - measured 4% (14x14x256), 10% (28x28x512)
         // and 17% (14x14x512) with pairs, while 128-wide tiles (64-cycle MMAs) stay 25% faster with windows.
-        const char* pairs_env = getenv("LBC_CTA2");
-        if (c.mode == A_WINDOW && c.bn == 256 && d.c >= 256 && d.c % 128 == 0 && !(pairs_env && atoi(pairs_env) == 0) &&
-            !getenv("LBC_KEEP_WINDOW")) {
+        if (c.mode == A_WINDOW && c.bn == 256 && d.c >= 256 && d.c % 128 == 0 && o.cta_pairs != 0 && o.keep_window != 1) {
             c.mode = A_IM2COL;
             c.s_pad = d.s;
             c.rows_per_tile = c.cols_per_tile = c.row_tiles = c.col_tiles = c.wt = 0;
@@ -1290,7 +1287,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // N tiles of <= 128 columns leave TMEM room for the two accumulators of a pair, double-buffered.
     c.pair = 0;
     if (c.mode == A_WINDOW && !c16 && (size_t)d.k * c.packed_row_bytes > 80u * 1024u && (d.k <= 128 || d.k % 128 == 0) &&
-        d.n * c.row_tiles * c.col_tiles >= 2 && allow_pair && getenv("LBC_PAIR")) {   // opt-in: measured gains are marginal (r01)
+        d.n * c.row_tiles * c.col_tiles >= 2 && allow_pair && o.paired_tiles == 1) {   // opt-in: measured gains are marginal (r01)
         c.pair = 1;
         c.bn = d.k <= 128 ? d.k : 128;
         c.tiles_n = d.k / c.bn;
@@ -1306,7 +1303,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // the two SMs of a TPC removes a third of that traffic.
     {
         const size_t full_b = (size_t)c.k_blocks * c.bn * c.bkb;
-        const bool streams = !((size_t)c.tiles_n * full_b <= 80u * 1024u) || getenv("LBC_NO_RESB");
+        const bool streams = !((size_t)c.tiles_n * full_b <= 80u * 1024u) || o.resident_filter == 0;
         const bool possible = !c.pair && !c16 && streams && c.bn % 32 == 0 && c.tiles_m >= 2;
         // Pairing couples the two CTAs' pipelines (one MMA stream waits for both producers and both epilogues), which
         // costs where the epilogue is the bound: short K loops (1x1 channel expansions) measured 10-15% slower in pairs,
@@ -1314,7 +1311,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         // instruction) against ~16 cycles per output column of epilogue.
         const int mma_cycles = c.k_blocks * (c.bkb / 32) * (c.bn / 2);
         bool want = mma_cycles >= 16 * c.bn;
-        if (const char* v = getenv("LBC_CTA2")) want = atoi(v) != 0;       // development / test override
+        if (o.cta_pairs >= 0) want = o.cta_pairs != 0;       // test / tuning override
         c.cta2 = (possible && want) ? 1 : 0;
     }
 
@@ -1329,7 +1326,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     c.warp_store = 0;
     {
         bool want = c.bn == 256 && !c.cta2 && c.k_blocks * (c.bkb / 32) <= 8;
-        if (const char* v = getenv("LBC_WARP_STORE")) want = atoi(v) != 0;     // development / test override
+        if (o.warp_store >= 0) want = o.warp_store != 0;     // test / tuning override
         if (c.mode != A_WINDOW && d.out_mode == LBC_OUT_INT8 && want && (c.bn == 256 || c.bn == 128 || c.bn == 64 || c.bn == 32)) {
             c.warp_store = 1;
             if (c.bn == 128) c.panel_bytes = 64;
@@ -1339,11 +1336,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     c.panel_swz_bits = c.panel_bytes == 128 ? 3 : c.panel_bytes == 64 ? 2 : c.panel_bytes == 32 ? 1 : 0;
 
     // ---- accumulator stages and epilogue teams
-    c.n_acc = (4 * c.bn <= 512 && (c.pair || !getenv("LBC_TWO_ACC"))) ? 4 : 2;
-    c.team_warps = (c.n_acc == 4 && c.bn <= 64 && !getenv("LBC_BIG_TEAMS")) ? 4 : 8;
+    c.n_acc = (4 * c.bn <= 512 && (c.pair || o.four_acc != 0)) ? 4 : 2;
+    c.team_warps = (c.n_acc == 4 && c.bn <= 64 && o.small_teams != 0) ? 4 : 8;
     // narrow tiles: 8 accumulator stages and two tiles per epilogue iteration (see the kernel's tpi == 2 path)
     c.tpi = 1;
-    if (c.team_warps == 4 && c.tiles_n == 1 && !c.pair && !c.cta2 && !c.warp_store && c.bn == c.panel_bytes && !getenv("LBC_TPI1")) {
+    if (c.team_warps == 4 && c.tiles_n == 1 && !c.pair && !c.cta2 && !c.warp_store && c.bn == c.panel_bytes && o.tiles_per_iter2 != 0) {
         c.tpi = 2;
         c.n_acc = 8;
     }
@@ -1355,12 +1352,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     const uint32_t ctl_bytes = round_up((uint32_t)sizeof(Ctl), 256);
     c.a_block_bytes = (c.mode == A_WINDOW) ? 0 : (uint32_t)(kBlockM * c.bkc);
     c.b_block_bytes = (uint32_t)((c.cta2 ? c.bn / 2 : c.bn) * c.bkb);     // a pair's CTAs hold half of the B rows each
-    // tuning knobs (development aids; the defaults are what ships)
-    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
-    const uint32_t tps_cap = (uint32_t)env_int("LBC_TPS_KB", 48) * 1024u;
-    const int max_win = std::min(kMaxWinStages, env_int("LBC_MAX_WIN", kMaxWinStages));
-    const int max_stages = std::min(kMaxStages, env_int("LBC_MAX_STAGES", kMaxStages));
-    const int max_bufs = std::max(1, std::min(3, env_int("LBC_STAGE_BUFS", 3)));
+    // tuning limits (lbc_plan_options; the defaults are what ships)
+    const uint32_t tps_cap = (uint32_t)limit(o.tps_kb, 48) * 1024u;
+    const int max_win = std::min(kMaxWinStages, limit(o.max_win_stages, kMaxWinStages));
+    const int max_stages = std::min(kMaxStages, limit(o.max_stages, kMaxStages));
+    const int max_bufs = std::max(1, std::min(3, limit(o.stage_bufs, 3)));
     // blocks per ring stage: group small B blocks (window mode) so one mbarrier round trip feeds several MMAs
     bool fits = false;
     uint32_t stage_bytes = 0;
@@ -1388,8 +1384,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.tiles_n * c.k_blocks * c.b_block_bytes;      // all N tiles
-    const bool res_b_ok = !c.pair && !c.cta2 && (c.tiles_n == 1 || !getenv("LBC_RESB_ONE_TILE")) && c.b_total_bytes <= (uint32_t)env_int("LBC_RESB_KB", 80) * 1024u &&
-                          !getenv("LBC_NO_RESB");
+    const bool res_b_ok = !c.pair && !c.cta2 && c.b_total_bytes <= (uint32_t)limit(o.resident_kb, 80) * 1024u && o.resident_filter != 0;
     for (int pass = 0; pass < 2 && !fits; ++pass)
     for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs)
     for (int fold_try = 1; fold_try >= 0 && !fits; --fold_try) {     // with the bias-fold blocks if they fit, else without   // three staging panels per team when they fit, else two, else one
@@ -1403,7 +1398,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         // gain nothing (their per-tile bookkeeping dominates) and pay for the extra MMA per tile.  LBC_FOLD=0/1 overrides.
         {
             bool want = c.bn >= 128;
-            if (const char* v = getenv("LBC_FOLD")) want = atoi(v) != 0;
+            if (o.fold_bias >= 0) want = o.fold_bias != 0;
             c.fold = (c.res_b && want && fold_try) ? 1 : 0;
             if (!fold_try && !(c.res_b && want)) continue;      // nothing to drop: this variant was already tried
         }
@@ -1459,7 +1454,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
     const double issue_cycles = 450.0 + 75.0 * c.k_blocks * (c.bkb / 32);   // + per-tile fixed cost of the issuing warp
     const double a_bytes = c.mode == A_WINDOW ? (double)c.win_tx_bytes * c.cblocks : (double)kBlockM * c.c_pad * (c.mode == A_TILED ? 1 : d.r * d.s);
     const double hbm_cycles = (a_bytes + (double)kBlockM * c.bn) / 22.5;
-    if (c.res_b && c.bn <= 128 && issue_cycles > hbm_cycles && !getenv("LBC_ONE_MMA")) {
+    if (c.res_b && c.bn <= 128 && issue_cycles > hbm_cycles && o.two_mma_warps != 0) {
         if (c.mode == A_WINDOW && c.win_stages >= 4) { c.n_mma = 2; c.win_stages &= ~1; }
         else if (c.mode != A_WINDOW && c.stages >= 4) { c.n_mma = 2; c.stages &= ~1; }
     }
@@ -1507,8 +1502,10 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, boo
         const int32_t pairs = c.row_tiles * c.col_tiles * c.it_imgs / 2 * c.tiles_n;
         c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, pairs);
     }
-    if (const char* v = getenv("LBC_MAX_GRID")) c.grid = std::max(1, std::min(c.grid, atoi(v)));   // tests: many tiles per CTA
+    if (o.max_grid > 0) c.grid = std::max(1, std::min(c.grid, (int)o.max_grid));   // tests: many tiles per CTA
     if (c.cta2) c.grid = std::max(2, c.grid & ~1);
+    c.reverse = o.reverse == 1 ? 1 : 0;
+    c.pdl = o.pdl != 0 ? 1 : 0;
     *cfg = c;
     return LBC_OK;
 }
@@ -1597,7 +1594,7 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
 }
 
 lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
-                        cudaStream_t stream)
+                        const IgemmRuntime& rt, cudaStream_t stream)
 {
     const IgemmConfig& c = l.cfg;
     const lbc_conv_desc& d = g.d;
@@ -1657,9 +1654,10 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     }
     prm.off_b = c.off_b; prm.off_stage = c.off_stage; prm.off_ctl = c.off_ctl;
     prm.fold = c.fold; prm.off_fold = c.off_fold;
-    // reversed traversal (IgemmLaunch::reverse, set by the network runner; LBC_SNAKE=1 forces it for the tests)
-    prm.rev_m = (l.reverse || getenv("LBC_SNAKE")) ? (c.mode == A_WINDOW ? d.n : c.tiles_m) : 0;
-    prm.trace = g_trace_buf; prm.trace_tiles = g_trace_tiles;
+    // reversed traversal (IgemmLaunch::reverse, set by the network runner; lbc_plan_options::reverse for single layers)
+    prm.rev_m = (l.reverse || c.reverse) ? (c.mode == A_WINDOW ? d.n : c.tiles_m) : 0;
+    prm.trace = rt.trace; prm.trace_tiles = rt.trace_tiles;
+    prm.flag = rt.flag;
     // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one
     // "channel chunk" of cblocks*inner blocks.
     if (c.mode == A_WINDOW) { prm.mma_outer = c.cblocks; prm.mma_inner = c.inner; }
@@ -1684,14 +1682,15 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.cta2 ? 2 : c.res_b ? (c.fold ? 3 : 1) : 0];
     LBC_REQUIRE(fn != nullptr, LBC_ERR_UNSUPPORTED, "igemm: no kernel for this configuration");
     {
+        int dev_ord = 0;
+        LBC_CUDA_TRY(cudaGetDevice(&dev_ord));
         std::lock_guard<std::mutex> lk(g_attr_mu);
-        if (!g_attr_set) {
+        if (first_use_on_device(g_attr_devices, dev_ord)) {
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 3; ++j)
                     for (int r = 0; r < 4; ++r)
                         if (table[i][j][r])
                             LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            g_attr_set = true;
         }
     }
     // programmatic stream serialisation: this kernel's on-chip prologue may overlap the previous kernel's tail; its
@@ -1703,7 +1702,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     lc.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = getenv("LBC_NO_PDL") ? 0 : 1;
+    attr[0].val.programmaticStreamSerializationAllowed = c.pdl ? 1 : 0;
     lc.attrs = attr;
     lc.numAttrs = 1;
     if (c.cta2) {
@@ -1718,24 +1717,5 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     return LBC_OK;
 }
 
-void igemm_set_trace(long long* device_buf, int32_t tiles)
-{
-    g_trace_buf = device_buf;
-    g_trace_tiles = tiles;
-}
-
-lbc_status igemm_check_timeout()
-{
-    int flag = 0;
-    LBC_CUDA_TRY(cudaMemcpyFromSymbol(&flag, g_timeout_flag, sizeof(int)));
-    if (flag) {
-        int zero = 0;
-        cudaMemcpyToSymbol(g_timeout_flag, &zero, sizeof(int));
-        set_error(flag == 2 ? "igemm: dynamic shared memory base is not 1024-byte aligned"
-                            : "igemm: device pipeline watchdog fired (mbarrier wait exceeded 2 s)");
-        return LBC_ERR_KERNEL_TIMEOUT;
-    }
-    return LBC_OK;
-}
 
 }  // namespace lbc

@@ -9,8 +9,8 @@ from .conv import ConvDesc, _ptr, _stream_ptr
 
 
 class Net:
-    def __init__(self, layers):
-        """layers: [(name, ConvDesc, input_name_or_None)]"""
+    def __init__(self, layers, options: dict | None = None):
+        """layers: [(name, ConvDesc, input_name_or_None)]; options: lbc_plan_options fields applied to every layer"""
         self._lib = load_library()
         self.names = [l[0] for l in layers]
         self.descs: list[ConvDesc] = [l[1] for l in layers]
@@ -20,7 +20,11 @@ class Net:
         arr = (CConvDesc * n)(*[d.c_struct() for d in self.descs])
         inp = (ctypes.c_int32 * n)(*self.input_of)
         self._h = ctypes.c_void_p()
-        check(self._lib.lbc_net_create(arr, inp, n, ctypes.byref(self._h)))
+        if options:
+            opt = _capi.plan_options(**options)
+            check(self._lib.lbc_net_create_ex(arr, inp, n, ctypes.byref(opt), ctypes.byref(self._h)))
+        else:
+            check(self._lib.lbc_net_create(arr, inp, n, ctypes.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -57,19 +57,25 @@ int32_t oracle_out_dim(int32_t in, int32_t pad, int32_t dil, int32_t k, int32_t 
     return (in + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
 }
 
-/* Requantise one accumulator: the reference's rounding mode (RNE, then saturate).
- * One fp32 multiply, no FMA (this TU is built with -ffp-contract=off). */
+/* Requantise one accumulator: the reference's rule quantize() =
+ *   max(-128, min(__float2int_rn(v * scale), 127))          (conv2DForward3x3WinogradFused.cuh:39-46)
+ * i.e. ROUND (half-to-even, saturating to int32, NaN -> 0 as cvt.rni.s32.f32 defines it) and THEN clamp; ReLU raises
+ * the lower clamp to 0.  One fp32 multiply, no FMA (this TU is built with -ffp-contract=off). */
 int8_t oracle_requant(int32_t acc, int32_t bias, float scale, int relu)
 {
     int32_t t = (int32_t)((uint32_t)acc + (uint32_t)bias); /* int32 wraparound */
     volatile float f = (float)t;                           /* cvt.rn.f32.s32   */
     f = f * scale;
-    float lo = relu ? 0.0f : -128.0f;
     float g = f;
-    if (isnan(g)) g = lo;      /* fmaxf(NaN, lo) == lo on the device */
-    if (g < lo) g = lo;
-    if (g > 127.0f) g = 127.0f;
-    return (int8_t)lrintf(g);  /* default rounding mode: half-to-even */
+    long q;
+    if (isnan(g)) q = 0;                         /* __float2int_rn(NaN) == 0 */
+    else if (g >= 2147483648.0f) q = 2147483647L;  /* saturating conversion */
+    else if (g <= -2147483648.0f) q = -2147483647L - 1;
+    else q = lrintf(g);                          /* default rounding mode: half-to-even */
+    const long lo = relu ? 0 : -128;
+    if (q < lo) q = lo;
+    if (q > 127) q = 127;
+    return (int8_t)q;
 }
 
 /*

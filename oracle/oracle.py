@@ -236,12 +236,14 @@ def ref_conv2d_forward(x_nchw: np.ndarray, w_oihw: np.ndarray) -> np.ndarray:
 # numpy restatement (independent of the C code)
 # ---------------------------------------------------------------------------------------------------
 def np_requant(t: np.ndarray, scale: np.ndarray, relu: bool) -> np.ndarray:
-    """t int32 [..., K] (acc+bias), scale f32[K] -> int8. RNE then saturate (quantization.py:27-49)."""
-    f = t.astype(np.float32) * scale.astype(np.float32)  # one fp32 multiply
-    lo = np.float32(0.0 if relu else -128.0)
-    f = np.where(np.isnan(f), lo, f)
-    f = np.clip(f, lo, np.float32(127.0))
-    return np.rint(f).astype(np.int8)  # np.rint = half-to-even
+    """t int32 [..., K] (acc+bias), scale f32[K] -> int8.  The reference's quantize(): round half-to-even FIRST
+    (__float2int_rn: NaN -> 0), then clamp to [relu ? 0 : -128, 127] (conv2DForward3x3WinogradFused.cuh:39-46;
+    quantization.py:27-49 clamps then rounds, identical for integer bounds and finite values)."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        f = t.astype(np.float32) * scale.astype(np.float32)  # one fp32 multiply
+    f = np.where(np.isnan(f), np.float32(0.0), f)            # __float2int_rn(NaN) == 0
+    q = np.rint(np.clip(f, np.float32(-1e9), np.float32(1e9)))   # np.rint = half-to-even; +-inf end up at the clamps
+    return np.clip(q, 0.0 if relu else -128.0, 127.0).astype(np.int8)
 
 
 def np_conv_nhwc(d: ConvDesc, x: np.ndarray, w_krsc: np.ndarray, bias, scale) -> np.ndarray:

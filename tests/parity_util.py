@@ -12,12 +12,13 @@ def lbc_desc(od: ODesc):
     return lbc.ConvDesc(**od.__dict__)
 
 
-def run_gpu(od: ODesc, x, w, bias, scale, force=0, w_layout="krsc"):
-    """Returns (y numpy, kernel name, ms).  x NHWC int8, w KRSC int8 numpy arrays."""
+def run_gpu(od: ODesc, x, w, bias, scale, force=0, w_layout="krsc", options=None):
+    """Returns (y numpy, kernel name, ms).  x NHWC int8, w KRSC int8 numpy arrays.
+    options: lbc_plan_options fields (dict) forcing planner decisions."""
     import torch
     import lowbitdnn_project_b200 as lbc
     dev = torch.device("cuda:0")
-    plan = lbc.ConvPlan(lbc_desc(od), force=force)
+    plan = lbc.ConvPlan(lbc_desc(od), force=force, options=options)
     if w_layout == "oihw":
         wt = torch.from_numpy(np.ascontiguousarray(w.transpose(0, 3, 1, 2))).to(dev)
         wp = plan.prepack(wt.reshape(-1), lbc.W_OIHW)
@@ -34,7 +35,7 @@ def run_gpu(od: ODesc, x, w, bias, scale, force=0, w_layout="krsc"):
     return out, name, ms
 
 
-def check_case(od: ODesc, layer=0, style="full", force=0, use_bias=True, w_layout="krsc", bias_range=None):
+def check_case(od: ODesc, layer=0, style="full", force=0, use_bias=True, w_layout="krsc", bias_range=None, options=None):
     """Runs GPU and oracle on identical seeded inputs; returns (mismatches, total, kernel, detail).
     bias_range: replace the synthetic biases by uniform int32 values in [-bias_range, bias_range]."""
     x, w, bias, scale = oracle.synth(od, layer=layer, style=style)
@@ -43,7 +44,7 @@ def check_case(od: ODesc, layer=0, style="full", force=0, use_bias=True, w_layou
     if not use_bias:
         bias = None
     want = oracle.conv_nhwc(od, x, w, bias, scale)
-    got, name, ms = run_gpu(od, x, w, bias, scale if od.out_mode == 0 else None, force=force, w_layout=w_layout)
+    got, name, ms = run_gpu(od, x, w, bias, scale if od.out_mode == 0 else None, force=force, w_layout=w_layout, options=options)
     assert got.shape == want.shape and got.dtype == want.dtype, (got.shape, want.shape, got.dtype, want.dtype)
     bad = got != want
     nbad = int(bad.sum())

@@ -126,31 +126,26 @@ def test_pixel_group_rewrite_needs_divisible_pixels():
 
 @pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.stride_h == 1 and c.r > 1][:6],
                          ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}")
-def test_igemm_im2col_path_on_stride1_shapes(d, monkeypatch):
+def test_igemm_im2col_path_on_stride1_shapes(d):
     """The same stride-1 layers with the window planner disabled: the TMA im2col path stays covered."""
-    monkeypatch.setenv("LBC_NO_WINDOW", "1")
-    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM, options={"window": 0}) == "igemm_tc"
 
 
 @pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.c >= 32], ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
-def test_igemm_cta_pairs_forced(d, monkeypatch):
+def test_igemm_cta_pairs_forced(d):
     """Every igemm shape that can run in CTA pairs (two-CTA clusters, cta_group::2 MMAs, half of the filter rows per CTA)
     does so here regardless of the planner's preference, with the resident-filter variant switched off so that small
     filter matrices stream too."""
-    monkeypatch.setenv("LBC_CTA2", "1")
-    monkeypatch.setenv("LBC_NO_RESB", "1")
-    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM, options={"cta_pairs": 1, "resident_filter": 0}) == "igemm_tc"
 
 
 @pytest.mark.parametrize("d", [c for c in IGEMM_CASES if c.r == 1 or c.stride_h > 1],
                          ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
-def test_igemm_per_warp_stores_forced(d, monkeypatch):
+def test_igemm_per_warp_stores_forced(d):
     """Ring-mode layers with the per-warp epilogue (own 32-row staging buffer and TMA store per warp, no team barrier)
     forced on for every N tile it supports (256 / 128 / 64 / 32 columns), and forced off."""
-    monkeypatch.setenv("LBC_WARP_STORE", "1")
-    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
-    monkeypatch.setenv("LBC_WARP_STORE", "0")
-    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM) == "igemm_tc"
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM, options={"warp_store": 1}) == "igemm_tc"
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), force=IGEMM, options={"warp_store": 0}) == "igemm_tc"
 
 
 FOLD_EXTRA_CASES = [
@@ -167,17 +162,16 @@ FOLD_EXTRA_CASES = [
 
 
 @pytest.mark.parametrize("d", IGEMM_CASES + FOLD_EXTRA_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
-def test_igemm_bias_folded_into_mma(d, monkeypatch):
+def test_igemm_bias_folded_into_mma(d):
     """Resident-filter layers with the bias fed through the first MMA of every tile (constant A block x bias digits)
     instead of the epilogue's add, forced on for every N tile width, int8 and raw int32 outputs.  _check's biases are a few
     thousand; the second call uses biases beyond the digit range, which the kernel must detect and add the classic way."""
-    monkeypatch.setenv("LBC_FOLD", "1")
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
-    assert _check(D(**{**d.__dict__, "out_mode": 1})) in ("igemm_tc", "stem_tc")
-    assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000) in ("igemm_tc", "stem_tc")
-    assert _check(D(**{**d.__dict__, "out_mode": 1}), bias_range=3_000_000) in ("igemm_tc", "stem_tc")
-    monkeypatch.setenv("LBC_FOLD", "0")
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    on, off = {"fold_bias": 1}, {"fold_bias": 0}
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options=on) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 1}), options=on) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000, options=on) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 1}), bias_range=3_000_000, options=on) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options=off) in ("igemm_tc", "stem_tc")
 
 
 MULTI_TILE_CASES = [
@@ -202,29 +196,25 @@ MULTI_TILE_CASES = [
 
 @pytest.mark.parametrize("grid", [1, 3])
 @pytest.mark.parametrize("d", MULTI_TILE_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
-def test_many_tiles_per_cta(d, grid, monkeypatch):
+def test_many_tiles_per_cta(d, grid):
     """Cap the persistent grid so every CTA walks many tiles: ring/window phases, TMEM accumulator reuse, the
     alternating MMA warps and the staging ring all wrap several times (a full-size layer does this on 148 SMs)."""
-    monkeypatch.setenv("LBC_MAX_GRID", str(grid))
-    monkeypatch.setenv("LBC_PAIR", "1")      # the opt-in paired-tile mode stays covered (cases marked "paired tiles")
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
-    monkeypatch.delenv("LBC_PAIR")
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    g = {"max_grid": grid}
+    # the opt-in paired-tile mode stays covered (cases marked "paired tiles")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options={**g, "paired_tiles": 1}) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options=g) in ("igemm_tc", "stem_tc")
     # CTA pairs (cta_group::2) forced on wherever the layer streams its filter matrix, then forced off: the planner's own
     # choice between the two only depends on the K-loop length
-    monkeypatch.setenv("LBC_CTA2", "1")
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options={**g, "cta_pairs": 1}) in ("igemm_tc", "stem_tc")
     if d.r == 3 and d.c >= 128:
-        assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"
-    monkeypatch.setenv("LBC_CTA2", "0")
-    monkeypatch.setenv("LBC_WARP_STORE", "1")    # ... and the per-warp epilogue with and without CTA pairs
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
-    monkeypatch.setenv("LBC_CTA2", "1")
-    assert _check(D(**{**d.__dict__, "out_mode": 0})) in ("igemm_tc", "stem_tc")
-    monkeypatch.delenv("LBC_CTA2")
-    monkeypatch.delenv("LBC_WARP_STORE")
+        assert _check(D(**{**d.__dict__, "out_mode": 1}), options={**g, "cta_pairs": 1}) == "igemm_tc"
+    # ... and the per-warp epilogue with and without CTA pairs
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options={**g, "cta_pairs": 0, "warp_store": 1}) in ("igemm_tc", "stem_tc")
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options={**g, "cta_pairs": 1, "warp_store": 1}) in ("igemm_tc", "stem_tc")
+    # reversed traversal (what a network's alternate layers do)
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), options={**g, "reverse": 1}) in ("igemm_tc", "stem_tc")
     if grid == 1 and d.r == 3 and d.c >= 64:
-        assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"    # raw accumulators through the same walk
+        assert _check(D(**{**d.__dict__, "out_mode": 1}), options=g) == "igemm_tc"    # raw accumulators through the same walk
 
 
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
@@ -348,25 +338,25 @@ def test_folded_bias_digit_boundaries():
     D(n=4, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # two MMA warps, two tiles per epilogue iteration
     D(n=4, h=28, w=28, c=128, k=512, r=1, s=1, relu=1),                        # resident filter matrix over two N tiles
 ], ids=lambda d: f"c{d.c}k{d.k}r{d.r}")
-def test_repeated_launches_are_identical(d, monkeypatch):
+def test_repeated_launches_are_identical(d):
     """The same plan launched ten times back to back (no host synchronisation in between, so launches overlap through
     programmatic dependent launch) on a grid capped to 8 CTAs: every run must reproduce the oracle bit for bit - a race in
     the TMEM / staging / ring reuse or across the PDL boundary would show up as a run-to-run difference."""
     import torch
     import lowbitdnn_project_b200 as lbc
     from tests.parity_util import lbc_desc
-    monkeypatch.setenv("LBC_MAX_GRID", "8")
     od = D(**{**d.__dict__, "out_mode": 0})
     x, w, bias, scale = oracle.synth(od, layer=3)
     want = oracle.conv_nhwc(od, x, w, bias, scale)
     dev = torch.device("cuda:0")
-    plan = lbc.ConvPlan(lbc_desc(od))
+    plan = lbc.ConvPlan(lbc_desc(od), options={"max_grid": 8})
     wp = plan.prepack(torch.from_numpy(w).to(dev).reshape(-1), lbc.W_KRSC)
     xt, bt, st = torch.from_numpy(x).to(dev), torch.from_numpy(bias).to(dev), torch.from_numpy(scale).to(dev)
     outs = [plan.empty_output(dev) for _ in range(10)]
     for y in outs:
         plan.run(xt, wp, bt, st, out=y)
     torch.cuda.synchronize()
+    plan.check_status()
     for i, y in enumerate(outs):
         assert np.array_equal(y.cpu().numpy(), want), f"launch {i} differs"
     plan.close()

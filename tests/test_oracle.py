@@ -128,7 +128,7 @@ def test_requant_rounding_rule():
         (-255, 0, 0.5, False, -128),  # -127.5 -> -128 (even) / clamp
         (10, -7, 1.0, False, 3),
         (2**31 - 1, 1, 1.0, False, -128),  # int32 wraparound of acc+bias
-        (7, 0, float("nan"), False, -128),
+        (7, 0, float("nan"), False, 0),     # __float2int_rn(NaN) == 0, then the clamp (WinogradFused.cuh:39-46)
         (7, 0, float("nan"), True, 0),
         (7, 0, float("inf"), False, 127),
         (7, 0, -float("inf"), False, -128),

@@ -41,7 +41,7 @@ CASES = [
     ("gemm_c256_k320", D(n=1, h=8, w=8, c=256, k=320, r=1, s=1), IGEMM),
     ("gemm_big", D(n=8, h=56, w=56, c=256, k=64, r=1, s=1, out_mode=0, relu=1), IGEMM),
     # --- igemm, im2col TMA
-    ("i2c_1x1_forced", D(n=1, h=16, w=16, c=128, k=128, r=1, s=1), IGEMM, {"LBC_FORCE_IM2COL": "1"}),
+    ("i2c_1x1_forced", D(n=1, h=16, w=16, c=128, k=128, r=1, s=1), IGEMM, {"force_im2col": 1}),
     ("i2c_3x3_valid", D(n=1, h=10, w=10, c=64, k=64, r=3, s=3), IGEMM),
     ("i2c_3x3_p1_c64", D(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1), IGEMM),
     ("i2c_3x3_p1_c256", D(n=2, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1), IGEMM),
@@ -53,8 +53,8 @@ CASES = [
     ("i2c_small_tensor", D(n=1, h=6, w=6, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1), IGEMM),
     ("i2c_resnet_l3", D(n=8, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
     # --- same stride-1 shapes with the window path disabled (pure im2col coverage)
-    ("nowin_3x3_p1_c64", D(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1), IGEMM, {"LBC_NO_WINDOW": "1"}),
-    ("nowin_3x3_c256_i8", D(n=2, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM, {"LBC_NO_WINDOW": "1"}),
+    ("nowin_3x3_p1_c64", D(n=1, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1), IGEMM, {"window": 0}),
+    ("nowin_3x3_c256_i8", D(n=2, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM, {"window": 0}),
     # --- window path specifics
     ("win_56_c64_i8", D(n=3, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
     ("win_28_c128_i8", D(n=3, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, out_mode=0, relu=1), IGEMM),
@@ -71,7 +71,7 @@ CASES = [
 ]
 
 
-def run_case(label, desc, force):
+def run_case(label, desc, force, options=None):
     import numpy as np
     from oracle.oracle import ConvDesc as OD
     from tests.parity_util import check_case
@@ -79,13 +79,13 @@ def run_case(label, desc, force):
     od = OD(**desc)
     t0 = time.time()
     try:
-        plan = lbc.ConvPlan(lbc.ConvDesc(**desc), force=force)
+        plan = lbc.ConvPlan(lbc.ConvDesc(**desc), force=force, options=options)
         descr = plan.describe()
         plan.close()
     except Exception as e:  # noqa: BLE001
         return {"label": label, "status": "plan_error", "error": str(e)}
     try:
-        nbad, total, name, detail = check_case(od, layer=1, force=force)
+        nbad, total, name, detail = check_case(od, layer=1, force=force, options=options)
     except Exception as e:  # noqa: BLE001
         return {"label": label, "status": "run_error", "error": str(e)[:600], "plan": descr}
     return {"label": label, "status": "ok" if nbad == 0 else "mismatch", "bad": nbad, "total": total, "kernel": name,
@@ -102,7 +102,7 @@ def main():
 
     if a.case is not None:
         c = CASES[int(a.case)]
-        print("DIAG_RESULT " + json.dumps(run_case(c[0], c[1], c[2])), flush=True)
+        print("DIAG_RESULT " + json.dumps(run_case(c[0], c[1], c[2], c[3] if len(c) > 3 else None)), flush=True)
         return
     if a.probes:
         import lowbitdnn_project_b200 as lbc
@@ -121,12 +121,10 @@ def main():
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     results = []
 
-    def sub(args, env_extra=None, timeout=180):
-        env = dict(os.environ)
-        env.update(env_extra or {})
+    def sub(args, timeout=180):
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__)] + args, capture_output=True, text=True,
-                               timeout=timeout, env=env, cwd=ROOT)
+                               timeout=timeout, cwd=ROOT)
         except subprocess.TimeoutExpired:
             return {"status": "timeout"}
         for line in r.stdout.splitlines():
@@ -139,7 +137,7 @@ def main():
     for i, c in enumerate(CASES):
         if a.only and a.only not in c[0]:
             continue
-        res = sub(["--case", str(i)], env_extra=(c[3] if len(c) > 3 else None))
+        res = sub(["--case", str(i)])
         res.setdefault("label", c[0])
         results.append(res)
         print(json.dumps(res)[:1500], flush=True)

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--layers", default="")
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--opt", action="append", default=[], help="planner option key=value (lbc_plan_options field), repeatable")
     a = ap.parse_args()
     import torch
     import lowbitdnn_project_b200 as lbc
@@ -29,7 +30,7 @@ def main():
     for i, (name, d, _) in enumerate(layers):
         if want and name not in want:
             continue
-        plan = lbc.ConvPlan(d)
+        plan = lbc.ConvPlan(d, options={k: int(v) for k, v in (o.split("=") for o in a.opt)} or None)
         rng = np.random.default_rng(i)
         cg = d.c // d.groups
         w = torch.from_numpy(rng.integers(-127, 128, size=(d.k * d.r * d.s * cg,), dtype=np.int8)).to(dev)

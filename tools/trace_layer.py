@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--layers", default="l1.1.conv2")
     ap.add_argument("--tiles", type=int, default=24)
     ap.add_argument("--skip", type=int, default=6)
+    ap.add_argument("--opt", action="append", default=[], help="planner option key=value (lbc_plan_options field), repeatable")
     a = ap.parse_args()
     import torch
     import lowbitdnn_project_b200 as lbc
@@ -28,7 +29,7 @@ def main():
     for i, (name, d, _) in enumerate(layers):
         if name not in a.layers.split(","):
             continue
-        plan = lbc.ConvPlan(d)
+        plan = lbc.ConvPlan(d, options={k: int(v) for k, v in (o.split("=") for o in a.opt)} or None)
         cg = d.c // d.groups
         w = torch.randint(-127, 128, (d.k * d.r * d.s * cg,), dtype=torch.int8, device=dev)
         wp = plan.prepack(w)
@@ -40,9 +41,9 @@ def main():
             plan.run(x, wp, bias, scale, out=y)
         ntile = a.tiles + a.skip
         buf = torch.zeros(ntile * 16 + 2 * 148, dtype=torch.int64, device=dev)
-        _capi.check(lib.lbc_debug_set_trace(ctypes.c_void_p(buf.data_ptr()), ntile))
+        plan.set_trace(buf, ntile)
         _, ms = plan.run(x, wp, bias, scale, out=y, timed=True)
-        _capi.check(lib.lbc_debug_set_trace(None, 0))
+        plan.set_trace(None, 0)
         raw = buf.cpu().numpy()
         t = raw[:ntile * 16].reshape(ntile, 16)
         cta = raw[ntile * 16:].reshape(148, 2)
