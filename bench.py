@@ -2,7 +2,8 @@
 """
 bench.py — headline benchmark of liblowbit-cnn on B200: ResNet-50 int8 convolution stack, images/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--network resnet50] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-gpu] [--network resnet50]
+                    [--batch B] [--scaling weak|strong]
 
 A "step" is one pass of the hot path (all 53 convolutions of ResNet-50, batch 512 per GPU, fused
 bias/requant/ReLU epilogues) over one batch of synthetic int8 input.  Rank 0 prints ONE JSON line.
@@ -16,9 +17,14 @@ bias/requant/ReLU epilogues) over one batch of synthetic int8 input.  Rank 0 pri
 --impl reference times the reference's own CPU implementation (cpp/int8conv/refConv2DForward.hpp compiled
 unmodified into oracle/_ref) on a bounded sample, on rank 0 only.
 
-Multi-GPU: one process per GPU (torchrun), the batch dimension is sharded — every rank owns `batch` images
-and a replica of the weights; there is no collective on the convolution path.  NCCL is used only to gather
-per-rank timings and output checksums.
+Multi-GPU: one process per GPU (torchrun), the batch dimension is sharded and the weights are replicated; there is
+no collective on the convolution path.  NCCL is used only to gather per-rank timings and output checksums.
+  --scaling weak   (default) every rank owns `batch` images (512 per GPU): per-GPU work fixed as N grows
+  --scaling strong the configuration's batch (512) is the GLOBAL batch, split over the ranks with
+                   shard.image_range (64 images per GPU at 8 GPUs)
+
+After the timed region every rank re-computes the first images of EVERY layer's output with the CPU oracle chained
+over the same graph and compares them with the resident GPU outputs; a mismatch makes the run fail (exit 3).
 """
 from __future__ import annotations
 
@@ -156,6 +162,51 @@ def cpu_baseline_port(layers, budget_s: float = 15.0):
             "sample": f"{images} image(s) x all {len(layers)} layers at batch 1, oracle/cpu_ref.c with {threads} OpenMP threads, {el:.1f} s"}
 
 
+def parity_check(net, layers, rank, images=2):
+    """The checker leg: first `images` images of every layer's resident output against the oracle chained over the same
+    graph (same synthetic inputs and parameters as the timed run).  Returns (layers checked, list of mismatching layers)."""
+    from oracle import oracle
+    from oracle.oracle import ConvDesc as OD
+    outs, bad = {}, []
+    for i, (name, d, src) in enumerate(layers):
+        n = min(images, d.n)
+        x = synth_input(d, i + 1000 * rank)[:n] if src is None else outs[src]
+        w, b, s = synth_params(d, i)
+        outs[name] = oracle.conv_nhwc(OD(**{**d.__dict__, "n": n}), np.ascontiguousarray(x), w, b, s)
+        got = net.read_output(i, images=n)
+        if not np.array_equal(got, outs[name]):
+            bad.append(name)
+    return len(layers), bad
+
+
+def host_link_probe(nbytes_h2d, nbytes_d2h, barrier, iters=5):
+    """Pinned-memory copy bandwidth of this rank's host link with every rank copying at the same time (both
+    directions at once, the way the pipelined e2e path uses the link).  Returns (h2d GB/s, d2h GB/s)."""
+    import torch
+    hx = torch.empty(nbytes_h2d, dtype=torch.uint8).pin_memory()
+    hy = torch.empty(nbytes_d2h, dtype=torch.uint8).pin_memory()
+    dx = torch.empty(nbytes_h2d, dtype=torch.uint8, device="cuda")
+    dy = torch.empty(nbytes_d2h, dtype=torch.uint8, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for timed in (False, True):
+        barrier()
+        with torch.cuda.stream(s_up):
+            ev[0].record()
+            for _ in range(iters):
+                dx.copy_(hx, non_blocking=True)
+            ev[1].record()
+        with torch.cuda.stream(s_dn):
+            ev[2].record()
+            for _ in range(iters):
+                hy.copy_(dy, non_blocking=True)
+            ev[3].record()
+        torch.cuda.synchronize()
+    up = nbytes_h2d * iters / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9
+    dn = nbytes_d2h * iters / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9
+    return up, dn
+
+
 REF_SAMPLE = (1, 64, 10, 10, 64, 8, 8, 3, 3)   # config 1 (56x56x64->64 3x3) cropped to 8x8 outputs, pre-padded
 
 
@@ -194,7 +245,86 @@ def reference_arm(args, layers):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.ref_full:
+        # BASELINE config 1 in full (N1, 56x56x64 -> 64, 3x3 s1 p1, pre-padded to 58x58): the one configuration the
+        # reference CPU path can run as configured; minutes, so opt-in
+        fb, fic, fih, fiw, foc, foh, fow, fkh, fkw = 1, 64, 58, 58, 64, 56, 56, 3, 3
+        xf = np.zeros((fb, fic, fih, fiw), dtype=np.int8)
+        xf[:, :, 1:-1, 1:-1] = rng.integers(-128, 128, size=(fb, fic, 56, 56), dtype=np.int8)
+        wf = rng.integers(-128, 128, size=(foc, fic, fkh, fkw), dtype=np.int8)
+        t0 = time.perf_counter()
+        yf = oracle.ref_conv2d_forward(xf, wf)
+        sec = time.perf_counter() - t0
+        assert np.array_equal(yf, oracle.ref_style_nchw_valid(xf, wf))
+        macs = fb * foc * foh * fow * fic * fkh * fkw
+        out["config1_full"] = {"shape": "refConv2DForward<1,64,58,58,64,56,56,3,3>", "seconds": sec, "mmac_per_s": macs / sec / 1e6,
+                               "threads": cores, "images_per_s_extrapolated": (macs / sec) / net_macs_per_image,
+                               "checked": "equal to the oracle restatement"}
     emit_json(out)
+
+
+def reference_gpu_arm(args):
+    """The reference's own tensor-core kernel (CUDAConv2DForward3x3TensorCoures, wmma m32n8k16, compiled unmodified for
+    sm_100a from /root/reference into oracle/_ref/libref_wmma.so with a torch-free host) on ITS OWN benchmark shape
+    (check.cu:31-41: 16x128x130x130 (*) 128x128x3x3, VALID, int32 out), next to liblowbit-cnn on the same shape and bytes.
+    Checker / yardstick only: nothing here is on the product path."""
+    import ctypes
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_wmma.so")
+    if not os.path.exists(so):
+        emit_json({"impl": "reference-gpu", "unavailable": "oracle/_ref/libref_wmma.so missing (built only where /root/reference exists: make -C oracle ref_gpu)"})
+        return
+    assert torch.cuda.is_available()
+    ref = ctypes.CDLL(so)
+    ref.ref_wmma_conv3x3.restype = ctypes.c_float
+    ref.ref_wmma_conv3x3.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int]
+    shp = (ctypes.c_int32 * 7)()
+    ref.ref_wmma_shape(shp)
+    n, c, h, w, k, p, q = list(shp)
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(7)
+    x = torch.from_numpy(rng.integers(-128, 128, size=(n, h, w, c), dtype=np.int8)).to(dev)
+    wk = torch.from_numpy(rng.integers(-127, 128, size=(k, 3, 3, c), dtype=np.int8)).to(dev)
+    x_v = lbc.nhwc_to_vect_c(x, 16)                      # [N][C/16][H][W][16]  (utils.cuh:20-26)
+    w_v = lbc.nhwc_to_vect_c(wk, 16)                     # [K][C/16][3][3][16]
+    y_v = torch.empty((n, k // 16, p, q, 16), dtype=torch.int32, device=dev)
+    ops = 2.0 * n * p * q * k * c * 9
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 2)):
+            fn()
+        ms = []
+        for _ in range(max(args.steps, 5)):
+            lbc.flush_l2()
+            torch.cuda.synchronize()
+            ms.append(fn())
+        return float(np.median(ms))
+
+    ms_ref = timed(lambda: ref.ref_wmma_conv3x3(x_v.data_ptr(), w_v.data_ptr(), y_v.data_ptr(), 1))
+    assert ms_ref > 0, "the reference kernel failed to launch"
+    out = {"impl": "reference-gpu", "metric": "int8_conv3x3_tops", "unit": "TOPS", "higher_is_better": True, "data": "synthetic",
+           "config": {"workload": f"reference check.cu shape: N{n} {h}x{w}x{c} -> {k}, 3x3 VALID, int32 out", "l2": "flushed before every launch"},
+           "reference": {"kernel": "CUDAConv2DForward3x3TensorCoures (wmma m32n8k16, unmodified, sm_100a)", "ms": ms_ref,
+                         "tops": ops / ms_ref / 1e9}}
+    for mode, name in ((lbc.OUT_INT32, "ours_int32"), (lbc.OUT_INT8, "ours_int8_fused_epilogue")):
+        plan = lbc.ConvPlan(lbc.ConvDesc(n=n, h=h, w=w, c=c, k=k, r=3, s=3, relu=1, out_mode=mode))
+        wp = plan.prepack(wk.reshape(-1), lbc.W_KRSC)
+        bias = torch.zeros(k, dtype=torch.int32, device=dev)
+        scale = torch.full((k,), 2.0**-11, dtype=torch.float32, device=dev)
+        y = plan.empty_output(dev)
+        ms = timed(lambda: plan.run(x, wp, bias, scale, out=y, timed=True)[1])
+        out[name] = {"ms": ms, "tops": ops / ms / 1e9, "plan": plan.describe()}
+        if mode == lbc.OUT_INT32:
+            same = bool(torch.equal(lbc.nhwc_to_vect_c(y, 16), y_v))
+            out["parity_int32_vs_reference_kernel"] = "bit-exact" if same else "MISMATCH"
+        plan.close()
+    out["value"] = out["ours_int32"]["tops"]
+    out["speedup_int32_vs_reference_kernel"] = ms_ref / out["ours_int32"]["ms"]
+    out["speedup_int8_vs_reference_kernel"] = ms_ref / out["ours_int8_fused_epilogue"]["ms"]
+    emit_json(out)
+    if out["parity_int32_vs_reference_kernel"] != "bit-exact":
+        sys.exit(3)
 
 
 _JSON_FD = None
@@ -216,10 +346,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: `batch` images per GPU; strong: `batch` is the global batch, split over the ranks")
     ap.add_argument("--network", default="resnet50")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-full", action="store_true",
+                    help="--impl reference: also run BASELINE config 1 in full through the reference CPU path (minutes)")
     ap.add_argument("--layer-report", default=None, help="write the per-layer table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -237,11 +371,20 @@ def main():
     nets = lbc.networks
     if args.batch is None:
         args.batch = nets.DEFAULT_BATCH[args.network]
+    config_batch = args.batch
+    if args.scaling == "strong" and args.impl == "ours":
+        first, last = lbc.shard.image_range(config_batch, world, rank)     # this rank's slice of the global batch
+        args.batch = last - first
+        assert args.batch > 0, f"rank {rank} of {world} has no image of a global batch of {config_batch}"
     layers = nets.NETWORKS[args.network](args.batch)
 
     if args.impl == "reference":
         if rank == 0:
             reference_arm(args, layers)
+        return
+    if args.impl == "reference-gpu":
+        if rank == 0:
+            reference_gpu_arm(args)
         return
 
     import torch
@@ -323,8 +466,17 @@ def main():
     # the pipelined path must give the same bytes as the blocking one for the same input
     assert zlib.crc32(ys[0].numpy().tobytes()) == checksum, "pipelined e2e output differs from the blocking path"
 
+    # ---- host link ceiling of the e2e path: all ranks copy at once, both directions ----------------------------
+    link_up, link_dn = host_link_probe(int(x_host.numel()), int(y_host.numel()), barrier)
+
+    # ---- parity of what was just timed: every layer's resident output (after the last run) against the oracle ----
+    n_checked, bad_layers = parity_check(net, layers, rank, images=2)
+    if bad_layers:
+        log(f"[rank {rank}] PARITY FAILURE in layers: {bad_layers}")
+
     # ---- gather (NCCL): max over ranks; checksums ------------------------------------------------------------
-    job = lbc.shard.gather(lbc.shard.RankStats(ms_total, e2e_ms, checksum, args.batch), world, device=dev)
+    job = lbc.shard.gather(lbc.shard.RankStats(ms_total, e2e_ms, checksum, args.batch, len(bad_layers), link_up, link_dn),
+                           world, device=dev)
     ms_total, e2e_ms = job.ms_total, job.e2e_ms
     ms_per_step = ms_total / args.steps
     images_per_step = job.images
@@ -341,6 +493,11 @@ def main():
             share[group.get(k, k)] = share.get(group.get(k, k), 0.0) + ms
         dom = max(share, key=share.get)
         sel = [i for i, k in enumerate(kinds) if group.get(k, k) == dom]
+        # The per-layer pass records an event after every launch, which breaks the programmatic-dependent-launch overlap
+        # between layers: its sum exceeds the un-instrumented step.  Only the SHARES come from it; every time below is
+        # that share of the timed region's ms_per_step, so kernel_ms_per_step <= ms_per_step by construction.
+        instrumented_ms = float(per_layer.sum())
+        per_layer = per_layer * (ms_per_step / instrumented_ms)
         dom_ms = sum(per_layer[i] for i in sel)
         dom_ops = sum(works[i][0] for i in sel)
         dom_bytes = sum(works[i][1] for i in sel)
@@ -380,8 +537,11 @@ def main():
             log("traffic file unreadable:", e)
         roofline.update({
             "kernel": {"igemm_tc": "igemm_i8_kernel", "direct": "direct_conv_kernel", "depthwise": "depthwise_kernel"}[dom],
-            "launches_per_step": len(sel), "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / float(per_layer.sum()),
-            "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs; int8 peak = on-box tcgen05 kind::i8 MMA-only probe)",
+            "launches_per_step": len(sel), "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
+            "instrumented_pass_ms": instrumented_ms,
+            "timing_note": "kernel_ms_per_step = the kernel's share of the per-launch event pass x ms_per_step of the timed region",
+            "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs); tensor fractions are against the BURST on-box tcgen05 "
+                           "kind::i8 MMA-only probe (int8_mma_peak_tops), nominal dense int8 is 4500 TOPS",
             "achieved_tops": tops, "achieved_gbs": gbs, "int8_mma_peak_tops": int8_peak,
             "int8_mma_sustained_tops": int8_sustained,
             "roofline_ms": roof_ms, "frac_of_mixed_roofline": roof_ms / dom_ms,
@@ -390,17 +550,24 @@ def main():
         out = {
             "metric": METRIC, "value": images_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": f"{args.network}_conv_stack_b{args.batch}", "network": args.network,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": f"{args.network}_conv_stack_b{config_batch}", "network": args.network,
                        "batch_per_gpu": args.batch, "global_batch": images_per_step, "layers": len(layers),
-                       "parallelism": f"batch-sharded x{world}, no collective on the conv path",
-                       "l2": "no flush: every layer reads >= 25 MB produced by an earlier launch; 11.2 GB touched per step vs 126 MB L2"},
+                       "parallelism": f"batch-sharded x{world} ({args.scaling} scaling), no collective on the conv path",
+                       "l2": f"no flush: a step touches {sum(w[1] for w in works) / 1e9:.2f} GB (algorithmic) against 126 MB of L2; "
+                             f"the smallest layer input is {min(d.n * d.h * d.w * d.c for _, d, _ in layers) / 1e6:.1f} MB"},
+            "parity": "bit-exact" if job.bad_layers == 0 else f"MISMATCH in {job.bad_layers} layer outputs (summed over ranks)",
+            "parity_checked_images": 2, "parity_checked_layers": n_checked,
             "tops_per_gpu": total_ops / (ms_per_step * 1e-3) / 1e12,
             "clocks": clocks,
             "e2e": {"value": images_per_step / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(x_host.numel()), "d2h_bytes_per_step": int(y_host.numel()),
                     "ms_per_step": e2e_ms,
                     "serial_ms_per_step": serial_ms,
+                    "host_link_gbs": {"h2d_per_rank_min": job.link_up, "d2h_per_rank_min": job.link_dn,
+                                      "how": f"pinned copies of the step's input / output sizes on {world} rank(s) at once, both directions at once"},
+                    "host_link_ceiling": args.batch / max(int(x_host.numel()) / (job.link_up * 1e9), int(y_host.numel()) / (job.link_dn * 1e9),
+                                                         ms_per_step * 1e-3) * world,
                     "note": "lbc_net_submit_host x steps + lbc_net_sync_host: every step copies its own pinned host input H2D, runs all "
                             "layers and copies the last layer's output D2H; copies of neighbouring steps overlap compute. "
                             "serial_ms_per_step = one blocking lbc_net_run_host call"},
@@ -428,6 +595,8 @@ def main():
     net.close()
     if world > 1:
         dist.destroy_process_group()
+    if job.bad_layers:
+        sys.exit(3)
 
 
 def _count(net):

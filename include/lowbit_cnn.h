@@ -214,6 +214,9 @@ lbc_status  lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w
                                     const int32_t* bias_host, const float* scale_host);
 /* Fill the resident input buffer of a layer whose input_of == -1 from HOST memory (NHWC int8). */
 lbc_status  lbc_net_set_input_host(lbc_net* net, int32_t layer, const int8_t* x_host);
+/* Copy the first `max_bytes` bytes (0 = all) of one layer's resident output (NHWC, int8 or int32 per its descriptor:
+ * image-major, so a prefix is a whole number of images) to HOST memory; synchronises the device. */
+lbc_status  lbc_net_read_output_host(const lbc_net* net, int32_t layer, void* y_host, size_t max_bytes);
 /* Device pointers of a layer's input/output activations (valid until lbc_net_destroy). */
 lbc_status  lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_dev, void** y_dev);
 /* Run all layers on `stream` with the network input already resident in HBM (x_dev NHWC of layer(s)

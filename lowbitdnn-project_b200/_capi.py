@@ -87,6 +87,7 @@ _PROTOS = {
     "lbc_net_layer_plan": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp)]),
     "lbc_net_set_params_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "lbc_net_set_input_host": (ctypes.c_int, [_vp, _i32, _vp]),
+    "lbc_net_read_output_host": (ctypes.c_int, [_vp, _i32, _vp, ctypes.c_size_t]),
     "lbc_net_layer_io": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "lbc_net_run": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "lbc_net_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),

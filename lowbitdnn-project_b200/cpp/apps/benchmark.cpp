@@ -89,7 +89,7 @@ int main(int argc, char** argv)
     }
 finished:
     std::ofstream o(out);
-    o << "{\n  \"repeats\": " << repeats << ",\n  \"benchmarks\": [\n";
+    o << "{\n  \"repeats\": " << repeats << ",\n  \"configs\": " << mini_json::dump(configs) << ",\n  \"benchmarks\": [\n";
     for (size_t i = 0; i < rows.size(); ++i) o << "    " << rows[i] << (i + 1 < rows.size() ? ",\n" : "\n");
     o << "  ]\n}\n";
     std::clog << "Finished." << std::endl;

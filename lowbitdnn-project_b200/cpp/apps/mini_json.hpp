@@ -3,6 +3,7 @@
 // true/false/null — enough for cpp/apps/config.json.
 #pragma once
 #include <cctype>
+#include <cstdio>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -104,6 +105,32 @@ inline std::string quote(const std::string& s)
     std::string o = "\"";
     for (char c : s) { if (c == '"' || c == '\\') o += '\\'; o += c; }
     return o + "\"";
+}
+
+// compact serialisation (numbers that are whole print without a fraction)
+inline std::string dump(const Value& v)
+{
+    switch (v.kind) {
+        case Value::Null: return "null";
+        case Value::Bool: return v.b ? "true" : "false";
+        case Value::Number: {
+            char buf[64];
+            if (v.num == (double)(long long)v.num) std::snprintf(buf, sizeof buf, "%lld", (long long)v.num);
+            else std::snprintf(buf, sizeof buf, "%.17g", v.num);
+            return buf;
+        }
+        case Value::String: return quote(v.str);
+        case Value::Array: {
+            std::string o = "[";
+            for (size_t i = 0; i < v.arr.size(); ++i) o += (i ? ", " : "") + dump(v.arr[i]);
+            return o + "]";
+        }
+        default: {
+            std::string o = "{";
+            for (size_t i = 0; i < v.obj.size(); ++i) o += (i ? ", " : "") + quote(v.obj[i].first) + ": " + dump(v.obj[i].second);
+            return o + "}";
+        }
+    }
 }
 
 }  // namespace mini_json

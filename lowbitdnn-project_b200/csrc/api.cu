@@ -983,6 +983,16 @@ lbc_status lbc_net_set_input_host(lbc_net* net, int32_t layer, const int8_t* x_h
     return LBC_OK;
 }
 
+lbc_status lbc_net_read_output_host(const lbc_net* net, int32_t layer, void* y_host, size_t max_bytes)
+{
+    LBC_REQUIRE(net && y_host && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad argument");
+    const lbc_net::Layer& L = net->layers[layer];
+    const size_t all = out_bytes(L.plan->g);
+    LBC_CUDA_TRY(cudaDeviceSynchronize());
+    LBC_CUDA_TRY(cudaMemcpy(y_host, L.y, (max_bytes && max_bytes < all) ? max_bytes : all, cudaMemcpyDeviceToHost));
+    return LBC_OK;
+}
+
 lbc_status lbc_net_layer_io(const lbc_net* net, int32_t layer, const void** x_dev, void** y_dev)
 {
     LBC_REQUIRE(net && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");

@@ -55,6 +55,20 @@ class Net:
         check(self._lib.lbc_net_layer_io(self._h, layer, ctypes.byref(x), ctypes.byref(y)))
         return x.value, y.value
 
+    def read_output(self, layer: int, images: int | None = None):
+        """One layer's resident output (its first `images` images, default all) as a numpy array (NHWC; int8 or int32
+        per the layer's out_mode)."""
+        import numpy as np
+        d = self.descs[layer]
+        p, q = d.out_hw
+        n = d.n if images is None else min(images, d.n)
+        out = np.empty((n, p, q, d.k), dtype=np.int8 if d.out_mode == _capi.OUT_INT8 else np.int32)
+        check(self._lib.lbc_net_read_output_host(self._h, layer, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
+        return out
+
+    def check_status(self) -> None:
+        check(self._lib.lbc_net_check(self._h))
+
     def layer_kernel(self, layer: int) -> str:
         plan = ctypes.c_void_p()
         check(self._lib.lbc_net_layer_plan(self._h, layer, ctypes.byref(plan)))

@@ -37,9 +37,10 @@ def _worker(rank, world, port, q):
     sh = _shard()
     first, last = sh.image_range(512, world, rank)
     # rank 1 is the slow one: the job time must be ITS time, on every rank
-    st = sh.RankStats(ms_total=10.0 + 5.0 * rank, e2e_ms=2.0 + rank, checksum=1000 + rank, images=last - first)
+    st = sh.RankStats(ms_total=10.0 + 5.0 * rank, e2e_ms=2.0 + rank, checksum=1000 + rank, images=last - first,
+                      bad_layers=rank, link_up=20.0 - rank, link_dn=15.0 + rank)
     job = sh.gather(st, world)
-    q.put((rank, job.ms_total, job.e2e_ms, job.images, job.checksums))
+    q.put((rank, job.ms_total, job.e2e_ms, job.images, job.checksums, job.bad_layers, job.link_up, job.link_dn))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -55,5 +56,7 @@ def test_gather_max_over_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, ms, e2e, images, sums in res:
+    for rank, ms, e2e, images, sums, bad, up, dn in res:
         assert ms == 15.0 and e2e == 3.0 and images == 512 and sums == [1000, 1001]
+        # a parity failure on ANY rank fails the job; the host-link figure is the slowest rank's
+        assert bad == 1 and up == 19.0 and dn == 15.0
