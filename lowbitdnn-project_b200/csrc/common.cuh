@@ -103,6 +103,7 @@ struct IgemmConfig {
     uint16_t a_tab[192];
     uint16_t b_tab[192]; // resident-B window mode: matching B-descriptor offsets
     int32_t res_b;       // filter matrix resident in shared memory (loaded once per CTA)
+    int32_t res_one;     // ... only the CTA's own N tile of it (N-stationary schedule, grid % tiles_n == 0)
     int32_t n_mma;       // MMA-issuing warps (1 or 2)
     int32_t pair;        // two M tiles per CTA step share every B block (window A, streaming B)
     int32_t it_imgs;     // pair modes: image (ring modes: M tile) radix of the tile numbering, padded so tiles come in pairs

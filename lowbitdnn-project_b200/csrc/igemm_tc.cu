@@ -107,7 +107,11 @@ struct IgemmParams {
     int32_t n_tab;
     uint16_t a_tab[kMaxTab];
     uint16_t b_tab[kMaxTab];      // resident-B window mode: B-descriptor offsets of the same MMAs (relative to the chunk)
-    int32_t res_b;                // 1: the whole filter matrix stays in shared memory (loaded once per CTA)
+    int32_t res_b;                // 1: the filter matrix stays in shared memory (loaded once per CTA)
+    int32_t res_one;              // with res_b: only THIS CTA's N tile is resident.  The persistent grid is a multiple of
+                                  // tiles_n and tiles are numbered N-tile-fastest, so CTA b only ever works on N tile
+                                  // b % tiles_n ("N-stationary"): the 256->1024 / 512->2048 expansions keep their 64 / 128 KB
+                                  // tile instead of re-streaming it from L2 for every M tile (96 -> 32 KB of fill per tile)
     int32_t n_mma;                // MMA-issuing warps (1 or 2); CTA-local tile L belongs to warp L % n_mma and to the
                                   // L % n_mma-th sub-ring of the A ring / window ring (stages / n_mma stages each)
     uint32_t b_total_bytes;       // resident B: bytes of the filter matrix
@@ -331,8 +335,8 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
 
 // One-time set-up of the bias-fold operand blocks (see IgemmParams::fold), by the 512 epilogue threads.
 // Called before the role computes its per-thread constants, so its temporaries do not overlap their live ranges.
-__device__ __forceinline__ void write_fold_blocks(uint8_t* fold_base, uint32_t etid, int32_t bn, int32_t k_out, int32_t k_mod,
-                                               const int32_t* __restrict__ bias, uint32_t* fold_ok)
+__device__ __forceinline__ void write_fold_blocks(uint8_t* fold_base, uint32_t etid, int32_t bn, int32_t c_first, int32_t k_out,
+                                               int32_t k_mod, const int32_t* __restrict__ bias, uint32_t* fold_ok)
 {
     // [A': 4 KB][B': bn x 32 B], both as 8-row x 16-byte core matrices (K chunks 128 B apart, 8-row groups 256 B apart)
     // A': every row = 31 x 127, then 1.  16-byte piece i sits at i * 16 and belongs to K chunk (i >> 3) & 1.
@@ -340,11 +344,12 @@ __device__ __forceinline__ void write_fold_blocks(uint8_t* fold_base, uint32_t e
         const uint32_t last = ((i >> 3) & 1u) ? 0x017f7f7fu : 0x7f7f7f7fu;
         *reinterpret_cast<uint4*>(fold_base + i * 16u) = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, last);
     }
-    // B': one thread per output channel
+    // B': one thread per output channel (local row c holds global channel c_first + c)
     bool ok = true;
     for (uint32_t c = etid; c < (uint32_t)bn; c += kEpiWarps * 32u) {
-        const bool in = (int32_t)c < k_out;
-        const int32_t kp = k_mod ? (int32_t)c % k_mod : (int32_t)c;
+        const int32_t kc = c_first + (int32_t)c;
+        const bool in = kc < k_out;
+        const int32_t kp = k_mod ? kc % k_mod : kc;
         int32_t b = (in && bias) ? __ldg(bias + kp) : 0;
         if (b > 500000 || b < -500000) { ok = false; b = 0; }
         int32_t q = (b + (b >= 0 ? 63 : -63)) / 127;          // bias = 127 * q + r0, |r0| <= 63
@@ -496,7 +501,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes);
                 const int32_t nblk = prm.cblocks * prm.inner;
                 uint8_t* dst = smem_b;
-                for (int32_t nt = 0; nt < prm.tiles_n; ++nt) {
+                // every N tile, or (N-stationary) only the one this CTA works on
+                const int32_t nt0 = prm.res_one ? (int32_t)(blockIdx.x % (uint32_t)prm.tiles_n) : 0;
+                const int32_t nt1 = prm.res_one ? nt0 + 1 : prm.tiles_n;
+                for (int32_t nt = nt0; nt < nt1; ++nt) {
                     int32_t bcol = 0;
                     for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb)
                         ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, nt * prm.bn);
@@ -729,8 +737,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t tiles_n_u = (uint32_t)prm.tiles_n;
         const uint32_t nb_step = RESB ? (uint32_t)tile_step % tiles_n_u : 0u;
         uint32_t n_blk = RESB ? (blockIdx.x + which * gridDim.x) % tiles_n_u : 0u;
-        const uint32_t b_tile16 = b_block16 * (uint32_t)(prm.cblocks * prm.inner);      // one N tile of the resident matrix
-        const uint32_t fold_tile16 = (bn * 32u) >> 4;
+        // one N tile of the resident matrix (N-stationary: the only resident tile sits at offset 0)
+        const uint32_t b_tile16 = prm.res_one ? 0u : b_block16 * (uint32_t)(prm.cblocks * prm.inner);
+        const uint32_t fold_tile16 = prm.res_one ? 0u : (bn * 32u) >> 4;
         // (a pair leader counts its own tiles; the peer's tile of each step shares the MMAs)
         for (int32_t tile = active ? (int32_t)(blockIdx.x + which * gridDim.x) : num_tiles; tile < num_tiles;
              tile += tile_step, local += (int32_t)n_mma) {
@@ -836,7 +845,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // (first thing in the role, while nothing else is live: its temporaries must not cost the tile loops registers)
         bool fold = false;
         if (MAYFOLD && prm.fold) {
-            write_fold_blocks(smem + prm.off_fold, e * 32u + lane, prm.bn * prm.tiles_n, prm.k_out, prm.k_mod, bias, &ctl->fold_ok);
+            write_fold_blocks(smem + prm.off_fold, e * 32u + lane, prm.res_one ? prm.bn : prm.bn * prm.tiles_n,
+                              prm.res_one ? (int32_t)(blockIdx.x % (uint32_t)prm.tiles_n) * prm.bn : 0, prm.k_out, prm.k_mod, bias,
+                              &ctl->fold_ok);
             ptx::fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&ctl->bias_ready);
@@ -1384,7 +1395,22 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     // Resident filter matrix: one N tile and the whole packed matrix small enough to leave room for a deep A side.
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.tiles_n * c.k_blocks * c.b_block_bytes;      // all N tiles
-    const bool res_b_ok = !c.pair && !c.cta2 && c.b_total_bytes <= (uint32_t)limit(o.resident_kb, 80) * 1024u && o.resident_filter != 0;
+    bool res_b_ok = !c.pair && !c.cta2 && c.b_total_bytes <= (uint32_t)limit(o.resident_kb, 80) * 1024u && o.resident_filter != 0;
+    // N-stationary: the matrix as a whole is too large, but one N tile fits and the persistent grid can be a multiple of
+    // tiles_n, so every CTA keeps "its" N tile for the whole launch (see IgemmParams::res_one)
+    c.res_one = 0;
+    {
+        const uint32_t one_tile = (uint32_t)c.k_blocks * c.b_block_bytes;
+        int grid0 = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
+        if (o.max_grid > 0) grid0 = std::max(1, std::min(grid0, (int)o.max_grid));
+        const int grid_ns = grid0 - grid0 % c.tiles_n;
+        if (!res_b_ok && !c.pair && !c.cta2 && c.tiles_n > 1 && one_tile <= 128u * 1024u && grid_ns >= c.tiles_n &&
+            o.resident_filter != 0 && o.n_stationary != 0) {
+            c.res_one = 1;
+            c.b_total_bytes = one_tile;
+            res_b_ok = true;
+        }
+    }
     for (int pass = 0; pass < 2 && !fits; ++pass)
     for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs)
     for (int fold_try = 1; fold_try >= 0 && !fits; --fold_try) {     // with the bias-fold blocks if they fit, else without   // three staging panels per team when they fit, else two, else one
@@ -1402,7 +1428,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
             c.fold = (c.res_b && want && fold_try) ? 1 : 0;
             if (!fold_try && !(c.res_b && want)) continue;      // nothing to drop: this variant was already tried
         }
-        const uint32_t fold_bytes = c.fold ? round_up(4096u + (uint32_t)(c.bn * c.tiles_n) * 32u, 1024) : 0u;
+        const uint32_t fold_bytes = c.fold ? round_up(4096u + (uint32_t)(c.res_one ? c.bn : c.bn * c.tiles_n) * 32u, 1024) : 0u;
         if (stage_bytes + ctl_bytes + fold_bytes >= 227u * 1024u) continue;
         const uint32_t budget = 227 * 1024 - stage_bytes - ctl_bytes - fold_bytes;
         uint32_t win_total = 0;
@@ -1486,6 +1512,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     uint32_t cols = 32;
     while (cols < (uint32_t)(c.n_acc * c.bn)) cols <<= 1;
     c.tmem_cols = cols;
+    if (!c.res_b) c.res_one = 0;       // the resident variant did not fit: plain streaming
     c.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
     c.it_imgs = d.n;
     if (c.cta2) {
@@ -1504,6 +1531,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     }
     if (o.max_grid > 0) c.grid = std::max(1, std::min(c.grid, (int)o.max_grid));   // tests: many tiles per CTA
     if (c.cta2) c.grid = std::max(2, c.grid & ~1);
+    if (c.res_one) c.grid -= c.grid % c.tiles_n;      // >= tiles_n by the planner's check above
     c.reverse = o.reverse == 1 ? 1 : 0;
     c.pdl = o.pdl != 0 ? 1 : 0;
     *cfg = c;
@@ -1617,7 +1645,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps; prm.warp_store = c.warp_store;
     prm.n_tab = c.n_tab;
     for (int i = 0; i < c.n_tab; ++i) { prm.a_tab[i] = c.a_tab[i]; prm.b_tab[i] = c.b_tab[i]; }
-    prm.res_b = c.res_b; prm.b_total_bytes = c.b_total_bytes; prm.n_mma = c.n_mma;
+    prm.res_b = c.res_b; prm.res_one = c.res_one; prm.b_total_bytes = c.b_total_bytes; prm.n_mma = c.n_mma;
     // digits of the CTA stride in the (img | rt | ct | n_blk) tile numbering
     prm.it_cols = c.mode == A_WINDOW ? c.col_tiles : 1;
     prm.it_rows = c.mode == A_WINDOW ? c.row_tiles : 1;
