@@ -352,6 +352,8 @@ def main():
     ap.add_argument("--network", default="resnet50")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the config's batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[],
+                    help="planner option key=value (lbc_plan_options field) applied to every layer; A/B experiments only")
     ap.add_argument("--ref-full", action="store_true",
                     help="--impl reference: also run BASELINE config 1 in full through the reference CPU path (minutes)")
     ap.add_argument("--layer-report", default=None, help="write the per-layer table (JSON) here")
@@ -397,7 +399,7 @@ def main():
 
     # ---- build the network, load synthetic parameters / resident inputs --------------------------------
     t_setup = time.time()
-    net = lbc.Net(layers)
+    net = lbc.Net(layers, options={k: int(v) for k, v in (o.split("=") for o in args.opt)} or None)
     for i, (_, d, src) in enumerate(layers):
         w, b, s = synth_params(d, i)
         net.set_params(i, w, b, s)
@@ -554,6 +556,7 @@ def main():
             "config": {"workload": f"{args.network}_conv_stack_b{config_batch}", "network": args.network,
                        "batch_per_gpu": args.batch, "global_batch": images_per_step, "layers": len(layers),
                        "parallelism": f"batch-sharded x{world} ({args.scaling} scaling), no collective on the conv path",
+                       **({"planner_options": args.opt} if args.opt else {}),
                        "l2": f"no flush: a step touches {sum(w[1] for w in works) / 1e9:.2f} GB (algorithmic) against 126 MB of L2; "
                              f"the smallest layer input is {min(d.n * d.h * d.w * d.c for _, d, _ in layers) / 1e6:.1f} MB"},
             "parity": "bit-exact" if job.bad_layers == 0 else f"MISMATCH in {job.bad_layers} layer outputs (summed over ranks)",

@@ -110,7 +110,7 @@ typedef struct lbc_plan_options {
     int32_t small_teams;         /* 0: 2 x 8-warp epilogue teams even on narrow tiles                               */
     int32_t four_acc;            /* 0: two TMEM accumulator stages where four would fit                             */
     int32_t n_stationary;        /* CTAs keep one N tile of the filter matrix resident and walk M (multi-N-tile)    */
-    int32_t epi_pipeline;        /* software-pipelined TMEM drain (next chunk's tcgen05.ld under this chunk's ALU)  */
+    int32_t epi_pipeline;        /* reserved (the pipelined TMEM drain is a compile-time switch, LBC_EPI_PIPE)      */
     int32_t max_grid;            /* cap on persistent CTAs (tests: many tiles per CTA)                              */
     int32_t max_bn;              /* cap on the N tile width                                                         */
     int32_t max_stages;          /* cap on operand ring stages                                                      */
@@ -118,7 +118,8 @@ typedef struct lbc_plan_options {
     int32_t stage_bufs;          /* cap on output staging panels per epilogue team (1..3)                           */
     int32_t tps_kb;              /* cap (KB) on the B bytes grouped into one ring stage in window mode              */
     int32_t resident_kb;         /* largest filter matrix (KB) kept resident                                        */
-    int32_t reserved[8];
+    int32_t epi_split;           /* tri-state: both epilogue teams drain every tile (column split) on > 128-wide tiles */
+    int32_t reserved[7];
 } lbc_plan_options;
 
 typedef struct lbc_plan lbc_plan;     /* opaque; immutable after creation and safe to share between threads and

@@ -35,7 +35,7 @@ class CPlanOptions(ctypes.Structure):
         "struct_size", "cta_pairs", "warp_store", "fold_bias", "paired_tiles", "resident_filter", "window", "keep_window",
         "force_im2col", "pixel_groups", "dw_tiled", "reverse", "pdl", "two_mma_warps", "tiles_per_iter2", "small_teams",
         "four_acc", "n_stationary", "epi_pipeline", "max_grid", "max_bn", "max_stages", "max_win_stages", "stage_bufs",
-        "tps_kb", "resident_kb")] + [("reserved", ctypes.c_int32 * 8)]
+        "tps_kb", "resident_kb", "epi_split")] + [("reserved", ctypes.c_int32 * 7)]
 
 
 def plan_options(**kw) -> CPlanOptions:

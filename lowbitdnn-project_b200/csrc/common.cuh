@@ -98,6 +98,7 @@ struct IgemmConfig {
     int32_t stage_bufs;  // staging panels per epilogue team
     int32_t warp_store;  // ring modes: every epilogue warp stages and TMA-stores its own 32 rows (no team barrier per panel)
     int32_t team_warps;  // 8 (two epilogue teams) or 4 (four teams, N tile <= 64)
+    int32_t epi_split;   // both epilogue teams drain every tile (panels / column halves) instead of alternate tiles
     int32_t k_mod;       // bias/scale index modulo (pixel-group rewrite), 0 = none
     int32_t n_tab;       // MMA issue table: A-descriptor offsets (16-byte units) of one channel chunk
     uint16_t a_tab[192];

@@ -50,6 +50,19 @@ namespace lbc {
 
 namespace {
 
+// Epilogue formulation switches (bit-exact either way; compile-time so that A/B builds can be compared):
+//   LBC_EPI_PIPE   two 16-column register buffers, the tcgen05.ld of chunk i+1 in flight while chunk i is converted
+//   LBC_EPI_F32X2  the per-channel scale multiply as packed mul.rn.f32x2 (FMUL2: one issue slot per two outputs)
+// (LBC_EPI_PIPE is off: holding a second 16-register buffer across the conversion makes every variant spill at the
+//  96-register cap of a 640-thread CTA - 0.5 KB stack frames - and four epilogue warps per scheduler already cover the
+//  TMEM latency; the epilogue is bound by pipe throughput, ~2 cycles per ALU instruction, not by latency.)
+#ifndef LBC_EPI_PIPE
+#define LBC_EPI_PIPE 0
+#endif
+#ifndef LBC_EPI_F32X2
+#define LBC_EPI_F32X2 1
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 16;                          // epilogue warps: 2 teams of 8 or 4 teams of 4
 constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA (even tiles) + TMEM alloc, 2: window TMA, 3: MMA (odd tiles)
@@ -91,6 +104,13 @@ struct IgemmParams {
     int32_t stage_bufs;           // staging panels per epilogue team (2 or 3: TMA stores drain while later panels fill)
     int32_t team_warps;           // 8: two epilogue teams (wide N tiles); 4: four teams (N tile <= 64 columns)
     int32_t warp_store;           // 1: each epilogue warp owns a 32-row staging buffer and issues its own TMA stores
+    // Column-split epilogue (N tiles > 128 columns, i.e. two TMEM accumulator stages): both 8-warp teams drain EVERY tile,
+    // each its own panels (int8) / column half (int32), instead of alternate tiles.  With alternate tiles a team holds an
+    // accumulator stage for a whole ~2900-cycle drain (two drains share the issue slots), and with only two stages the
+    // MMA of tile k+2 cannot start before the drain of tile k has ended: a latency chain MMA -> drain -> MMA that ran the
+    // 1x1 channel expansions at ~2100-2600 cycles per tile against ~1500 of epilogue work (traces, r02).  Sharing the
+    // tile halves the time a stage is held, so the MMA of the next tile hides completely behind the drain.
+    int32_t epi_split;
     // Bias folded into the MMA (resident-filter kernels): the first MMA of every tile multiplies a constant A block (every
     // row = 31 x 127, 1) with a B block of per-channel bias digits (bias = 127 * sum(d_0..d_30) + d_31), so the
     // accumulator starts at the bias and the epilogue skips its add and the bias fetch (1.25 of its 4.75 instructions
@@ -252,6 +272,22 @@ __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, vol
 // int32, the saturating int32 -> int8 pack clamps to [-128, 127], and with RELU the clamp at zero is applied to the
 // PACKED bytes (sign-replicating PRMT + AND: 2 instructions per 4 outputs instead of 4 IMNMX).
 // FOLD: the accumulator already contains the bias (see IgemmParams::fold)
+// two independent round-to-nearest fp32 products in one instruction (FMUL2); each lane is the same IEEE multiply as
+// __fmul_rn, so the results are bit-identical to the scalar form
+__device__ __forceinline__ void fmul2_rn(float& a, float& b, float sa, float sb)
+{
+#if LBC_EPI_F32X2
+    uint64_t x, s, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(sa), "f"(sb));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(s));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r));
+#else
+    a = __fmul_rn(a, sa);
+    b = __fmul_rn(b, sb);
+#endif
+}
+
 template <bool RELU, bool FOLD>
 __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, const int32_t* bi)
 {
@@ -260,10 +296,11 @@ __device__ __forceinline__ uint4 requant16(const uint32_t* v, const float* sc, c
     for (int t = 0; t < 4; ++t) {
         const float4 f = *reinterpret_cast<const float4*>(sc + 4 * t);
         const int4 b = FOLD ? make_int4(0, 0, 0, 0) : *reinterpret_cast<const int4*>(bi + 4 * t);
-        const int32_t q0 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 0] + b.x), f.x));
-        const int32_t q1 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 1] + b.y), f.y));
-        const int32_t q2 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 2] + b.z), f.z));
-        const int32_t q3 = __float2int_rn(__fmul_rn(__int2float_rn((int32_t)v[4 * t + 3] + b.w), f.w));
+        float x0 = __int2float_rn((int32_t)v[4 * t + 0] + b.x), x1 = __int2float_rn((int32_t)v[4 * t + 1] + b.y);
+        float x2 = __int2float_rn((int32_t)v[4 * t + 2] + b.z), x3 = __int2float_rn((int32_t)v[4 * t + 3] + b.w);
+        fmul2_rn(x0, x1, f.x, f.y);
+        fmul2_rn(x2, x3, f.z, f.w);
+        const int32_t q0 = __float2int_rn(x0), q1 = __float2int_rn(x1), q2 = __float2int_rn(x2), q3 = __float2int_rn(x3);
         uint32_t r = pack4_sat_s8(q0, q1, q2, q3);
         if (RELU) {
             uint32_t neg;
@@ -319,6 +356,24 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
                                           int32_t col0)
 {
     int32_t c = c0;
+#if LBC_EPI_PIPE
+    // Software pipeline over 16-column chunks with two register buffers: right after the wait that completes chunk i the
+    // load of chunk i+1 is issued, so its TMEM latency runs under the ~75 instructions that convert chunk i.
+    // (tcgen05.wait::ld waits for every outstanding load of the thread, hence exactly one load in flight at a wait.)
+    uint32_t va[16], vb[16];
+    if (c + 16 <= c1) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, va);
+    while (c + 16 <= c1) {
+        ptx::tmem_ld_wait_dep16(va);
+        if (c + 32 <= c1) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(c + 16), vb);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, va, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
+        c += 16;
+        if (c + 16 > c1) break;
+        ptx::tmem_ld_wait_dep16(vb);
+        if (c + 32 <= c1) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(c + 16), va);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, vb, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
+        c += 16;
+    }
+#else
     for (; c + 32 <= c1; c += 32) {
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
@@ -331,6 +386,7 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
         ptx::tmem_ld_wait_dep16(v16);
         epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
     }
+#endif
 }
 
 // One-time set-up of the bias-fold operand blocks (see IgemmParams::fold), by the 512 epilogue threads.
@@ -457,7 +513,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         for (int i = 0; i < prm.n_acc; ++i) {
             ptx::mbar_init(&ctl->tmem_full[i], 1);
-            ptx::mbar_init(&ctl->tmem_empty[i], (uint32_t)prm.team_warps * (CTA2 ? 2u : 1u));   // pair: both CTAs' teams
+            // one arrival per warp that drains the stage: a team, or (column-split epilogue) all 16 warps; pair: both CTAs
+            ptx::mbar_init(&ctl->tmem_empty[i], (uint32_t)(prm.epi_split ? kEpiWarps : prm.team_warps) * (CTA2 ? 2u : 1u));
         }
         ptx::mbar_init(&ctl->bfull, 1);
         ptx::mbar_init(&ctl->bias_ready, kEpiWarps);
@@ -884,12 +941,20 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         uint32_t sbuf = 0;
         float* sc = ctl->scale[team];
         int32_t* bi = ctl->bias[team];
+        // Column-split epilogue (IgemmParams::epi_split): both teams walk every tile of the CTA; int8 mode deals the panels
+        // of a tile to the teams (panel index = team, team + 2, ...), int32 mode gives each team one half of the columns.
+        const bool split = prm.epi_split != 0;
+        const int32_t i32_first = ((prm.bn / 16 + 1) / 2) * 16;                 // int32 + split: team 0 owns [0, first)
+        const int32_t pbase0 = (split && !int8_out && team) ? i32_first : 0;    // first column of this team's range
         // columns of a panel handled by this warp: [pc_begin, pc_end), multiples of 16
-        const int32_t pcols = int8_out ? prm.panel_bytes : prm.bn;   // int32 mode: the whole N tile is one "panel"
+        // (int32 mode: the team's whole column range is one "panel")
+        const int32_t pcols = int8_out ? prm.panel_bytes : !split ? prm.bn : team ? prm.bn - i32_first : i32_first;
         const int32_t psplit = small_teams ? pcols : ((pcols / 16 + 1) / 2) * 16;
         const int32_t pc_begin = half ? psplit : 0;
         const int32_t pc_end = half ? pcols : psplit;
         const int32_t n_panels = int8_out ? prm.n_panels : 1;
+        const int32_t p_first = (split && int8_out) ? (int32_t)team : 0;        // team path: this team's panels
+        const int32_t p_step = (split && int8_out) ? (int32_t)n_teams : 1;
 
         const uint32_t lane_row = quarter * 32 + lane;            // TMEM lane == row of the MMA tile
         EpiThread et;
@@ -989,10 +1054,12 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         } else {
         TileIter it;
         // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
-        it.init(prm, prm.pair ? first_tile + (int32_t)team : (int32_t)(blockIdx.x + team * gridDim.x), !prm.pair);
+        // column-split: every team takes every tile of the CTA
+        it.init(prm, prm.pair ? first_tile + (int32_t)team : split ? (int32_t)blockIdx.x : (int32_t)(blockIdx.x + team * gridDim.x),
+                !prm.pair && !split);
         for (; it.tile < num_tiles;) {
-            // CTA-local tile index (it.local counts pairs / team steps)
-            const int32_t tile = prm.pair ? 2 * it.local + (int32_t)team : it.local * (int32_t)n_teams + (int32_t)team;
+            // CTA-local tile index (it.local counts pairs / team steps / plain CTA steps)
+            const int32_t tile = prm.pair ? 2 * it.local + (int32_t)team : split ? it.local : it.local * (int32_t)n_teams + (int32_t)team;
             struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.image(), it.p0(prm), it.q0(prm), it.m0()};
             const int32_t col0 = tc.n_blk * prm.bn;
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
@@ -1036,15 +1103,18 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t wrow_off = lane * (uint32_t)prm.panel_bytes;
                 const uint32_t wswz = ((wrow_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
                 const int32_t n_halves = small_teams ? 1 : 2;
+                // panels dealt to the warp sets of the team, or (column-split) to the warp sets of both teams
+                const int32_t w_first = split ? (int32_t)team * n_halves + (int32_t)half : (int32_t)half;
+                const int32_t w_step = split ? (int32_t)n_teams * n_halves : n_halves;
                 EpiThread wt = et;
                 wt.valid = true;
-                for (int32_t pnl = (int32_t)half; pnl < n_panels; pnl += n_halves) {
+                for (int32_t pnl = w_first; pnl < n_panels; pnl += w_step) {
                     const int32_t pbase = pnl * pcols;
                     if (lane == 0) ptx::tma_store_wait_read<0>();      // the previous store has read this buffer out
                     __syncwarp();
                     epi_run<kFold>(true, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz,
                                   y32, -1, col0);
-                    if (pnl + n_halves >= n_panels) {
+                    if (pnl + w_step >= n_panels) {
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -1063,8 +1133,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
                 if (issuer) trace_ev(prm, tracing, tile, EV_E_STORED);
             } else
-            for (int32_t pnl = 0; pnl < n_panels; ++pnl) {
-                const int32_t pbase = pnl * pcols;
+            for (int32_t pnl = p_first; pnl < n_panels; pnl += p_step) {
+                const int32_t pbase = pnl * pcols + pbase0;
                 if (nbufs == 1 && int8_out) {
                     // a single staging panel (shared memory is tight): its previous store must have read it out
                     if (issuer) ptx::tma_store_wait_read<0>();
@@ -1073,7 +1143,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
                 epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s,
                               row_off, swz_mask, y32, out_row, col0);
-                if (pnl == n_panels - 1) {
+                if (pnl + p_step >= n_panels) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -1103,7 +1173,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                 ptx::tma_store_2d_s(&tm_out, staging_s, cbyte, tc.m0);
                         }
                         ptx::tma_store_commit();
-                        if (pnl == n_panels - 1) trace_ev(prm, tracing, tile, EV_E_STORED);
+                        if (pnl + p_step >= n_panels) trace_ev(prm, tracing, tile, EV_E_STORED);
                     }
                     if (++sbuf == nbufs) sbuf = 0;
                 }
@@ -1341,6 +1411,22 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         if (c.mode != A_WINDOW && d.out_mode == LBC_OUT_INT8 && want && (c.bn == 256 || c.bn == 128 || c.bn == 64 || c.bn == 32)) {
             c.warp_store = 1;
             if (c.bn == 128) c.panel_bytes = 64;
+        }
+    }
+    // ---- column-split epilogue (see IgemmParams::epi_split): N tiles with only two TMEM accumulator stages
+    c.epi_split = 0;
+    {
+        const bool two_acc = !(4 * c.bn <= 512 && (c.pair || o.four_acc != 0));
+        bool can = two_acc && !c.pair;
+        if (d.out_mode == LBC_OUT_INT8) {
+            if (c.warp_store) can = can && c.bn == 256;                     // four 64-byte panels: one per (team, warp set)
+            else can = can && (c.bn / c.panel_bytes) % 2 == 0;              // panels dealt alternately to the two teams
+        }
+        bool want = true;
+        if (o.epi_split >= 0) want = o.epi_split != 0;
+        if (can && want) {
+            c.epi_split = 1;
+            if (c.warp_store && d.out_mode == LBC_OUT_INT8) c.panel_bytes = 64;
         }
     }
     c.n_panels = c.bn / c.panel_bytes;
@@ -1643,6 +1729,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.tmem_cols = c.tmem_cols; prm.n_acc = c.n_acc; prm.tpi = c.tpi;
     prm.panel_bytes = c.panel_bytes; prm.panel_swz_bits = c.panel_swz_bits; prm.n_panels = c.n_panels;
     prm.stage_bufs = c.stage_bufs; prm.k_mod = c.k_mod; prm.team_warps = c.team_warps; prm.warp_store = c.warp_store;
+    prm.epi_split = c.epi_split;
     prm.n_tab = c.n_tab;
     for (int i = 0; i < c.n_tab; ++i) { prm.a_tab[i] = c.a_tab[i]; prm.b_tab[i] = c.b_tab[i]; }
     prm.res_b = c.res_b; prm.res_one = c.res_one; prm.b_total_bytes = c.b_total_bytes; prm.n_mma = c.n_mma;

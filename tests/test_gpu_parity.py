@@ -217,6 +217,54 @@ def test_many_tiles_per_cta(d, grid):
         assert _check(D(**{**d.__dict__, "out_mode": 1}), options=g) == "igemm_tc"    # raw accumulators through the same walk
 
 
+# ---- column-split epilogue and N-stationary filter tiles (r02) ------------------------------------------------
+SPLIT_CASES = [c for c in IGEMM_CASES + FOLD_EXTRA_CASES + MULTI_TILE_CASES if c.k > 128]     # N tiles > 128 columns
+
+
+@pytest.mark.parametrize("d", SPLIT_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_igemm_column_split_epilogue(d):
+    """N tiles with two TMEM accumulator stages: both epilogue teams drain every tile (alternate panels in int8 mode,
+    column halves in int32 mode; four 64-byte panels with per-warp stores), forced on and off, with every way the
+    operands can arrive (resident / streamed / CTA pairs) and with few CTAs so that the accumulator stages wrap."""
+    for opts in ({"epi_split": 1}, {"epi_split": 0}, {"epi_split": 1, "warp_store": 1}, {"epi_split": 1, "warp_store": 0},
+                 {"epi_split": 1, "cta_pairs": 1, "resident_filter": 0}, {"epi_split": 1, "max_grid": 2},
+                 {"epi_split": 1, "max_grid": 3, "warp_store": 1, "fold_bias": 1}, {"epi_split": 1, "max_grid": 2, "reverse": 1}):
+        assert _check(D(**{**d.__dict__, "out_mode": 0}), options=opts) == "igemm_tc", opts
+    for opts in ({"epi_split": 1}, {"epi_split": 1, "max_grid": 2}, {"epi_split": 1, "cta_pairs": 1, "resident_filter": 0}):
+        assert _check(D(**{**d.__dict__, "out_mode": 1}), options=opts) == "igemm_tc", opts
+
+
+N_STATIONARY_CASES = [
+    D(n=2, h=14, w=14, c=256, k=1024, r=1, s=1, relu=1),                       # ResNet-50 l3.x.conv3: 4 N tiles of 64 KB
+    D(n=3, h=7, w=7, c=512, k=2048, r=1, s=1, relu=1),                         # l4.x.conv3: 8 N tiles of 128 KB
+    D(n=2, h=28, w=28, c=256, k=512, r=1, s=1, stride_h=2, stride_w=2),        # l2.0.downsample: im2col A, 2 N tiles
+    D(n=2, h=14, w=14, c=512, k=1024, r=1, s=1, stride_h=2, stride_w=2),       # l3.0.downsample: 4 N tiles of 128 KB
+    D(n=2, h=14, w=14, c=256, k=608, r=1, s=1, relu=1),                        # ragged last N tile (3 x 208 columns for 608)
+    D(n=2, h=14, w=14, c=32, k=640, r=3, s=3, pad_h=1, pad_w=1, relu=1),       # window A, 3 N tiles of 224 columns
+    D(n=2, h=9, w=9, c=320, k=1280, r=1, s=1, relu=1),                         # MobileNetV2 `last`: 64-byte K chunks
+]
+
+
+@pytest.mark.parametrize("d", N_STATIONARY_CASES, ids=lambda d: f"n{d.n}h{d.h}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_igemm_n_stationary_filter_tiles(d):
+    """Filter matrices too large to be resident as a whole: every CTA keeps the N tile it works on (grid a multiple of
+    tiles_n), with and without the folded bias, with the grid capped to one and to several CTAs per N tile, and with
+    grids that cannot be N-stationary at all (fewer CTAs than N tiles -> the planner must stream)."""
+    import lowbitdnn_project_b200 as lbc
+    from tests.parity_util import lbc_desc
+    plan = lbc.ConvPlan(lbc_desc(D(**{**d.__dict__, "out_mode": 0})))
+    assert "n-stationary" in plan.describe(), plan.describe()
+    plan.close()
+    tiles_n = -(-d.k // 256)
+    for opts in ({}, {"n_stationary": 0}, {"fold_bias": 0}, {"fold_bias": 1}, {"max_grid": tiles_n}, {"max_grid": 2 * tiles_n + 1},
+                 {"max_grid": tiles_n - 1}, {"max_grid": 3 * tiles_n, "reverse": 1}, {"epi_split": 0, "max_grid": 2 * tiles_n},
+                 {"warp_store": 1, "max_grid": 2 * tiles_n}, {"warp_store": 0}):
+        assert _check(D(**{**d.__dict__, "out_mode": 0}), options=opts or None) == "igemm_tc", opts
+    for opts in ({}, {"max_grid": 2 * tiles_n}):
+        assert _check(D(**{**d.__dict__, "out_mode": 1}), options=opts or None) == "igemm_tc", opts
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000, options={"fold_bias": 1}) == "igemm_tc"
+
+
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
 STEM_CASES = [
     D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),    # ResNet stem
