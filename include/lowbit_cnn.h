@@ -122,6 +122,30 @@ typedef struct lbc_plan_options {
     int32_t reserved[7];
 } lbc_plan_options;
 
+/* int8 NHWC pooling window (max-pool).  Output size: 1 + (in + 2*pad - window) / stride, as the reference's cuDNN
+ * pooling computes it (python/qtorch/cpp/pool2d.cuh:76-78). */
+typedef struct lbc_pool_desc {
+    int32_t n, h, w, c;
+    int32_t kh, kw;
+    int32_t stride_h, stride_w;
+    int32_t pad_h, pad_w;
+} lbc_pool_desc;
+
+/* One node of a network graph (lbc_net_create_graph). */
+typedef enum lbc_node_kind {
+    LBC_NODE_CONV = 0,           /* `conv`: a convolution (planned by the tile/layout planner)                      */
+    LBC_NODE_MAXPOOL = 1,        /* `pool`: int8 max-pool of the producer's output                                  */
+    LBC_NODE_ADD = 2             /* saturating int8 add of two producers (+ ReLU when `relu`): the residual join    */
+} lbc_node_kind;
+typedef struct lbc_node {
+    int32_t kind;                /* lbc_node_kind                                                                   */
+    int32_t input_of;            /* producer node index, or -1: fed from outside (network input / resident buffer)  */
+    int32_t input2_of;           /* LBC_NODE_ADD: the second operand's producer (>= 0)                              */
+    int32_t relu;                /* LBC_NODE_ADD: clamp at zero after the add                                       */
+    lbc_conv_desc conv;          /* LBC_NODE_CONV                                                                   */
+    lbc_pool_desc pool;          /* LBC_NODE_MAXPOOL (n/h/w/c must equal the producer's output)                     */
+} lbc_node;
+
 typedef struct lbc_plan lbc_plan;     /* opaque; immutable after creation and safe to share between threads and
                                          streams (per-run scratch is allocated stream-ordered per call)            */
 typedef struct lbc_net  lbc_net;      /* opaque: a fixed chain/list of planned convolutions           */
@@ -182,6 +206,17 @@ lbc_status  lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const 
                               const int32_t* bias, const float* scale, void* y_host,
                               lbc_stream stream, float* elapsed_ms);
 
+/* ---- int8 ops between convolutions (NHWC int8 device buffers) ----------------------------------- */
+/* Max-pool: replaces max_pool2d(input, kernel, stride, padding) of python/qtorch/cpp/pool2d.cuh:54-92 (cuDNN
+ * CUDNN_POOLING_MAX_DETERMINISTIC on int8): padding never wins, plain integer max. */
+lbc_status  lbc_pool_out_shape(const lbc_pool_desc* d, int32_t* p, int32_t* q);
+lbc_status  lbc_maxpool2d_run(const lbc_pool_desc* d, const int8_t* x_nhwc, int8_t* y_nhwc, lbc_stream stream);
+/* Residual join: y[i] = clamp(a[i] + b[i], relu ? 0 : -128, 127) over n_elements int8 values (y may alias a or b). */
+lbc_status  lbc_add_relu_run(const int8_t* a, const int8_t* b, int8_t* y, size_t n_elements, int32_t relu, lbc_stream stream);
+/* Global average pool over H*W with the convolutions' requantisation rule: y[n][c] = sat_int8(rint(sum * scale)). */
+lbc_status  lbc_global_avgpool_run(const int8_t* x_nhwc, int32_t n, int32_t hw, int32_t c, float scale, int8_t* y_nc,
+                                   lbc_stream stream);
+
 /* ---- layout converters (reference tensor formats) -------------------------------------------- */
 /* NCHW int8/int32 -> [N][C/V][H][W][V]  (utils.cuh:20-26) and back (utils.cuh:11-17). elt = 1 or 4. */
 lbc_status  lbc_to_vect_c(const void* src_nchw, void* dst_vect, int32_t n, int32_t c, int32_t h, int32_t w,
@@ -208,6 +243,10 @@ lbc_status  lbc_net_create(const lbc_conv_desc* descs, const int32_t* input_of, 
 lbc_status  lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of, int32_t n_layers,
                               const lbc_plan_options* opt, lbc_net** net);
 lbc_status  lbc_net_check(lbc_net* net);              /* as lbc_conv_plan_check, for every layer of the network */
+/* A network as a graph of convolutions, max-pools and residual adds (a whole int8 ResNet runs on the device: the conv ->
+ * pool -> relu chains of python/tmp.py:43-56 and the bottleneck's residual join).  Nodes must be listed in topological
+ * order.  Every lbc_net_* call below works on graph networks; per-layer parameters only exist for LBC_NODE_CONV nodes. */
+lbc_status  lbc_net_create_graph(const lbc_node* nodes, int32_t n_nodes, const lbc_plan_options* opt, lbc_net** net);
 lbc_status  lbc_net_destroy(lbc_net* net);
 lbc_status  lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan** plan);
 /* Load parameters for one layer from HOST memory (weights in `layout`, bias int32[K], scale f32[K]). */

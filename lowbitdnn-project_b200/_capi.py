@@ -29,6 +29,19 @@ class CConvDesc(ctypes.Structure):
         "dil_h", "dil_w", "groups", "relu", "out_mode")]
 
 
+class CPoolDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("n", "h", "w", "c", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w")]
+
+
+class CNode(ctypes.Structure):
+    """lbc_node: one node of a network graph."""
+    _fields_ = [("kind", ctypes.c_int32), ("input_of", ctypes.c_int32), ("input2_of", ctypes.c_int32), ("relu", ctypes.c_int32),
+                ("conv", CConvDesc), ("pool", CPoolDesc)]
+
+
+NODE_CONV, NODE_MAXPOOL, NODE_ADD = 0, 1, 2
+
+
 class CPlanOptions(ctypes.Structure):
     """lbc_plan_options (include/lowbit_cnn.h); build one with plan_options(**kw)."""
     _fields_ = [(n, ctypes.c_int32) for n in (
@@ -72,6 +85,10 @@ _PROTOS = {
     "lbc_conv_prepack_weights": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "lbc_conv_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
     "lbc_conv_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "lbc_pool_out_shape": (ctypes.c_int, [ctypes.POINTER(CPoolDesc), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
+    "lbc_maxpool2d_run": (ctypes.c_int, [ctypes.POINTER(CPoolDesc), _vp, _vp, _vp]),
+    "lbc_add_relu_run": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t, _i32, _vp]),
+    "lbc_global_avgpool_run": (ctypes.c_int, [_vp, _i32, _i32, _i32, ctypes.c_float, _vp, _vp]),
     "lbc_to_vect_c": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
     "lbc_from_vect_c": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
     "lbc_nhwc_to_vect_c": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
@@ -83,6 +100,7 @@ _PROTOS = {
     "lbc_net_create_ex": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), _i32, ctypes.POINTER(CPlanOptions),
                                          ctypes.POINTER(_vp)]),
     "lbc_net_check": (ctypes.c_int, [_vp]),
+    "lbc_net_create_graph": (ctypes.c_int, [ctypes.POINTER(CNode), _i32, ctypes.POINTER(CPlanOptions), ctypes.POINTER(_vp)]),
     "lbc_net_destroy": (ctypes.c_int, [_vp]),
     "lbc_net_layer_plan": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_vp)]),
     "lbc_net_set_params_host": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),

@@ -23,7 +23,7 @@ LIB = os.path.join(LIBDIR, "liblowbit_cnn.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
-SOURCES = ["api.cu", "depthwise.cu", "direct_conv.cu", "igemm_tc.cu", "layout.cu", "probes.cu"]
+SOURCES = ["api.cu", "depthwise.cu", "direct_conv.cu", "igemm_tc.cu", "layout.cu", "pool_add.cu", "probes.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-ccbin", HOSTCXX, "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

@@ -668,6 +668,61 @@ lbc_status lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const v
     return check_flag(plan->flag);
 }
 
+// ---- int8 ops between convolutions --------------------------------------------------------------------
+static lbc_status pool_geom(const lbc_pool_desc* d, int32_t* p, int32_t* q)
+{
+    LBC_REQUIRE(d, LBC_ERR_INVALID_ARG, "null pooling descriptor");
+    LBC_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->c > 0 && d->kh > 0 && d->kw > 0 && d->stride_h > 0 && d->stride_w > 0 &&
+                    d->pad_h >= 0 && d->pad_w >= 0,
+                LBC_ERR_INVALID_ARG, "pooling descriptor has a bad extent");
+    LBC_REQUIRE(d->pad_h < d->kh && d->pad_w < d->kw, LBC_ERR_INVALID_ARG, "pooling padding must be smaller than the window");
+    LBC_REQUIRE(d->h + 2 * d->pad_h >= d->kh && d->w + 2 * d->pad_w >= d->kw, LBC_ERR_INVALID_ARG, "pooling window larger than the padded input");
+    *p = 1 + (d->h + 2 * d->pad_h - d->kh) / d->stride_h;      // cudnnGetPooling2dForwardOutputDim (pool2d.cuh:76-78)
+    *q = 1 + (d->w + 2 * d->pad_w - d->kw) / d->stride_w;
+    return LBC_OK;
+}
+
+lbc_status lbc_pool_out_shape(const lbc_pool_desc* d, int32_t* p, int32_t* q)
+{
+    int32_t pp = 0, qq = 0;
+    lbc_status st = pool_geom(d, &pp, &qq);
+    if (st != LBC_OK) return st;
+    if (p) *p = pp;
+    if (q) *q = qq;
+    return LBC_OK;
+}
+
+lbc_status lbc_maxpool2d_run(const lbc_pool_desc* d, const int8_t* x, int8_t* y, lbc_stream stream)
+{
+    int32_t p = 0, q = 0;
+    lbc_status st = pool_geom(d, &p, &q);
+    if (st != LBC_OK) return st;
+    LBC_REQUIRE(x && y, LBC_ERR_INVALID_ARG, "lbc_maxpool2d_run: null x/y");
+    DeviceInfo dev;
+    st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    return launch_maxpool(*d, p, q, x, y, dev.sm_count, (cudaStream_t)stream);
+}
+
+lbc_status lbc_add_relu_run(const int8_t* a, const int8_t* b, int8_t* y, size_t n_elements, int32_t relu, lbc_stream stream)
+{
+    LBC_REQUIRE(a && b && y && n_elements > 0, LBC_ERR_INVALID_ARG, "lbc_add_relu_run: null operand or empty tensor");
+    DeviceInfo dev;
+    lbc_status st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    return launch_add_relu(a, b, y, n_elements, relu, dev.sm_count, (cudaStream_t)stream);
+}
+
+lbc_status lbc_global_avgpool_run(const int8_t* x, int32_t n, int32_t hw, int32_t c, float scale, int8_t* y, lbc_stream stream)
+{
+    LBC_REQUIRE(x && y && n > 0 && hw > 0 && c > 0, LBC_ERR_INVALID_ARG, "lbc_global_avgpool_run: bad argument");
+    LBC_REQUIRE(n <= 65535, LBC_ERR_UNSUPPORTED, "lbc_global_avgpool_run: more than 65535 images");
+    DeviceInfo dev;
+    lbc_status st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    return launch_global_avgpool(x, y, n, hw, c, scale, (cudaStream_t)stream);
+}
+
 // ---- layout converters -------------------------------------------------------------------------------
 static lbc_status permute_checked(const void* src, void* dst, int32_t d0, int32_t d1, int32_t d2, int32_t d3,
                                   int32_t d4, int p0, int p1, int p2, int p3, int p4, int32_t elt, lbc_stream stream)
@@ -750,7 +805,15 @@ lbc_status lbc_flush_l2(lbc_stream stream)
 // ======================================================================================================
 struct lbc_net {
     struct Layer {
-        lbc_plan* plan = nullptr;
+        int32_t kind = LBC_NODE_CONV;
+        lbc_plan* plan = nullptr;        // LBC_NODE_CONV only
+        lbc_pool_desc pool{};            // LBC_NODE_MAXPOOL
+        int32_t add_relu = 0;            // LBC_NODE_ADD
+        int32_t input2_of = -1;          // LBC_NODE_ADD: second operand
+        // activation geometry of every node kind: input NHWC (conv / pool; add: both operands) and output NHWC
+        int32_t in_n = 0, in_h = 0, in_w = 0, in_c = 0, out_p = 0, out_q = 0, out_k = 0, out_elt = 1;
+        size_t in_bytes() const { return (size_t)in_n * in_h * in_w * in_c; }
+        size_t out_bytes() const { return (size_t)in_n * out_p * out_q * out_k * out_elt; }
         int32_t input_of = -1;
         void* w = nullptr;       // packed weights
         int32_t* bias = nullptr;
@@ -767,6 +830,7 @@ struct lbc_net {
     std::vector<cudaEvent_t> events;   // n_layers + 1
     std::mutex mu;
     int* flag = nullptr;               // device watchdog word shared by every layer's plan
+    int sm_count = 148;
     // layer 0 resolved against each of the pipelined host path's two input buffers (see Pipe)
     ResolvedLaunch first_rl[2];
     bool first_rl_ok[2] = {false, false};
@@ -793,6 +857,7 @@ const void* layer_input(const lbc_net* net, int i)
 lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
 {
     lbc_net::Layer& L = net->layers[i];
+    if (L.kind != LBC_NODE_CONV) return LBC_OK;          // pool / add nodes have nothing to encode
     const int8_t* x = x_override ? x_override : (const int8_t*)layer_input(net, i);
     if (L.resolved && L.rl.x == x) return LBC_OK;
     lbc_status st = resolve(L.plan, x, L.w, L.bias, L.scale, L.y, &L.rl);
@@ -804,6 +869,23 @@ lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
     return st;
 }
 
+// put node i on the stream; `rl` = the encoded launch to use for a convolution node (its own, or layer 0's per-buffer one),
+// `x_override` = the input buffer of a non-conv node 0 in the pipelined host path
+lbc_status net_launch_node(lbc_net* net, int i, const ResolvedLaunch* rl, const void* x_override, cudaStream_t s)
+{
+    lbc_net::Layer& L = net->layers[i];
+    switch (L.kind) {
+        case LBC_NODE_CONV: return launch(rl ? *rl : L.rl, s);
+        case LBC_NODE_MAXPOOL:
+            return launch_maxpool(L.pool, L.out_p, L.out_q, (const int8_t*)(x_override ? x_override : layer_input(net, i)), (int8_t*)L.y,
+                                  net->sm_count, s);
+        case LBC_NODE_ADD:
+            return launch_add_relu((const int8_t*)layer_input(net, i), (const int8_t*)net->layers[L.input2_of].y, (int8_t*)L.y,
+                                   L.out_bytes(), L.add_relu, net->sm_count, s);
+        default: set_error("node %d has unknown kind %d", i, L.kind); return LBC_ERR_INVALID_ARG;
+    }
+}
+
 lbc_status net_enqueue(lbc_net* net, const int8_t* x_dev, cudaStream_t s, bool timed)
 {
     const int n = (int)net->layers.size();
@@ -811,7 +893,7 @@ lbc_status net_enqueue(lbc_net* net, const int8_t* x_dev, cudaStream_t s, bool t
     for (int i = 0; i < n; ++i) {
         lbc_status st = net_resolve(net, i, (i == 0 && x_dev) ? x_dev : nullptr);
         if (st != LBC_OK) return st;
-        st = launch(net->layers[i].rl, s);
+        st = net_launch_node(net, i, nullptr, (i == 0 && x_dev) ? x_dev : nullptr, s);
         if (st != LBC_OK) return st;
         if (timed) LBC_CUDA_TRY(cudaEventRecord(net->events[i + 1], s));
     }
@@ -857,6 +939,21 @@ lbc_status lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of
                              lbc_net** out)
 {
     LBC_REQUIRE(descs && out && n_layers > 0, LBC_ERR_INVALID_ARG, "null argument");
+    std::vector<lbc_node> nodes((size_t)n_layers);
+    for (int i = 0; i < n_layers; ++i) {
+        lbc_node nd{};
+        nd.kind = LBC_NODE_CONV;
+        nd.input_of = input_of ? input_of[i] : (i == 0 ? -1 : i - 1);
+        nd.input2_of = -1;
+        nd.conv = descs[i];
+        nodes[(size_t)i] = nd;
+    }
+    return lbc_net_create_graph(nodes.data(), n_layers, opt_in, out);
+}
+
+lbc_status lbc_net_create_graph(const lbc_node* nodes, int32_t n_layers, const lbc_plan_options* opt_in, lbc_net** out)
+{
+    LBC_REQUIRE(nodes && out && n_layers > 0, LBC_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     DeviceInfo dev;
     lbc_status st = current_device(&dev);
@@ -872,6 +969,7 @@ lbc_status lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of
     opt.reverse = -1;
     lbc_net* net = new (std::nothrow) lbc_net();
     LBC_REQUIRE(net, LBC_ERR_ALLOC, "out of host memory");
+    net->sm_count = dev.sm_count;
     if (cudaMalloc((void**)&net->flag, sizeof(int)) != cudaSuccess || cudaMemset(net->flag, 0, sizeof(int)) != cudaSuccess) {
         cudaGetLastError();
         delete net;
@@ -881,45 +979,92 @@ lbc_status lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of
     net->layers.resize(n_layers);
     for (int i = 0; i < n_layers && st == LBC_OK; ++i) {
         lbc_net::Layer& L = net->layers[i];
-        L.input_of = input_of ? input_of[i] : (i == 0 ? -1 : i - 1);
-        if (L.input_of >= i) {
-            set_error("layer %d: input_of (%d) must reference an earlier layer", i, L.input_of);
+        const lbc_node& nd = nodes[i];
+        L.kind = nd.kind;
+        L.input_of = nd.input_of;
+        L.input2_of = nd.kind == LBC_NODE_ADD ? nd.input2_of : -1;
+        if (L.input_of >= i || L.input2_of >= i || L.input_of < -1) {
+            set_error("node %d: inputs (%d, %d) must reference earlier nodes", i, L.input_of, L.input2_of);
             st = LBC_ERR_INVALID_ARG;
             break;
         }
-        st = plan_build(&descs[i], LBC_KERNEL_AUTO, dev, &opt, false, net->flag, &L.plan);
-        if (st != LBC_OK) break;
-        const ConvGeom& g = L.plan->g;
+        // what the producer hands over: int8 NHWC of (n, p, q, k)
+        auto produced = [&](int32_t src, int32_t* n, int32_t* h, int32_t* w, int32_t* c) {
+            const lbc_net::Layer& P = net->layers[src];
+            *n = P.in_n; *h = P.out_p; *w = P.out_q; *c = P.out_k;
+            return P.out_elt == 1;
+        };
+        if (nd.kind == LBC_NODE_CONV) {
+            st = plan_build(&nd.conv, LBC_KERNEL_AUTO, dev, &opt, false, net->flag, &L.plan);
+            if (st != LBC_OK) break;
+            const ConvGeom& g = L.plan->g;
+            L.in_n = g.d.n; L.in_h = g.d.h; L.in_w = g.d.w; L.in_c = g.d.c;
+            L.out_p = g.p; L.out_q = g.q; L.out_k = g.d.k; L.out_elt = (int32_t)out_elt(g);
+        } else if (nd.kind == LBC_NODE_MAXPOOL) {
+            L.pool = nd.pool;
+            st = pool_geom(&L.pool, &L.out_p, &L.out_q);
+            if (st != LBC_OK) break;
+            L.in_n = L.pool.n; L.in_h = L.pool.h; L.in_w = L.pool.w; L.in_c = L.pool.c;
+            L.out_k = L.pool.c;
+        } else if (nd.kind == LBC_NODE_ADD) {
+            if (L.input_of < 0 || L.input2_of < 0) {
+                set_error("node %d: an add needs two producer nodes", i);
+                st = LBC_ERR_INVALID_ARG;
+                break;
+            }
+            int32_t n2, h2, w2, c2;
+            produced(L.input_of, &L.in_n, &L.in_h, &L.in_w, &L.in_c);
+            const bool ok2 = produced(L.input2_of, &n2, &h2, &w2, &c2);
+            if (!ok2 || n2 != L.in_n || h2 != L.in_h || w2 != L.in_w || c2 != L.in_c) {
+                set_error("node %d: the operands of the add differ (%dx%dx%dx%d vs %dx%dx%dx%d)", i, L.in_n, L.in_h, L.in_w, L.in_c, n2, h2, w2, c2);
+                st = LBC_ERR_INVALID_ARG;
+                break;
+            }
+            L.add_relu = nd.relu;
+            L.out_p = L.in_h; L.out_q = L.in_w; L.out_k = L.in_c;
+        } else {
+            set_error("node %d: unknown kind %d", i, nd.kind);
+            st = LBC_ERR_INVALID_ARG;
+            break;
+        }
         if (L.input_of >= 0) {
-            const ConvGeom& pg = net->layers[L.input_of].plan->g;
-            if (pg.d.out_mode != LBC_OUT_INT8 || pg.d.n != g.d.n || pg.p != g.d.h || pg.q != g.d.w || pg.d.k != g.d.c) {
-                set_error("layer %d: input %dx%dx%dx%d does not match the output of layer %d (%dx%dx%dx%d)", i, g.d.n,
-                          g.d.h, g.d.w, g.d.c, L.input_of, pg.d.n, pg.p, pg.q, pg.d.k);
+            int32_t pn, ph, pw, pc;
+            const bool int8_src = produced(L.input_of, &pn, &ph, &pw, &pc);
+            if (!int8_src || pn != L.in_n || ph != L.in_h || pw != L.in_w || pc != L.in_c) {
+                set_error("layer %d: input %dx%dx%dx%d does not match the output of layer %d (%dx%dx%dx%d)", i, L.in_n, L.in_h,
+                          L.in_w, L.in_c, L.input_of, pn, ph, pw, pc);
                 st = LBC_ERR_INVALID_ARG;
                 break;
             }
         }
         {
-            const bool tc = L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC ||
-                            L.plan->kind == LBC_KERNEL_DEPTHWISE;      // (the tiled depthwise kernel mirrors its tile index)
+            const bool tc = L.kind == LBC_NODE_CONV &&
+                            (L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC ||
+                             L.plan->kind == LBC_KERNEL_DEPTHWISE);      // (the tiled depthwise kernel mirrors its tile index)
             const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
             // a producer that ran forwards finished on the last images: start there; CUDA-core kernels always run forwards
             L.reverse = tc && L.input_of >= 0 && !producer_rev && snake;
         }
-        const size_t wb = packed_weight_bytes(L.plan);
-        bool ok = cudaMalloc(&L.w, wb) == cudaSuccess && cudaMalloc((void**)&L.bias, sizeof(int32_t) * g.d.k) == cudaSuccess &&
-                  cudaMalloc((void**)&L.scale, sizeof(float) * g.d.k) == cudaSuccess && cudaMalloc(&L.y, out_bytes(g)) == cudaSuccess;
-        if (ok && L.input_of < 0) ok = cudaMalloc(&L.x_own, in_bytes(g)) == cudaSuccess;
+        bool ok = cudaMalloc(&L.y, L.out_bytes()) == cudaSuccess;
+        size_t wb = 0;
+        if (ok && L.kind == LBC_NODE_CONV) {
+            wb = packed_weight_bytes(L.plan);
+            ok = cudaMalloc(&L.w, wb) == cudaSuccess && cudaMalloc((void**)&L.bias, sizeof(int32_t) * L.out_k) == cudaSuccess &&
+                 cudaMalloc((void**)&L.scale, sizeof(float) * L.out_k) == cudaSuccess;
+        }
+        if (ok && L.input_of < 0) ok = cudaMalloc(&L.x_own, L.in_bytes()) == cudaSuccess;
         if (!ok) {
             cudaGetLastError();
             set_error("layer %d: device allocation failed", i);
             st = LBC_ERR_ALLOC;
             break;
         }
-        cudaMemset(L.w, 0, wb);
-        cudaMemset(L.bias, 0, sizeof(int32_t) * g.d.k);
-        cudaMemset(L.scale, 0, sizeof(float) * g.d.k);
-        if (L.x_own) cudaMemset(L.x_own, 0, in_bytes(g));
+        if (L.kind == LBC_NODE_CONV) {
+            cudaMemset(L.w, 0, wb);
+            cudaMemset(L.bias, 0, sizeof(int32_t) * L.out_k);
+            cudaMemset(L.scale, 0, sizeof(float) * L.out_k);
+        }
+        if (L.x_own) cudaMemset(L.x_own, 0, L.in_bytes());
     }
     if (st == LBC_OK) {
         net->events.assign(n_layers + 1, nullptr);
@@ -946,6 +1091,8 @@ lbc_status lbc_net_create_ex(const lbc_conv_desc* descs, const int32_t* input_of
 lbc_status lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan** plan)
 {
     LBC_REQUIRE(net && plan && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");
+    LBC_REQUIRE(net->layers[layer].kind == LBC_NODE_CONV, LBC_ERR_INVALID_ARG, "node %d is not a convolution (kind %d)", layer,
+                net->layers[layer].kind);
     *plan = net->layers[layer].plan;
     return LBC_OK;
 }
@@ -955,6 +1102,7 @@ lbc_status lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w_
 {
     LBC_REQUIRE(net && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");
     lbc_net::Layer& L = net->layers[layer];
+    LBC_REQUIRE(L.kind == LBC_NODE_CONV, LBC_ERR_INVALID_ARG, "node %d is not a convolution: it has no parameters", layer);
     const ConvGeom& g = L.plan->g;
     if (w_host) {
         const size_t raw = (size_t)g.d.k * g.d.r * g.d.s * g.cg;
@@ -981,7 +1129,7 @@ lbc_status lbc_net_set_input_host(lbc_net* net, int32_t layer, const int8_t* x_h
     LBC_REQUIRE(net && x_host && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad argument");
     lbc_net::Layer& L = net->layers[layer];
     LBC_REQUIRE(L.x_own, LBC_ERR_INVALID_ARG, "layer %d takes its input from layer %d, not from a resident buffer", layer, L.input_of);
-    LBC_CUDA_TRY(cudaMemcpy(L.x_own, x_host, in_bytes(L.plan->g), cudaMemcpyHostToDevice));
+    LBC_CUDA_TRY(cudaMemcpy(L.x_own, x_host, L.in_bytes(), cudaMemcpyHostToDevice));
     return LBC_OK;
 }
 
@@ -989,7 +1137,7 @@ lbc_status lbc_net_read_output_host(const lbc_net* net, int32_t layer, void* y_h
 {
     LBC_REQUIRE(net && y_host && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad argument");
     const lbc_net::Layer& L = net->layers[layer];
-    const size_t all = out_bytes(L.plan->g);
+    const size_t all = L.out_bytes();
     LBC_CUDA_TRY(cudaDeviceSynchronize());
     LBC_CUDA_TRY(cudaMemcpy(y_host, L.y, (max_bytes && max_bytes < all) ? max_bytes : all, cudaMemcpyDeviceToHost));
     return LBC_OK;
@@ -1030,10 +1178,10 @@ lbc_status lbc_net_run_host(lbc_net* net, const int8_t* x_host, void* y_host, lb
     lbc_net::Layer& last = net->layers[n - 1];
     LBC_REQUIRE(first.x_own, LBC_ERR_INVALID_ARG, "layer 0 must take the network input");
     LBC_CUDA_TRY(cudaEventRecord(net->events[0], s));
-    LBC_CUDA_TRY(cudaMemcpyAsync(first.x_own, x_host, in_bytes(first.plan->g), cudaMemcpyHostToDevice, s));
+    LBC_CUDA_TRY(cudaMemcpyAsync(first.x_own, x_host, first.in_bytes(), cudaMemcpyHostToDevice, s));
     lbc_status st = net_enqueue(net, nullptr, s, false);
     if (st != LBC_OK) return st;
-    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, last.y, out_bytes(last.plan->g), cudaMemcpyDeviceToHost, s));
+    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, last.y, last.out_bytes(), cudaMemcpyDeviceToHost, s));
     LBC_CUDA_TRY(cudaEventRecord(net->events[n], s));
     LBC_CUDA_TRY(cudaEventSynchronize(net->events[n]));
     if (total_ms) LBC_CUDA_TRY(cudaEventElapsedTime(total_ms, net->events[0], net->events[n]));
@@ -1051,7 +1199,7 @@ static lbc_status pipe_init(lbc_net* net)
     if (!pp.h2d) LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.h2d, cudaStreamNonBlocking));
     if (!pp.d2h) LBC_CUDA_TRY(cudaStreamCreateWithFlags(&pp.d2h, cudaStreamNonBlocking));
     pp.x_buf[0] = first.x_own;
-    if (!pp.x_buf[1] && cudaMalloc(&pp.x_buf[1], in_bytes(first.plan->g)) != cudaSuccess) {
+    if (!pp.x_buf[1] && cudaMalloc(&pp.x_buf[1], first.in_bytes()) != cudaSuccess) {
         cudaGetLastError();
         pp.x_buf[1] = nullptr;
         set_error("lbc_net_submit_host: cannot allocate the second input buffer");
@@ -1080,13 +1228,13 @@ lbc_status lbc_net_submit_host(lbc_net* net, const int8_t* x_host, void* y_host,
     // upload: the buffer is free once layer 0 of the step two submissions ago has run
     if (pp.submitted == 0) LBC_CUDA_TRY(cudaEventRecord(pp.t_first, pp.h2d));
     if (pp.submitted >= 2) LBC_CUDA_TRY(cudaStreamWaitEvent(pp.h2d, pp.x_used[b], 0));
-    LBC_CUDA_TRY(cudaMemcpyAsync(pp.x_buf[b], x_host, in_bytes(first.plan->g), cudaMemcpyHostToDevice, pp.h2d));
+    LBC_CUDA_TRY(cudaMemcpyAsync(pp.x_buf[b], x_host, first.in_bytes(), cudaMemcpyHostToDevice, pp.h2d));
     LBC_CUDA_TRY(cudaEventRecord(pp.up_done[b], pp.h2d));
     // compute: layer 0 waits for its upload; the last layer waits until the previous result has been downloaded
     LBC_CUDA_TRY(cudaStreamWaitEvent(s, pp.up_done[b], 0));
     for (int i = 0; i < n; ++i) {
-        const ResolvedLaunch* rl = &net->layers[i].rl;
-        if (i == 0) {
+        const ResolvedLaunch* rl = nullptr;
+        if (i == 0 && net->layers[0].kind == LBC_NODE_CONV) {
             // layer 0 alternates between the two input buffers: keep one encoded launch per buffer
             if (!net->first_rl_ok[b]) {
                 lbc_net::Layer& L = net->layers[0];
@@ -1102,14 +1250,14 @@ lbc_status lbc_net_submit_host(lbc_net* net, const int8_t* x_host, void* y_host,
             if (st != LBC_OK) return st;
         }
         if (i == n - 1 && pp.submitted >= 1) LBC_CUDA_TRY(cudaStreamWaitEvent(s, pp.d2h_done, 0));
-        st = launch(*rl, s);
+        st = net_launch_node(net, i, rl, i == 0 ? pp.x_buf[b] : nullptr, s);
         if (st != LBC_OK) return st;
         if (i == 0) LBC_CUDA_TRY(cudaEventRecord(pp.x_used[b], s));
     }
     LBC_CUDA_TRY(cudaEventRecord(pp.comp_done, s));
     // download
     LBC_CUDA_TRY(cudaStreamWaitEvent(pp.d2h, pp.comp_done, 0));
-    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, last.y, out_bytes(last.plan->g), cudaMemcpyDeviceToHost, pp.d2h));
+    LBC_CUDA_TRY(cudaMemcpyAsync(y_host, last.y, last.out_bytes(), cudaMemcpyDeviceToHost, pp.d2h));
     LBC_CUDA_TRY(cudaEventRecord(pp.d2h_done, pp.d2h));
     ++pp.submitted;
     return LBC_OK;
@@ -1139,7 +1287,7 @@ lbc_status lbc_net_launches(const lbc_net* net, int32_t* launches)
 {
     LBC_REQUIRE(net && launches, LBC_ERR_INVALID_ARG, "null argument");
     int32_t n = 0;
-    for (const auto& L : net->layers) n += (L.plan->kind == LBC_KERNEL_STEM_TC) ? 2 : 1;
+    for (const auto& L : net->layers) n += (L.kind == LBC_NODE_CONV && L.plan->kind == LBC_KERNEL_STEM_TC) ? 2 : 1;
     *launches = n;
     return LBC_OK;
 }

@@ -164,6 +164,11 @@ lbc_status launch_prepack_depthwise(const int8_t* src, int32_t src_layout, int8_
 lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,
                            cudaStream_t stream);
 
+// pool_add.cu — int8 ops between convolutions
+lbc_status launch_maxpool(const lbc_pool_desc& d, int32_t p, int32_t q, const int8_t* x, int8_t* y, int sm_count, cudaStream_t stream);
+lbc_status launch_add_relu(const int8_t* a, const int8_t* b, int8_t* y, size_t n, int32_t relu, int sm_count, cudaStream_t stream);
+lbc_status launch_global_avgpool(const int8_t* x, int8_t* y, int32_t n, int32_t hw, int32_t c, float scale, cudaStream_t stream);
+
 // probes.cu
 lbc_status probe_int8_mma_peak(int32_t iters, double* tops, cudaStream_t stream);
 lbc_status probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, cudaStream_t stream);

@@ -1422,7 +1422,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
             if (c.warp_store) can = can && c.bn == 256;                     // four 64-byte panels: one per (team, warp set)
             else can = can && (c.bn / c.panel_bytes) % 2 == 0;              // panels dealt alternately to the two teams
         }
-        bool want = true;
+        // Measured (r02, ResNet-50 N=512): a loss where the epilogue is the bound - the 1x1 channel expansions went from
+        // 105 to 150 us (64->256) and 62 to 82 us (128->512): with all 16 warps on one tile the per-tile fixed costs (waits,
+        // fences, store issue: ~1000 cycles) are no longer hidden behind the other team's drain, and each warp converts
+        // half as many columns per tile - and neutral (+-2%) on the MMA-bound layers.  Kept as an option, off by default.
+        bool want = false;
         if (o.epi_split >= 0) want = o.epi_split != 0;
         if (can && want) {
             c.epi_split = 1;
@@ -1490,7 +1494,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         int grid0 = std::min(dev.sm_count > 0 ? dev.sm_count : 148, c.tiles_m * c.tiles_n);
         if (o.max_grid > 0) grid0 = std::max(1, std::min(grid0, (int)o.max_grid));
         const int grid_ns = grid0 - grid0 % c.tiles_n;
-        if (!res_b_ok && !c.pair && !c.cta2 && c.tiles_n > 1 && one_tile <= 128u * 1024u && grid_ns >= c.tiles_n &&
+        // Measured (r02): -5% on 256->1024 @14x14 and 256->512 stride 2 (64 KB tiles); 128 KB tiles (512->1024, 512->2048)
+        // leave room for only three A stages and came out 0 to 7% slower, so the planner's own limit is 64 KB
+        // (n_stationary = 1 raises it to 128 KB for the tests).
+        const uint32_t one_limit = (o.n_stationary == 1 ? 128u : 64u) * 1024u;
+        if (!res_b_ok && !c.pair && !c.cta2 && c.tiles_n > 1 && one_tile <= one_limit && grid_ns >= c.tiles_n &&
             o.resident_filter != 0 && o.n_stationary != 0) {
             c.res_one = 1;
             c.b_total_bytes = one_tile;

@@ -6,6 +6,7 @@ import ctypes
 from . import _capi
 from ._capi import CConvDesc, check, load_library
 from .conv import ConvDesc, _ptr, _stream_ptr
+from .ops import AddDesc, PoolDesc
 
 
 class Net:
@@ -13,18 +14,37 @@ class Net:
         """layers: [(name, ConvDesc, input_name_or_None)]; options: lbc_plan_options fields applied to every layer"""
         self._lib = load_library()
         self.names = [l[0] for l in layers]
-        self.descs: list[ConvDesc] = [l[1] for l in layers]
+        self.descs = [l[1] for l in layers]           # ConvDesc, or PoolDesc / AddDesc in a graph network
         idx = {n: i for i, n in enumerate(self.names)}
-        self.input_of = [(-1 if l[2] is None else idx[l[2]]) for l in layers]
         n = len(layers)
-        arr = (CConvDesc * n)(*[d.c_struct() for d in self.descs])
-        inp = (ctypes.c_int32 * n)(*self.input_of)
         self._h = ctypes.c_void_p()
-        if options:
-            opt = _capi.plan_options(**options)
-            check(self._lib.lbc_net_create_ex(arr, inp, n, ctypes.byref(opt), ctypes.byref(self._h)))
-        else:
-            check(self._lib.lbc_net_create(arr, inp, n, ctypes.byref(self._h)))
+        opt = _capi.plan_options(**options) if options else None
+        if all(isinstance(d, ConvDesc) for d in self.descs):
+            self.input_of = [(-1 if l[2] is None else idx[l[2]]) for l in layers]
+            arr = (CConvDesc * n)(*[d.c_struct() for d in self.descs])
+            inp = (ctypes.c_int32 * n)(*self.input_of)
+            if opt is not None:
+                check(self._lib.lbc_net_create_ex(arr, inp, n, ctypes.byref(opt), ctypes.byref(self._h)))
+            else:
+                check(self._lib.lbc_net_create(arr, inp, n, ctypes.byref(self._h)))
+            return
+        # graph network: convolutions, max-pools and residual adds (an add names its two producers as a pair)
+        nodes = (_capi.CNode * n)()
+        self.input_of = []
+        for i, (_, d, src) in enumerate(layers):
+            nd = nodes[i]
+            nd.input2_of = -1
+            if isinstance(d, AddDesc):
+                a, b = src
+                nd.kind, nd.input_of, nd.input2_of, nd.relu = _capi.NODE_ADD, idx[a], idx[b], d.relu
+            else:
+                nd.input_of = -1 if src is None else idx[src]
+                if isinstance(d, PoolDesc):
+                    nd.kind, nd.pool = _capi.NODE_MAXPOOL, d.c_struct()
+                else:
+                    nd.kind, nd.conv = _capi.NODE_CONV, d.c_struct()
+            self.input_of.append(nd.input_of)
+        check(self._lib.lbc_net_create_graph(nodes, n, ctypes.byref(opt) if opt is not None else None, ctypes.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -62,7 +82,8 @@ class Net:
         d = self.descs[layer]
         p, q = d.out_hw
         n = d.n if images is None else min(images, d.n)
-        out = np.empty((n, p, q, d.k), dtype=np.int8 if d.out_mode == _capi.OUT_INT8 else np.int32)
+        k = d.k if isinstance(d, ConvDesc) else d.c
+        out = np.empty((n, p, q, k), dtype=np.int32 if getattr(d, "out_mode", _capi.OUT_INT8) == _capi.OUT_INT32 else np.int8)
         check(self._lib.lbc_net_read_output_host(self._h, layer, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
         return out
 
@@ -70,6 +91,10 @@ class Net:
         check(self._lib.lbc_net_check(self._h))
 
     def layer_kernel(self, layer: int) -> str:
+        if isinstance(self.descs[layer], PoolDesc):
+            return "maxpool"
+        if isinstance(self.descs[layer], AddDesc):
+            return "add_relu"
         plan = ctypes.c_void_p()
         check(self._lib.lbc_net_layer_plan(self._h, layer, ctypes.byref(plan)))
         k = ctypes.c_int32()
@@ -77,6 +102,8 @@ class Net:
         return _capi.KERNEL_NAMES[k.value]
 
     def layer_describe(self, layer: int) -> str:
+        if not isinstance(self.descs[layer], ConvDesc):
+            return f"{self.layer_kernel(layer)} {self.descs[layer]}"
         plan = ctypes.c_void_p()
         check(self._lib.lbc_net_layer_plan(self._h, layer, ctypes.byref(plan)))
         buf = ctypes.create_string_buffer(512)

@@ -8,6 +8,7 @@ torchvision topologies; ResNet-50 is v1.5 (stride on the 3x3).  All convs: bias 
 from __future__ import annotations
 
 from .conv import ConvDesc
+from .ops import AddDesc, PoolDesc
 
 
 def _cd(n, h, c, k, r, stride=1, pad=None, groups=1, relu=1):
@@ -93,20 +94,85 @@ def mobilenet_v2(n=1024):
     return L
 
 
+def resnet50_full(n=32):
+    """ResNet-50 as ONE int8 graph: conv1 -> 3x3/2 max-pool -> 16 bottlenecks whose residual joins are saturating int8
+    adds + ReLU (conv3 and the downsample convolutions requantise without ReLU, as in the torchvision topology).
+    Entries: (name, ConvDesc | PoolDesc | AddDesc, input name | (a, b) for an add)."""
+    L = [("conv1", _cd(n, 224, 3, 64, 7, stride=2, pad=3), None),
+         ("maxpool", PoolDesc(n, 112, 112, 64, 3, 3, 2, 2, 1, 1), "conv1")]
+    h, cin, prev = 56, 64, "maxpool"
+    for stage, (mid, blocks) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        out = mid * 4
+        for b in range(blocks):
+            stride = 2 if (b == 0 and stage > 1) else 1
+            pre = f"l{stage}.{b}"
+            L.append((pre + ".conv1", _cd(n, h, cin, mid, 1), prev))
+            L.append((pre + ".conv2", _cd(n, h, mid, mid, 3, stride=stride), pre + ".conv1"))
+            h2 = h // stride
+            L.append((pre + ".conv3", _cd(n, h2, mid, out, 1, relu=0), pre + ".conv2"))
+            identity = prev
+            if b == 0:
+                L.append((pre + ".downsample", _cd(n, h, cin, out, 1, stride=stride, relu=0), prev))
+                identity = pre + ".downsample"
+            L.append((pre + ".add", AddDesc(n, h2, h2, out, relu=1), (pre + ".conv3", identity)))
+            prev, h, cin = pre + ".add", h2, out
+    return L
+
+
+def resnet18_full(n=32):
+    L = [("conv1", _cd(n, 224, 3, 64, 7, stride=2, pad=3), None),
+         ("maxpool", PoolDesc(n, 112, 112, 64, 3, 3, 2, 2, 1, 1), "conv1")]
+    h, cin, prev = 56, 64, "maxpool"
+    for stage, ch in enumerate((64, 128, 256, 512), start=1):
+        for b in range(2):
+            stride = 2 if (b == 0 and stage > 1) else 1
+            pre = f"l{stage}.{b}"
+            L.append((pre + ".conv1", _cd(n, h, cin, ch, 3, stride=stride), prev))
+            h2 = h // stride
+            L.append((pre + ".conv2", _cd(n, h2, ch, ch, 3, relu=0), pre + ".conv1"))
+            identity = prev
+            if b == 0 and stage > 1:
+                L.append((pre + ".downsample", _cd(n, h, cin, ch, 1, stride=stride, relu=0), prev))
+                identity = pre + ".downsample"
+            L.append((pre + ".add", AddDesc(n, h2, h2, ch, relu=1), (pre + ".conv2", identity)))
+            prev, h, cin = pre + ".add", h2, ch
+    return L
+
+
+def vgg16_full(n=16):
+    """VGG-16's convolutional part with its 2x2/2 max-pools between the blocks."""
+    cfg = [(64, 2, 224), (128, 2, 112), (256, 3, 56), (512, 3, 28), (512, 3, 14)]
+    L, cin, prev = [], 3, None
+    for bi, (ch, reps, h) in enumerate(cfg, start=1):
+        for r in range(reps):
+            name = f"conv{bi}_{r + 1}"
+            L.append((name, _cd(n, h, cin, ch, 3), prev))
+            prev, cin = name, ch
+        L.append((f"pool{bi}", PoolDesc(n, h, h, ch, 2, 2, 2, 2, 0, 0), prev))
+        prev = f"pool{bi}"
+    return L
+
+
 NETWORKS = {
     "single_3x3": single_3x3,
     "resnet18": resnet18,
     "resnet50": resnet50,
     "vgg16": vgg16,
     "mobilenet_v2": mobilenet_v2,
+    "resnet50_full": resnet50_full,
+    "resnet18_full": resnet18_full,
+    "vgg16_full": vgg16_full,
 }
-DEFAULT_BATCH = {"single_3x3": 1, "resnet18": 256, "resnet50": 512, "vgg16": 128, "mobilenet_v2": 1024}
+DEFAULT_BATCH = {"single_3x3": 1, "resnet18": 256, "resnet50": 512, "vgg16": 128, "mobilenet_v2": 1024,
+                 "resnet50_full": 512, "resnet18_full": 256, "vgg16_full": 128}
 
 
 def total_work(layers):
     """(GMAC, algorithmic GB) over a layer list, host arithmetic only."""
     macs = byts = 0
     for _, d, _ in layers:
+        if not isinstance(d, ConvDesc):
+            continue
         p = (d.h + 2 * d.pad_h - (d.dil_h * (d.r - 1) + 1)) // d.stride_h + 1
         q = (d.w + 2 * d.pad_w - (d.dil_w * (d.s - 1) + 1)) // d.stride_w + 1
         cg = d.c // d.groups

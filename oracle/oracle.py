@@ -288,3 +288,36 @@ def synth(d: ConvDesc, layer: int = 0, style: str = "full"):
     bias = rw.integers(-2**15, 2**15, size=(d.k,), dtype=np.int32)
     scale = (rw.uniform(0.5, 2.0, size=(d.k,)) * 2.0**-7 / np.sqrt(d.r * d.s * cg)).astype(np.float32)
     return x, w, bias, scale
+
+
+# ---------------------------------------------------------------------------------------------------
+# int8 ops between convolutions (restated in numpy; integer arithmetic, so there is one right answer)
+# ---------------------------------------------------------------------------------------------------
+def pool_out_dim(i: int, pad: int, k: int, stride: int) -> int:
+    """cudnnGetPooling2dForwardOutputDim as the reference uses it (python/qtorch/cpp/pool2d.cuh:76-78)."""
+    return 1 + (i + 2 * pad - k) // stride
+
+
+def max_pool_nhwc(x: np.ndarray, kh: int, kw: int, sh: int, sw: int, ph: int, pw: int) -> np.ndarray:
+    """int8 NHWC max-pool, padding never wins (cuDNN CUDNN_POOLING_MAX_DETERMINISTIC, pool2d.cuh:40-43)."""
+    n, h, w, c = x.shape
+    p, q = pool_out_dim(h, ph, kh, sh), pool_out_dim(w, pw, kw, sw)
+    xp = np.full((n, h + 2 * ph + sh, w + 2 * pw + sw, c), -128, dtype=np.int8)
+    xp[:, ph:ph + h, pw:pw + w, :] = x
+    out = np.full((n, p, q, c), -128, dtype=np.int8)
+    for a in range(kh):
+        for b in range(kw):
+            out = np.maximum(out, xp[:, a:a + (p - 1) * sh + 1:sh, b:b + (q - 1) * sw + 1:sw, :])
+    return out
+
+
+def add_relu(a: np.ndarray, b: np.ndarray, relu: bool) -> np.ndarray:
+    """Residual join: exact int sum, saturated to int8 (the quantizer's saturation: WinogradFused.cuh:39-46), ReLU."""
+    s = a.astype(np.int32) + b.astype(np.int32)
+    return np.clip(s, 0 if relu else -128, 127).astype(np.int8)
+
+
+def global_avg_pool(x: np.ndarray, scale: float) -> np.ndarray:
+    """[N,H,W,C] int8 -> [N,C] int8 through the convolutions' requantisation rule with one scale."""
+    t = x.astype(np.int32).sum(axis=(1, 2), dtype=np.int32)
+    return np_requant(t, np.full((x.shape[3],), scale, dtype=np.float32), relu=False)

@@ -252,17 +252,19 @@ def test_igemm_n_stationary_filter_tiles(d):
     grids that cannot be N-stationary at all (fewer CTAs than N tiles -> the planner must stream)."""
     import lowbitdnn_project_b200 as lbc
     from tests.parity_util import lbc_desc
-    plan = lbc.ConvPlan(lbc_desc(D(**{**d.__dict__, "out_mode": 0})))
+    ns = {"n_stationary": 1}     # (forced: on its own the planner keeps tiles of up to 64 KB, the option allows 128 KB)
+    plan = lbc.ConvPlan(lbc_desc(D(**{**d.__dict__, "out_mode": 0})), options=ns)
     assert "n-stationary" in plan.describe(), plan.describe()
     plan.close()
     tiles_n = -(-d.k // 256)
     for opts in ({}, {"n_stationary": 0}, {"fold_bias": 0}, {"fold_bias": 1}, {"max_grid": tiles_n}, {"max_grid": 2 * tiles_n + 1},
-                 {"max_grid": tiles_n - 1}, {"max_grid": 3 * tiles_n, "reverse": 1}, {"epi_split": 0, "max_grid": 2 * tiles_n},
+                 {"max_grid": tiles_n - 1}, {"max_grid": 3 * tiles_n, "reverse": 1}, {"epi_split": 1, "max_grid": 2 * tiles_n},
                  {"warp_store": 1, "max_grid": 2 * tiles_n}, {"warp_store": 0}):
-        assert _check(D(**{**d.__dict__, "out_mode": 0}), options=opts or None) == "igemm_tc", opts
+        assert _check(D(**{**d.__dict__, "out_mode": 0}), options={**ns, **opts}) == "igemm_tc", opts
+    assert _check(D(**{**d.__dict__, "out_mode": 0})) == "igemm_tc"            # the planner's own choice
     for opts in ({}, {"max_grid": 2 * tiles_n}):
-        assert _check(D(**{**d.__dict__, "out_mode": 1}), options=opts or None) == "igemm_tc", opts
-    assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000, options={"fold_bias": 1}) == "igemm_tc"
+        assert _check(D(**{**d.__dict__, "out_mode": 1}), options={**ns, **opts}) == "igemm_tc", opts
+    assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000, options={**ns, "fold_bias": 1}) == "igemm_tc"
 
 
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------

@@ -156,3 +156,25 @@ def test_out_dim_formula():
     assert oracle.out_dim(56, 1, 1, 3, 1) == 56
     assert oracle.out_dim(56, 0, 1, 1, 2) == 28
     assert oracle.out_dim(130, 0, 1, 3, 1) == 128  # check.cu:31-41
+
+
+def test_pool_and_add_restatements_against_torch_cpu():
+    """The numpy max-pool / residual-add restatements against an independent implementation (torch on the CPU, fp32 is
+    exact for int8 values): window, stride and padding combinations incl. the reference's own (python/tmp.py:43-56)."""
+    import torch
+    rng = np.random.default_rng(21)
+    for (h, w, c, k, s, p) in [(12, 12, 8, 2, 2, 0), (9, 11, 5, 3, 1, 0), (14, 14, 16, 3, 2, 1), (7, 7, 4, (3, 2), (2, 1), (1, 0))]:
+        pair = lambda v: (v, v) if isinstance(v, int) else v
+        (kh, kw), (sh, sw), (ph, pw) = pair(k), pair(s), pair(p)
+        x = rng.integers(-128, 128, size=(2, h, w, c), dtype=np.int8)
+        want = torch.nn.functional.max_pool2d(torch.from_numpy(x).permute(0, 3, 1, 2).float(), (kh, kw), (sh, sw), (ph, pw))
+        got = oracle.max_pool_nhwc(x, kh, kw, sh, sw, ph, pw)
+        assert np.array_equal(got, want.permute(0, 2, 3, 1).numpy().astype(np.int8))
+    a = rng.integers(-128, 128, size=(1000,), dtype=np.int8)
+    b = rng.integers(-128, 128, size=(1000,), dtype=np.int8)
+    for relu in (False, True):
+        want = [min(127, max(0 if relu else -128, int(u) + int(v))) for u, v in zip(a, b)]
+        assert oracle.add_relu(a, b, relu).tolist() == want
+    x = rng.integers(-128, 128, size=(2, 3, 5, 7), dtype=np.int8)
+    want = np.rint(np.clip(x.astype(np.int64).sum(axis=(1, 2)).astype(np.float32) * np.float32(0.07), -128, 127)).astype(np.int8)
+    assert np.array_equal(oracle.global_avg_pool(x, 0.07), want)
