@@ -234,6 +234,25 @@ lbc_status  lbc_nchw_to_nhwc(const void* src, void* dst, int32_t n, int32_t c, i
 lbc_status  lbc_nhwc_to_nchw(const void* src, void* dst, int32_t n, int32_t c, int32_t h, int32_t w,
                              int32_t elt_bytes, lbc_stream stream);
 
+/* ---- backward passes as int8 convolutions ------------------------------------------------------ */
+/* The reference computes both gradients of its QConv2D with the SAME int8 forward convolution on re-laid operands
+ * (python/qtorch/nn/functional/qconv2d.py:90-114; the dp4a drafts cpp/int8conv/conv2DBackwardData3x3.cuh:61-64,126-127 and
+ * conv2DBackwardWeights3x3.cuh:15-100 state the same sums).  These helpers derive the descriptors and operand layouts so
+ * that lbc_conv_plan_create / lbc_conv_run (LBC_OUT_INT32) produce the exact int32 gradients.  Stride 1, dilation 1,
+ * groups 1, padding <= filter - 1, as in the reference (qconv2d.py:84-88).
+ *   data gradient    dx[n,h,w,c] = sum_{k,r,s} dy[n,h+pad-r,w+pad-s,k] * w[k,r,s,c]
+ *                    = conv(dy as input [N,P,Q,K], filter w'[c][r'][s'][k] = w[k][R-1-r'][S-1-s'][c], padding R-1-pad)
+ *   weight gradient  dw[k,r,s,c] = sum_{n,p,q} dy[n,p,q,k] * x[n,p-pad+r,q-pad+s,c]
+ *                    = conv(x^T as input [C,H,W,N], filter dy^T [K][P][Q][N], padding pad) -> int32 [C][R][S][K];
+ *                    lbc_nhwc_to_chwn turns it into [K][R][S][C]. */
+lbc_status  lbc_conv_dgrad_desc(const lbc_conv_desc* fwd, lbc_conv_desc* dgrad);
+lbc_status  lbc_conv_wgrad_desc(const lbc_conv_desc* fwd, lbc_conv_desc* wgrad);
+/* w [K][R][S][C] (device) -> the data-gradient filter [C][R][S][K], rotated by 180 degrees. */
+lbc_status  lbc_conv_dgrad_weights(const lbc_conv_desc* fwd, const int8_t* w_krsc, int8_t* w_dgrad, lbc_stream stream);
+/* [N][H][W][C] -> [C][H][W][N] (elt_bytes 1 or 4): the operand transposes of the weight gradient, and its result. */
+lbc_status  lbc_nhwc_to_chwn(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, int32_t elt_bytes,
+                             lbc_stream stream);
+
 /* ---- networks: a list of convolutions run back to back (benchmark apps) ------------------------ */
 /* `input_of[i]` = index of the layer whose OUTPUT feeds layer i, or -1 for the network input.  The
  * network owns its packed weights, bias, scale and activation buffers (synthetic or caller-loaded). */

@@ -95,6 +95,10 @@ _PROTOS = {
     "lbc_vect_c_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i32] * 6 + [_vp]),
     "lbc_nchw_to_nhwc": (ctypes.c_int, [_vp, _vp] + [_i32] * 5 + [_vp]),
     "lbc_nhwc_to_nchw": (ctypes.c_int, [_vp, _vp] + [_i32] * 5 + [_vp]),
+    "lbc_conv_dgrad_desc": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(CConvDesc)]),
+    "lbc_conv_wgrad_desc": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(CConvDesc)]),
+    "lbc_conv_dgrad_weights": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _vp, _vp, _vp]),
+    "lbc_nhwc_to_chwn": (ctypes.c_int, [_vp, _vp] + [_i32] * 5 + [_vp]),
     "lbc_conv_plan_dry": (ctypes.c_int, [ctypes.POINTER(CConvDesc), _i32, _i32, ctypes.POINTER(_i32), ctypes.c_char_p, ctypes.c_size_t]),
     "lbc_net_create": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), _i32, ctypes.POINTER(_vp)]),
     "lbc_net_create_ex": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(_i32), _i32, ctypes.POINTER(CPlanOptions),

@@ -227,3 +227,47 @@ def conv2DForward3x3(rinput, rkernel):
     torch.cuda.current_stream().synchronize()
     plan.close()
     return out, ms
+
+
+# ---- backward passes as int8 convolutions (qconv2d.py:90-114) ----------------------------------------------
+def _desc_from_c(cd: CConvDesc) -> ConvDesc:
+    return ConvDesc(**{n: getattr(cd, n) for n, _ in CConvDesc._fields_})
+
+
+def conv_backward_data(desc: ConvDesc, dy, w_krsc, stream=None):
+    """dx (int32 NHWC [N,H,W,C]) of `desc` for dy int8 NHWC [N,P,Q,K] and the forward filter w int8 [K,R,S,C]: the forward
+    engine on the 180-degree-rotated, transposed filter with padding R-1-pad (conv2DBackwardData3x3.cuh:61-64,126-127)."""
+    import torch
+    lib = load_library()
+    fwd, dg = desc.c_struct(), CConvDesc()
+    check(lib.lbc_conv_dgrad_desc(ctypes.byref(fwd), ctypes.byref(dg)))
+    assert dy.is_cuda and dy.dtype == torch.int8 and dy.is_contiguous() and tuple(dy.shape) == (dg.n, dg.h, dg.w, dg.c)
+    assert w_krsc.is_cuda and w_krsc.dtype == torch.int8 and w_krsc.is_contiguous()
+    w2 = torch.empty(desc.c * desc.r * desc.s * desc.k, dtype=torch.int8, device=dy.device)
+    check(lib.lbc_conv_dgrad_weights(ctypes.byref(fwd), _ptr(w_krsc), _ptr(w2), _stream_ptr(stream)))
+    plan = ConvPlan(_desc_from_c(dg))
+    dx = plan.run(dy, plan.prepack(w2, _capi.W_KRSC, stream=stream), stream=stream)
+    plan.close()
+    return dx
+
+
+def conv_backward_weights(desc: ConvDesc, x, dy, stream=None):
+    """dw (int32 [K,R,S,C]) of `desc` for x int8 NHWC and dy int8 NHWC [N,P,Q,K]: a convolution over the batch - x^T
+    [C,H,W,N] as the input, dy^T [K,P,Q,N] as a P x Q filter (qconv2d.py:96-103; conv2DBackwardWeights3x3.cuh:15-100)."""
+    import torch
+    lib = load_library()
+    fwd, wg = desc.c_struct(), CConvDesc()
+    check(lib.lbc_conv_wgrad_desc(ctypes.byref(fwd), ctypes.byref(wg)))
+    p, q = desc.out_hw
+    assert x.is_cuda and x.dtype == torch.int8 and x.is_contiguous() and tuple(x.shape) == (desc.n, desc.h, desc.w, desc.c)
+    assert dy.is_cuda and dy.dtype == torch.int8 and dy.is_contiguous() and tuple(dy.shape) == (desc.n, p, q, desc.k)
+    xt = torch.empty((desc.c, desc.h, desc.w, desc.n), dtype=torch.int8, device=x.device)
+    dyt = torch.empty((desc.k, p, q, desc.n), dtype=torch.int8, device=x.device)
+    check(lib.lbc_nhwc_to_chwn(_ptr(x), _ptr(xt), desc.n, desc.h, desc.w, desc.c, 1, _stream_ptr(stream)))
+    check(lib.lbc_nhwc_to_chwn(_ptr(dy), _ptr(dyt), desc.n, p, q, desc.k, 1, _stream_ptr(stream)))
+    plan = ConvPlan(_desc_from_c(wg))
+    dw_crsk = plan.run(xt, plan.prepack(dyt.reshape(-1), _capi.W_KRSC, stream=stream), stream=stream)     # [C][R][S][K]
+    plan.close()
+    dw = torch.empty((desc.k, desc.r, desc.s, desc.c), dtype=torch.int32, device=x.device)
+    check(lib.lbc_nhwc_to_chwn(_ptr(dw_crsk), _ptr(dw), desc.c, desc.r, desc.s, desc.k, 4, _stream_ptr(stream)))
+    return dw

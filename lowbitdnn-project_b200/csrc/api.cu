@@ -781,6 +781,65 @@ lbc_status lbc_nhwc_to_nchw(const void* src, void* dst, int32_t n, int32_t c, in
     return permute_checked(src, dst, n, h, w, c, 1, 0, 3, 1, 2, 4, elt, stream);
 }
 
+// ---- backward passes as int8 convolutions --------------------------------------------------------------
+static lbc_status backward_geom(const lbc_conv_desc* fwd, ConvGeom* g)
+{
+    lbc_status st = make_geom(fwd, g);
+    if (st != LBC_OK) return st;
+    const lbc_conv_desc& d = *fwd;
+    LBC_REQUIRE(d.stride_h == 1 && d.stride_w == 1 && d.dil_h == 1 && d.dil_w == 1 && d.groups == 1, LBC_ERR_UNSUPPORTED,
+                "backward convolutions need stride 1, dilation 1, groups 1 (as the reference: qconv2d.py:84-88)");
+    LBC_REQUIRE(d.pad_h <= d.r - 1 && d.pad_w <= d.s - 1, LBC_ERR_UNSUPPORTED, "backward convolutions need padding <= filter - 1");
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_dgrad_desc(const lbc_conv_desc* fwd, lbc_conv_desc* dg)
+{
+    LBC_REQUIRE(fwd && dg, LBC_ERR_INVALID_ARG, "null descriptor");
+    ConvGeom g;
+    lbc_status st = backward_geom(fwd, &g);
+    if (st != LBC_OK) return st;
+    *dg = *fwd;
+    dg->h = g.p; dg->w = g.q; dg->c = fwd->k; dg->k = fwd->c;
+    dg->pad_h = fwd->r - 1 - fwd->pad_h;
+    dg->pad_w = fwd->s - 1 - fwd->pad_w;
+    dg->relu = 0;
+    dg->out_mode = LBC_OUT_INT32;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_wgrad_desc(const lbc_conv_desc* fwd, lbc_conv_desc* wg)
+{
+    LBC_REQUIRE(fwd && wg, LBC_ERR_INVALID_ARG, "null descriptor");
+    ConvGeom g;
+    lbc_status st = backward_geom(fwd, &g);
+    if (st != LBC_OK) return st;
+    *wg = *fwd;
+    wg->n = fwd->c; wg->c = fwd->n; wg->k = fwd->k;     // "images" = input channels, channels = batch
+    wg->r = g.p; wg->s = g.q;                           // the filter is dy: P x Q taps
+    wg->relu = 0;
+    wg->out_mode = LBC_OUT_INT32;
+    return LBC_OK;
+}
+
+lbc_status lbc_conv_dgrad_weights(const lbc_conv_desc* fwd, const int8_t* w_krsc, int8_t* w_dgrad, lbc_stream stream)
+{
+    LBC_REQUIRE(fwd && w_krsc && w_dgrad, LBC_ERR_INVALID_ARG, "null argument");
+    ConvGeom g;
+    lbc_status st = backward_geom(fwd, &g);
+    if (st != LBC_OK) return st;
+    DeviceInfo dev;
+    st = current_device(&dev);
+    if (st != LBC_OK) return st;
+    return launch_dgrad_weights(w_krsc, w_dgrad, fwd->k, fwd->r, fwd->s, fwd->c, (cudaStream_t)stream);
+}
+
+lbc_status lbc_nhwc_to_chwn(const void* src, void* dst, int32_t n, int32_t h, int32_t w, int32_t c, int32_t elt, lbc_stream stream)
+{
+    LBC_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, LBC_ERR_INVALID_ARG, "bad extents");
+    return permute_checked(src, dst, n, h, w, c, 1, 3, 1, 2, 0, 4, elt, stream);
+}
+
 // ---- probes ------------------------------------------------------------------------------------------
 lbc_status lbc_probe_int8_mma_peak(int32_t iters, double* tops, lbc_stream stream)
 {

@@ -161,6 +161,7 @@ lbc_status launch_prepack_stem(const int8_t* src, int32_t src_layout, int8_t* ds
 lbc_status launch_blockdiag(const int8_t* src, int8_t* dst, int32_t k, int32_t c, int32_t f, cudaStream_t stream);
 lbc_status launch_prepack_depthwise(const int8_t* src, int32_t src_layout, int8_t* dst, int32_t c, int32_t r,
                                     int32_t s, cudaStream_t stream);                         // -> [R][S][C]
+lbc_status launch_dgrad_weights(const int8_t* src, int8_t* dst, int32_t k, int32_t r, int32_t s, int32_t c, cudaStream_t stream);
 lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,
                            cudaStream_t stream);
 

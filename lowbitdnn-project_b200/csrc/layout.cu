@@ -281,6 +281,28 @@ lbc_status launch_prepack_depthwise(const int8_t* src, int32_t /*src_layout*/, i
 }
 
 // dst dim j takes source dim perm[j]; `dims` are the SOURCE extents.
+// dst [C][R][S][K] <- src [K][R][S][C] rotated by 180 degrees in (R, S): the filter of the data-gradient convolution
+__global__ void __launch_bounds__(256) dgrad_weights_kernel(const int8_t* __restrict__ src, int8_t* __restrict__ dst, int32_t k,
+                                                            int32_t r, int32_t s, int32_t c)
+{
+    const int64_t total = (int64_t)k * r * s * c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t ik = (int32_t)(i % k);
+        int64_t t = i / k;
+        const int32_t is = (int32_t)(t % s); t /= s;
+        const int32_t ir = (int32_t)(t % r); t /= r;
+        const int32_t ic = (int32_t)t;
+        dst[i] = src[(((int64_t)ik * r + (r - 1 - ir)) * s + (s - 1 - is)) * c + ic];
+    }
+}
+
+lbc_status launch_dgrad_weights(const int8_t* src, int8_t* dst, int32_t k, int32_t r, int32_t s, int32_t c, cudaStream_t stream)
+{
+    dgrad_weights_kernel<<<grid_for((int64_t)k * r * s * c), 256, 0, stream>>>(src, dst, k, r, s, c);
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
+
 lbc_status launch_permute5(const void* src, void* dst, const int32_t dims[5], const int32_t perm[5], int32_t elt,
                            cudaStream_t stream)
 {
