@@ -20,6 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "liblowbit_cnn.so")
+LIB_TRACE = os.path.join(LIBDIR, "liblowbit_cnn_trace.so")     # same sources, igemm_tc.cu with -DLBC_TRACE=1 (tools/trace_layer.py)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
@@ -43,9 +44,9 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def _compile(src: str, verbose: bool) -> str:
-    obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-    cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+def _compile(src: str, verbose: bool, defines: tuple = (), suffix: str = "") -> str:
+    obj = os.path.join(OBJDIR, src.replace(".cu", suffix + ".o"))
+    cmd = [NVCC, *FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -62,14 +63,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     stamp_file = os.path.join(OBJDIR, "stamp")
     stamp = _stamp()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+    if not force and os.path.exists(LIB) and os.path.exists(LIB_TRACE) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return LIB
-    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES) + 1) as ex:
+        trace_obj = ex.submit(_compile, "igemm_tc.cu", False, ("-DLBC_TRACE=1",), "_trace")
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [NVCC, "-shared", "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        trace_obj = trace_obj.result()
+    for out, these in ((LIB, objs), (LIB_TRACE, [trace_obj if o.endswith("igemm_tc.o") else o for o in objs])):
+        cmd = [NVCC, "-shared", "-ccbin", HOSTCXX, "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *these]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp_file, "w") as fh:
         fh.write(stamp)
     return LIB

@@ -524,6 +524,8 @@ lbc_status lbc_conv_plan_destroy(lbc_plan* plan)
 lbc_status lbc_conv_plan_set_trace(lbc_plan* plan, void* device_buf, int32_t tiles)
 {
     LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan");
+    LBC_REQUIRE(!device_buf || igemm_trace_compiled(), LBC_ERR_UNSUPPORTED,
+                "pipeline tracing is compiled out of this build: load lib/liblowbit_cnn_trace.so (built with -DLBC_TRACE=1)");
     plan->trace = device_buf ? reinterpret_cast<long long*>(device_buf) : nullptr;
     plan->trace_tiles = device_buf ? tiles : 0;
     return LBC_OK;
@@ -551,12 +553,12 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
         static const char* modes[] = {"tiled", "im2col", "window"};
         snprintf(buf, buf_len,
                  "%s N%d %dx%dx%d->%d %dx%d s%d p%d | M=%lld tile 128x%d kchunk %dB x%d kblocks stages %dx%d+%dw b=%s "
-                 "a=%s(%dx%d px/tile) tiles %dx%d grid %d smem %zu tmem %u epi=%s",
+                 "a=%s(%dx%d px/tile) tiles %dx%d grid %d smem %zu tmem %u sbufs %d epi=%s",
                  plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : plan->pw_factor > 1 ? "igemm_tc(pixel-groups)" : "igemm_tc",
                  d.n, d.h, d.w, d.c, d.k, d.r, d.s,
                  d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.tps, c.win_stages,
                  c.res_b ? (c.res_one ? "resident,n-stationary" : c.n_mma == 2 ? "resident,2mma" : "resident") : c.pair ? "ring,paired-tiles" : c.cta2 ? "ring,cta-pair" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
-                 c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols,
+                 c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols, c.stage_bufs,
                  d.out_mode != LBC_OUT_INT8 ? (c.fold ? "int32,bias-in-mma" : "int32")
                  : c.warp_store ? (c.epi_split ? (c.fold ? "warp-stores,split,bias-in-mma" : "warp-stores,split")
                                                : (c.fold ? "warp-stores,bias-in-mma" : "warp-stores"))

@@ -136,6 +136,7 @@ struct IgemmLaunch {
     int32_t reverse = 0;   // walk the M tiles / images last-to-first (L2 reuse of the producer's most recent output)
 };
 bool igemm_supported(const ConvGeom& g, std::string* why);
+bool igemm_trace_compiled();      // the library was built with -DLBC_TRACE=1 (lib/liblowbit_cnn_trace.so)
 lbc_status igemm_make_config(const ConvGeom& g, const DeviceInfo& dev, const lbc_plan_options& opt, IgemmConfig* cfg);
 lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceInfo& dev, const int8_t* x,
                         const int8_t* w_packed, void* y, IgemmLaunch* out);

@@ -63,6 +63,13 @@ namespace {
 #define LBC_EPI_F32X2 1
 #endif
 
+// Pipeline tracing (clock64 stamps of CTA 0, see lbc_conv_plan_set_trace) is compiled in only with -DLBC_TRACE=1
+// (lib/liblowbit_cnn_trace.so, used by tools/trace_layer.py): the three stamps per epilogue tile were ~30 of the ~220
+// instructions a warp spends per tile outside its conversion loop (ncu source counters, r02).
+#ifndef LBC_TRACE
+#define LBC_TRACE 0
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kEpiWarps = 16;                          // epilogue warps: 2 teams of 8 or 4 teams of 4
 constexpr int kFirstEpiWarp = 4;                       // warp 0: ring TMA, 1: MMA (even tiles) + TMEM alloc, 2: window TMA, 3: MMA (odd tiles)
@@ -187,6 +194,10 @@ struct Ctl {
 
 // Persistent tile walk without divisions in the loop: the digits are decoded once (init) and then advanced by the
 // digits of gridDim.x with carries (next).  In the ring modes it_cols == it_rows == 1 and `img` is the M-tile index.
+// W: window modes (tiles are (image, row tile, column tile)); ring modes have it_cols == it_rows == 1, so their digits
+// and carries vanish at compile time.  `nm` (N-tile-major numbering: CTA pairs / paired tiles) is a run-time flag only
+// where the kernel variant can have both numberings.
+template <bool W>
 struct TileIter {
     int32_t tile, n_blk, ct, rt, img, local;
     // loop constants, copied into registers once: the producer roles are single warps whose per-tile instruction count
@@ -194,9 +205,10 @@ struct TileIter {
     int32_t stride, tiles_n, cols, rows, imgs, s_nb, s_ct, s_rt, s_img, rpt, cpt, rev_m;
     bool pair;
     // team_steps: advance by an epilogue team's stride (n_teams tiles of the CTA's sequence) per next()
-    __device__ __forceinline__ void init(const IgemmParams& prm, int32_t t0, bool team_steps = false)
+    __device__ __forceinline__ void init(const IgemmParams& prm, int32_t t0, bool nm, bool team_steps = false)
     {
-        stride = prm.tile_stride; tiles_n = prm.tiles_n; cols = prm.it_cols; rows = prm.it_rows; imgs = prm.it_imgs;
+        stride = prm.tile_stride; tiles_n = prm.tiles_n; imgs = prm.it_imgs;
+        cols = W ? prm.it_cols : 1; rows = W ? prm.it_rows : 1;
         s_nb = prm.step_nb; s_ct = prm.step_ct; s_rt = prm.step_rt; s_img = prm.step_img;
         if (team_steps) {
             stride = prm.team_stride;
@@ -204,7 +216,7 @@ struct TileIter {
         }
         rpt = prm.rows_per_tile; cpt = prm.cols_per_tile;
         rev_m = prm.rev_m;
-        pair = prm.n_major != 0;
+        pair = nm;
         tile = t0;
         local = 0;
         int32_t mt;
@@ -216,29 +228,38 @@ struct TileIter {
             n_blk = t0 % tiles_n;
             mt = t0 / tiles_n;
         }
-        ct = mt % cols;
-        rt = (mt / cols) % rows;
-        img = mt / (cols * rows);
+        if (W) {
+            ct = mt % cols;
+            rt = (mt / cols) % rows;
+            img = mt / (cols * rows);
+        } else {
+            ct = rt = 0;
+            img = mt;
+        }
     }
     __device__ __forceinline__ void next(const IgemmParams&)
     {
         tile += stride;
         ++local;
         if (pair) {
-            ct += s_ct;
-            if (ct >= cols) { ct -= cols; ++rt; }
-            rt += s_rt;
-            if (rt >= rows) { rt -= rows; ++img; }
+            if (W) {
+                ct += s_ct;
+                if (ct >= cols) { ct -= cols; ++rt; }
+                rt += s_rt;
+                if (rt >= rows) { rt -= rows; ++img; }
+            }
             img += s_img;
             if (img >= imgs) { img -= imgs; ++n_blk; }
             n_blk += s_nb;
         } else {
             n_blk += s_nb;
-            if (n_blk >= tiles_n) { n_blk -= tiles_n; ++ct; }
-            ct += s_ct;
-            if (ct >= cols) { ct -= cols; ++rt; }
-            rt += s_rt;
-            if (rt >= rows) { rt -= rows; ++img; }
+            if (W) {
+                if (n_blk >= tiles_n) { n_blk -= tiles_n; ++ct; }
+                ct += s_ct;
+                if (ct >= cols) { ct -= cols; ++rt; }
+                rt += s_rt;
+                if (rt >= rows) { rt -= rows; ++img; }
+            } else if (n_blk >= tiles_n) { n_blk -= tiles_n; ++img; }
             img += s_img;
         }
     }
@@ -324,13 +345,24 @@ template <int NG, bool OUT8, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_consume(const IgemmParams& prm, const float* sc, const int32_t* bi,
                                             const uint32_t* v, int32_t c, int32_t pc, const EpiThread& et,
                                             uint32_t staging, uint32_t row_off, uint32_t swz_mask, int32_t* y32,
-                                            int64_t out_row, int32_t col0)
+                                            int64_t out_row, int32_t col0, int32_t& wait_mode)
 {
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         const int32_t cc = c + 16 * g;
         if (OUT8) {
             const uint4 r = requant16<RELU, FOLD>(v + 16 * g, sc + cc, bi + cc);
+            // per-warp stores: the staging buffer may still be being read by this warp's earlier TMA store.  The wait sits
+            // HERE, behind the first group's conversion, so that the store's smem-read latency runs under ~75 instructions
+            // instead of in front of them (1: wait for every store, 2: all but the most recent one - two buffers)
+            if (wait_mode) {
+                if (ptx::lane_id() == 0) {
+                    if (wait_mode == 2) ptx::tma_store_wait_read<1>();
+                    else ptx::tma_store_wait_read<0>();
+                }
+                __syncwarp();
+                wait_mode = 0;
+            }
             // swizzle: the XOR term depends only on the staging row (a panel row never crosses a 128-byte line), so
             // `swz_mask` arrives here already as this thread's ((row_off >> 7) & mask) << 4
             // `staging` arrives as a 32-bit shared-window address (one conversion per panel, not one per store)
@@ -353,7 +385,7 @@ template <bool OUT8, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* sc, const int32_t* bi, uint32_t taddr,
                                           int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et, uint32_t staging,
                                           uint32_t row_off, uint32_t swz_mask, int32_t* y32, int64_t out_row,
-                                          int32_t col0)
+                                          int32_t col0, int32_t wait_mode)
 {
     int32_t c = c0;
 #if LBC_EPI_PIPE
@@ -365,12 +397,12 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
     while (c + 16 <= c1) {
         ptx::tmem_ld_wait_dep16(va);
         if (c + 32 <= c1) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(c + 16), vb);
-        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, va, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, va, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0, wait_mode);
         c += 16;
         if (c + 16 > c1) break;
         ptx::tmem_ld_wait_dep16(vb);
         if (c + 32 <= c1) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(c + 16), va);
-        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, vb, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, vb, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0, wait_mode);
         c += 16;
     }
 #else
@@ -378,13 +410,13 @@ __device__ __forceinline__ void epi_drain(const IgemmParams& prm, const float* s
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)c, v);
         ptx::tmem_ld_wait_dep(v);
-        epi_consume<2, OUT8, RELU, FOLD>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
+        epi_consume<2, OUT8, RELU, FOLD>(prm, sc, bi, v, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0, wait_mode);
     }
     if (c + 16 <= c1) {
         uint32_t v16[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c, v16);
         ptx::tmem_ld_wait_dep16(v16);
-        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0);
+        epi_consume<1, OUT8, RELU, FOLD>(prm, sc, bi, v16, c, c - pbase, et, staging, row_off, swz_mask, y32, out_row, col0, wait_mode);
     }
 #endif
 }
@@ -436,9 +468,9 @@ template <bool MAY_FOLD>
 __device__ __forceinline__ void epi_run(bool int8_out, bool relu, bool fold, const IgemmParams& prm, const float* sc,
                                         const int32_t* bi, uint32_t taddr, int32_t pbase, int32_t c0, int32_t c1, const EpiThread& et,
                                         uint32_t staging, uint32_t row_off, uint32_t swz_mask, int32_t* y32, int64_t out_row,
-                                        int32_t col0)
+                                        int32_t col0, int32_t wait_mode = 0)
 {
-#define LBC_EPI(O8, RL, FD) epi_drain<O8, RL, FD>(prm, sc, bi, taddr, pbase, c0, c1, et, staging, row_off, swz_mask, y32, out_row, col0)
+#define LBC_EPI(O8, RL, FD) epi_drain<O8, RL, FD>(prm, sc, bi, taddr, pbase, c0, c1, et, staging, row_off, swz_mask, y32, out_row, col0, wait_mode)
     if (MAY_FOLD && fold) {
         if (int8_out && relu) LBC_EPI(true, true, true);
         else if (int8_out) LBC_EPI(true, false, true);
@@ -490,7 +522,12 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t lane = threadIdx.x & 31;
     volatile int* tflag = prm.flag;
     const uint32_t cta_rank = CTA2 ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
-    const bool tracing = prm.trace != nullptr && blockIdx.x == 0;
+    // what the template parameters already decide (the run-time flags only matter where a variant can have both)
+    constexpr bool kWindow = (KM >= 2);
+    const bool pair_mode = kWindow && !RESB && !CTA2 && prm.pair != 0;   // paired tiles: window A, streaming B, no CTA pairs
+    const bool n_major = CTA2 || pair_mode;                               // N-tile-major tile numbering
+    using Iter = TileIter<kWindow>;
+    const bool tracing = LBC_TRACE && prm.trace != nullptr && blockIdx.x == 0;
 
     if ((ptx::smem_u32(smem) & 1023u) != 0) {       // swizzle atoms need a 1024-byte aligned base
         if (threadIdx.x == 0) *tflag = 2;
@@ -502,7 +539,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_b);
         ptx::prefetch_tensormap(&tm_out);
-        const uint32_t consumers = prm.pair ? 2u : 1u;   // pair mode: both MMA warps read every stage
+        const uint32_t consumers = pair_mode ? 2u : 1u;   // pair mode: both MMA warps read every stage
         for (int i = 0; i < prm.stages; ++i) {
             ptx::mbar_init(&ctl->full[i], 1);
             ptx::mbar_init(&ctl->empty[i], consumers);
@@ -537,17 +574,16 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     // Programmatic dependent launch: everything above is on-chip set-up (barriers, TMEM, descriptor prefetch) and may
     // overlap the tail of the previous kernel in the stream; from here on global memory is read and written.
     ptx::griddep_wait();
-    if (prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
+    if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
     // pair mode counts the padded tile space (dummy tiles of the padding image load zeros and store nothing)
-    const int32_t num_tiles = prm.n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
-    const int32_t first_tile = prm.pair ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
+    const int32_t num_tiles = n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
+    const int32_t first_tile = pair_mode ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
 
     // The three issue roles below run with ALL 32 lanes of their warp executing the (warp-uniform) loops; only
     // the TMA / MMA / commit instructions themselves are predicated on one elected lane.  Keeping the loops
     // convergent lets the compiler hold addresses and descriptors in uniform registers; a `lane == 0` branch
     // around the whole loop made every tcgen05.mma cost ~150 scalar instructions (ncu, r01 v2).
-    constexpr bool kWindow = (KM >= 2);
     constexpr bool kRing = !(kWindow && RESB);      // resident B + window A: no ring at all
     if (warp == 0) {
         // ===================== ring producer: B blocks (+ A blocks in TILED / IM2COL) =====================
@@ -585,8 +621,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint32_t a_block = prm.a_block_bytes, b_block = prm.b_block_bytes;
             const uint32_t a_stage = prm.a_stage_bytes, b_stage = prm.b_stage_bytes;
             bool ok = true;
-            TileIter it;
-            for (it.init(prm, first_tile); it.tile < num_tiles && ok; it.next(prm)) {
+            Iter it;
+            for (it.init(prm, first_tile, n_major); it.tile < num_tiles && ok; it.next(prm)) {
                 const int32_t m0 = it.m0();
                 int32_t w_base = 0, h_base = 0, n0 = 0;
                 if (KM == A_IM2COL) {
@@ -658,15 +694,15 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const int32_t pad_w = prm.pad_w, pad_h = prm.pad_h, cblocks = prm.cblocks, bkc = prm.bkc;
             const uint32_t n_mma_mask = (uint32_t)(prm.n_mma - 1), win_stage_bytes = prm.win_stage_bytes;
             const uint32_t win_sub_bytes = prm.win_sub_bytes;
-            const bool pair = prm.pair != 0;
+            const bool pair = pair_mode;
             const uint32_t win_tx = (pair || CTA2) ? 2u * prm.win_tx_bytes : prm.win_tx_bytes;
             const uint32_t wfull0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->wfull[0]), 0) : 0u;
-            TileIter it;
-            for (it.init(prm, first_tile); it.tile < num_tiles && ok; it.next(prm)) {
+            Iter it;
+            for (it.init(prm, first_tile, n_major); it.tile < num_tiles && ok; it.next(prm)) {
                 const int32_t wq = it.q0(prm) - pad_w, wp = it.p0(prm) - pad_h;
                 int32_t wq1 = 0, wp1 = 0, img1 = 0;
                 if (pair) {                                             // the second tile of the pair
-                    const TileIter it1 = it.succ(prm);
+                    const Iter it1 = it.succ(prm);
                     wq1 = it1.q0(prm) - pad_w; wp1 = it1.p0(prm) - pad_h; img1 = it1.image();
                 }
                 const uint32_t sub = (uint32_t)it.local & n_mma_mask;
@@ -720,13 +756,13 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int32_t tps = prm.tps, mma_outer = prm.mma_outer, n_tab = prm.n_tab;
         // this warp's sub-ring: stages [ring_lo, ring_hi) of the A/B ring and [win_lo, win_hi) of the window ring
         const uint32_t ring_len = (uint32_t)prm.stages / n_mma, win_len = (uint32_t)prm.win_stages / n_mma;
-        const uint32_t sub_ring = prm.pair ? 0u : which;   // pair mode: both warps walk the whole (single) ring
+        const uint32_t sub_ring = pair_mode ? 0u : which;   // pair mode: both warps walk the whole (single) ring
         const uint32_t ring_lo = sub_ring * ring_len, ring_hi = ring_lo + ring_len;
         const uint32_t win_lo = sub_ring * win_len, win_hi = win_lo + win_len;
         const uint32_t bn = (uint32_t)prm.bn;
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 8 ? 3u : prm.n_acc == 4 ? 2u : 1u;
         uint32_t stage = ring_lo, phase = 0, ws = win_lo, wphase = 0;
-        const bool active = (which < n_mma || prm.pair) && cta_rank == 0;   // CTA pairs: only the leader issues
+        const bool active = (which < n_mma || pair_mode) && cta_rank == 0;   // CTA pairs: only the leader issues
         bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
         bool wready = (kWindow && active) ? ptx::mbar_test(&ctl->wfull[ws], wphase) : true;
         if (RESB && active) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
@@ -740,7 +776,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const uint64_t dfb = ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem + prm.off_fold) + 4096u, 128u, 256u);
             fa_lo = (uint32_t)dfa; fa_hi = (uint32_t)(dfa >> 32); fb_lo = (uint32_t)dfb; fb_hi = (uint32_t)(dfb >> 32);
         }
-        if (kWindow && !RESB && !CTA2 && prm.pair) {
+        if (pair_mode) {
             // ---- pair mode: two M tiles per step share every B block (see IgemmParams::pair).  Warp `which` issues
             // the MMAs of the which-th tile of the pair: both read the same B stage and the same window stage (one
             // window each), so those stages are released by TWO commits (their empty barriers count 2).
@@ -958,7 +994,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
         const uint32_t lane_row = quarter * 32 + lane;            // TMEM lane == row of the MMA tile
         EpiThread et;
-        if (prm.mode == A_WINDOW) {
+        if (kWindow) {
             et.wrow = (int32_t)lane_row / prm.wt;
             et.wcol = (int32_t)lane_row - et.wrow * prm.wt;
             et.valid = et.wcol < prm.cols_per_tile && et.wrow < prm.rows_per_tile;
@@ -984,9 +1020,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             // CTA-local tiles per iteration - adjacent TMEM stages, one staging panel each - so the per-iteration
             // bookkeeping (iterator, barriers, waits, store issue), which is a third of this role's instructions on
             // 64-column tiles, is paid once per two tiles.
-            TileIter ia, ib;
-            ia.init(prm, (int32_t)(blockIdx.x + (2u * team) * gridDim.x), true);
-            ib.init(prm, (int32_t)(blockIdx.x + (2u * team + 1u) * gridDim.x), true);
+            Iter ia, ib;
+            ia.init(prm, (int32_t)(blockIdx.x + (2u * team) * gridDim.x), n_major, true);
+            ib.init(prm, (int32_t)(blockIdx.x + (2u * team + 1u) * gridDim.x), n_major, true);
             // per-channel parameters: a single N tile, loaded once
             for (int32_t c = (int32_t)tt_id; c < prm.bn; c += (int32_t)team_threads) {
                 const bool in = c < prm.k_out;
@@ -1003,14 +1039,14 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll 1
                 for (uint32_t sub = 0; sub < 2; ++sub) {
                     if (sub == 1 && !have_b) break;
-                    const TileIter& it2 = sub ? ib : ia;
+                    const Iter& it2 = sub ? ib : ia;
                     const uint32_t acc = acc0 + sub;
                     ptx::mbar_wait_s(tmem_full_s + acc * 8u, acc_phase, tflag);
                     ptx::tc_fence_after();
                     if (issuer) trace_ev(prm, tracing, tile0 + (int32_t)sub, EV_E_START);
                     int64_t out_row = -1;
                     if (!int8_out) {
-                        if (prm.mode == A_WINDOW) {
+                        if (kWindow) {
                             const int32_t pp = it2.p0(prm) + et.wrow, qq = it2.q0(prm) + et.wcol;
                             if (et.valid && pp < prm.p && qq < prm.q && it2.image() < prm.n_img) out_row = ((int64_t)it2.image() * prm.p + pp) * prm.q + qq;
                         } else {
@@ -1038,7 +1074,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         }
                         ptx::named_bar_sync(bar_id, team_threads);
                         if (issuer) {
-                            if (prm.mode == A_WINDOW) {
+                            if (kWindow) {
                                 if (it2.image() < prm.n_img) ptx::tma_store_4d_s(&tm_out, staging_s, 0, it2.q0(prm), it2.p0(prm), it2.image());
                             } else {
                                 ptx::tma_store_2d_s(&tm_out, staging_s, 0, it2.m0());
@@ -1052,14 +1088,14 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
             if (issuer && int8_out) ptx::tma_store_wait<0>();
         } else {
-        TileIter it;
+        Iter it;
         // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
         // column-split: every team takes every tile of the CTA
-        it.init(prm, prm.pair ? first_tile + (int32_t)team : split ? (int32_t)blockIdx.x : (int32_t)(blockIdx.x + team * gridDim.x),
-                !prm.pair && !split);
+        it.init(prm, pair_mode ? first_tile + (int32_t)team : split ? (int32_t)blockIdx.x : (int32_t)(blockIdx.x + team * gridDim.x),
+                n_major, !pair_mode && !split);
         for (; it.tile < num_tiles;) {
             // CTA-local tile index (it.local counts pairs / team steps / plain CTA steps)
-            const int32_t tile = prm.pair ? 2 * it.local + (int32_t)team : split ? it.local : it.local * (int32_t)n_teams + (int32_t)team;
+            const int32_t tile = pair_mode ? 2 * it.local + (int32_t)team : split ? it.local : it.local * (int32_t)n_teams + (int32_t)team;
             struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.image(), it.p0(prm), it.q0(prm), it.m0()};
             const int32_t col0 = tc.n_blk * prm.bn;
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
@@ -1084,7 +1120,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
             int64_t out_row = -1;   // int32 mode: global output row of this lane
             if (!int8_out) {
-                if (prm.mode == A_WINDOW) {
+                if (kWindow) {
                     const int32_t pp = tc.p0 + et.wrow, qq = tc.q0 + et.wcol;
                     if (et.valid && pp < prm.p && qq < prm.q && tc.img < prm.n_img) out_row = ((int64_t)tc.img * prm.p + pp) * prm.q + qq;
                 } else {
@@ -1099,7 +1135,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 // ---- ring modes, int8 output: no team barrier at all.  The warp converts whole panels (its 32 rows x
                 // <= 128 columns, panels dealt round-robin to the two warp sets of an 8-warp team) into its OWN swizzled
                 // staging buffer and stores them with its own TMA store; lane 0 tracks the buffer through its bulk group.
-                const uint32_t wbuf = ptx::smem_u32(staging) + e * (32u * (uint32_t)prm.panel_bytes);
+                // stage_bufs staging buffers per warp (2 where shared memory allows): with one, the wait below exposes the
+                // smem-read latency of the store issued a moment ago on every panel; with two it waits for the store before
+                const uint32_t wbytes = 32u * (uint32_t)prm.panel_bytes;
+                const uint32_t wbuf0 = ptx::smem_u32(staging) + e * nbufs * wbytes;
                 const uint32_t wrow_off = lane * (uint32_t)prm.panel_bytes;
                 const uint32_t wswz = ((wrow_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
                 const int32_t n_halves = small_teams ? 1 : 2;
@@ -1110,10 +1149,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 wt.valid = true;
                 for (int32_t pnl = w_first; pnl < n_panels; pnl += w_step) {
                     const int32_t pbase = pnl * pcols;
-                    if (lane == 0) ptx::tma_store_wait_read<0>();      // the previous store has read this buffer out
-                    __syncwarp();
+                    const uint32_t wbuf = wbuf0 + sbuf * wbytes;
+                    // (the wait for the buffer's last store to have read it out happens inside, before the first smem store)
                     epi_run<kFold>(true, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz,
-                                  y32, -1, col0);
+                                  y32, -1, col0, nbufs >= 2 ? 2 : 1);
                     if (pnl + w_step >= n_panels) {
                         ptx::tc_fence_before();
                         __syncwarp();
@@ -1130,6 +1169,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                         if (cbyte < prm.k_out) ptx::tma_store_2d_s(&tm_out, wbuf, cbyte, tc.m0 + (int32_t)(quarter * 32u));
                         ptx::tma_store_commit();
                     }
+                    if (++sbuf == nbufs) sbuf = 0;
                 }
                 if (issuer) trace_ev(prm, tracing, tile, EV_E_STORED);
             } else
@@ -1165,7 +1205,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (issuer) {
                         const int32_t cbyte = col0 + pbase;
                         if (cbyte < prm.k_out) {
-                            if (prm.mode == A_WINDOW) {
+                            if (kWindow) {
                                 if (tc.img < prm.n_img)   // the pair modes pad the tile space with dummy tiles
                                     ptx::tma_store_4d_s(&tm_out, staging_s, cbyte, tc.q0, tc.p0, tc.img);
                             }
@@ -1192,7 +1232,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (CTA2) ptx::cluster_sync();     // neither CTA may leave while its peer still reads its operands / signals its barriers
     else __syncthreads();
     // trace mode: every CTA also leaves its own start / end time (its SM's cycle counter) behind the per-tile stamps
-    if (prm.trace != nullptr && threadIdx.x == 0) {
+    if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) {
         long long* cta_times = prm.trace + (size_t)prm.trace_tiles * 16;
         cta_times[2 * blockIdx.x + 1] = clock64();
     }
@@ -1274,6 +1314,8 @@ lbc_status encode_tiled_u8_4d(CUtensorMap* tm, const void* base, const uint64_t 
     LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(rank 4) failed: %d", (int)r);
     return LBC_OK;
 }
+
+bool igemm_trace_compiled() { return LBC_TRACE != 0; }
 
 bool igemm_supported(const ConvGeom& g, std::string* why)
 {
@@ -1506,13 +1548,13 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         }
     }
     for (int pass = 0; pass < 2 && !fits; ++pass)
-    for (int bufs = c.warp_store ? 1 : max_bufs; bufs >= 1 && !fits; --bufs)
+    for (int bufs = c.warp_store ? std::min(2, max_bufs) : max_bufs; bufs >= 1 && !fits; --bufs)
     for (int fold_try = 1; fold_try >= 0 && !fits; --fold_try) {     // with the bias-fold blocks if they fit, else without   // three staging panels per team when they fit, else two, else one
         c.res_b = (pass == 0 && res_b_ok) ? 1 : 0;
         if (pass == 0 && !res_b_ok) break;
         c.stage_bufs = bufs;
         stage_bytes = d.out_mode == LBC_OUT_INT8 ? round_up((uint32_t)(n_teams * bufs * kBlockM * c.panel_bytes), 1024) : 0;
-        if (c.warp_store) stage_bytes = (uint32_t)(kEpiWarps * 32 * c.panel_bytes);   // one 32-row panel per epilogue warp
+        if (c.warp_store) stage_bytes = (uint32_t)(kEpiWarps * 32 * c.panel_bytes * bufs);   // 32-row panels, `bufs` per epilogue warp
         // bias folded into the MMA (resident filter matrix only): a 4 KB constant A block + bn x 32 B of bias digits
         // Enabled for N tiles >= 128 columns: -11% time on the 64->256 expansions, -2% on 128-wide tiles; narrow tiles
         // gain nothing (their per-tile bookkeeping dominates) and pay for the extra MMA per tile.  LBC_FOLD=0/1 overrides.

@@ -22,7 +22,8 @@ def main():
     import torch
     import lowbitdnn_project_b200 as lbc
     from lowbitdnn_project_b200 import _capi
-    lib = lbc.load_library()
+    # the build with the pipeline stamps compiled in (lowbitdnn-project_b200/build.py makes both)
+    _capi._lib = _capi.load_library(os.path.join(os.path.dirname(_capi.LIB_PATH), "liblowbit_cnn_trace.so"))
     nets = lbc.networks
     layers = nets.NETWORKS[a.network](nets.DEFAULT_BATCH[a.network])
     dev = torch.device("cuda:0")
