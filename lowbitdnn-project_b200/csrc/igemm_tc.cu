@@ -1015,7 +1015,68 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         constexpr bool kFold = decltype(fold_tag)::value;
         int32_t cur_nblk = -1;
         const uint32_t tmem_empty0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->tmem_empty[0]), 0) : 0u;   // the leader's barriers
-        if (!CTA2 && prm.tpi == 2) {
+        if (!LBC_TRACE && !kWindow && !CTA2 && prm.warp_store && !split && !small_teams && n_panels == 2 && prm.n_acc == 2) {
+            // ---- lean loop for the hottest epilogue-bound shape: ring modes, 256-wide tiles, per-warp stores (the 1x1
+            // channel expansions).  Everything a tile needs is a running register: two teams and two accumulator stages
+            // mean team t ALWAYS drains stage t (only the phase bit flips), the warp's panel, TMEM address, staging buffers
+            // and swizzle term never change, and the tile index advances by (n_blk, m) digit steps.  The general loop below
+            // spent ~190 instructions per warp and tile on re-deriving these (ncu source counters, r02: as many samples as
+            // the conversion loop itself); this one spends ~40.
+            const uint32_t full_bar = tmem_full_s + team * 8u, empty_bar = tmem_empty_s + team * 8u;
+            const uint32_t taddr = tmem_lane_base + team * bn_u;
+            const int32_t pbase = (int32_t)half * pcols;                       // this warp's panel: columns [pbase, pbase + 128)
+            const uint32_t wbuf0 = ptx::smem_u32(staging) + e * nbufs * (32u * 128u);
+            const uint32_t wrow_off = lane * 128u, wswz = (lane & 7u) << 4;
+            const int32_t tiles_n = prm.tiles_n, tiles_m = prm.tiles_m, s_nb = prm.tstep_nb, s_m = prm.tstep_img, rev = prm.rev_m;
+            const int32_t bn = prm.bn, k_out = prm.k_out, row_in_tile = (int32_t)(quarter * 32u);
+            const int32_t wait_mode = nbufs >= 2 ? 2 : 1;
+            const bool relu = prm.relu != 0;
+            EpiThread wt = et;
+            wt.valid = true;
+            uint32_t phase = 0, wbuf = wbuf0;
+            int32_t n_blk, m;
+            {
+                const int32_t t0 = (int32_t)(blockIdx.x + team * gridDim.x);
+                n_blk = t0 % tiles_n;
+                m = t0 / tiles_n;
+            }
+            for (; m < tiles_m;) {
+                const int32_t col0 = n_blk * bn;
+                if (n_blk != cur_nblk) {       // per-channel parameters of this N tile -> smem (only when the N tile changes)
+                    ptx::named_bar_sync(bar_id, team_threads);
+                    for (int32_t c = (int32_t)tt_id; c < bn; c += (int32_t)team_threads) {
+                        const int32_t kc = col0 + c;
+                        const bool in = kc < k_out;
+                        const int32_t kp = prm.k_mod ? kc % prm.k_mod : kc;
+                        sc[c] = (in && scale) ? __ldg(scale + kp) : 0.0f;
+                        bi[c] = (in && bias) ? __ldg(bias + kp) : 0;
+                    }
+                    cur_nblk = n_blk;
+                    ptx::named_bar_sync(bar_id, team_threads);
+                }
+                ptx::mbar_wait_s(full_bar, phase, tflag);
+                ptx::tc_fence_after();
+                epi_run<kFold>(true, relu, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz, nullptr, -1,
+                              col0, wait_mode);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_s(empty_bar);
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const int32_t cbyte = col0 + pbase;
+                    const int32_t mm = (rev > 0) ? rev - 1 - m : m;
+                    if (cbyte < k_out) ptx::tma_store_2d_s(&tm_out, wbuf, cbyte, mm * kBlockM + row_in_tile);
+                    ptx::tma_store_commit();
+                }
+                if (nbufs >= 2) wbuf ^= (wbuf0 ^ (wbuf0 + 32u * 128u));      // toggle between the warp's two buffers
+                phase ^= 1u;
+                n_blk += s_nb;
+                if (n_blk >= tiles_n) { n_blk -= tiles_n; ++m; }
+                m += s_m;
+            }
+            if (lane == 0) ptx::tma_store_wait<0>();
+        } else if (!CTA2 && prm.tpi == 2) {
             // ---- narrow N tiles (<= 64 columns, one N tile, 8 accumulator stages): a 4-warp team takes TWO consecutive
             // CTA-local tiles per iteration - adjacent TMEM stages, one staging panel each - so the per-iteration
             // bookkeeping (iterator, barriers, waits, store issue), which is a third of this role's instructions on
