@@ -518,7 +518,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint8_t* staging = smem + prm.off_stage;
     Ctl* ctl = reinterpret_cast<Ctl*>(smem + prm.off_ctl);
 
-    const uint32_t warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: the compiler then KNOWS it is warp-uniform, so the role dispatch is a uniform branch
+    // and everything a role derives from it (ring halves, stage cursors, descriptors) can live on the uniform datapath
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const uint32_t lane = threadIdx.x & 31;
     volatile int* tflag = prm.flag;
     const uint32_t cta_rank = CTA2 ? ptx::cluster_ctarank() : 0u;   // 0 = leader of the pair
@@ -763,14 +765,14 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t acc_mask = (uint32_t)prm.n_acc - 1u, acc_shift = prm.n_acc == 8 ? 3u : prm.n_acc == 4 ? 2u : 1u;
         uint32_t stage = ring_lo, phase = 0, ws = win_lo, wphase = 0;
         const bool active = (which < n_mma || pair_mode) && cta_rank == 0;   // CTA pairs: only the leader issues
-        bool ready = (kRing && active) ? ptx::mbar_test(&ctl->full[stage], phase) : true;
-        bool wready = (kWindow && active) ? ptx::mbar_test(&ctl->wfull[ws], wphase) : true;
-        if (RESB && active) ptx::mbar_wait_soft(&ctl->bfull, 0, tflag);
+        bool ready = (kRing && active) ? ptx::mbar_test_u(&ctl->full[stage], phase) : true;
+        bool wready = (kWindow && active) ? ptx::mbar_test_u(&ctl->wfull[ws], wphase) : true;
+        if (RESB && active) ptx::mbar_wait_soft_u(&ctl->bfull, 0, tflag);
         // bias folded into the MMA: the epilogue warps write the constant A block and the bias-digit B block first
         bool fold = false;
         uint32_t fa_lo = 0, fa_hi = 0, fb_lo = 0, fb_hi = 0;
         if (MAYFOLD && prm.fold && active) {
-            ptx::mbar_wait_soft(&ctl->bias_ready, 0, tflag);
+            ptx::mbar_wait_soft_u(&ctl->bias_ready, 0, tflag);
             fold = *reinterpret_cast<volatile uint32_t*>(&ctl->fold_ok) != 0;
             const uint64_t dfa = ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem + prm.off_fold), 128u, 256u);
             const uint64_t dfb = ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem + prm.off_fold) + 4096u, 128u, 256u);
@@ -785,23 +787,23 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int32_t tile = first_tile; tile < num_tiles; tile += prm.tile_stride, ++lp) {
                 const uint32_t acc = ((uint32_t)(2 * lp) & acc_mask) + which;
                 const uint32_t acc_phase = ((uint32_t)(2 * lp) >> acc_shift) & 1u;
-                ptx::mbar_wait_soft(&ctl->tmem_empty[acc], acc_phase ^ 1, tflag);
+                ptx::mbar_wait_soft_u(&ctl->tmem_empty[acc], acc_phase ^ 1, tflag);
                 ptx::tc_fence_after();
                 if (leader && which == 0) trace_ev(prm, tracing, lp, EV_M_START);
                 const uint32_t tmem_d = tmem_base + acc * bn;
                 uint32_t accumulate = 0;
                 for (int32_t cb = 0; cb < mma_outer; ++cb) {
-                    if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
+                    if (!wready) ptx::mbar_wait_soft_u(&ctl->wfull[ws], wphase, tflag);
                     const uint32_t a_base = da_lo + ws * a_stage16 + which * win_sub16;
                     if (cb == 0 && leader && which == 0) trace_ev(prm, tracing, lp, EV_M_WIN);
                     int32_t j = 0;
                     for (int32_t st = 0; st < inner_stages; ++st) {
-                        if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
+                        if (!ready) ptx::mbar_wait_soft_u(&ctl->full[stage], phase, tflag);
                         ptx::tc_fence_after();
                         if (st == 0 && cb == 0 && leader && which == 0) trace_ev(prm, tracing, lp, EV_M_FULL);
                         uint32_t nstage = stage + 1, nphase = phase;
                         if (nstage == ring_hi) { nstage = ring_lo; nphase ^= 1; }
-                        const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
+                        const bool ready_next = ptx::mbar_test_u(&ctl->full[nstage], nphase);
                         uint32_t b_lo = db_lo + stage * b_stage16;
                         for (int32_t t = 0; t < tps; ++t) {
 #pragma unroll
@@ -818,7 +820,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     }
                     ptx::mma_commit_pred(&ctl->wempty[ws], leader);
                     if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
-                    wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
+                    wready = ptx::mbar_test_u(&ctl->wfull[ws], wphase);
                 }
                 ptx::mma_commit_pred(&ctl->tmem_full[acc], leader);
                 if (leader && which == 0) trace_ev(prm, tracing, lp, EV_M_DONE);
@@ -838,7 +840,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
              tile += tile_step, local += (int32_t)n_mma) {
             const uint32_t acc_stage = (uint32_t)local & acc_mask;
             const uint32_t acc_phase = ((uint32_t)local >> acc_shift) & 1u;
-            ptx::mbar_wait_soft(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
+            ptx::mbar_wait_soft_u(&ctl->tmem_empty[acc_stage], acc_phase ^ 1, tflag);
             ptx::tc_fence_after();
             if (leader) trace_ev(prm, tracing, local, EV_M_START);
             const uint32_t tmem_d = tmem_base + acc_stage * bn;
@@ -853,7 +855,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 // ---- window A, resident B: per channel chunk one wait, then a flat run of table-driven MMAs
                 uint32_t b_base = db_n;
                 for (int32_t cb = 0; cb < mma_outer; ++cb, b_base += b_chunk16) {
-                    if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
+                    if (!wready) ptx::mbar_wait_soft_u(&ctl->wfull[ws], wphase, tflag);
                     ptx::tc_fence_after();
                     const uint32_t a_base = da_lo + ws * a_stage16;
                     if (cb == 0 && leader) trace_ev(prm, tracing, local, EV_M_WIN);
@@ -876,26 +878,26 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     }
                     ptx::mma_commit_pred(&ctl->wempty[ws], leader);
                     if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
-                    wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
+                    wready = ptx::mbar_test_u(&ctl->wfull[ws], wphase);
                 }
             } else {
                 uint32_t b_res = db_n;    // resident B (ring modes): walks the blocks of the tile in order
                 for (int32_t cb = 0; cb < mma_outer; ++cb) {
                     uint32_t a_base = da_lo;
                     if (kWindow) {
-                        if (!wready) ptx::mbar_wait_soft(&ctl->wfull[ws], wphase, tflag);
+                        if (!wready) ptx::mbar_wait_soft_u(&ctl->wfull[ws], wphase, tflag);
                         a_base = da_lo + ws * a_stage16;
                         if (cb == 0 && leader) trace_ev(prm, tracing, local, EV_M_WIN);
                     }
                     int32_t j = 0;   // index into the chunk's A-offset table
                     for (int32_t st = 0; st < inner_stages; ++st) {
-                        if (!ready) ptx::mbar_wait_soft(&ctl->full[stage], phase, tflag);
+                        if (!ready) ptx::mbar_wait_soft_u(&ctl->full[stage], phase, tflag);
                         ptx::tc_fence_after();
                         if (st == 0 && cb == 0 && leader) trace_ev(prm, tracing, local, EV_M_FULL);
                         // probe the NEXT stage now: the (non-blocking) test's latency overlaps this stage's MMA issue
                         uint32_t nstage = stage + 1, nphase = phase;
                         if (nstage == ring_hi) { nstage = ring_lo; nphase ^= 1; }
-                        const bool ready_next = ptx::mbar_test(&ctl->full[nstage], nphase);
+                        const bool ready_next = ptx::mbar_test_u(&ctl->full[nstage], nphase);
                         if (!kWindow) a_base = da_lo + stage * a_stage16;
                         uint32_t b_lo = RESB ? b_res : db_lo + stage * b_stage16;
                         for (int32_t t = 0; t < tps; ++t) {
@@ -915,7 +917,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     if (kWindow) {
                         mma_commit<CTA2>(&ctl->wempty[ws], leader);
                         if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
-                        wready = ptx::mbar_test(&ctl->wfull[ws], wphase);
+                        wready = ptx::mbar_test_u(&ctl->wfull[ws], wphase);
                     }
                 }
             }

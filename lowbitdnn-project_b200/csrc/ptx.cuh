@@ -361,6 +361,36 @@ __device__ __forceinline__ void mbar_wait_soft(uint64_t* bar, uint32_t parity, v
     }
 }
 
+// Warp-uniform forms for the issue roles (all 32 lanes execute them convergently on the same barrier).  The lanes' results
+// are identical, but a per-thread predicate makes every branch that depends on it "divergent" for the compiler, and
+// everything computed under such control flow lives in vector registers: each tcgen05.mma then needs its descriptors moved
+// to the uniform datapath one R2UR at a time (~13 instructions per MMA, SASS r02).  A vote result is uniform BY
+// CONSTRUCTION, so with these the loop state, the descriptor arithmetic and the table loads stay on the uniform datapath.
+__device__ __forceinline__ bool mbar_test_u(uint64_t* bar, uint32_t parity)
+{
+    return __all_sync(0xffffffffu, mbar_test(bar, parity));
+}
+
+__device__ __forceinline__ void mbar_wait_soft_u(uint64_t* bar, uint32_t parity, volatile int* timeout_flag,
+                                                 uint64_t budget_ns = 2000000000ull)
+{
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if ((++spins & 0x3ff) == 0) {
+            const bool expired = globaltimer_ns() - t0 > budget_ns;
+            if (__any_sync(0xffffffffu, expired || *timeout_flag != 0)) {
+                if (expired) {
+                    *timeout_flag = 1;
+                    __threadfence();
+                }
+                return;
+            }
+        }
+    }
+}
+
 // Arrives (count 1) on `bar` once every previously issued tcgen05.mma of this thread has completed.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint64_t* bar)
