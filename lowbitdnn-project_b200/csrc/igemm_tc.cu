@@ -283,9 +283,10 @@ struct TileIter {
 };
 
 // bounded wait for the single-thread roles: false => give up (the watchdog flag is set)
+// (whole warps call it convergently: the vote-based form keeps the producers' loop state on the uniform datapath)
 __device__ __forceinline__ bool wait_or_quit(uint64_t* bar, uint32_t parity, volatile int* flag)
 {
-    return ptx::mbar_wait(bar, parity, flag);
+    return ptx::mbar_wait_u(bar, parity, flag);
 }
 
 // One 16-column group of one output pixel: requantise (bias/scale from smem) and return 16 packed int8.

@@ -391,6 +391,28 @@ __device__ __forceinline__ void mbar_wait_soft_u(uint64_t* bar, uint32_t parity,
     }
 }
 
+// bounded wait, warp-uniform result: false => the watchdog tripped (give up)
+__device__ __forceinline__ bool mbar_wait_u(uint64_t* bar, uint32_t parity, volatile int* timeout_flag,
+                                            uint64_t budget_ns = 2000000000ull)
+{
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return true;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if ((++spins & 0x3ff) == 0) {
+            const bool expired = globaltimer_ns() - t0 > budget_ns;
+            if (__any_sync(0xffffffffu, expired || *timeout_flag != 0)) {
+                if (expired) {
+                    *timeout_flag = 1;
+                    __threadfence();
+                }
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
 // Arrives (count 1) on `bar` once every previously issued tcgen05.mma of this thread has completed.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint64_t* bar)
