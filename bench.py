@@ -236,7 +236,7 @@ def reference_arm(args, layers):
               f"outputs), {cores} OpenMP threads; images/s = sample MAC rate / {net_macs_per_image / 1e9:.3f} GMAC per ResNet-50 image "
               "(extrapolated from the reference CPU path)")
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if args.network == "resnet50" else f"{args.network}_int8_conv_images_per_sec", "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
         "config": {"workload": f"{args.network}_conv_stack_b{args.batch}", "network": args.network,
@@ -550,7 +550,7 @@ def main():
         })
         total_ops = sum(w[0] for w in works)
         out = {
-            "metric": METRIC, "value": images_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC if args.network == "resnet50" else f"{args.network}_int8_conv_images_per_sec", "value": images_per_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": f"{args.network}_conv_stack_b{config_batch}", "network": args.network,

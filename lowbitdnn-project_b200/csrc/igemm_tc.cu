@@ -1418,7 +1418,15 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     auto limit = [](int32_t v, int dflt) { return v > 0 ? (int)v : dflt; };
     // ---- N tile: the whole K_out when it fits one 256-wide tile, else an even split into the fewest tiles
     // (multiples of 16; a ragged last tile is handled by TMA zero-fill on loads and clipping on stores)
-    const int max_bn = std::max(16, std::min(256, limit(o.max_bn, 256)));
+    int max_bn = std::max(16, std::min(256, limit(o.max_bn, 256)));
+    // Small problems (a strong-scaled batch: 64 images per GPU leave ResNet-50's stage 4 with 25 M tiles): when 256-wide
+    // tiles would occupy less than half of the SMs, 128-wide ones put twice as many CTAs to work (l4.x.conv2 at N = 64:
+    // 16.8 -> 13.6 us, r02); the narrower MMA's lower efficiency does not matter on an under-filled chip.
+    if (o.max_bn <= 0 && d.k > 128) {
+        const int64_t m_tiles = (g.m_total + kBlockM - 1) / kBlockM;
+        const int64_t n_tiles = (d.k + 255) / 256;
+        if (2 * m_tiles * n_tiles <= (dev.sm_count > 0 ? dev.sm_count : 148)) max_bn = 128;
+    }
     c.tiles_n = (d.k + max_bn - 1) / max_bn;
     c.bn = ((d.k + c.tiles_n - 1) / c.tiles_n + 15) / 16 * 16;
     c.tiles_n = (d.k + c.bn - 1) / c.bn;
