@@ -173,6 +173,8 @@ def parity_check(net, layers, rank, images=2):
         x = synth_input(d, i + 1000 * rank)[:n] if src is None else outs[src]
         w, b, s = synth_params(d, i)
         outs[name] = oracle.conv_nhwc(OD(**{**d.__dict__, "n": n}), np.ascontiguousarray(x), w, b, s)
+        if net.fused_into(i) >= 0:
+            continue              # absorbed by its consumer's fused launch (checked through the consumer's output)
         got = net.read_output(i, images=n)
         if not np.array_equal(got, outs[name]):
             bad.append(name)
@@ -588,7 +590,15 @@ def main():
             for i, (name, d, _) in enumerate(layers):
                 ops, byts = works[i]
                 ms = float(per_layer[i])
-                rep.append({"layer": name, "kernel": kinds[i], "plan": net.layer_describe(i), "ms": ms,
+                into = net.fused_into(i)
+                if into >= 0:      # no launch of its own: its work is in the consumer's (fused) line
+                    rep.append({"layer": name, "kernel": kinds[i], "plan": f"fused into {layers[into][0]}", "ms": 0.0, "tops": 0.0,
+                                "gbs": 0.0, "ai": ops / byts, "frac_tc": 0.0, "frac_hbm": 0.0, "fused_into": layers[into][0]})
+                    continue
+                src = [j for j in range(len(layers)) if net.fused_into(j) == i]
+                if src:            # a fused pair: both convolutions' algorithmic work over the one launch
+                    ops, byts = ops + works[src[0]][0], byts + works[src[0]][1]
+                rep.append({"layer": name + (f" (+{layers[src[0]][0]})" if src else ""), "kernel": kinds[i], "plan": net.layer_describe(i), "ms": ms,
                             "tops": ops / ms / 1e9, "gbs": byts / ms / 1e6, "ai": ops / byts,
                             "frac_tc": ops / ms / 1e9 / (tc_peak / 1e12), "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"]})
             with open(args.layer_report, "w") as fh:

@@ -119,7 +119,8 @@ typedef struct lbc_plan_options {
     int32_t tps_kb;              /* cap (KB) on the B bytes grouped into one ring stage in window mode              */
     int32_t resident_kb;         /* largest filter matrix (KB) kept resident                                        */
     int32_t epi_split;           /* tri-state: both epilogue teams drain every tile (column split) on > 128-wide tiles */
-    int32_t reserved[7];
+    int32_t fuse;                /* networks: run conv(R x S -> 64) -> conv(1x1 -> 256) pairs as one fused launch (0: never)  */
+    int32_t reserved[6];
 } lbc_plan_options;
 
 /* int8 NHWC pooling window (max-pool).  Output size: 1 + (in + 2*pad - window) / stride, as the reference's cuDNN
@@ -146,6 +147,7 @@ typedef struct lbc_node {
     lbc_pool_desc pool;          /* LBC_NODE_MAXPOOL (n/h/w/c must equal the producer's output)                     */
 } lbc_node;
 
+typedef struct lbc_fused_plan lbc_fused_plan;   /* opaque: two convolutions run as one launch (lbc_fused_tail_*)            */
 typedef struct lbc_plan lbc_plan;     /* opaque; immutable after creation and safe to share between threads and
                                          streams (per-run scratch is allocated stream-ordered per call)            */
 typedef struct lbc_net  lbc_net;      /* opaque: a fixed chain/list of planned convolutions           */
@@ -205,6 +207,19 @@ lbc_status  lbc_conv_plan_check(const lbc_plan* plan);
 lbc_status  lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const void* w_packed,
                               const int32_t* bias, const float* scale, void* y_host,
                               lbc_stream stream, float* elapsed_ms);
+
+/* ---- fused bottleneck tail ----------------------------------------------------------------------- */
+/* conv_a (R x S, stride 1, 64 output channels, int8 out) followed by conv_b (1x1, 64 -> 256, int8 out) on conv_a's output,
+ * in ONE kernel: conv_a's requantised tile stays in shared memory as the second GEMM's operand, the middle tensor never
+ * touches HBM (the conv -> relu -> conv chain of python/tmp.py:43-56; ResNet-50's stage-1 conv2 -> conv3).  The result is
+ * bit-identical to running the two convolutions one after the other.  LBC_ERR_UNSUPPORTED for any other pair.
+ * The weights are packed with the two single-layer plans (lbc_fused_tail_plan_parts + lbc_conv_prepack_weights). */
+lbc_status  lbc_fused_tail_plan_create(const lbc_conv_desc* conv_a, const lbc_conv_desc* conv_b, lbc_fused_plan** plan);
+lbc_status  lbc_fused_tail_plan_destroy(lbc_fused_plan* plan);
+lbc_status  lbc_fused_tail_plan_parts(const lbc_fused_plan* plan, const lbc_plan** plan_a, const lbc_plan** plan_b);
+lbc_status  lbc_fused_tail_run(const lbc_fused_plan* plan, const int8_t* x_nhwc, const void* wa_packed, const int32_t* bias_a,
+                               const float* scale_a, const void* wb_packed, const int32_t* bias_b, const float* scale_b,
+                               void* y_nhwc, lbc_stream stream, float* elapsed_ms);
 
 /* ---- int8 ops between convolutions (NHWC int8 device buffers) ----------------------------------- */
 /* Max-pool: replaces max_pool2d(input, kernel, stride, padding) of python/qtorch/cpp/pool2d.cuh:54-92 (cuDNN
@@ -268,6 +283,8 @@ lbc_status  lbc_net_check(lbc_net* net);              /* as lbc_conv_plan_check,
 lbc_status  lbc_net_create_graph(const lbc_node* nodes, int32_t n_nodes, const lbc_plan_options* opt, lbc_net** net);
 lbc_status  lbc_net_destroy(lbc_net* net);
 lbc_status  lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan** plan);
+/* *into = the layer whose fused launch absorbs `layer` (its own output is then never materialised), or -1. */
+lbc_status  lbc_net_layer_fused_into(const lbc_net* net, int32_t layer, int32_t* into);
 /* Load parameters for one layer from HOST memory (weights in `layout`, bias int32[K], scale f32[K]). */
 lbc_status  lbc_net_set_params_host(lbc_net* net, int32_t layer, const int8_t* w_host, int32_t layout,
                                     const int32_t* bias_host, const float* scale_host);

@@ -7,7 +7,7 @@ tests and the benchmark harness; importing it never falls back to PyTorch or to 
 from . import _capi
 from ._capi import (KERNEL_AUTO, KERNEL_DEPTHWISE, KERNEL_DIRECT, KERNEL_IGEMM_TC, OUT_INT8, OUT_INT32, W_KRSC,
                     W_OIHW, LbcError, load_library)
-from .conv import (ConvDesc, ConvPlan, conv2DForward3x3, conv_backward_data, conv_backward_weights, from_vect_c, nchw_to_nhwc,
+from .conv import (ConvDesc, ConvPlan, FusedTailPlan, conv2DForward3x3, conv_backward_data, conv_backward_weights, from_vect_c, nchw_to_nhwc,
                    nhwc_to_nchw, nhwc_to_vect_c, to_vect_c, vect_c_to_nhwc)
 from .net import Net
 from .ops import AddDesc, PoolDesc, add_relu, global_avg_pool, max_pool2d
@@ -15,7 +15,7 @@ from . import networks
 from . import shard
 
 __all__ = [
-    "ConvDesc", "ConvPlan", "Net", "networks", "shard", "LbcError", "load_library",
+    "ConvDesc", "ConvPlan", "FusedTailPlan", "Net", "networks", "shard", "LbcError", "load_library",
     "PoolDesc", "AddDesc", "max_pool2d", "add_relu", "global_avg_pool",
     "conv_backward_data", "conv_backward_weights", "conv2DForward3x3", "to_vect_c", "from_vect_c", "nhwc_to_vect_c", "vect_c_to_nhwc", "nchw_to_nhwc", "nhwc_to_nchw",
     "OUT_INT8", "OUT_INT32", "W_KRSC", "W_OIHW", "KERNEL_AUTO", "KERNEL_DIRECT", "KERNEL_IGEMM_TC", "KERNEL_DEPTHWISE",

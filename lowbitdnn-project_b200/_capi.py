@@ -48,7 +48,7 @@ class CPlanOptions(ctypes.Structure):
         "struct_size", "cta_pairs", "warp_store", "fold_bias", "paired_tiles", "resident_filter", "window", "keep_window",
         "force_im2col", "pixel_groups", "dw_tiled", "reverse", "pdl", "two_mma_warps", "tiles_per_iter2", "small_teams",
         "four_acc", "n_stationary", "epi_pipeline", "max_grid", "max_bn", "max_stages", "max_win_stages", "stage_bufs",
-        "tps_kb", "resident_kb", "epi_split")] + [("reserved", ctypes.c_int32 * 7)]
+        "tps_kb", "resident_kb", "epi_split", "fuse")] + [("reserved", ctypes.c_int32 * 6)]
 
 
 def plan_options(**kw) -> CPlanOptions:
@@ -85,6 +85,11 @@ _PROTOS = {
     "lbc_conv_prepack_weights": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "lbc_conv_run": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
     "lbc_conv_run_host": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_float)]),
+    "lbc_fused_tail_plan_create": (ctypes.c_int, [ctypes.POINTER(CConvDesc), ctypes.POINTER(CConvDesc), ctypes.POINTER(_vp)]),
+    "lbc_fused_tail_plan_destroy": (ctypes.c_int, [_vp]),
+    "lbc_fused_tail_plan_parts": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "lbc_fused_tail_run": (ctypes.c_int, [_vp] * 10 + [ctypes.POINTER(ctypes.c_float)]),
+    "lbc_net_layer_fused_into": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(_i32)]),
     "lbc_pool_out_shape": (ctypes.c_int, [ctypes.POINTER(CPoolDesc), ctypes.POINTER(_i32), ctypes.POINTER(_i32)]),
     "lbc_maxpool2d_run": (ctypes.c_int, [ctypes.POINTER(CPoolDesc), _vp, _vp, _vp]),
     "lbc_add_relu_run": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_size_t, _i32, _vp]),

@@ -271,3 +271,52 @@ def conv_backward_weights(desc: ConvDesc, x, dy, stream=None):
     dw = torch.empty((desc.k, desc.r, desc.s, desc.c), dtype=torch.int32, device=x.device)
     check(lib.lbc_nhwc_to_chwn(_ptr(dw_crsk), _ptr(dw), desc.c, desc.r, desc.s, desc.k, 4, _stream_ptr(stream)))
     return dw
+
+
+class FusedTailPlan:
+    """lbc_fused_plan: conv_a (R x S, stride 1, -> 64 channels) and conv_b (1x1, 64 -> 256) as ONE launch."""
+
+    def __init__(self, conv_a: ConvDesc, conv_b: ConvDesc):
+        self._lib = load_library()
+        self.a, self.b = conv_a, conv_b
+        self._h = ctypes.c_void_p()
+        ca, cb = conv_a.c_struct(), conv_b.c_struct()
+        check(self._lib.lbc_fused_tail_plan_create(ctypes.byref(ca), ctypes.byref(cb), ctypes.byref(self._h)))
+        pa, pb = ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._lib.lbc_fused_tail_plan_parts(self._h, ctypes.byref(pa), ctypes.byref(pb)))
+        self._pa, self._pb = pa, pb
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.lbc_fused_tail_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _prepack(self, part, w, n_elts):
+        import torch
+        assert w.is_cuda and w.dtype == torch.int8 and w.is_contiguous() and w.numel() == n_elts
+        nb = ctypes.c_size_t()
+        check(self._lib.lbc_conv_packed_weight_bytes(part, ctypes.byref(nb)))
+        out = torch.empty(nb.value, dtype=torch.int8, device=w.device)
+        check(self._lib.lbc_conv_prepack_weights(part, _ptr(w), _capi.W_KRSC, _ptr(out), _stream_ptr(None)))
+        return out
+
+    def prepack(self, wa_krsc, wb_krsc):
+        """int8 CUDA tensors [64][R][S][C] and [256][1][1][64] -> the two packed filter matrices."""
+        a, b = self.a, self.b
+        return self._prepack(self._pa, wa_krsc, a.k * a.r * a.s * a.c), self._prepack(self._pb, wb_krsc, b.k * b.c)
+
+    def run(self, x, wa, bias_a, scale_a, wb, bias_b, scale_b, out=None, stream=None, timed: bool = False):
+        import torch
+        b = self.b
+        p, q = b.out_hw
+        y = out if out is not None else torch.empty((b.n, p, q, b.k), dtype=torch.int8, device=x.device)
+        ms = ctypes.c_float()
+        check(self._lib.lbc_fused_tail_run(self._h, _ptr(x), _ptr(wa), _ptr(bias_a), _ptr(scale_a), _ptr(wb), _ptr(bias_b), _ptr(scale_b),
+                                           _ptr(y), _stream_ptr(stream), ctypes.byref(ms) if timed else None))
+        return (y, ms.value) if timed else y

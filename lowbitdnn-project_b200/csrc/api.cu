@@ -6,8 +6,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <array>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace lbc {
@@ -106,7 +108,7 @@ void default_options(lbc_plan_options* o)
     o->keep_window = o->force_im2col = 0;
     o->reverse = -1;
     o->pdl = o->two_mma_warps = o->tiles_per_iter2 = o->small_teams = o->four_acc = -1;
-    o->n_stationary = o->epi_pipeline = o->epi_split = -1;
+    o->n_stationary = o->epi_pipeline = o->epi_split = o->fuse = -1;
 }
 
 }  // namespace lbc
@@ -160,6 +162,13 @@ struct lbc_plan {
     mutable std::mutex mu;
     mutable void* x_dev = nullptr;
     mutable void* y_dev = nullptr;
+};
+
+struct lbc_fused_plan {
+    lbc_plan* a = nullptr;       // the R x S convolution (window mode, resident filter)
+    lbc_plan* b = nullptr;       // the 1x1 convolution
+    mutable std::mutex cache_mu;
+    mutable std::vector<std::pair<std::array<const void*, 4>, FusedLaunch>> cache;   // (x, wa, wb, y) -> encoded launch
 };
 
 namespace {
@@ -670,6 +679,86 @@ lbc_status lbc_conv_run_host(const lbc_plan* plan, const int8_t* x_host, const v
     return check_flag(plan->flag);
 }
 
+// ---- fused bottleneck tail ----------------------------------------------------------------------------
+lbc_status lbc_fused_tail_plan_destroy(lbc_fused_plan* plan)
+{
+    if (!plan) return LBC_OK;
+    lbc_conv_plan_destroy(plan->a);
+    lbc_conv_plan_destroy(plan->b);
+    delete plan;
+    return LBC_OK;
+}
+
+lbc_status lbc_fused_tail_plan_create(const lbc_conv_desc* conv_a, const lbc_conv_desc* conv_b, lbc_fused_plan** out)
+{
+    LBC_REQUIRE(conv_a && conv_b && out, LBC_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    lbc_fused_plan* f = new (std::nothrow) lbc_fused_plan();
+    LBC_REQUIRE(f, LBC_ERR_ALLOC, "out of host memory");
+    lbc_status st = lbc_conv_plan_create(conv_a, LBC_KERNEL_AUTO, &f->a);
+    if (st == LBC_OK) st = lbc_conv_plan_create(conv_b, LBC_KERNEL_AUTO, &f->b);
+    if (st == LBC_OK) {
+        std::string why;
+        if (f->a->kind != LBC_KERNEL_IGEMM_TC || f->b->kind != LBC_KERNEL_IGEMM_TC || f->a->pw_factor != 1 || f->b->pw_factor != 1 ||
+            !fused_tail_supported(f->a->g, f->a->cfg, f->b->g, f->b->cfg, &why)) {
+            set_error("this pair of convolutions cannot run fused: %s", why.empty() ? "not tensor-core layers" : why.c_str());
+            st = LBC_ERR_UNSUPPORTED;
+        }
+    }
+    if (st != LBC_OK) {
+        char keep[512];
+        strncpy(keep, last_error(), sizeof keep);
+        keep[sizeof keep - 1] = 0;
+        lbc_fused_tail_plan_destroy(f);
+        set_error("%s", keep);
+        return st;
+    }
+    *out = f;
+    return LBC_OK;
+}
+
+lbc_status lbc_fused_tail_plan_parts(const lbc_fused_plan* plan, const lbc_plan** plan_a, const lbc_plan** plan_b)
+{
+    LBC_REQUIRE(plan, LBC_ERR_INVALID_ARG, "null plan");
+    if (plan_a) *plan_a = plan->a;
+    if (plan_b) *plan_b = plan->b;
+    return LBC_OK;
+}
+
+lbc_status lbc_fused_tail_run(const lbc_fused_plan* plan, const int8_t* x, const void* wa, const int32_t* bias_a, const float* scale_a,
+                              const void* wb, const int32_t* bias_b, const float* scale_b, void* y, lbc_stream stream, float* elapsed_ms)
+{
+    LBC_REQUIRE(plan && x && wa && wb && y && scale_a && scale_b, LBC_ERR_INVALID_ARG, "lbc_fused_tail_run: null argument");
+    FusedLaunch fl;
+    bool hit = false;
+    const std::array<const void*, 4> key = {x, wa, wb, y};
+    {
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        for (const auto& c : plan->cache)
+            if (c.first == key) { fl = c.second; hit = true; break; }
+    }
+    if (!hit) {
+        lbc_status st = fused_tail_encode(plan->a->g, plan->a->cfg, plan->b->g, plan->a->dev, x, (const int8_t*)wa, (const int8_t*)wb, y, &fl);
+        if (st != LBC_OK) return st;
+        std::lock_guard<std::mutex> lk(plan->cache_mu);
+        if (plan->cache.size() >= 4) plan->cache.erase(plan->cache.begin());
+        plan->cache.emplace_back(key, fl);
+    }
+    EpilogueParams epa{bias_a, scale_a, plan->a->g.d.relu, LBC_OUT_INT8}, epb{bias_b, scale_b, plan->b->g.d.relu, LBC_OUT_INT8};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!elapsed_ms) return fused_tail_launch(plan->a->g, plan->b->g, fl, epa, epb, runtime_of(plan->a), s);
+    EventPair ev;
+    lbc_status st = ev.init();
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaEventRecord(ev.a, s));
+    st = fused_tail_launch(plan->a->g, plan->b->g, fl, epa, epb, runtime_of(plan->a), s);
+    if (st != LBC_OK) return st;
+    LBC_CUDA_TRY(cudaEventRecord(ev.b, s));
+    LBC_CUDA_TRY(cudaEventSynchronize(ev.b));
+    LBC_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, ev.a, ev.b));
+    return check_flag(plan->a->flag);
+}
+
 // ---- int8 ops between convolutions --------------------------------------------------------------------
 static lbc_status pool_geom(const lbc_pool_desc* d, int32_t* p, int32_t* q)
 {
@@ -871,6 +960,11 @@ struct lbc_net {
         lbc_pool_desc pool{};            // LBC_NODE_MAXPOOL
         int32_t add_relu = 0;            // LBC_NODE_ADD
         int32_t input2_of = -1;          // LBC_NODE_ADD: second operand
+        // fused bottleneck tail: `fused_into` >= 0 -> this convolution is absorbed by that (1x1) layer's launch and its own
+        // output is never written; `fused_from` >= 0 on the absorbing layer, whose launch then reads `fused_from`'s input
+        int32_t fused_into = -1, fused_from = -1;
+        FusedLaunch fl{};
+        const void* fl_x = nullptr;
         // activation geometry of every node kind: input NHWC (conv / pool; add: both operands) and output NHWC
         int32_t in_n = 0, in_h = 0, in_w = 0, in_c = 0, out_p = 0, out_q = 0, out_k = 0, out_elt = 1;
         size_t in_bytes() const { return (size_t)in_n * in_h * in_w * in_c; }
@@ -918,7 +1012,7 @@ const void* layer_input(const lbc_net* net, int i)
 lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
 {
     lbc_net::Layer& L = net->layers[i];
-    if (L.kind != LBC_NODE_CONV) return LBC_OK;          // pool / add nodes have nothing to encode
+    if (L.kind != LBC_NODE_CONV || L.fused_into >= 0 || L.fused_from >= 0) return LBC_OK;   // nothing to encode here
     const int8_t* x = x_override ? x_override : (const int8_t*)layer_input(net, i);
     if (L.resolved && L.rl.x == x) return LBC_OK;
     lbc_status st = resolve(L.plan, x, L.w, L.bias, L.scale, L.y, &L.rl);
@@ -936,7 +1030,23 @@ lbc_status net_launch_node(lbc_net* net, int i, const ResolvedLaunch* rl, const 
 {
     lbc_net::Layer& L = net->layers[i];
     switch (L.kind) {
-        case LBC_NODE_CONV: return launch(rl ? *rl : L.rl, s);
+        case LBC_NODE_CONV: {
+            if (L.fused_into >= 0) return LBC_OK;                       // absorbed by the consumer's fused launch
+            if (L.fused_from >= 0) {
+                lbc_net::Layer& A = net->layers[L.fused_from];
+                const void* x = (L.fused_from == 0 && x_override) ? x_override : layer_input(net, L.fused_from);
+                if (L.fl_x != x) {
+                    lbc_status st = fused_tail_encode(A.plan->g, A.plan->cfg, L.plan->g, A.plan->dev, (const int8_t*)x, (const int8_t*)A.w,
+                                                      (const int8_t*)L.w, L.y, &L.fl);
+                    if (st != LBC_OK) return st;
+                    L.fl.reverse = A.reverse ? 1 : 0;
+                    L.fl_x = x;
+                }
+                const EpilogueParams epa{A.bias, A.scale, A.plan->g.d.relu, LBC_OUT_INT8}, epb{L.bias, L.scale, L.plan->g.d.relu, LBC_OUT_INT8};
+                return fused_tail_launch(A.plan->g, L.plan->g, L.fl, epa, epb, runtime_of(A.plan), s);
+            }
+            return launch(rl ? *rl : L.rl, s);
+        }
         case LBC_NODE_MAXPOOL:
             return launch_maxpool(L.pool, L.out_p, L.out_q, (const int8_t*)(x_override ? x_override : layer_input(net, i)), (int8_t*)L.y,
                                   net->sm_count, s);
@@ -1127,6 +1237,35 @@ lbc_status lbc_net_create_graph(const lbc_node* nodes, int32_t n_layers, const l
         }
         if (L.x_own) cudaMemset(L.x_own, 0, L.in_bytes());
     }
+    if (st == LBC_OK && opt.fuse != 0) {
+        // fused bottleneck tails: a convolution whose ONLY consumer is a 1x1 convolution, both shapes the fused kernel covers
+        std::vector<int> consumers((size_t)n_layers, 0);
+        for (int i = 0; i < n_layers; ++i) {
+            if (net->layers[i].input_of >= 0) ++consumers[(size_t)net->layers[i].input_of];
+            if (net->layers[i].input2_of >= 0) ++consumers[(size_t)net->layers[i].input2_of];
+        }
+        for (int j = 1; j < n_layers; ++j) {
+            lbc_net::Layer& B = net->layers[j];
+            const int i = B.input_of;
+            if (B.kind != LBC_NODE_CONV || i < 0) continue;
+            lbc_net::Layer& A = net->layers[i];
+            if (A.kind != LBC_NODE_CONV || consumers[(size_t)i] != 1 || A.fused_from >= 0 || A.fused_into >= 0) continue;
+            if (A.plan->kind != LBC_KERNEL_IGEMM_TC || B.plan->kind != LBC_KERNEL_IGEMM_TC || A.plan->pw_factor != 1 || B.plan->pw_factor != 1)
+                continue;
+            if (!fused_tail_supported(A.plan->g, A.plan->cfg, B.plan->g, B.plan->cfg, nullptr)) continue;
+            A.fused_into = j;
+            B.fused_from = i;
+        }
+        // traversal directions again, now that a fused pair is one launch that walks conv A's tiles
+        for (int i = 0; i < n_layers; ++i) {
+            lbc_net::Layer& L = net->layers[i];
+            if (L.fused_from >= 0) { L.reverse = net->layers[L.fused_from].reverse; continue; }
+            const bool tc = L.kind == LBC_NODE_CONV &&
+                            (L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC || L.plan->kind == LBC_KERNEL_DEPTHWISE);
+            const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
+            L.reverse = tc && L.input_of >= 0 && !producer_rev && snake;
+        }
+    }
     if (st == LBC_OK) {
         net->events.assign(n_layers + 1, nullptr);
         for (auto& e : net->events)
@@ -1155,6 +1294,13 @@ lbc_status lbc_net_layer_plan(const lbc_net* net, int32_t layer, const lbc_plan*
     LBC_REQUIRE(net->layers[layer].kind == LBC_NODE_CONV, LBC_ERR_INVALID_ARG, "node %d is not a convolution (kind %d)", layer,
                 net->layers[layer].kind);
     *plan = net->layers[layer].plan;
+    return LBC_OK;
+}
+
+lbc_status lbc_net_layer_fused_into(const lbc_net* net, int32_t layer, int32_t* into)
+{
+    LBC_REQUIRE(net && into && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad layer index");
+    *into = net->layers[layer].fused_into;
     return LBC_OK;
 }
 
@@ -1198,6 +1344,8 @@ lbc_status lbc_net_read_output_host(const lbc_net* net, int32_t layer, void* y_h
 {
     LBC_REQUIRE(net && y_host && layer >= 0 && layer < (int)net->layers.size(), LBC_ERR_INVALID_ARG, "bad argument");
     const lbc_net::Layer& L = net->layers[layer];
+    LBC_REQUIRE(L.fused_into < 0, LBC_ERR_UNSUPPORTED, "layer %d runs fused into layer %d: its output is never materialised", layer,
+                L.fused_into);
     const size_t all = L.out_bytes();
     LBC_CUDA_TRY(cudaDeviceSynchronize());
     LBC_CUDA_TRY(cudaMemcpy(y_host, L.y, (max_bytes && max_bytes < all) ? max_bytes : all, cudaMemcpyDeviceToHost));
@@ -1348,7 +1496,7 @@ lbc_status lbc_net_launches(const lbc_net* net, int32_t* launches)
 {
     LBC_REQUIRE(net && launches, LBC_ERR_INVALID_ARG, "null argument");
     int32_t n = 0;
-    for (const auto& L : net->layers) n += (L.kind == LBC_NODE_CONV && L.plan->kind == LBC_KERNEL_STEM_TC) ? 2 : 1;
+    for (const auto& L : net->layers) n += L.fused_into >= 0 ? 0 : (L.kind == LBC_NODE_CONV && L.plan->kind == LBC_KERNEL_STEM_TC) ? 2 : 1;
     *launches = n;
     return LBC_OK;
 }

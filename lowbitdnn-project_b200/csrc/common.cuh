@@ -142,6 +142,24 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
                         const int8_t* w_packed, void* y, IgemmLaunch* out);
 lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
                         const IgemmRuntime& rt, cudaStream_t stream);
+// Fused bottleneck tail (igemm_fused_tail_kernel): conv A (R x S, stride 1, 64 output channels, window mode with a resident
+// filter) -> int8 -> conv B (1x1, 64 -> 256) in one launch.  `cfg_a` is conv A's own plan config; the fused launch re-carves
+// shared memory around it.
+struct FusedLaunch {
+    CUtensorMap tm_a, tm_b1, tm_b2, tm_out;
+    IgemmConfig cfg_a;           // window geometry, issue tables, K chunking of conv A (ring depths recomputed for the fused carve-up)
+    int32_t k2, relu2, stage_bufs2, win_stages;
+    uint32_t off_b1, off_b2, off_a2, off_stage2, off_ctl2, b1_bytes, b2_bytes;
+    size_t smem_bytes;
+    int32_t grid;
+    int32_t reverse = 0;
+};
+bool fused_tail_supported(const ConvGeom& ga, const IgemmConfig& cfg_a, const ConvGeom& gb, const IgemmConfig& cfg_b, std::string* why);
+lbc_status fused_tail_encode(const ConvGeom& ga, const IgemmConfig& cfg_a, const ConvGeom& gb, const DeviceInfo& dev, const int8_t* x,
+                             const int8_t* wa_packed, const int8_t* wb_packed, void* y, FusedLaunch* out);
+lbc_status fused_tail_launch(const ConvGeom& ga, const ConvGeom& gb, const FusedLaunch& l, const EpilogueParams& epa,
+                             const EpilogueParams& epb, const IgemmRuntime& rt, cudaStream_t stream);
+
 // per-device one-time kernel attributes: true the first time it is called for `device` under `mask`
 bool first_use_on_device(uint64_t (&mask)[4], int device);
 

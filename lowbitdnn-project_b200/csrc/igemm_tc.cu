@@ -1311,6 +1311,290 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
 }
 
+// =====================================================================================================
+// Fused bottleneck tail (first slice): an R x S stride-1 convolution with 64 output channels (window A,
+// resident filter) whose ReLU'd int8 result never leaves the SM - the epilogue writes it as a K-major, 64-byte-swizzled
+// operand tile into shared memory and a second MMA warp multiplies it by the resident [256][64] filter of the following
+// 1x1 convolution.  Only the 4x wider result goes to HBM: one write and one read of the middle tensor per bottleneck less
+// (ResNet-50 stage 1: 2 x 103 MB per block), one launch less, and the second convolution's MMAs (256 tensor cycles per
+// tile) run on a pipe that the first one leaves half idle.  The chain being replaced: conv -> relu -> conv of
+// python/tmp.py:43-56, run as two launches.
+//
+//   TMEM     D1: 4 stages x 64 columns [0, 256)      D2: one stage of 256 columns [256, 512)
+//   warp 0   loads both filter matrices once          warp 2   window producer (one halo window per tile and channel chunk)
+//   warp 1   MMA1: tile L -> D1[L & 3]                warp 3   MMA2: A2[L & 1] (smem) x B2 -> D2
+//   warps 4-19 (one group of 16):  per step  epi1(L + 1): D1 -> bias1/scale1/ReLU -> int8 -> A2[(L + 1) & 1]
+//                                            epi2(L):     D2 -> bias2/scale2/[ReLU] -> int8 -> staging -> TMA store
+//   so MMA2(L + 1) (which needs A2 written and D2 drained) runs under epi1(L + 2): its latency is hidden.
+// The halo rows of a window tile flow through both GEMMs as garbage rows and are dropped by the epilogue's row compaction,
+// exactly as in the unfused window kernel.
+struct FusedParams {
+    IgemmParams a;                 // the first convolution (window mode, resident filter, one N tile of 64 columns)
+    int32_t k2, relu2;             // second convolution: output channels (256), ReLU
+    int32_t c_mid;                 // channels between the two (== a.bn == 64)
+    int32_t stage_bufs2;           // staging panels per team for the final output
+    uint32_t off_b2, off_a2, off_stage2, off_ctl2, b1_bytes, b2_bytes;
+};
+
+struct FusedCtl {
+    uint64_t wfull[kMaxWinStages];
+    uint64_t wempty[kMaxWinStages];
+    uint64_t d1_full[4], d1_empty[4];
+    uint64_t a2_full[2], a2_empty[2];
+    uint64_t d2_full, d2_empty;
+    uint64_t bfull;
+    uint32_t tmem_base;
+    alignas(16) float scale1[64];
+    alignas(16) int32_t bias1[64];
+    alignas(16) float scale2[256];
+    alignas(16) int32_t bias2[256];
+};
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+igemm_fused_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b1,
+                        const __grid_constant__ CUtensorMap tm_b2, const __grid_constant__ CUtensorMap tm_out, const FusedParams fp,
+                        const int32_t* __restrict__ bias1, const float* __restrict__ scale1, const int32_t* __restrict__ bias2,
+                        const float* __restrict__ scale2)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const IgemmParams& prm = fp.a;
+    uint8_t* smem_a = smem;                                   // window ring
+    uint8_t* smem_b1 = smem + prm.off_b;
+    uint8_t* smem_b2 = smem + fp.off_b2;
+    uint8_t* smem_a2 = smem + fp.off_a2;                      // two 128 x 64 B operand tiles for the second GEMM
+    uint8_t* staging = smem + fp.off_stage2;
+    FusedCtl* ctl = reinterpret_cast<FusedCtl*>(smem + fp.off_ctl2);
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const uint32_t lane = threadIdx.x & 31;
+    volatile int* tflag = prm.flag;
+    using Iter = TileIter<true>;
+    constexpr uint32_t kA2Bytes = kBlockM * 64u;
+    constexpr uint32_t kD2Col = 256u;
+
+    if ((ptx::smem_u32(smem) & 1023u) != 0) {
+        if (threadIdx.x == 0) *tflag = 2;
+        return;
+    }
+    ptx::griddep_launch_dependents();
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a);
+        ptx::prefetch_tensormap(&tm_b1);
+        ptx::prefetch_tensormap(&tm_b2);
+        ptx::prefetch_tensormap(&tm_out);
+        for (int i = 0; i < prm.win_stages; ++i) {
+            ptx::mbar_init(&ctl->wfull[i], 1);
+            ptx::mbar_init(&ctl->wempty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            ptx::mbar_init(&ctl->d1_full[i], 1);
+            ptx::mbar_init(&ctl->d1_empty[i], kEpiWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&ctl->a2_full[i], kEpiWarps);
+            ptx::mbar_init(&ctl->a2_empty[i], 1);
+        }
+        ptx::mbar_init(&ctl->d2_full, 1);
+        ptx::mbar_init(&ctl->d2_empty, kEpiWarps);
+        ptx::mbar_init(&ctl->bfull, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&ctl->tmem_base, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    ptx::griddep_wait();
+    const uint32_t tmem_base = ctl->tmem_base;
+    const int32_t num_tiles = prm.tiles_m;                    // one N tile
+
+    if (warp == 0) {
+        // ---- both filter matrices, once
+        if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&ctl->bfull, fp.b1_bytes + fp.b2_bytes);
+            const int32_t nblk = prm.cblocks * prm.inner;
+            uint8_t* dst = smem_b1;
+            int32_t bcol = 0;
+            for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb) ptx::tma_load_2d(dst, &tm_b1, &ctl->bfull, bcol, 0);
+            ptx::tma_load_2d(smem_b2, &tm_b2, &ctl->bfull, 0, 0);
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ---- window producer
+        const bool leader = ptx::elect_one();
+        const int32_t pad_w = prm.pad_w, pad_h = prm.pad_h, cblocks = prm.cblocks, bkc = prm.bkc;
+        const uint32_t win_stages = (uint32_t)prm.win_stages, win_stage_bytes = prm.win_stage_bytes, win_tx = prm.win_tx_bytes;
+        uint32_t ws = 0, wphase = 0;
+        bool ok = true;
+        Iter it;
+        for (it.init(prm, (int32_t)blockIdx.x, false); it.tile < num_tiles && ok; it.next(prm)) {
+            const int32_t wq = it.q0(prm) - pad_w, wp = it.p0(prm) - pad_h;
+            int32_t c0 = 0;
+            for (int32_t cb = 0; cb < cblocks; ++cb, c0 += bkc) {
+                ok = wait_or_quit(&ctl->wempty[ws], wphase ^ 1, tflag);
+                if (!ok) break;
+                if (leader) {
+                    ptx::mbar_expect_tx(&ctl->wfull[ws], win_tx);
+                    ptx::tma_load_4d(smem_a + ws * win_stage_bytes, &tm_a, &ctl->wfull[ws], c0, wq, wp, it.image());
+                }
+                if (++ws == win_stages) { ws = 0; wphase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- MMA1: the R x S convolution, tile L -> D1[L & 3]
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)prm.bn);
+        const uint64_t db_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_b1), (uint32_t)prm.bkb);
+        const uint64_t da_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_a), (uint32_t)prm.bkc);
+        const uint32_t da_lo = (uint32_t)da_base, da_hi = (uint32_t)(da_base >> 32);
+        const uint32_t db_lo = (uint32_t)db_base, db_hi = (uint32_t)(db_base >> 32);
+        const uint32_t a_stage16 = prm.win_stage_bytes >> 4;
+        const uint32_t b_chunk16 = (prm.b_block_bytes >> 4) * (uint32_t)prm.inner;
+        const int32_t cblocks = prm.cblocks, n_tab = prm.n_tab;
+        const uint32_t win_stages = (uint32_t)prm.win_stages, bn = (uint32_t)prm.bn;
+        uint32_t ws = 0, wphase = 0;
+        ptx::mbar_wait_soft_u(&ctl->bfull, 0, tflag);
+        int32_t local = 0;
+        for (int32_t tile = (int32_t)blockIdx.x; tile < num_tiles; tile += (int32_t)gridDim.x, ++local) {
+            const uint32_t st = (uint32_t)local & 3u, ph = ((uint32_t)local >> 2) & 1u;
+            ptx::mbar_wait_soft_u(&ctl->d1_empty[st], ph ^ 1, tflag);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + st * bn;
+            uint32_t accumulate = 0, b_base = db_lo;
+            for (int32_t cb = 0; cb < cblocks; ++cb, b_base += b_chunk16) {
+                ptx::mbar_wait_soft_u(&ctl->wfull[ws], wphase, tflag);
+                ptx::tc_fence_after();
+                const uint32_t a_base = da_lo + ws * a_stage16;
+                for (int32_t j = 0; j < n_tab; ++j) {
+                    ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j], da_hi, b_base + (uint32_t)prm.b_tab[j], db_hi, idesc,
+                                          accumulate, leader);
+                    accumulate = 1;
+                }
+                ptx::mma_commit_pred(&ctl->wempty[ws], leader);
+                if (++ws == win_stages) { ws = 0; wphase ^= 1; }
+            }
+            ptx::mma_commit_pred(&ctl->d1_full[st], leader);
+        }
+    } else if (warp == 3) {
+        // ---- MMA2: the 1x1 convolution on the tile the epilogue just requantised, A2[L & 1] x B2 -> D2
+        const uint32_t leader = ptx::elect_one() ? 1u : 0u;
+        const uint32_t idesc = ptx::make_idesc_i8(kBlockM, (uint32_t)fp.k2);
+        const uint64_t da = ptx::make_kmajor_desc(ptx::smem_u32(smem_a2), 64u);
+        const uint64_t db = ptx::make_kmajor_desc(ptx::smem_u32(smem_b2), 64u);
+        const uint32_t da_lo = (uint32_t)da, da_hi = (uint32_t)(da >> 32), db_lo = (uint32_t)db, db_hi = (uint32_t)(db >> 32);
+        const uint32_t ksteps = (uint32_t)fp.c_mid / 32u;
+        ptx::mbar_wait_soft_u(&ctl->bfull, 0, tflag);
+        int32_t local = 0;
+        for (int32_t tile = (int32_t)blockIdx.x; tile < num_tiles; tile += (int32_t)gridDim.x, ++local) {
+            const uint32_t buf = (uint32_t)local & 1u;
+            ptx::mbar_wait_soft_u(&ctl->a2_full[buf], ((uint32_t)local >> 1) & 1u, tflag);
+            ptx::mbar_wait_soft_u(&ctl->d2_empty, ((uint32_t)local & 1u) ^ 1u, tflag);
+            ptx::tc_fence_after();
+            const uint32_t a_lo = da_lo + buf * (kA2Bytes >> 4);
+            for (uint32_t k = 0; k < ksteps; ++k)
+                ptx::mma_i8_ss_pred32(tmem_base + kD2Col, a_lo + 2u * k, da_hi, db_lo + 2u * k, db_hi, idesc, k ? 1u : 0u, leader);
+            ptx::mma_commit_pred(&ctl->d2_full, leader);
+            ptx::mma_commit_pred(&ctl->a2_empty[buf], leader);
+        }
+    } else if (warp >= kFirstEpiWarp) {
+        // ---- epilogue: one group of 16 warps
+        const uint32_t e = warp - kFirstEpiWarp;
+        const uint32_t quarter = warp & 3;                        // TMEM lanes [32*quarter, +32)
+        const uint32_t cg = e >> 2;                               // epi1: 16 columns each; epi2: team = cg >> 1, half = cg & 1
+        const uint32_t team = cg >> 1, half = cg & 1u;
+        const uint32_t tid = e * 32u + lane;
+        const bool issuer = ((e & 7u) == 0u) && lane == 0;        // first thread of each team
+        for (uint32_t c = tid; c < 64u; c += kEpiWarps * 32u) {
+            ctl->scale1[c] = (int32_t)c < prm.k_out ? __ldg(scale1 + c) : 0.0f;
+            ctl->bias1[c] = ((int32_t)c < prm.k_out && bias1) ? __ldg(bias1 + c) : 0;
+        }
+        for (uint32_t c = tid; c < 256u; c += kEpiWarps * 32u) {
+            ctl->scale2[c] = (int32_t)c < fp.k2 ? __ldg(scale2 + c) : 0.0f;
+            ctl->bias2[c] = ((int32_t)c < fp.k2 && bias2) ? __ldg(bias2 + c) : 0;
+        }
+        ptx::named_bar_sync(1, kEpiWarps * 32);
+        const uint32_t lane_row = quarter * 32 + lane;
+        EpiThread et;                                             // window compaction of the final output (as the unfused kernel)
+        et.wrow = (int32_t)lane_row / prm.wt;
+        et.wcol = (int32_t)lane_row - et.wrow * prm.wt;
+        et.valid = et.wcol < prm.cols_per_tile && et.wrow < prm.rows_per_tile;
+        et.srow = (uint32_t)(et.wrow * prm.cols_per_tile + et.wcol);
+        EpiThread e1;                                             // the operand tile keeps EVERY MMA row, halo rows included
+        e1.wrow = e1.wcol = 0; e1.valid = true; e1.srow = lane_row;
+        const uint32_t tmem_lane_base = tmem_base + ((quarter * 32u) << 16);
+        const uint32_t a2_row_off = lane_row * 64u, a2_swz = ((a2_row_off >> 7) & 3u) << 4;
+        const uint32_t a2_s = ptx::smem_u32(smem_a2);
+        const uint32_t row_off = et.srow * 128u, swz = ((row_off >> 7) & 7u) << 4;
+        const uint32_t nbufs = (uint32_t)fp.stage_bufs2, panel_smem = kBlockM * 128u;
+        const uint32_t team_staging_s = ptx::smem_u32(staging) + team * nbufs * panel_smem;
+        const bool relu1 = prm.relu != 0, relu2 = fp.relu2 != 0;
+        const uint32_t bn1 = (uint32_t)prm.bn;
+        uint32_t sbuf = 0;
+
+        // D1[T & 3] -> int8 operand tile A2[T & 1]
+        auto epi1 = [&](int32_t T) {
+            const uint32_t st = (uint32_t)T & 3u, buf = (uint32_t)T & 1u;
+            ptx::mbar_wait(&ctl->d1_full[st], ((uint32_t)T >> 2) & 1u, tflag);
+            ptx::mbar_wait(&ctl->a2_empty[buf], (((uint32_t)T >> 1) & 1u) ^ 1u, tflag);     // MMA2(T - 2) has read this buffer
+            ptx::tc_fence_after();
+            epi_run<false>(true, relu1, false, prm, ctl->scale1, ctl->bias1, tmem_lane_base + st * bn1, 0, (int32_t)(16u * cg),
+                           (int32_t)(16u * cg + 16u), e1, a2_s + buf * kA2Bytes, a2_row_off, a2_swz, nullptr, -1, 0);
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) {
+                ptx::mbar_arrive(&ctl->a2_full[buf]);
+                ptx::mbar_arrive(&ctl->d1_empty[st]);
+            }
+        };
+        // D2 -> int8 NHWC output: team t stages and stores panel t (128 columns), its two warp sets 64 columns each
+        auto epi2 = [&](int32_t T, int32_t img, int32_t p0, int32_t q0) {
+            ptx::mbar_wait(&ctl->d2_full, (uint32_t)T & 1u, tflag);
+            ptx::tc_fence_after();
+            const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
+            const int32_t pbase = (int32_t)(team * 128u);
+            if (nbufs == 1) {
+                if (issuer) ptx::tma_store_wait_read<0>();
+                if (team == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+                else asm volatile("bar.sync 3, 256;" ::: "memory");
+            }
+            epi_run<false>(true, relu2, false, prm, ctl->scale2, ctl->bias2, tmem_lane_base + kD2Col, pbase, pbase + (int32_t)(half * 64u),
+                           pbase + (int32_t)(half * 64u) + 64, et, staging_s, row_off, swz, nullptr, -1, 0);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ctl->d2_empty);
+            ptx::fence_proxy_async();
+            if (issuer && nbufs >= 2) ptx::tma_store_wait_read<0>();      // the buffer the next tile goes to has been read out
+            if (team == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+            else asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (issuer) {
+                if (img < prm.n_img && pbase < fp.k2) ptx::tma_store_4d_s(&tm_out, staging_s, pbase, q0, p0, img);
+                ptx::tma_store_commit();
+            }
+            if (++sbuf == nbufs) sbuf = 0;
+        };
+        Iter it;
+        it.init(prm, (int32_t)blockIdx.x, false);
+        int32_t L = 0;
+        if (it.tile < num_tiles) epi1(0);
+        while (it.tile < num_tiles) {
+            const int32_t img = it.image(), p0 = it.p0(prm), q0 = it.q0(prm);
+            it.next(prm);
+            if (it.tile < num_tiles) epi1(L + 1);
+            epi2(L, img, p0, q0);
+            ++L;
+        }
+        if (issuer) ptx::tma_store_wait<0>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1836,12 +2120,11 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
     return LBC_OK;
 }
 
-lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
-                        const IgemmRuntime& rt, cudaStream_t stream)
+// kernel parameters of a launch: geometry, tiling, smem carve-up, iteration digits
+static void fill_params(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, const IgemmRuntime& rt, IgemmParams& prm)
 {
     const IgemmConfig& c = l.cfg;
     const lbc_conv_desc& d = g.d;
-    IgemmParams prm{};
     prm.m_total = g.m_total;
     prm.k_out = d.k; prm.n_img = d.n; prm.p = g.p; prm.q = g.q;
     prm.mode = c.mode; prm.bn = c.bn; prm.bkc = c.bkc; prm.bkb = c.bkb;
@@ -1906,6 +2189,14 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     // "channel chunk" of cblocks*inner blocks.
     if (c.mode == A_WINDOW) { prm.mma_outer = c.cblocks; prm.mma_inner = c.inner; }
     else { prm.mma_outer = 1; prm.mma_inner = c.cblocks * c.inner; }
+}
+
+lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueParams& ep, void* y,
+                        const IgemmRuntime& rt, cudaStream_t stream)
+{
+    const IgemmConfig& c = l.cfg;
+    IgemmParams prm{};
+    fill_params(g, l, ep, rt, prm);
     const int km = c.mode == A_WINDOW ? (c.bkc == 16 ? 3 : 2) : c.mode;
     const int ks = c.bkb / 32;
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams, const int32_t*,
@@ -1961,5 +2252,148 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     return LBC_OK;
 }
 
+
+// ---- fused bottleneck tail: host side --------------------------------------------------------------------------------
+bool fused_tail_supported(const ConvGeom& ga, const IgemmConfig& ca, const ConvGeom& gb, const IgemmConfig& cb, std::string* why)
+{
+    auto no = [&](const char* m) { if (why) *why = m; return false; };
+    const lbc_conv_desc& a = ga.d;
+    const lbc_conv_desc& b = gb.d;
+    if (ca.mode != A_WINDOW || ca.bkc == 16) return no("conv A is not a window-mode layer");
+    if (!ca.res_b || ca.tiles_n != 1 || ca.bn != 64 || a.k != 64) return no("conv A needs 64 output channels and a resident filter");
+    if (ca.pair || ca.cta2 || ca.res_one) return no("conv A must not run in pairs");
+    if (a.out_mode != LBC_OUT_INT8 || b.out_mode != LBC_OUT_INT8) return no("both convolutions must produce int8");
+    if (b.r != 1 || b.s != 1 || b.stride_h != 1 || b.stride_w != 1 || b.pad_h != 0 || b.pad_w != 0 || b.groups != 1)
+        return no("conv B is not a plain 1x1");
+    if (b.c != a.k || b.n != a.n || b.h != ga.p || b.w != ga.q) return no("conv B does not consume conv A's output");
+    if (b.k != 256) return no("conv B needs 256 output channels");
+    if (cb.mode != A_TILED || cb.bkc != 64 || cb.cblocks != 1) return no("conv B's filter is not packed as [256][64]");
+    return true;
+}
+
+lbc_status fused_tail_encode(const ConvGeom& ga, const IgemmConfig& ca, const ConvGeom& gb, const DeviceInfo& dev, const int8_t* x,
+                             const int8_t* wa_packed, const int8_t* wb_packed, void* y, FusedLaunch* out)
+{
+    lbc_status st = resolve_driver_entry_points();
+    if (st != LBC_OK) return st;
+    LBC_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wa_packed) | reinterpret_cast<uintptr_t>(wb_packed) |
+                  reinterpret_cast<uintptr_t>(y)) & 15) == 0,
+                LBC_ERR_INVALID_ARG, "fused tail: x, packed weights and y must be 16-byte aligned");
+    const lbc_conv_desc& a = ga.d;
+    const lbc_conv_desc& b = gb.d;
+    FusedLaunch f{};
+    f.cfg_a = ca;
+    f.k2 = b.k;
+    f.relu2 = b.relu;
+    // shared memory: [window ring][B1][B2][A2 x 2][output staging: 2 teams x bufs x 16 KB][control]
+    f.b1_bytes = (uint32_t)ca.k_blocks * ca.b_block_bytes;
+    f.b2_bytes = (uint32_t)b.k * 64u;
+    const uint32_t ctl_bytes = round_up((uint32_t)sizeof(FusedCtl), 1024);
+    const uint32_t fixed = round_up(f.b1_bytes, 1024) + round_up(f.b2_bytes, 1024) + 2u * kBlockM * 64u + ctl_bytes;
+    bool fits = false;
+    for (int bufs = 2; bufs >= 1 && !fits; --bufs) {
+        const uint32_t stage = 2u * (uint32_t)bufs * kBlockM * 128u;
+        if (fixed + stage + 4u * ca.win_stage_bytes > 227u * 1024u) continue;
+        const int wins = (int)std::min<uint32_t>(kMaxWinStages, (227u * 1024u - fixed - stage) / ca.win_stage_bytes);
+        if (wins < (bufs == 2 ? 6 : 4)) continue;
+        f.stage_bufs2 = bufs;
+        f.win_stages = wins;
+        fits = true;
+    }
+    LBC_REQUIRE(fits, LBC_ERR_UNSUPPORTED, "fused tail: the window ring does not fit next to both filter matrices");
+    f.off_b1 = (uint32_t)f.win_stages * ca.win_stage_bytes;
+    f.off_b2 = f.off_b1 + round_up(f.b1_bytes, 1024);
+    f.off_a2 = f.off_b2 + round_up(f.b2_bytes, 1024);
+    f.off_stage2 = f.off_a2 + 2u * kBlockM * 64u;
+    f.off_ctl2 = f.off_stage2 + 2u * (uint32_t)f.stage_bufs2 * kBlockM * 128u;
+    f.smem_bytes = f.off_ctl2 + ctl_bytes;
+    f.grid = std::min(dev.sm_count > 0 ? dev.sm_count : 148, ca.tiles_m);
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    {   // B1: conv A's packed filter matrix [64 rows][packed_row_bytes], box {bkb, 64}
+        const cuuint64_t dims[2] = {(cuuint64_t)ca.packed_row_bytes, (cuuint64_t)a.k};
+        const cuuint64_t strides[1] = {(cuuint64_t)ca.packed_row_bytes};
+        const cuuint32_t box[2] = {(cuuint32_t)ca.bkb, (cuuint32_t)ca.bn};
+        CUresult r = g_encode_tiled(&f.tm_b1, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wa_packed, dims, strides, box, ones,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ca.bkb), promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(B1) failed: %d", (int)r);
+    }
+    {   // B2: conv B's packed filter matrix [256 rows][64 B], one box
+        const cuuint64_t dims[2] = {64, (cuuint64_t)b.k};
+        const cuuint64_t strides[1] = {64};
+        const cuuint32_t box[2] = {64, (cuuint32_t)b.k};
+        CUresult r = g_encode_tiled(&f.tm_b2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)wb_packed, dims, strides, box, ones,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(B2) failed: %d", (int)r);
+    }
+    {   // A: the halo window of conv A's input (as igemm_encode's window map)
+        const cuuint64_t dims[4] = {(cuuint64_t)a.c, (cuuint64_t)a.w, (cuuint64_t)a.h, (cuuint64_t)a.n};
+        const cuuint64_t strides[3] = {(cuuint64_t)a.c, (cuuint64_t)a.c * a.w, (cuuint64_t)a.c * a.w * a.h};
+        const cuuint32_t box[4] = {(cuuint32_t)ca.bkc, (cuuint32_t)ca.wt, (cuuint32_t)(ca.rows_per_tile + (a.r - 1) * a.dil_h), 1};
+        CUresult r = g_encode_tiled(&f.tm_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)x, dims, strides, box, ones,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ca.bkc), promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(A window) failed: %d", (int)r);
+    }
+    {   // output of conv B: (K2, Q, P, N), one 128-byte panel of a window tile per store
+        const cuuint64_t dims[4] = {(cuuint64_t)b.k, (cuuint64_t)gb.q, (cuuint64_t)gb.p, (cuuint64_t)b.n};
+        const cuuint64_t strides[3] = {(cuuint64_t)b.k, (cuuint64_t)b.k * gb.q, (cuuint64_t)b.k * gb.q * gb.p};
+        const cuuint32_t box[4] = {128, (cuuint32_t)ca.cols_per_tile, (cuuint32_t)ca.rows_per_tile, 1};
+        CUresult r = g_encode_tiled(&f.tm_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, y, dims, strides, box, ones,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+    }
+    *out = f;
+    return LBC_OK;
+}
+
+lbc_status fused_tail_launch(const ConvGeom& ga, const ConvGeom& gb, const FusedLaunch& l, const EpilogueParams& epa,
+                             const EpilogueParams& epb, const IgemmRuntime& rt, cudaStream_t stream)
+{
+    FusedParams fp{};
+    IgemmLaunch la{};
+    la.cfg = l.cfg_a;
+    la.cfg.win_stages = l.win_stages;
+    la.cfg.n_mma = 1;
+    la.cfg.grid = l.grid;
+    la.cfg.tpi = 1;
+    la.cfg.team_warps = 8;
+    la.reverse = l.reverse;
+    fill_params(ga, la, epa, rt, fp.a);
+    fp.a.off_b = l.off_b1;
+    fp.k2 = l.k2;
+    fp.relu2 = l.relu2;
+    fp.c_mid = ga.d.k;
+    fp.stage_bufs2 = l.stage_bufs2;
+    fp.off_b2 = l.off_b2; fp.off_a2 = l.off_a2; fp.off_stage2 = l.off_stage2; fp.off_ctl2 = l.off_ctl2;
+    fp.b1_bytes = l.b1_bytes; fp.b2_bytes = l.b2_bytes;
+    using FusedFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const FusedParams, const int32_t*,
+                             const float*, const int32_t*, const float*);
+    const FusedFn fn = igemm_fused_tail_kernel;
+    {
+        static std::mutex mu;
+        static uint64_t done[4] = {0, 0, 0, 0};
+        int dev_ord = 0;
+        LBC_CUDA_TRY(cudaGetDevice(&dev_ord));
+        std::lock_guard<std::mutex> lk(mu);
+        if (first_use_on_device(done, dev_ord)) {
+            LBC_CUDA_TRY(cudaFuncSetAttribute(igemm_fused_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        }
+    }
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)l.grid);
+    lc.blockDim = dim3(kNumThreads);
+    lc.dynamicSmemBytes = l.smem_bytes;
+    lc.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = l.cfg_a.pdl ? 1 : 0;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    (void)gb;
+    LBC_CUDA_TRY(cudaLaunchKernelEx(&lc, fn, l.tm_a, l.tm_b1, l.tm_b2, l.tm_out, fp, epa.bias, epa.scale, epb.bias, epb.scale));
+    LBC_CUDA_TRY(cudaGetLastError());
+    return LBC_OK;
+}
 
 }  // namespace lbc

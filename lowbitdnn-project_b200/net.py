@@ -87,6 +87,12 @@ class Net:
         check(self._lib.lbc_net_read_output_host(self._h, layer, out.ctypes.data_as(ctypes.c_void_p), out.nbytes))
         return out
 
+    def fused_into(self, layer: int) -> int:
+        """Index of the layer whose fused launch absorbs `layer` (its own output is then never materialised), or -1."""
+        v = ctypes.c_int32()
+        check(self._lib.lbc_net_layer_fused_into(self._h, layer, ctypes.byref(v)))
+        return v.value
+
     def check_status(self) -> None:
         check(self._lib.lbc_net_check(self._h))
 

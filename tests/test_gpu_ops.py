@@ -104,6 +104,8 @@ def test_whole_int8_graph_matches_oracle(name, batch):
     torch.cuda.synchronize()
     net.check_status()
     for i, (lname, _, _) in enumerate(layers):
+        if net.fused_into(i) >= 0:
+            continue
         assert np.array_equal(net.read_output(i), want[lname]), f"{name}: node {i} {lname} ({net.layer_kernel(i)})"
     # the host path: network input in, last node out
     d0 = layers[0][1]

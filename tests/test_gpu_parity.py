@@ -410,3 +410,61 @@ def test_repeated_launches_are_identical(d):
     for i, y in enumerate(outs):
         assert np.array_equal(y.cpu().numpy(), want), f"launch {i} differs"
     plan.close()
+
+
+# ---- fused bottleneck tail: conv(R x S -> 64) -> conv(1x1 -> 256) in one launch (r02) -------------------------
+FUSED_CASES = [
+    # (n, h, w, c_in, r, pad, relu_a, relu_b)
+    (2, 56, 56, 64, 3, 1, 1, 1),        # ResNet-50 l1.x.conv2 -> conv3
+    (3, 28, 28, 64, 3, 1, 1, 0),        # no ReLU after the 1x1 (the full-graph bottleneck)
+    (2, 14, 14, 128, 3, 1, 1, 1),       # 128-byte K chunks, 8-row window tiles
+    (1, 20, 224, 32, 3, 1, 1, 1),       # column tiles, 32-byte K chunks
+    (3, 19, 23, 64, 5, 2, 0, 1),        # 5x5, ragged edges, no ReLU in between
+    (2, 9, 40, 64, 1, 0, 1, 1),         # conv A itself a 1 x 3 filter below
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES, ids=lambda c: "n%dh%dw%dc%dr%d" % c[:5])
+def test_fused_tail_equals_the_two_layer_chain(case):
+    """The fused launch must reproduce conv A -> int8 -> conv B bit for bit (oracle chain), for every window geometry the
+    first convolution can have, repeated launches included."""
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    n, h, w, c, r, pad, relu_a, relu_b = case
+    s = 3 if (r == 1) else r
+    da = D(n=n, h=h, w=w, c=c, k=64, r=r, s=s, pad_h=pad, pad_w=(1 if r == 1 else pad), relu=relu_a)
+    db = D(n=n, h=da.p, w=da.q, c=64, k=256, r=1, s=1, relu=relu_b)
+    xa, wa, ba, sa = oracle.synth(da, layer=11)
+    _, wb, bb, sb = oracle.synth(db, layer=12)
+    mid = oracle.conv_nhwc(da, xa, wa, ba, sa)
+    want = oracle.conv_nhwc(db, mid, wb, bb, sb)
+    from tests.parity_util import lbc_desc
+    dev = torch.device("cuda:0")
+    plan = lbc.FusedTailPlan(lbc_desc(da), lbc_desc(db))
+    wpa, wpb = plan.prepack(torch.from_numpy(wa).to(dev).reshape(-1), torch.from_numpy(wb).to(dev).reshape(-1))
+    t = lambda a: torch.from_numpy(a).to(dev)
+    x, tba, tsa, tbb, tsb = t(xa), t(ba), t(sa), t(bb), t(sb)
+    outs = [plan.run(x, wpa, tba, tsa, wpb, tbb, tsb) for _ in range(3)]
+    y, ms = plan.run(x, wpa, tba, tsa, wpb, tbb, tsb, timed=True)
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs + [y]):
+        got = o.cpu().numpy()
+        if not np.array_equal(got, want):
+            from tests.parity_util import mismatch_report
+            raise AssertionError(f"launch {i}:\n" + mismatch_report(got, want))
+    assert ms > 0
+    plan.close()
+
+
+def test_fused_tail_refuses_other_pairs():
+    import lowbitdnn_project_b200 as lbc
+    a = lbc.ConvDesc(n=1, h=14, w=14, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1)
+    for bad_a, bad_b in [
+        (a.replace(k=128), lbc.ConvDesc(n=1, h=14, w=14, c=128, k=256, r=1, s=1)),          # 128 channels in between
+        (a, lbc.ConvDesc(n=1, h=14, w=14, c=64, k=128, r=1, s=1)),                           # 1x1 to 128
+        (a.replace(stride_h=2, stride_w=2), lbc.ConvDesc(n=1, h=7, w=7, c=64, k=256, r=1, s=1)),   # stride 2: no window mode
+        (a, lbc.ConvDesc(n=1, h=14, w=14, c=64, k=256, r=3, s=3, pad_h=1, pad_w=1)),         # second conv not 1x1
+    ]:
+        with pytest.raises(lbc.LbcError) as e:
+            lbc.FusedTailPlan(bad_a, bad_b)
+        assert e.value.status == 2
