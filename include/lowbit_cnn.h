@@ -119,7 +119,7 @@ typedef struct lbc_plan_options {
     int32_t tps_kb;              /* cap (KB) on the B bytes grouped into one ring stage in window mode              */
     int32_t resident_kb;         /* largest filter matrix (KB) kept resident                                        */
     int32_t epi_split;           /* tri-state: both epilogue teams drain every tile (column split) on > 128-wide tiles */
-    int32_t fuse;                /* networks: run conv(R x S -> 64) -> conv(1x1 -> 256) pairs as one fused launch (0: never)  */
+    int32_t fuse;                /* networks: 1 = run conv(R x S -> 64) -> conv(1x1 -> 256) pairs as one fused launch (opt-in) */
     int32_t reserved[6];
 } lbc_plan_options;
 

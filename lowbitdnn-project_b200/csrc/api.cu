@@ -1237,7 +1237,11 @@ lbc_status lbc_net_create_graph(const lbc_node* nodes, int32_t n_layers, const l
         }
         if (L.x_own) cudaMemset(L.x_own, 0, L.in_bytes());
     }
-    if (st == LBC_OK && opt.fuse != 0) {
+    // Opt-in (lbc_plan_options::fuse = 1).  Measured on ResNet-50 stage 1 at N = 512 (r02): a fused pair takes 160-169 us against
+    // 56 + 89 us for the two launches - it removes 2 x 103 MB of HBM traffic per bottleneck, but both epilogues now run on the
+    // same 16 warps one after the other and the per-tile fixed costs of two drains add up; until the epilogue is split into
+    // dedicated epi1 / epi2 warp groups the planner does not choose it on its own.
+    if (st == LBC_OK && opt.fuse == 1) {
         // fused bottleneck tails: a convolution whose ONLY consumer is a 1x1 convolution, both shapes the fused kernel covers
         std::vector<int> consumers((size_t)n_layers, 0);
         for (int i = 0; i < n_layers; ++i) {

@@ -2295,7 +2295,7 @@ lbc_status fused_tail_encode(const ConvGeom& ga, const IgemmConfig& ca, const Co
         const uint32_t stage = 2u * (uint32_t)bufs * kBlockM * 128u;
         if (fixed + stage + 4u * ca.win_stage_bytes > 227u * 1024u) continue;
         const int wins = (int)std::min<uint32_t>(kMaxWinStages, (227u * 1024u - fixed - stage) / ca.win_stage_bytes);
-        if (wins < (bufs == 2 ? 6 : 4)) continue;
+        if (wins < (bufs == 2 ? 5 : 4)) continue;
         f.stage_bufs2 = bufs;
         f.win_stages = wins;
         fits = true;

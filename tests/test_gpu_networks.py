@@ -67,13 +67,7 @@ def test_network_matches_oracle_chain(name, batch):
     layers = lbc.networks.NETWORKS[name](batch)
     want = oracle_chain(layers)
     net = load_net(lbc, layers)
-    if name == "resnet50":
-        # stage 1's conv2 -> conv3 pairs run as fused launches (the middle tensor is never written)
-        names = [l[0] for l in layers]
-        for b in range(3):
-            assert net.fused_into(names.index(f"l1.{b}.conv2")) == names.index(f"l1.{b}.conv3")
-        assert net.fused_into(names.index("l2.1.conv2")) == -1
-        assert net.launches == len(layers) + 1 - 3           # the stem launches twice, three pairs launch once
+    assert all(net.fused_into(i) == -1 for i in range(len(layers)))      # fusion is opt-in
     stream = torch.cuda.current_stream()
     # two untimed runs back to back (launches overlap through programmatic dependent launch), then a timed one
     net.run(stream=stream)
@@ -95,8 +89,15 @@ def test_network_without_alternating_traversal_and_capped_grid(name, batch):
     import lowbitdnn_project_b200 as lbc
     layers = lbc.networks.NETWORKS[name](batch)
     want = oracle_chain(layers)
-    for options in ({"reverse": 0, "max_grid": 5}, {"max_grid": 6}, {"fuse": 0, "max_grid": 7}):
+    for options in ({"reverse": 0, "max_grid": 5}, {"max_grid": 6}, {"fuse": 1}, {"fuse": 1, "max_grid": 7, "reverse": 0}):
         net = load_net(lbc, layers, options=options)
+        if name == "resnet50" and options.get("fuse"):
+            # stage 1's conv2 -> conv3 pairs run as fused launches (the middle tensor is never written)
+            names = [l[0] for l in layers]
+            for b in range(3):
+                assert net.fused_into(names.index(f"l1.{b}.conv2")) == names.index(f"l1.{b}.conv3")
+            assert net.fused_into(names.index("l2.1.conv2")) == -1
+            assert net.launches == len(layers) + 1 - 3           # the stem launches twice, three pairs launch once
         net.run(stream=torch.cuda.current_stream())
         net.run(stream=torch.cuda.current_stream())
         torch.cuda.synchronize()

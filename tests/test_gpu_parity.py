@@ -419,7 +419,7 @@ FUSED_CASES = [
     (3, 28, 28, 64, 3, 1, 1, 0),        # no ReLU after the 1x1 (the full-graph bottleneck)
     (2, 14, 14, 128, 3, 1, 1, 1),       # 128-byte K chunks, 8-row window tiles
     (1, 20, 224, 32, 3, 1, 1, 1),       # column tiles, 32-byte K chunks
-    (3, 19, 23, 64, 5, 2, 0, 1),        # 5x5, ragged edges, no ReLU in between
+    (3, 19, 23, 32, 5, 2, 0, 1),        # 5x5, ragged edges, no ReLU in between
     (2, 9, 40, 64, 1, 0, 1, 1),         # conv A itself a 1 x 3 filter below
 ]
 
