@@ -117,6 +117,11 @@ def synth_input(d, layer: int):
 
 
 def layer_work(d):
+    if not hasattr(d, "groups"):        # graph nodes between convolutions: pure byte movers
+        p, q = d.out_hw
+        if hasattr(d, "kh"):            # max-pool: input once, output once
+            return 0.0, float(d.n * d.h * d.w * d.c + d.n * p * q * d.c)
+        return 0.0, float(3 * d.n * d.h * d.w * d.c)      # residual add: two operands in, one out
     p = (d.h + 2 * d.pad_h - (d.dil_h * (d.r - 1) + 1)) // d.stride_h + 1
     q = (d.w + 2 * d.pad_w - (d.dil_w * (d.s - 1) + 1)) // d.stride_w + 1
     cg = d.c // d.groups
@@ -146,6 +151,8 @@ def cpu_baseline_port(layers, budget_s: float = 15.0):
     threads = oracle.max_threads()
     prepared = []
     for i, (_, d, _) in enumerate(layers):
+        if not hasattr(d, "groups"):
+            continue                    # (pool / add nodes: negligible CPU work, convolutions only)
         od = OD(**{**d.__dict__, "n": 1})
         x, w, b, s = oracle.synth(od, layer=i)
         prepared.append((od, x, w, b, s))
@@ -170,6 +177,14 @@ def parity_check(net, layers, rank, images=2):
     outs, bad = {}, []
     for i, (name, d, src) in enumerate(layers):
         n = min(images, d.n)
+        if not hasattr(d, "groups"):    # max-pool / residual add nodes of a graph network
+            if hasattr(d, "kh"):
+                outs[name] = oracle.max_pool_nhwc(outs[src], d.kh, d.kw, d.stride_h, d.stride_w, d.pad_h, d.pad_w)
+            else:
+                outs[name] = oracle.add_relu(outs[src[0]], outs[src[1]], bool(d.relu))
+            if not np.array_equal(net.read_output(i, images=n), outs[name]):
+                bad.append(name)
+            continue
         x = synth_input(d, i + 1000 * rank)[:n] if src is None else outs[src]
         w, b, s = synth_params(d, i)
         outs[name] = oracle.conv_nhwc(OD(**{**d.__dict__, "n": n}), np.ascontiguousarray(x), w, b, s)
@@ -403,6 +418,8 @@ def main():
     t_setup = time.time()
     net = lbc.Net(layers, options={k: int(v) for k, v in (o.split("=") for o in args.opt)} or None)
     for i, (_, d, src) in enumerate(layers):
+        if not hasattr(d, "groups"):
+            continue                    # pool / add nodes have no parameters
         w, b, s = synth_params(d, i)
         net.set_params(i, w, b, s)
         if src is None:
@@ -410,7 +427,7 @@ def main():
     d0, dl = layers[0][1], layers[-1][1]
     pl, ql = dl.out_hw
     x_host = torch.from_numpy(synth_input(d0, 1000 * rank)).pin_memory()
-    y_host = torch.empty((dl.n, pl, ql, dl.k), dtype=torch.int8).pin_memory()
+    y_host = torch.empty((dl.n, pl, ql, dl.k if hasattr(dl, "k") else dl.c), dtype=torch.int8).pin_memory()
     stream = torch.cuda.current_stream()
     log(f"[rank {rank}] setup {time.time() - t_setup:.1f}s; kernels: "
         + ", ".join(f"{k}x{v}" for k, v in sorted(_count(net).items())))
@@ -491,7 +508,7 @@ def main():
         works = [layer_work(d) for _, d, _ in layers]
         # dominant kernel = the one with the largest share of the step
         # the small-C stem runs the same igemm_i8_kernel (after its space-to-depth pass), so it counts with it
-        group = {"stem_tc": "igemm_tc"}
+        group = {"stem_tc": "igemm_tc", "maxpool": "pool_add", "add_relu": "pool_add"}
         share = {}
         for k, ms in zip(kinds, per_layer):
             share[group.get(k, k)] = share.get(group.get(k, k), 0.0) + ms
@@ -540,7 +557,8 @@ def main():
         except Exception as e:  # noqa: BLE001
             log("traffic file unreadable:", e)
         roofline.update({
-            "kernel": {"igemm_tc": "igemm_i8_kernel", "direct": "direct_conv_kernel", "depthwise": "depthwise_kernel"}[dom],
+            "kernel": {"igemm_tc": "igemm_i8_kernel", "direct": "direct_conv_kernel", "depthwise": "depthwise_kernel",
+                       "pool_add": "maxpool / add_relu kernels"}[dom],
             "launches_per_step": len(sel), "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
             "instrumented_pass_ms": instrumented_ms,
             "timing_note": "kernel_ms_per_step = the kernel's share of the per-launch event pass x ms_per_step of the timed region",
