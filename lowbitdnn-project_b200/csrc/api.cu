@@ -569,6 +569,7 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
                  c.res_b ? (c.res_one ? "resident,n-stationary" : c.n_mma == 2 ? "resident,2mma" : "resident") : c.pair ? "ring,paired-tiles" : c.cta2 ? "ring,cta-pair" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols, c.stage_bufs,
                  d.out_mode != LBC_OUT_INT8 ? (c.fold ? "int32,bias-in-mma" : "int32")
+                 : (c.warp_store && c.team_warps == 4) ? (c.fold ? "narrow-warp-stores,bias-in-mma" : "narrow-warp-stores")
                  : c.warp_store ? (c.epi_split ? (c.fold ? "warp-stores,split,bias-in-mma" : "warp-stores,split")
                                                : (c.fold ? "warp-stores,bias-in-mma" : "warp-stores"))
                  : (c.epi_split && c.team_warps == 8) ? (c.fold ? "2x8-warp-teams,split,bias-in-mma" : "2x8-warp-teams,split")

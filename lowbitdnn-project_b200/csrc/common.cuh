@@ -132,6 +132,7 @@ struct IgemmLaunch {
     CUtensorMap tm_a;
     CUtensorMap tm_b;
     CUtensorMap tm_out;
+    CUtensorMap tm_out2;   // window tiles with per-warp stores: the ragged last run of a tile row (else a copy of tm_out)
     IgemmConfig cfg;
     int32_t reverse = 0;   // walk the M tiles / images last-to-first (L2 reuse of the producer's most recent output)
 };

@@ -510,7 +510,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar, uint32_t leader)
 template <int KM, int KS, bool RESB, bool CTA2, bool MAYFOLD>
 __global__ void __launch_bounds__(kNumThreads, 1)
 igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                const __grid_constant__ CUtensorMap tm_out, const IgemmParams prm,
+                const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2, const IgemmParams prm,
                 const int32_t* __restrict__ bias, const float* __restrict__ scale, void* __restrict__ y)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -546,6 +546,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         ptx::prefetch_tensormap(&tm_a);
         ptx::prefetch_tensormap(&tm_b);
         ptx::prefetch_tensormap(&tm_out);
+        ptx::prefetch_tensormap(&tm_out2);
         const uint32_t consumers = pair_mode ? 2u : 1u;   // pair mode: both MMA warps read every stage
         for (int i = 0; i < prm.stages; ++i) {
             ptx::mbar_init(&ctl->full[i], 1);
@@ -1081,6 +1082,78 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 n_blk += s_nb;
                 if (n_blk >= tiles_n) { n_blk -= tiles_n; ++m; }
                 m += s_m;
+            }
+            if (lane == 0) ptx::tma_store_wait<0>();
+        } else if (!CTA2 && prm.warp_store && small_teams && !split && prm.n_acc == 8) {
+            // ---- narrow N tiles (one tile of 32 / 64 columns, 8 accumulator stages) with per-warp stores, all A modes.
+            // A 128 x 64 tile is 8 KB of output against ~1000 cycles of per-team bookkeeping in the team paths below (two
+            // named barriers, the issuer's store wait, the iterator: traces r02 show 2450 cycles per team and tile of which
+            // 1300 convert) - the stems and every 64-channel layer ran at that pace, not at HBM's or the tensor pipe's.
+            // Here nothing is shared inside a team: the warp converts its 32 TMEM lanes x bn columns into its OWN staging
+            // buffer and stores them with its own TMA store; the team only shares the accumulator stage's barriers.
+            // Four teams and eight stages: team t drains stage t and t + 4 alternately, the phase flips every second tile.
+            // WINDOW tiles: the window pitch is a power of two >= 32 (the planner pads it), so a warp's 32 lanes are ONE
+            // run of <= 32 consecutive output pixels of one tile row: box {bn, 32, 1, 1} (tm_out), or the ragged last run
+            // of a row with box {bn, cols % 32, 1, 1} (tm_out2); warps whose lanes are all halo convert nothing.
+            for (int32_t c = (int32_t)tt_id; c < prm.bn; c += (int32_t)team_threads) {
+                const bool in = c < prm.k_out;
+                const int32_t kp = prm.k_mod ? c % prm.k_mod : c;
+                sc[c] = (in && scale) ? __ldg(scale + kp) : 0.0f;
+                bi[c] = (in && bias) ? __ldg(bias + kp) : 0;
+            }
+            ptx::named_bar_sync(bar_id, team_threads);
+            const uint32_t wbytes = 32u * (uint32_t)prm.panel_bytes;
+            const uint32_t wbuf0 = ptx::smem_u32(staging) + e * nbufs * wbytes;
+            const uint32_t wrow_off = lane * (uint32_t)prm.panel_bytes;
+            const uint32_t wswz = ((wrow_off >> 7) & ((1u << prm.panel_swz_bits) - 1u)) << 4;
+            const int32_t wait_mode = nbufs >= 2 ? 2 : 1;
+            const bool relu = prm.relu != 0;
+            const int32_t lane0_row = (int32_t)(quarter * 32u);
+            // this warp's run of output pixels inside a window tile
+            int32_t wr = 0, wc0 = 0, vc = 32;
+            if (kWindow) {
+                wr = lane0_row / prm.wt;
+                wc0 = lane0_row - wr * prm.wt;
+                vc = min(32, prm.cols_per_tile - wc0);
+            }
+            const bool has_rows = !kWindow || (vc > 0 && wr < prm.rows_per_tile);
+            const bool ragged = vc < 32;
+            EpiThread wt_ = et;
+            wt_.valid = true;
+            uint32_t acc = team, phase = 0, wbuf = wbuf0;
+            Iter it;
+            it.init(prm, (int32_t)(blockIdx.x + team * gridDim.x), n_major, true);
+            for (; it.tile < num_tiles; it.next(prm)) {
+                ptx::mbar_wait_s(tmem_full_s + acc * 8u, phase, tflag);
+                ptx::tc_fence_after();
+                if (issuer) trace_ev(prm, tracing, it.local * 4 + (int32_t)team, EV_E_START);
+                if (has_rows)
+                    epi_run<kFold>(true, relu, kFold, prm, sc, bi, tmem_lane_base + acc * bn_u, 0, 0, pcols, wt_, wbuf, wrow_off, wswz,
+                                  nullptr, -1, 0, wait_mode);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_s(tmem_empty_s + acc * 8u);
+                if (issuer) trace_ev(prm, tracing, it.local * 4 + (int32_t)team, EV_E_DRAINED);
+                if (has_rows) {
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (kWindow) {
+                            const int32_t pp = it.p0(prm) + wr, qq = it.q0(prm) + wc0, img = it.image();
+                            if (img < prm.n_img && pp < prm.p) {
+                                if (ragged) ptx::tma_store_4d_s(&tm_out2, wbuf, 0, qq, pp, img);
+                                else ptx::tma_store_4d_s(&tm_out, wbuf, 0, qq, pp, img);
+                            }
+                        } else {
+                            ptx::tma_store_2d_s(&tm_out, wbuf, 0, it.m0() + lane0_row);
+                        }
+                        ptx::tma_store_commit();
+                    }
+                    if (nbufs >= 2) wbuf ^= (wbuf0 ^ (wbuf0 + wbytes));      // toggle between the warp's two buffers
+                }
+                if (issuer) trace_ev(prm, tracing, it.local * 4 + (int32_t)team, EV_E_STORED);
+                acc ^= 4u;
+                if (acc == team) phase ^= 1u;
             }
             if (lane == 0) ptx::tma_store_wait<0>();
         } else if (!CTA2 && prm.tpi == 2) {
@@ -1734,6 +1807,18 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         const int row_tiles = (g.p + rows - 1) / rows;
         const double eff = (double)g.p * g.q / ((double)row_tiles * col_tiles * kBlockM);
         const bool s_ok = !c16 || d.s <= 8;
+        // Narrow N tiles (one tile of 32 / 64 columns, int8 out) drain with per-warp stores (see the kernel's narrow
+        // warp-store path), which needs a warp's 32 accumulator lanes to be one run of pixels of one tile row: pad the
+        // window pitch to a power of two >= 32 where that keeps the number of rows per tile (56 + 2 -> 64, 28 + 2 -> 32,
+        // 112 + 3 -> 128; the extra pixels per window row are fetched but never read by an MMA row that is stored).
+        if (d.out_mode == LBC_OUT_INT8 && (c.bn == 64 || c.bn == 32) && c.tiles_n == 1 && o.warp_store != 0 && o.small_teams != 0 &&
+            o.four_acc != 0) {
+            int wt2 = 32;
+            while (wt2 < wt) wt2 <<= 1;
+            int rows2 = 1;
+            while (rows2 < g.p && rows2 * wt2 + cols <= kBlockM) ++rows2;
+            if (wt2 <= kBlockM && rows2 == rows) wt = wt2;
+        }
         if (eff >= 0.55 && wt <= 256 && rows + ext_h <= 256 && s_ok && (rows - 1) * wt + cols <= kBlockM) {
             c.mode = A_WINDOW;
             c.s_pad = s_eff;
@@ -1806,11 +1891,17 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     // whole panels per warp - 256 -> 2 x 128 B, 128 -> 2 x 64 B for the two warp sets of a team, <= 64 -> one panel
     // Measured (r01): +5-10% on 256-wide tiles with a short K loop (the 1x1 channel expansions, whose epilogue is the
     // bound); a loss where the extra staging bytes cost ring depth (long K loops) and on narrow tiles (2 KB stores).
+    // Narrow tiles (r02): one N tile of 32 / 64 columns drains through the kernel's narrow warp-store path in every A mode
+    // (window tiles need the padded pitch above) - the team paths spent more cycles per tile on barriers and bookkeeping
+    // than on conversion, which made the stems and every 64-channel layer epilogue-bound.
     c.warp_store = 0;
+    const bool narrow_ws = (c.bn == 64 || c.bn == 32) && c.tiles_n == 1 && !c.pair && !c.cta2 && o.small_teams != 0 && o.four_acc != 0 &&
+                           (c.mode != A_WINDOW || (c.wt >= 32 && (c.wt & (c.wt - 1)) == 0));
     {
-        bool want = c.bn == 256 && !c.cta2 && c.k_blocks * (c.bkb / 32) <= 8;
+        bool want = (c.bn == 256 && !c.cta2 && c.k_blocks * (c.bkb / 32) <= 8) || narrow_ws;
         if (o.warp_store >= 0) want = o.warp_store != 0;     // test / tuning override
-        if (c.mode != A_WINDOW && d.out_mode == LBC_OUT_INT8 && want && (c.bn == 256 || c.bn == 128 || c.bn == 64 || c.bn == 32)) {
+        if ((c.mode != A_WINDOW || narrow_ws) && d.out_mode == LBC_OUT_INT8 && want &&
+            (c.bn == 256 || c.bn == 128 || c.bn == 64 || c.bn == 32)) {
             c.warp_store = 1;
             if (c.bn == 128) c.panel_bytes = 64;
         }
@@ -1847,6 +1938,8 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         c.tpi = 2;
         c.n_acc = 8;
     }
+    // narrow warp-store path: 8 stages, one tile per team step
+    if (c.warp_store && narrow_ws && c.team_warps == 4) c.n_acc = 8;
     const int n_teams = kEpiWarps / c.team_warps;
 
     // ---- smem carve-up: [A ring | window ring][B ring][output staging][control]
@@ -2097,14 +2190,23 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
     if (d.out_mode == LBC_OUT_INT8) {
         const CUtensorMapSwizzle oswz = cfg.panel_swz_bits ? swizzle_for(cfg.panel_bytes) : CU_TENSOR_MAP_SWIZZLE_NONE;
         CUresult r;
+        bool have_out2 = false;
         if (cfg.mode == A_WINDOW) {
             const cuuint64_t dims[4] = {(cuuint64_t)d.k, (cuuint64_t)g.q, (cuuint64_t)g.p, (cuuint64_t)d.n};
             const cuuint64_t strides[3] = {(cuuint64_t)d.k, (cuuint64_t)d.k * g.q, (cuuint64_t)d.k * g.q * g.p};
-            const cuuint32_t box[4] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)cfg.cols_per_tile,
-                                       (cuuint32_t)cfg.rows_per_tile, 1};
+            // per-warp stores: runs of 32 pixels of one tile row (and the ragged last run of a row)
+            const cuuint32_t box[4] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)(cfg.warp_store ? 32 : cfg.cols_per_tile),
+                                       (cuuint32_t)(cfg.warp_store ? 1 : cfg.rows_per_tile), 1};
             r = g_encode_tiled(&out->tm_out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, y, dims, strides, box, ones,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r == CUDA_SUCCESS && cfg.warp_store && cfg.cols_per_tile % 32 != 0) {
+                const cuuint32_t box2[4] = {(cuuint32_t)cfg.panel_bytes, (cuuint32_t)(cfg.cols_per_tile % 32), 1, 1};
+                r = g_encode_tiled(&out->tm_out2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, y, dims, strides, box2, ones,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                have_out2 = true;
+            }
         } else {
             const cuuint64_t dims[2] = {(cuuint64_t)d.k, (cuuint64_t)g.m_total};
             const cuuint64_t strides[1] = {(cuuint64_t)d.k};
@@ -2114,8 +2216,10 @@ lbc_status igemm_encode(const ConvGeom& g, const IgemmConfig& cfg, const DeviceI
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         }
         LBC_REQUIRE(r == CUDA_SUCCESS, LBC_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+        if (!have_out2) out->tm_out2 = out->tm_out;
     } else {
         out->tm_out = out->tm_b;   // unused in int32 mode; keep the parameter a valid descriptor
+        out->tm_out2 = out->tm_b;
     }
     return LBC_OK;
 }
@@ -2199,8 +2303,8 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     fill_params(g, l, ep, rt, prm);
     const int km = c.mode == A_WINDOW ? (c.bkc == 16 ? 3 : 2) : c.mode;
     const int ks = c.bkb / 32;
-    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams, const int32_t*,
-                              const float*, void*);
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const IgemmParams,
+                              const int32_t*, const float*, void*);
     // last index: 0 streaming B, 1 resident B, 2 streaming B in CTA pairs (not for 16-byte pixels), 3 resident B with the
     // bias-fold variant of the tile loops
 #define LBC_KERNELS(KM_, KS_) {igemm_i8_kernel<KM_, KS_, false, false, false>, igemm_i8_kernel<KM_, KS_, true, false, false>, \
@@ -2247,7 +2351,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     }
     const int32_t* bias_p = ep.bias;
     const float* scale_p = ep.scale;
-    LBC_CUDA_TRY(cudaLaunchKernelEx(&lc, fn, l.tm_a, l.tm_b, l.tm_out, prm, bias_p, scale_p, y));
+    LBC_CUDA_TRY(cudaLaunchKernelEx(&lc, fn, l.tm_a, l.tm_b, l.tm_out, l.tm_out2, prm, bias_p, scale_p, y));
     LBC_CUDA_TRY(cudaGetLastError());
     return LBC_OK;
 }

@@ -267,6 +267,48 @@ def test_igemm_n_stationary_filter_tiles(d):
     assert _check(D(**{**d.__dict__, "out_mode": 0}), bias_range=3_000_000, options={**ns, "fold_bias": 1}) == "igemm_tc"
 
 
+# ---- narrow N tiles with per-warp stores (r02): one tile of 32 / 64 columns, every A mode ---------------------
+NARROW_CASES = [
+    # window tiles: pitch padded to 32 / 64 / 128, runs of 32 pixels + a ragged last run, halo-only warps
+    D(n=3, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # 2 x 56 per tile, pitch 64, ragged run of 24
+    D(n=5, h=28, w=28, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # 4 x 28, pitch 32: every run ragged (28)
+    D(n=2, h=9, w=112, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1),                # 1 x 112, pitch 128, ragged run of 16
+    D(n=1, h=7, w=224, c=32, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # two column tiles of 112
+    D(n=2, h=11, w=150, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1, relu=1),       # column tiles of 75: run of 11, a halo-only warp
+    D(n=2, h=13, w=96, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1),                # 1 x 96: three full runs, no ragged one
+    D(n=3, h=7, w=48, c=32, k=32, r=3, s=3, pad_h=1, pad_w=1, relu=1),         # 2 x 48, pitch 64, odd P: ragged row tile
+    D(n=2, h=15, w=100, c=32, k=64, r=5, s=5, pad_h=2, pad_w=2, relu=1),       # pitch 128, run of 4
+    D(n=2, h=30, w=60, c=16, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # 16-byte pixels (paired taps)
+    D(n=2, h=45, w=224, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),   # ResNet stem rows (1 x 112)
+    D(n=2, h=40, w=224, c=3, k=32, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),   # MobileNetV2 stem rows
+    D(n=1, h=12, w=224, c=3, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1),        # VGG conv1_1 rows: two column tiles
+    # ring modes
+    D(n=3, h=28, w=28, c=64, k=64, r=1, s=1, relu=1),                          # tiled, resident filter
+    D(n=2, h=19, w=19, c=256, k=64, r=1, s=1),                                 # tiled, M tail (361 rows per image)
+    D(n=2, h=14, w=14, c=384, k=64, r=1, s=1, relu=1),
+    D(n=2, h=28, w=28, c=192, k=32, r=1, s=1),
+    D(n=3, h=29, w=29, c=64, k=64, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),   # im2col
+    D(n=2, h=14, w=14, c=1024, k=64, r=1, s=1),                                # streaming filter matrix (128 KB)
+]
+
+
+@pytest.mark.parametrize("d", NARROW_CASES, ids=lambda d: f"n{d.n}h{d.h}w{d.w}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
+def test_narrow_tiles_with_per_warp_stores(d):
+    """The planner's own choice, then the same layer with capped grids (every CTA walks many tiles: TMEM stages and both
+    staging buffers wrap), one staging buffer per warp, reversed traversal, and with the path switched off (team path)."""
+    import lowbitdnn_project_b200 as lbc
+    plan = lbc.ConvPlan(lbc.ConvDesc(**d.__dict__))
+    try:
+        if plan.kernel in ("igemm_tc", "stem_tc"):
+            assert "narrow-warp-stores" in plan.describe(), plan.describe()
+    finally:
+        plan.close()
+    assert _check(d) in ("igemm_tc", "stem_tc")
+    for options in ({"max_grid": 1}, {"max_grid": 3, "reverse": 1}, {"max_grid": 2, "stage_bufs": 1}, {"warp_store": 0},
+                    {"max_grid": 5, "two_mma_warps": 0}):
+        assert _check(d, options=options) in ("igemm_tc", "stem_tc")
+
+
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
 STEM_CASES = [
     D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),    # ResNet stem
