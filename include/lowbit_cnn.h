@@ -97,7 +97,7 @@ typedef struct lbc_plan_options {
     int32_t warp_store;          /* per-warp staging + TMA stores in the epilogue (ring modes)                      */
     int32_t fold_bias;           /* bias through the first MMA of every tile (resident filter matrix)               */
     int32_t paired_tiles;        /* two M tiles per CTA step share every B block (window A, streaming B); opt-in    */
-    int32_t resident_filter;     /* filter matrix kept in shared memory when it fits                                */
+    int32_t resident_filter;     /* filter matrix kept in shared memory when it fits (2: but not as halves in CTA pairs) */
     int32_t window;              /* shifted-window A operand for stride-1 RxS layers (0: TMA im2col instead)        */
     int32_t keep_window;         /* 1: keep the window mode where the planner would prefer im2col + CTA pairs        */
     int32_t force_im2col;        /* 1: TMA im2col A operand even for pure GEMMs                                     */

@@ -566,7 +566,7 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
                  plan->kind == LBC_KERNEL_STEM_TC ? "stem_tc(s2d->16ch)" : plan->pw_factor > 1 ? "igemm_tc(pixel-groups)" : "igemm_tc",
                  d.n, d.h, d.w, d.c, d.k, d.r, d.s,
                  d.stride_h, d.pad_h, (long long)plan->g.m_total, c.bn, c.bkc, c.k_blocks, c.stages, c.tps, c.win_stages,
-                 c.res_b ? (c.res_one ? "resident,n-stationary" : c.n_mma == 2 ? "resident,2mma" : "resident") : c.pair ? "ring,paired-tiles" : c.cta2 ? "ring,cta-pair" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
+                 c.res_b ? (c.cta2 ? "resident,cta-pair" : c.res_one ? "resident,n-stationary" : c.n_mma == 2 ? "resident,2mma" : "resident") : c.pair ? "ring,paired-tiles" : c.cta2 ? "ring,cta-pair" : "ring", modes[c.mode], c.rows_per_tile, c.cols_per_tile, c.tiles_m,
                  c.tiles_n, c.grid, c.smem_bytes, c.tmem_cols, c.stage_bufs,
                  d.out_mode != LBC_OUT_INT8 ? (c.fold ? "int32,bias-in-mma" : "int32")
                  : (c.warp_store && c.team_warps == 4) ? (c.fold ? "narrow-warp-stores,bias-in-mma" : "narrow-warp-stores")

@@ -598,17 +598,23 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const bool leader = ptx::elect_one();
         if (RESB) {
             // the whole filter matrix, once: per N tile, k_blocks boxes of [bn][bkb] side by side
+            // CTA pairs: each CTA keeps ITS half of the filter rows (cta_group::2 MMAs read B from both CTAs); the leader's
+            // barrier collects the bytes of both halves, so the one MMA-issuing thread waits on a single barrier
             if (leader) {
-                ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes);
+                if (!CTA2 || cta_rank == 0) ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes * (CTA2 ? 2u : 1u));
                 const int32_t nblk = prm.cblocks * prm.inner;
                 uint8_t* dst = smem_b;
                 // every N tile, or (N-stationary) only the one this CTA works on
                 const int32_t nt0 = prm.res_one ? (int32_t)(blockIdx.x % (uint32_t)prm.tiles_n) : 0;
                 const int32_t nt1 = prm.res_one ? nt0 + 1 : prm.tiles_n;
+                const uint32_t bfull0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->bfull), 0) : 0u;
+                const int32_t half_off = CTA2 ? (int32_t)cta_rank * (prm.bn >> 1) : 0;
                 for (int32_t nt = nt0; nt < nt1; ++nt) {
                     int32_t bcol = 0;
-                    for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb)
-                        ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, nt * prm.bn);
+                    for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb) {
+                        if (CTA2) ptx::tma_load_2d_2sm(dst, &tm_b, bfull0, bcol, nt * prm.bn + half_off);
+                        else ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, nt * prm.bn);
+                    }
                 }
             }
             __syncwarp();
@@ -663,7 +669,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                     ptx::tma_load_im2col_4d_2sm(dst_a, &tm_a, fbar, c0, w_base, h_base, n0, (uint16_t)off_w, (uint16_t)off_h);
                                 else if (KM == A_TILED)
                                     ptx::tma_load_2d_2sm(dst_a, &tm_a, fbar, c0, m0);
-                                ptx::tma_load_2d_2sm(dst_b, &tm_b, fbar, bcol, brow);
+                                if (!RESB) ptx::tma_load_2d_2sm(dst_b, &tm_b, fbar, bcol, brow);
                             }
                         } else if (leader) {
                             if (KM == A_IM2COL)
@@ -872,17 +878,17 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     for (; j + kBatch <= n_tab; j += kBatch) {
 #pragma unroll
                         for (int u = 0; u < kBatch; ++u) {
-                            ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j + u], da_hi, b_base + (uint32_t)prm.b_tab[j + u],
-                                                  db_hi, idesc, accumulate, leader);
+                            mma_issue<CTA2>(tmem_d, a_base + (uint32_t)prm.a_tab[j + u], da_hi, b_base + (uint32_t)prm.b_tab[j + u],
+                                            db_hi, idesc, accumulate, leader);
                             accumulate = 1;
                         }
                     }
                     for (; j < n_tab; ++j) {
-                        ptx::mma_i8_ss_pred32(tmem_d, a_base + (uint32_t)prm.a_tab[j], da_hi, b_base + (uint32_t)prm.b_tab[j], db_hi,
-                                              idesc, accumulate, leader);
+                        mma_issue<CTA2>(tmem_d, a_base + (uint32_t)prm.a_tab[j], da_hi, b_base + (uint32_t)prm.b_tab[j], db_hi,
+                                        idesc, accumulate, leader);
                         accumulate = 1;
                     }
-                    ptx::mma_commit_pred(&ctl->wempty[ws], leader);
+                    mma_commit<CTA2>(&ctl->wempty[ws], leader);
                     if (++ws == win_hi) { ws = win_lo; wphase ^= 1; }
                     wready = ptx::mbar_test_u(&ctl->wfull[ws], wphase);
                 }
@@ -1807,11 +1813,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         const int row_tiles = (g.p + rows - 1) / rows;
         const double eff = (double)g.p * g.q / ((double)row_tiles * col_tiles * kBlockM);
         const bool s_ok = !c16 || d.s <= 8;
-        // Narrow N tiles (one tile of 32 / 64 columns, int8 out) drain with per-warp stores (see the kernel's narrow
-        // warp-store path), which needs a warp's 32 accumulator lanes to be one run of pixels of one tile row: pad the
+        // Narrow N tiles (one tile of 32 / 64 columns, int8 out) can drain with per-warp stores (warp_store = 1, see the
+        // kernel's narrow warp-store path), which needs a warp's 32 accumulator lanes to be one run of pixels of one tile row: pad the
         // window pitch to a power of two >= 32 where that keeps the number of rows per tile (56 + 2 -> 64, 28 + 2 -> 32,
         // 112 + 3 -> 128; the extra pixels per window row are fetched but never read by an MMA row that is stored).
-        if (d.out_mode == LBC_OUT_INT8 && (c.bn == 64 || c.bn == 32) && c.tiles_n == 1 && o.warp_store != 0 && o.small_teams != 0 &&
+        if (d.out_mode == LBC_OUT_INT8 && (c.bn == 64 || c.bn == 32) && c.tiles_n == 1 && o.warp_store == 1 && o.small_teams != 0 &&
             o.four_acc != 0) {
             int wt2 = 32;
             while (wt2 < wt) wt2 <<= 1;
@@ -1865,6 +1871,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     if (c.mode == A_WINDOW) c.tiles_m = d.n * c.row_tiles * c.col_tiles;
     else c.tiles_m = (int32_t)((g.m_total + kBlockM - 1) / kBlockM);
 
+    bool pair_res = false;
     // ---- CTA-pair mode (see IgemmParams::cta2): layers whose filter matrix streams through the ring (too large to stay
     // resident, or several N tiles).  Their MMAs run at 128 operand bytes per cycle out of shared memory while TMA fills
     // the same banks, and ~80% tensor-pipe utilisation was the measured ceiling (profiles/r01_*); sharing B between
@@ -1879,6 +1886,13 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         // instruction) against ~16 cycles per output column of epilogue.
         const int mma_cycles = c.k_blocks * (c.bkb / 32) * (c.bn / 2);
         bool want = mma_cycles >= 16 * c.bn;
+        // A pair can keep the matrix resident as two halves (see res_b_ok below): then pairing also removes the filter
+        // stream, which is what bounds single-N-tile layers with a matrix of 80-256 KB (512 -> 256: 128 KB of B against
+        // 64 KB of A per tile, L2-bound), so it pays from half the K-loop length on.
+        pair_res = possible && c.tiles_n == 1 && o.resident_filter != 0 && o.resident_filter != 2 &&
+                   (c.mode == A_WINDOW || c.bkb == 128) &&
+                   full_b / 2 <= (size_t)limit(o.resident_kb, c.mode == A_WINDOW ? 80 : 128) * 1024u;
+        if (pair_res && mma_cycles >= 8 * c.bn) want = true;
         if (o.cta_pairs >= 0) want = o.cta_pairs != 0;       // test / tuning override
         c.cta2 = (possible && want) ? 1 : 0;
     }
@@ -1891,15 +1905,18 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     // whole panels per warp - 256 -> 2 x 128 B, 128 -> 2 x 64 B for the two warp sets of a team, <= 64 -> one panel
     // Measured (r01): +5-10% on 256-wide tiles with a short K loop (the 1x1 channel expansions, whose epilogue is the
     // bound); a loss where the extra staging bytes cost ring depth (long K loops) and on narrow tiles (2 KB stores).
-    // Narrow tiles (r02): one N tile of 32 / 64 columns drains through the kernel's narrow warp-store path in every A mode
-    // (window tiles need the padded pitch above) - the team paths spent more cycles per tile on barriers and bookkeeping
-    // than on conversion, which made the stems and every 64-channel layer epilogue-bound.
+    // Narrow tiles (r02): one N tile of 32 / 64 columns can drain through the kernel's narrow warp-store path in every A
+    // mode (window tiles need the padded pitch above).  It removes the team paths' per-tile barriers and store waits
+    // (2450 -> ~1700 cycles per team and tile in the traces) - and changes nothing: with 64-column MMAs the tensor pipe
+    // re-reads the 4 KB A operand for every 2 KB of B, 48 cycles of shared-memory bandwidth per 32-cycle MMA, and that
+    // (plus the window and staging traffic through the same banks) is what paces the stems and the 64-channel layers.
+    // Measured (r02, N=512): conv1 222 -> 228 us, 64->64 3x3 62.5 -> 66.6 us, 1x1 64->64 / 256->64 unchanged.  Opt-in.
     c.warp_store = 0;
     const bool narrow_ws = (c.bn == 64 || c.bn == 32) && c.tiles_n == 1 && !c.pair && !c.cta2 && o.small_teams != 0 && o.four_acc != 0 &&
                            (c.mode != A_WINDOW || (c.wt >= 32 && (c.wt & (c.wt - 1)) == 0));
     {
-        bool want = (c.bn == 256 && !c.cta2 && c.k_blocks * (c.bkb / 32) <= 8) || narrow_ws;
-        if (o.warp_store >= 0) want = o.warp_store != 0;     // test / tuning override
+        bool want = c.bn == 256 && !c.cta2 && c.k_blocks * (c.bkb / 32) <= 8;
+        if (o.warp_store >= 0) want = o.warp_store != 0;     // test / tuning override (the only way onto the narrow path)
         if ((c.mode != A_WINDOW || narrow_ws) && d.out_mode == LBC_OUT_INT8 && want &&
             (c.bn == 256 || c.bn == 128 || c.bn == 64 || c.bn == 32)) {
             c.warp_store = 1;
@@ -1981,6 +1998,11 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     // It removes the per-block ring handshake (~400 cycles each, measured) and the L2 re-fetch of B for every tile.
     c.b_total_bytes = (uint32_t)c.tiles_n * c.k_blocks * c.b_block_bytes;      // all N tiles
     bool res_b_ok = !c.pair && !c.cta2 && c.b_total_bytes <= (uint32_t)limit(o.resident_kb, 80) * 1024u && o.resident_filter != 0;
+    // CTA pairs with window A: each CTA holds half of the filter rows, so a matrix of up to twice the limit stays resident
+    // (128 -> 128 3x3: 2 x 72 KB).  Streaming it cost 74 KB of L2 reads per 2304-cycle tile and CTA - with the windows
+    // 42 B/clk/SM, which IS the chip's L2 bandwidth (~6300 B/clk over 148 SMs): the layer ran at 0.62 of the tensor peak.
+    // The ring modes get the same: 512 -> 256 and 1024 -> 256 keep 64 / 128 KB per CTA and stream only A.
+    if (c.cta2 && pair_res) res_b_ok = true;
     // N-stationary: the matrix as a whole is too large, but one N tile fits and the persistent grid can be a multiple of
     // tiles_n, so every CTA keeps "its" N tile for the whole launch (see IgemmParams::res_one)
     c.res_one = 0;
@@ -2014,6 +2036,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         {
             bool want = c.bn >= 128;
             if (o.fold_bias >= 0) want = o.fold_bias != 0;
+            if (c.cta2) want = false;                           // (no bias-fold variant of the CTA-pair kernels)
             c.fold = (c.res_b && want && fold_try) ? 1 : 0;
             if (!fold_try && !(c.res_b && want)) continue;      // nothing to drop: this variant was already tried
         }
@@ -2072,7 +2095,7 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     const double issue_cycles = 450.0 + 75.0 * c.k_blocks * (c.bkb / 32);   // + per-tile fixed cost of the issuing warp
     const double a_bytes = c.mode == A_WINDOW ? (double)c.win_tx_bytes * c.cblocks : (double)kBlockM * c.c_pad * (c.mode == A_TILED ? 1 : d.r * d.s);
     const double hbm_cycles = (a_bytes + (double)kBlockM * c.bn) / 22.5;
-    if (c.res_b && c.bn <= 128 && issue_cycles > hbm_cycles && o.two_mma_warps != 0) {
+    if (c.res_b && !c.cta2 && c.bn <= 128 && issue_cycles > hbm_cycles && o.two_mma_warps != 0) {
         if (c.mode == A_WINDOW && c.win_stages >= 4) { c.n_mma = 2; c.win_stages &= ~1; }
         else if (c.mode != A_WINDOW && c.stages >= 4) { c.n_mma = 2; c.stages &= ~1; }
     }
@@ -2307,10 +2330,13 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
                               const int32_t*, const float*, void*);
     // last index: 0 streaming B, 1 resident B, 2 streaming B in CTA pairs (not for 16-byte pixels), 3 resident B with the
     // bias-fold variant of the tile loops
+    // ... 4: resident B in CTA pairs (window A with >= 32-byte pixels; ring modes with 128-byte channel chunks)
 #define LBC_KERNELS(KM_, KS_) {igemm_i8_kernel<KM_, KS_, false, false, false>, igemm_i8_kernel<KM_, KS_, true, false, false>, \
                                (KM_ == 3 ? (KernelFn) nullptr : (KernelFn)igemm_i8_kernel<(KM_ == 3 ? 2 : KM_), KS_, false, true, false>), \
-                               igemm_i8_kernel<KM_, KS_, true, false, true>}
-    static const KernelFn table[4][3][4] = {
+                               igemm_i8_kernel<KM_, KS_, true, false, true>, \
+                               ((KM_ == 3 || (KM_ != 2 && KS_ != 4)) ? (KernelFn) nullptr \
+                                    : (KernelFn)igemm_i8_kernel<(KM_ == 3 ? 2 : KM_), ((KM_ != 2 && KS_ != 4) ? 4 : KS_), true, true, false>)}
+    static const KernelFn table[4][3][5] = {
         {LBC_KERNELS(0, 1), LBC_KERNELS(0, 2), LBC_KERNELS(0, 4)},
         {LBC_KERNELS(1, 1), LBC_KERNELS(1, 2), LBC_KERNELS(1, 4)},
         {LBC_KERNELS(2, 1), LBC_KERNELS(2, 2), LBC_KERNELS(2, 4)},
@@ -2318,7 +2344,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     };
 #undef LBC_KERNELS
     LBC_REQUIRE(ks == 1 || ks == 2 || ks == 4, LBC_ERR_UNSUPPORTED, "igemm: unsupported K block of %d bytes", c.bkb);
-    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.cta2 ? 2 : c.res_b ? (c.fold ? 3 : 1) : 0];
+    const KernelFn fn = table[km][ks == 4 ? 2 : ks - 1][c.cta2 ? (c.res_b ? 4 : 2) : c.res_b ? (c.fold ? 3 : 1) : 0];
     LBC_REQUIRE(fn != nullptr, LBC_ERR_UNSUPPORTED, "igemm: no kernel for this configuration");
     {
         int dev_ord = 0;
@@ -2327,7 +2353,7 @@ lbc_status igemm_launch(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
         if (first_use_on_device(g_attr_devices, dev_ord)) {
             for (int i = 0; i < 4; ++i)
                 for (int j = 0; j < 3; ++j)
-                    for (int r = 0; r < 4; ++r)
+                    for (int r = 0; r < 5; ++r)
                         if (table[i][j][r])
                             LBC_CUDA_TRY(cudaFuncSetAttribute(table[i][j][r], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         }

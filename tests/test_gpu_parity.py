@@ -294,19 +294,48 @@ NARROW_CASES = [
 
 @pytest.mark.parametrize("d", NARROW_CASES, ids=lambda d: f"n{d.n}h{d.h}w{d.w}c{d.c}k{d.k}r{d.r}s{d.stride_h}")
 def test_narrow_tiles_with_per_warp_stores(d):
-    """The planner's own choice, then the same layer with capped grids (every CTA walks many tiles: TMEM stages and both
-    staging buffers wrap), one staging buffer per warp, reversed traversal, and with the path switched off (team path)."""
+    """The narrow warp-store path on its own, then with capped grids (every CTA walks many tiles: TMEM stages and both
+    staging buffers wrap), one staging buffer per warp, reversed traversal; last the planner's default for the layer."""
+    import lowbitdnn_project_b200 as lbc
+    ws = {"warp_store": 1}                 # the path is opt-in (measured neutral to slightly slower, see the planner)
+    plan = lbc.ConvPlan(lbc.ConvDesc(**d.__dict__), options=ws)
+    try:
+        assert "narrow-warp-stores" in plan.describe(), plan.describe()
+    finally:
+        plan.close()
+    for options in ({}, {"max_grid": 1}, {"max_grid": 3, "reverse": 1}, {"max_grid": 2, "stage_bufs": 1}, {"max_grid": 5, "two_mma_warps": 0}):
+        assert _check(d, options={**ws, **options}) in ("igemm_tc", "stem_tc")
+    assert _check(d) in ("igemm_tc", "stem_tc")           # the planner's own choice (team path)
+
+
+# ---- CTA pairs with the filter matrix resident as two halves (r02): window A, one N tile -----------------------
+PAIR_RESIDENT_CASES = [
+    D(n=3, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # ResNet-50 l2.x.conv2; odd tile count
+    D(n=5, h=14, w=14, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1),
+    D(n=2, h=6, w=112, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1),      # VGG conv2_2 rows: 44 KB windows
+    D(n=2, h=19, w=23, c=64, k=64, r=5, s=5, pad_h=2, pad_w=2, relu=1),        # 100 KB matrix, 64-column tile (32 rows per CTA)
+    D(n=3, h=20, w=20, c=128, k=96, r=3, s=3, pad_h=1, pad_w=1),               # 96-column tile: 48 rows per CTA
+    D(n=2, h=20, w=20, c=128, k=128, r=3, s=3, pad_h=2, pad_w=2, dil_h=2, dil_w=2, relu=1),   # dilated taps
+    # ring modes: only A streams
+    D(n=3, h=14, w=14, c=512, k=256, r=1, s=1, relu=1),                        # ResNet-50 l3.0.conv1: 64 KB per CTA
+    D(n=3, h=9, w=9, c=1024, k=256, r=1, s=1),                                 # l3.x.conv1: 128 KB per CTA, M tail
+    D(n=3, h=27, w=27, c=128, k=128, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1),   # im2col (l2.0.conv2)
+    D(n=2, h=12, w=12, c=640, k=192, r=1, s=1, relu=1),                        # 192-column tile: 96 rows per CTA
+]
+
+
+@pytest.mark.parametrize("d", PAIR_RESIDENT_CASES, ids=lambda d: f"n{d.n}h{d.h}w{d.w}c{d.c}k{d.k}r{d.r}")
+def test_cta_pairs_with_resident_filter_halves(d):
     import lowbitdnn_project_b200 as lbc
     plan = lbc.ConvPlan(lbc.ConvDesc(**d.__dict__))
     try:
-        if plan.kernel in ("igemm_tc", "stem_tc"):
-            assert "narrow-warp-stores" in plan.describe(), plan.describe()
+        assert "b=resident,cta-pair" in plan.describe(), plan.describe()
     finally:
         plan.close()
-    assert _check(d) in ("igemm_tc", "stem_tc")
-    for options in ({"max_grid": 1}, {"max_grid": 3, "reverse": 1}, {"max_grid": 2, "stage_bufs": 1}, {"warp_store": 0},
-                    {"max_grid": 5, "two_mma_warps": 0}):
-        assert _check(d, options=options) in ("igemm_tc", "stem_tc")
+    assert _check(d) == "igemm_tc"
+    assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"
+    for options in ({"max_grid": 2}, {"max_grid": 4, "reverse": 1}, {"max_grid": 6, "stage_bufs": 1}, {"resident_filter": 2}):
+        assert _check(d, options=options) == "igemm_tc"
 
 
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
