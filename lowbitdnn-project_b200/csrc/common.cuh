@@ -135,6 +135,8 @@ struct IgemmLaunch {
     CUtensorMap tm_out2;   // window tiles with per-warp stores: the ragged last run of a tile row (else a copy of tm_out)
     IgemmConfig cfg;
     int32_t reverse = 0;   // walk the M tiles / images last-to-first (L2 reuse of the producer's most recent output)
+    int32_t early_b = 0;   // the packed weights are not written by anything earlier in the stream: a resident filter matrix
+                           // may be fetched before the programmatic-dependency wait (set by the network runner)
 };
 bool igemm_supported(const ConvGeom& g, std::string* why);
 bool igemm_trace_compiled();      // the library was built with -DLBC_TRACE=1 (lib/liblowbit_cnn_trace.so)

@@ -126,6 +126,7 @@ struct IgemmParams {
     int32_t fold;
     uint32_t off_fold;
     int32_t rev_m;                // ring modes: > 0 = number of M tiles, visited in reverse order (see TileIter::m0)
+    int32_t early_b;              // resident filter matrix: fetch it before griddepcontrol.wait (nothing in the stream writes it)
     int32_t k_mod;                // bias/scale index = channel % k_mod (pixel-group rewrite replicates them), 0 = plain
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
@@ -581,6 +582,32 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     ptx::tc_fence_after();
     // Programmatic dependent launch: everything above is on-chip set-up (barriers, TMEM, descriptor prefetch) and may
     // overlap the tail of the previous kernel in the stream; from here on global memory is read and written.
+    // ... with one exception: a resident filter matrix that no kernel in the stream writes (IgemmLaunch::early_b, set by
+    // the network runner, whose weights were uploaded long before) is fetched BEFORE the wait, so its 32-128 KB arrive
+    // while the previous layer drains.
+    auto load_resident_b = [&]() {
+        if (ptx::elect_one()) {
+            // CTA pairs: each CTA keeps ITS half of the filter rows (cta_group::2 MMAs read B from both CTAs); the leader's
+            // barrier collects the bytes of both halves, so the one MMA-issuing thread waits on a single barrier
+            if (!CTA2 || cta_rank == 0) ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes * (CTA2 ? 2u : 1u));
+            const int32_t nblk = prm.cblocks * prm.inner;
+            uint8_t* dst = smem_b;
+            // every N tile, or (N-stationary) only the one this CTA works on
+            const int32_t nt0 = prm.res_one ? (int32_t)(blockIdx.x % (uint32_t)prm.tiles_n) : 0;
+            const int32_t nt1 = prm.res_one ? nt0 + 1 : prm.tiles_n;
+            const uint32_t bfull0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->bfull), 0) : 0u;
+            const int32_t half_off = CTA2 ? (int32_t)cta_rank * (prm.bn >> 1) : 0;
+            for (int32_t nt = nt0; nt < nt1; ++nt) {
+                int32_t bcol = 0;
+                for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb) {
+                    if (CTA2) ptx::tma_load_2d_2sm(dst, &tm_b, bfull0, bcol, nt * prm.bn + half_off);
+                    else ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, nt * prm.bn);
+                }
+            }
+        }
+        __syncwarp();
+    };
+    if (RESB && prm.early_b && warp == 0) load_resident_b();
     ptx::griddep_wait();
     if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
@@ -598,26 +625,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const bool leader = ptx::elect_one();
         if (RESB) {
             // the whole filter matrix, once: per N tile, k_blocks boxes of [bn][bkb] side by side
-            // CTA pairs: each CTA keeps ITS half of the filter rows (cta_group::2 MMAs read B from both CTAs); the leader's
-            // barrier collects the bytes of both halves, so the one MMA-issuing thread waits on a single barrier
-            if (leader) {
-                if (!CTA2 || cta_rank == 0) ptx::mbar_expect_tx(&ctl->bfull, prm.b_total_bytes * (CTA2 ? 2u : 1u));
-                const int32_t nblk = prm.cblocks * prm.inner;
-                uint8_t* dst = smem_b;
-                // every N tile, or (N-stationary) only the one this CTA works on
-                const int32_t nt0 = prm.res_one ? (int32_t)(blockIdx.x % (uint32_t)prm.tiles_n) : 0;
-                const int32_t nt1 = prm.res_one ? nt0 + 1 : prm.tiles_n;
-                const uint32_t bfull0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->bfull), 0) : 0u;
-                const int32_t half_off = CTA2 ? (int32_t)cta_rank * (prm.bn >> 1) : 0;
-                for (int32_t nt = nt0; nt < nt1; ++nt) {
-                    int32_t bcol = 0;
-                    for (int32_t i = 0; i < nblk; ++i, dst += prm.b_block_bytes, bcol += prm.bkb) {
-                        if (CTA2) ptx::tma_load_2d_2sm(dst, &tm_b, bfull0, bcol, nt * prm.bn + half_off);
-                        else ptx::tma_load_2d(dst, &tm_b, &ctl->bfull, bcol, nt * prm.bn);
-                    }
-                }
-            }
-            __syncwarp();
+            if (!prm.early_b) load_resident_b();
         }
         if (kRing) {
             // one (stage, phase) cursor per sub-ring: with two MMA warps, even tiles flow through the first half of
@@ -1886,13 +1894,14 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
         // instruction) against ~16 cycles per output column of epilogue.
         const int mma_cycles = c.k_blocks * (c.bkb / 32) * (c.bn / 2);
         bool want = mma_cycles >= 16 * c.bn;
-        // A pair can keep the matrix resident as two halves (see res_b_ok below): then pairing also removes the filter
-        // stream, which is what bounds single-N-tile layers with a matrix of 80-256 KB (512 -> 256: 128 KB of B against
-        // 64 KB of A per tile, L2-bound), so it pays from half the K-loop length on.
+        // A pair can keep the matrix resident as two halves (see res_b_ok below), which removes the filter stream from L2.
+        // Ring modes (the kernels exist: 128-byte channel chunks) only with resident_filter = 3: measured slower there -
+        // 512 -> 256 65.5 -> 69.7 us, 1024 -> 256 38.9 -> 43.0 us, 3x3 stride 2 71.7 -> 73.8 us (r02, N=512, cold) - those
+        // layers wait for A from HBM, not for L2; window layers gain 4% (128 -> 128 @28x28) to 24% (@112x112, VGG conv2_2).
         pair_res = possible && c.tiles_n == 1 && o.resident_filter != 0 && o.resident_filter != 2 &&
-                   (c.mode == A_WINDOW || c.bkb == 128) &&
+                   (c.mode == A_WINDOW || (c.bkb == 128 && o.resident_filter == 3)) &&
                    full_b / 2 <= (size_t)limit(o.resident_kb, c.mode == A_WINDOW ? 80 : 128) * 1024u;
-        if (pair_res && mma_cycles >= 8 * c.bn) want = true;
+        if (pair_res && o.resident_filter == 3 && mma_cycles >= 8 * c.bn) want = true;
         if (o.cta_pairs >= 0) want = o.cta_pairs != 0;       // test / tuning override
         c.cta2 = (possible && want) ? 1 : 0;
     }
@@ -2001,7 +2010,6 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     // CTA pairs with window A: each CTA holds half of the filter rows, so a matrix of up to twice the limit stays resident
     // (128 -> 128 3x3: 2 x 72 KB).  Streaming it cost 74 KB of L2 reads per 2304-cycle tile and CTA - with the windows
     // 42 B/clk/SM, which IS the chip's L2 bandwidth (~6300 B/clk over 148 SMs): the layer ran at 0.62 of the tensor peak.
-    // The ring modes get the same: 512 -> 256 and 1024 -> 256 keep 64 / 128 KB per CTA and stream only A.
     if (c.cta2 && pair_res) res_b_ok = true;
     // N-stationary: the matrix as a whole is too large, but one N tile fits and the persistent grid can be a multiple of
     // tiles_n, so every CTA keeps "its" N tile for the whole launch (see IgemmParams::res_one)
@@ -2310,6 +2318,7 @@ static void fill_params(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.fold = c.fold; prm.off_fold = c.off_fold;
     // reversed traversal (IgemmLaunch::reverse, set by the network runner; lbc_plan_options::reverse for single layers)
     prm.rev_m = (l.reverse || c.reverse) ? (c.mode == A_WINDOW ? d.n : c.tiles_m) : 0;
+    prm.early_b = (l.early_b && c.res_b && c.pdl) ? 1 : 0;
     prm.trace = rt.trace; prm.trace_tiles = rt.trace_tiles;
     prm.flag = rt.flag;
     // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one

@@ -125,12 +125,12 @@ def test_planner_choices_on_resnet50(lbc):
         "l2.0.conv1": ["b=resident", "bias-in-mma", "tile 128x128"],                                 # 256 -> 128
         "l2.0.conv3": ["b=resident", "tiles 3136x2", "warp-stores,bias-in-mma"],                     # 128 -> 512, two N tiles
         "l2.1.conv2": ["b=resident,cta-pair", "a=window(4x28", "tile 128x128"],                      # 3x3, 128-wide: windows, filter halves resident
-        "l2.0.conv2": ["b=resident,cta-pair", "a=im2col"],                                           # ... and its stride-2 sibling
-        "l3.0.conv1": ["b=resident,cta-pair", "a=tiled", "tile 128x256"],                            # 512 -> 256: 64 KB per CTA
+        "l2.0.conv2": ["b=ring,cta-pair", "a=im2col"],                                               # its stride-2 sibling streams (measured)
+        "l3.0.conv1": ["b=ring ", "a=tiled", "tile 128x256"],                                        # 512 -> 256
         "l3.0.conv3": ["b=resident,n-stationary", "a=tiled", "tiles 784x4", "grid 148", "warp-stores,bias-in-mma"],   # 256 -> 1024: 64 KB tiles
         "l2.0.downsample": ["b=resident,n-stationary", "a=im2col", "tiles 3136x2"],                  # 256 -> 512, stride 2
         "l3.0.downsample": ["b=ring ", "a=im2col", "tiles 784x4"],                                   # 512 -> 1024: 128 KB tiles stream
-        "l3.1.conv1": ["b=resident,cta-pair", "a=tiled"],                                            # 1024 -> 256: 128 KB per CTA
+        "l3.1.conv1": ["b=ring,cta-pair", "a=tiled"],                                                # 1024 -> 256: long K loop
         "l3.1.conv2": ["b=ring,cta-pair", "a=im2col", "tile 128x256", "2x8-warp-teams"],             # wide 3x3 in pairs: im2col
         "l3.0.conv2": ["b=ring,cta-pair", "a=im2col"],                                               # stride 2
         "l4.1.conv2": ["b=ring,cta-pair", "a=im2col"],

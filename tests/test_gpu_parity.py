@@ -327,15 +327,19 @@ PAIR_RESIDENT_CASES = [
 @pytest.mark.parametrize("d", PAIR_RESIDENT_CASES, ids=lambda d: f"n{d.n}h{d.h}w{d.w}c{d.c}k{d.k}r{d.r}")
 def test_cta_pairs_with_resident_filter_halves(d):
     import lowbitdnn_project_b200 as lbc
-    plan = lbc.ConvPlan(lbc.ConvDesc(**d.__dict__))
+    # window layers get there by the planner's own choice; the ring modes (measured slower, see the planner) with
+    # resident_filter = 3, and at these small sizes only with the 256-wide N tile kept (max_bn)
+    base = {} if d.stride_h == 1 and d.r > 1 else {"resident_filter": 3, "max_bn": 256}
+    plan = lbc.ConvPlan(lbc.ConvDesc(**d.__dict__), options=base or None)
     try:
         assert "b=resident,cta-pair" in plan.describe(), plan.describe()
     finally:
         plan.close()
-    assert _check(d) == "igemm_tc"
-    assert _check(D(**{**d.__dict__, "out_mode": 1})) == "igemm_tc"
-    for options in ({"max_grid": 2}, {"max_grid": 4, "reverse": 1}, {"max_grid": 6, "stage_bufs": 1}, {"resident_filter": 2}):
-        assert _check(d, options=options) == "igemm_tc"
+    assert _check(d, options=base or None) == "igemm_tc"
+    assert _check(D(**{**d.__dict__, "out_mode": 1}), options=base or None) == "igemm_tc"
+    for options in ({"max_grid": 2}, {"max_grid": 4, "reverse": 1}, {"max_grid": 6, "stage_bufs": 1}):
+        assert _check(d, options={**base, **options}) == "igemm_tc"
+    assert _check(d, options={"resident_filter": 2}) == "igemm_tc"
 
 
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
