@@ -554,6 +554,9 @@ def main():
                 roofline["traffic_unit"] = "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean over the kernel's launches of one step)"
                 roofline["traffic_source"] = "profiles/" + tfiles[-1]
                 roofline["algorithmic_gb_per_launch"] = dom_bytes / len(sel) / 1e9
+                # the same launch list's share of the step (cold-cache, serialised launches); the live share below counts the
+                # stem's space-to-depth pre-pass (1.7% of the step, its own small kernel) with the stem's igemm launch
+                roofline["kernel_share_of_step_ncu"] = tr.get("share_of_step_ncu")
         except Exception as e:  # noqa: BLE001
             log("traffic file unreadable:", e)
         roofline.update({
@@ -561,7 +564,8 @@ def main():
                        "pool_add": "maxpool / add_relu kernels"}[dom],
             "launches_per_step": len(sel), "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
             "instrumented_pass_ms": instrumented_ms,
-            "timing_note": "kernel_ms_per_step = the kernel's share of the per-launch event pass x ms_per_step of the timed region",
+            "timing_note": "kernel_ms_per_step = the kernel's share of the per-launch event pass x ms_per_step of the timed region "
+                           "(per-LAYER events: the stem layer's time includes its space-to-depth pre-pass)",
             "peak_source": f"{peaks['source']} (MEASURED_PEAKS.json hbm_gbs); tensor fractions are against the BURST on-box tcgen05 "
                            "kind::i8 MMA-only probe (int8_mma_peak_tops), nominal dense int8 is 4500 TOPS",
             "achieved_tops": tops, "achieved_gbs": gbs, "int8_mma_peak_tops": int8_peak,
