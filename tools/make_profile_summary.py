@@ -28,6 +28,11 @@ NCU_METRICS = [
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
     "sm__cycles_elapsed.max", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    # shared-memory wavefronts of the tensor pipe (operand reads of tcgen05.mma) and of LSU (epilogue staging), TMA traffic
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum.per_second",
+    "l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_st.sum.per_second", "sm__memory_throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -69,12 +74,19 @@ def ncu_tables(rep, names, tag):
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {m: hdr.index(m) for m in NCU_METRICS if m in hdr}
     kcol = hdr.index("Kernel Name")
+    def short(v):
+        try:
+            f = float(v)
+            return f"{f:.0f}" if abs(f) >= 1000 else f"{f:.3g}"
+        except ValueError:
+            return v
+    cols = [names[i] if i < len(names) else f"launch{i}" for i in range(len(data))]
     out = [f"# {tag}: ncu --set full --clock-control none, one launch per layer (source: {os.path.basename(rep)})", "",
-           "| layer | kernel | " + " | ".join(idx) + " |", "|---|---|" + "---|" * len(idx)]
-    for i, r in enumerate(data):
-        nm = names[i] if i < len(names) else f"launch{i}"
-        kern = r[kcol].split("(")[0].split("::")[-1][:40]
-        out.append(f"| {nm} | {kern} | " + " | ".join(f"{r[j]} {units[j]}" for j in idx.values()) + " |")
+           "Clocks are not locked (the tool's default lock is off as the profiling recipe asks): under ncu the SMs ran at ~1.77 GHz.", "",
+           "| metric | unit | " + " | ".join(cols) + " |", "|---|---|" + "---|" * len(cols),
+           "| kernel |  | " + " | ".join(r[kcol].split("(")[0].split("::")[-1][:40] for r in data) + " |"]
+    for m, j in idx.items():
+        out.append(f"| {m} | {units[j]} | " + " | ".join(short(r[j]) for r in data) + " |")
     return "\n".join(out)
 
 
