@@ -144,3 +144,39 @@ def test_planner_choices_on_resnet50(lbc):
         if "cta-pair" in text:
             assert int(text.split("grid ")[1].split()[0]) % 2 == 0, text
         assert int(text.split("tmem ")[1].split()[0]) <= 512, text
+
+
+def test_plan_options_struct_is_checked_and_steers_the_planner(lbc):
+    """lbc_plan_options (the replacement of round 1's environment variables): the ctypes mirror has the header's size,
+    a wrong struct_size is refused, and the tri-states change the dry planner's answer the way the header says."""
+    import ctypes
+    from lowbitdnn_project_b200 import _capi
+    lib = lbc.load_library()
+    o = _capi.CPlanOptions()
+    lib.lbc_plan_options_init(ctypes.byref(o))
+    assert o.struct_size == ctypes.sizeof(_capi.CPlanOptions)
+    hdr = open(os.path.join(ROOT, "include", "lowbit_cnn.h")).read()
+    body = hdr[hdr.index("typedef struct lbc_plan_options"):hdr.index("} lbc_plan_options;")]
+    n_fields = len(re.findall(r"^\s*int32_t\s+[a-z_0-9]+;", body, re.M)) + sum(int(m) for m in re.findall(r"int32_t\s+reserved\[(\d+)\];", body))
+    assert n_fields * 4 == ctypes.sizeof(_capi.CPlanOptions), (n_fields, ctypes.sizeof(_capi.CPlanOptions))
+    assert o.cta_pairs == -1 and o.fuse == -1 and o.early_weights == -1 and o.max_grid == 0       # "planner decides" / "default"
+
+    def dry(d, **kw):
+        opt = _capi.plan_options(**kw)
+        kind, buf, cd = ctypes.c_int32(), ctypes.create_string_buffer(512), d.c_struct()
+        st = lib.lbc_conv_plan_dry_ex(ctypes.byref(cd), 0, ctypes.byref(opt), 148, ctypes.byref(kind), buf, 512)
+        return st, buf.value.decode()
+
+    d = lbc.ConvDesc(n=512, h=28, w=28, c=128, k=128, r=3, s=3, pad_h=1, pad_w=1, relu=1)
+    assert "b=resident,cta-pair" in dry(d)[1]
+    assert "b=ring,cta-pair" in dry(d, resident_filter=2)[1]
+    assert "cta-pair" not in dry(d, cta_pairs=0)[1]
+    assert "a=im2col" in dry(d, force_im2col=1)[1]
+    assert "grid 6 " in dry(d, max_grid=6)[1]
+    d64 = lbc.ConvDesc(n=512, h=56, w=56, c=64, k=64, r=3, s=3, pad_h=1, pad_w=1, relu=1)
+    assert "4x4-warp-teams" in dry(d64)[1] and "narrow-warp-stores" in dry(d64, warp_store=1)[1]
+    bad = _capi.plan_options()
+    bad.struct_size = 8
+    kind, buf, cd = ctypes.c_int32(), ctypes.create_string_buffer(512), d.c_struct()
+    assert lib.lbc_conv_plan_dry_ex(ctypes.byref(cd), 0, ctypes.byref(bad), 148, ctypes.byref(kind), buf, 512) != 0
+    assert b"struct_size" in lib.lbc_last_error_string()
