@@ -1216,8 +1216,10 @@ lbc_status lbc_net_create_graph(const lbc_node* nodes, int32_t n_layers, const l
                             (L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC ||
                              L.plan->kind == LBC_KERNEL_DEPTHWISE);      // (the tiled depthwise kernel mirrors its tile index)
             const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
-            // a producer that ran forwards finished on the last images: start there; CUDA-core kernels always run forwards
-            L.reverse = tc && L.input_of >= 0 && !producer_rev && snake;
+            // a producer that ran forwards finished on the last images: start there; CUDA-core kernels always run forwards.
+            // A small-C (stem) layer's producer is its own space-to-depth pre-pass, which always runs forwards.
+            const bool own_prepass = L.kind == LBC_NODE_CONV && L.plan->kind == LBC_KERNEL_STEM_TC;
+            L.reverse = tc && (L.input_of >= 0 ? !producer_rev : own_prepass) && snake;
         }
         bool ok = cudaMalloc(&L.y, L.out_bytes()) == cudaSuccess;
         size_t wb = 0;
@@ -1270,7 +1272,8 @@ lbc_status lbc_net_create_graph(const lbc_node* nodes, int32_t n_layers, const l
             const bool tc = L.kind == LBC_NODE_CONV &&
                             (L.plan->kind == LBC_KERNEL_IGEMM_TC || L.plan->kind == LBC_KERNEL_STEM_TC || L.plan->kind == LBC_KERNEL_DEPTHWISE);
             const bool producer_rev = L.input_of >= 0 && net->layers[L.input_of].reverse;
-            L.reverse = tc && L.input_of >= 0 && !producer_rev && snake;
+            const bool own_prepass = L.kind == LBC_NODE_CONV && L.plan->kind == LBC_KERNEL_STEM_TC;
+            L.reverse = tc && (L.input_of >= 0 ? !producer_rev : own_prepass) && snake;
         }
     }
     if (st == LBC_OK) {
