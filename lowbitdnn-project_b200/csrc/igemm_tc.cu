@@ -1887,7 +1887,9 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     {
         const size_t full_b = (size_t)c.k_blocks * c.bn * c.bkb;
         const bool streams = !((size_t)c.tiles_n * full_b <= 80u * 1024u) || o.resident_filter == 0;
-        const bool possible = !c.pair && !c16 && streams && c.bn % 32 == 0 && c.tiles_m >= 2;
+        // (a small matrix pairs only on request - cta_pairs = 1, window A - and then stays resident as two halves)
+        const bool small_on_request = !streams && o.cta_pairs == 1 && c.mode == A_WINDOW && c.tiles_n == 1 && o.resident_filter != 0;
+        const bool possible = !c.pair && !c16 && (streams || small_on_request) && c.bn % 32 == 0 && c.tiles_m >= 2;
         // Pairing couples the two CTAs' pipelines (one MMA stream waits for both producers and both epilogues), which
         // costs where the epilogue is the bound: short K loops (1x1 channel expansions) measured 10-15% slower in pairs,
         // long ones (3x3, wide 1x1 reductions) 5-25% faster.  Cross-over: MMA time per tile (128 cycles per N=256
