@@ -144,3 +144,32 @@ def test_network_host_paths_match_oracle():
     net.run(stream=stream)
     assert np.array_equal(net.read_output(len(chain) - 1), wants[1])
     net.close()
+
+
+def test_weights_replaced_between_runs_take_effect():
+    """Networks fetch resident filter matrices before the programmatic-dependency wait (lbc_plan_options.early_weights):
+    legal because nothing in the stream writes packed weights - lbc_net_set_params is device-synchronous.  Replace the
+    parameters of every layer between back-to-back runs and check that the next run sees exactly the new ones, with the
+    early fetch on (default) and off."""
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    layers = [l for l in lbc.networks.resnet50(2) if l[0].startswith(("l1.0", "l2.0")) and "downsample" not in l[0]]
+    layers = [(n, d, (layers[i - 1][0] if i else None)) for i, (n, d, _) in enumerate(layers)]
+    layers = [l for l in layers[:3]]                       # l1.0.conv1 -> conv2 -> conv3: all resident-filter layers
+    stream = torch.cuda.current_stream()
+    for options in (None, {"early_weights": 0}):
+        net = load_net(lbc, layers, options=options)
+        for gen in range(3):
+            if gen:
+                for i, (_, d, _) in enumerate(layers):
+                    net.set_params(i, *synth_params(d, i + 100 * gen))
+            net.run(stream=stream)
+            net.run(stream=stream)
+            torch.cuda.synchronize()
+            net.check_status()
+            out = {}
+            for i, (name, d, src) in enumerate(layers):
+                x = synth_input(d, i) if src is None else out[src]
+                out[name] = oracle.conv_nhwc(OD(**d.__dict__), x, *synth_params(d, i + 100 * gen))
+            compare(net, layers, out, f"generation {gen}, options {options}")
+        net.close()
