@@ -220,6 +220,31 @@ __device__ __forceinline__ uint32_t pack4_sat_s8(int32_t a, int32_t b, int32_t c
     return r;
 }
 
+// Four accumulators (bias already added) -> four requantised int8, packed: the same rule as requant_s32 + pack4_sat_s8 with
+// the clamp at zero applied to the PACKED bytes (sign-replicating PRMT + AND), so that nothing sits between the float ->
+// int conversions and the saturating pack and ptxas fuses them into two F2IP; the scale multiplies are two FMUL2
+// (mul.rn.f32x2: each lane the same IEEE product as __fmul_rn).  14 instructions per 4 outputs instead of 26.
+__device__ __forceinline__ uint32_t requant4_pack(const int32_t (&acc)[4], const float (&sc)[4], bool relu)
+{
+    float x0 = __int2float_rn(acc[0]), x1 = __int2float_rn(acc[1]), x2 = __int2float_rn(acc[2]), x3 = __int2float_rn(acc[3]);
+    uint64_t a, b, m, n;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "f"(sc[0]), "f"(sc[1]));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(a), "l"(m));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(x2), "f"(x3));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(n) : "f"(sc[2]), "f"(sc[3]));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(b), "l"(n));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(b));
+    uint32_t r = pack4_sat_s8(__float2int_rn(x0), __float2int_rn(x1), __float2int_rn(x2), __float2int_rn(x3));
+    if (relu) {
+        uint32_t neg;
+        asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(neg) : "r"(r));     // 0xff in every byte whose sign bit is set
+        r &= ~neg;
+    }
+    return r;
+}
+
 __device__ __forceinline__ int8_t requant_s8(int32_t acc, int32_t bias, float scale, int32_t lo)
 {
     return (int8_t)min(requant_s32(acc, bias, scale, lo), 127);

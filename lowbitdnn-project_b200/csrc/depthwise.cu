@@ -162,8 +162,7 @@ __global__ void __launch_bounds__(256) depthwise3x3_kernel(const DwParams g, con
         if (g.out_mode == LBC_OUT_INT32) {
             y32[o] = make_int4(acc[0], acc[1], acc[2], acc[3]);
         } else {
-            y8[o] = pack4_sat_s8(requant_s32(acc[0], 0, sc[0], lo), requant_s32(acc[1], 0, sc[1], lo),
-                                 requant_s32(acc[2], 0, sc[2], lo), requant_s32(acc[3], 0, sc[3], lo));
+            y8[o] = requant4_pack(acc, sc, lo == 0);
         }
     };
     auto compute = [&](const uint32_t(&va)[4], const uint32_t(&vb)[4], const uint32_t(&vc)[4], int32_t q) {
@@ -334,8 +333,7 @@ __global__ void __launch_bounds__(256) depthwise3x3_tiled_kernel(const __grid_co
         const uint32_t yoff1 = yoff0 + (uint32_t)g.q * (uint32_t)g.cq_total;
         auto emit = [&](const int32_t(&acc)[4], uint32_t o) {
             if (g.out_mode == LBC_OUT_INT32) y32[o] = make_int4(acc[0], acc[1], acc[2], acc[3]);
-            else y8[o] = pack4_sat_s8(requant_s32(acc[0], 0, sc[0], lo), requant_s32(acc[1], 0, sc[1], lo),
-                                      requant_s32(acc[2], 0, sc[2], lo), requant_s32(acc[3], 0, sc[3], lo));
+            else y8[o] = requant4_pack(acc, sc, lo == 0);
         };
         auto compute = [&](const uint32_t(&va)[4], const uint32_t(&vb)[4], const uint32_t(&vc)[4], int32_t j) {
             int32_t a0[4], a1[4];
