@@ -1097,7 +1097,10 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 if (n_blk >= tiles_n) { n_blk -= tiles_n; ++m; }
                 m += s_m;
             }
-            if (lane == 0) ptx::tma_store_wait<0>();
+            // (a CTA only has to outlive the READS of its staging buffers: the writes of a bulk store are memory operations
+            // of this grid like any other, complete before the grid does and visible after the next kernel's
+            // griddepcontrol.wait - waiting for them here kept every CTA ~1 us longer on its SM at the end of every launch)
+            if (lane == 0) ptx::tma_store_wait_read<0>();
         } else if (!CTA2 && prm.warp_store && small_teams && !split && prm.n_acc == 8) {
             // ---- narrow N tiles (one tile of 32 / 64 columns, 8 accumulator stages) with per-warp stores, all A modes.
             // A 128 x 64 tile is 8 KB of output against ~1000 cycles of per-team bookkeeping in the team paths below (two
@@ -1169,7 +1172,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 acc ^= 4u;
                 if (acc == team) phase ^= 1u;
             }
-            if (lane == 0) ptx::tma_store_wait<0>();
+            if (lane == 0) ptx::tma_store_wait_read<0>();
         } else if (!CTA2 && prm.tpi == 2) {
             // ---- narrow N tiles (<= 64 columns, one N tile, 8 accumulator stages): a 4-warp team takes TWO consecutive
             // CTA-local tiles per iteration - adjacent TMEM stages, one staging panel each - so the per-iteration
@@ -1241,7 +1244,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     }
                 }
             }
-            if (issuer && int8_out) ptx::tma_store_wait<0>();
+            if (issuer && int8_out) ptx::tma_store_wait_read<0>();
         } else {
         Iter it;
         // pair mode: team t takes the t-th tile of every pair (two teams); otherwise every n_teams-th tile
@@ -1375,7 +1378,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
             it.next(prm);
         }
-        if ((issuer || (prm.warp_store && lane == 0)) && int8_out) ptx::tma_store_wait<0>();
+        if ((issuer || (prm.warp_store && lane == 0)) && int8_out) ptx::tma_store_wait_read<0>();
         }
         };   // epilogue_tiles
         if (MAYFOLD && fold) epilogue_tiles(std::true_type{});
@@ -1672,7 +1675,7 @@ igemm_fused_tail_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
             epi2(L, img, p0, q0);
             ++L;
         }
-        if (issuer) ptx::tma_store_wait<0>();
+        if (issuer) ptx::tma_store_wait_read<0>();
     }
     ptx::tc_fence_before();
     __syncthreads();
