@@ -1,7 +1,7 @@
 # final_pass.sh — the measurement calls behind profiles/ (run each numbered block as ONE gpurun call; at most one ncu per call,
 # and only after the same command has exited 0 without it).
-#   bash tools/final_pass.sh 1      tests, bench line, per-layer tables of the four networks, ncu launch list of bench.py
-#   bash tools/final_pass.sh 2|3|4  ncu --set full over representative layers of resnet50 | vgg16 | mobilenet_v2
+#   bash tools/gpurun_scripts/final_pass.sh 1      tests, bench line, per-layer tables of the four networks, ncu launch list of bench.py
+#   bash tools/gpurun_scripts/final_pass.sh 2|3|4  ncu --set full over representative layers of resnet50 | vgg16 | mobilenet_v2
 set -u
 case "$1" in
 1)

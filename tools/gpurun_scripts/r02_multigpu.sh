@@ -1,4 +1,4 @@
-# r02 multi-GPU pass: bash tools/r02_multigpu.sh N  (one gpurun --gpus N call)
+# r02 multi-GPU pass: bash tools/gpurun_scripts/r02_multigpu.sh N  (one gpurun --gpus N call)
 set -u
 N=$1
 mkdir -p gpurun_out

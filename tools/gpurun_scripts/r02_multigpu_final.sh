@@ -1,4 +1,4 @@
-# final multi-GPU pass: bash tools/r02_multigpu_final.sh N  (one gpurun --gpus N call): ResNet-50 weak + strong, default steps
+# final multi-GPU pass: bash tools/gpurun_scripts/r02_multigpu_final.sh N  (one gpurun --gpus N call): ResNet-50 weak + strong, default steps
 set -u
 N=$1
 mkdir -p gpurun_out
