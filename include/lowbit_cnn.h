@@ -316,7 +316,8 @@ lbc_status  lbc_probe_int8_mma_peak(int32_t iters, double* tops, lbc_stream stre
 /* Streaming-copy probe (int4 loads/stores), GB/s read+write. */
 lbc_status  lbc_probe_hbm_copy(size_t bytes, int32_t iters, double* gbs, lbc_stream stream);
 /* Development aid, per plan: when device_buf != NULL, CTA 0 of the plan's tcgen05 kernel records clock64 stamps of its
- * pipeline events (16 int64 slots per local tile, `tiles` tiles, then 2 x grid CTA start/end stamps) into it.
+ * pipeline events (16 int64 slots per local tile, `tiles` tiles, then 2 x grid CTA start/end stamps, then 4 x grid
+ * %globaltimer stamps: kernel entry, set-up done, past the dependency wait, last store issued) into it.
  * NULL switches tracing off.  Not thread-safe against concurrent runs of the same plan.  The stamps are compiled in only
  * with -DLBC_TRACE=1 (lib/liblowbit_cnn_trace.so, built next to the product library); the product build returns
  * LBC_ERR_UNSUPPORTED for a non-NULL buffer. */

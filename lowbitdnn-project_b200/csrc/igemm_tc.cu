@@ -536,6 +536,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const bool n_major = CTA2 || pair_mode;                               // N-tile-major tile numbering
     using Iter = TileIter<kWindow>;
     const bool tracing = LBC_TRACE && prm.trace != nullptr && blockIdx.x == 0;
+    // trace build: four wall-clock stamps per CTA (%globaltimer, ns: comparable across SMs and launches) behind the
+    // 2 x grid clock64 stamps - kernel entry, set-up done, past griddepcontrol.wait, last store issued
+    long long* const gt = (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0)
+                              ? prm.trace + (size_t)prm.trace_tiles * 16 + 2 * (size_t)gridDim.x + 4 * (size_t)blockIdx.x : nullptr;
+    if (LBC_TRACE && gt) gt[0] = (long long)ptx::globaltimer_ns();
 
     if ((ptx::smem_u32(smem) & 1023u) != 0) {       // swizzle atoms need a 1024-byte aligned base
         if (threadIdx.x == 0) *tflag = 2;
@@ -608,7 +613,9 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         __syncwarp();
     };
     if (RESB && prm.early_b && warp == 0) load_resident_b();
+    if (LBC_TRACE && gt) gt[1] = (long long)ptx::globaltimer_ns();
     ptx::griddep_wait();
+    if (LBC_TRACE && gt) gt[2] = (long long)ptx::globaltimer_ns();
     if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
     // pair mode counts the padded tile space (dummy tiles of the padding image load zeros and store nothing)
@@ -1393,6 +1400,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) {
         long long* cta_times = prm.trace + (size_t)prm.trace_tiles * 16;
         cta_times[2 * blockIdx.x + 1] = clock64();
+        gt[3] = (long long)ptx::globaltimer_ns();
     }
     if (warp == 1) {
         ptx::tc_fence_after();
