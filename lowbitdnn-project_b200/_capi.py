@@ -48,7 +48,7 @@ class CPlanOptions(ctypes.Structure):
         "struct_size", "cta_pairs", "warp_store", "fold_bias", "paired_tiles", "resident_filter", "window", "keep_window",
         "force_im2col", "pixel_groups", "dw_tiled", "reverse", "pdl", "two_mma_warps", "tiles_per_iter2", "small_teams",
         "four_acc", "n_stationary", "epi_pipeline", "max_grid", "max_bn", "max_stages", "max_win_stages", "stage_bufs",
-        "tps_kb", "resident_kb", "epi_split", "fuse", "early_weights")] + [("reserved", ctypes.c_int32 * 5)]
+        "tps_kb", "resident_kb", "epi_split", "fuse", "early_weights", "tail_split")] + [("reserved", ctypes.c_int32 * 4)]
 
 
 def plan_options(**kw) -> CPlanOptions:

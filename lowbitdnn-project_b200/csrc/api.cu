@@ -110,6 +110,7 @@ void default_options(lbc_plan_options* o)
     o->pdl = o->two_mma_warps = o->tiles_per_iter2 = o->small_teams = o->four_acc = -1;
     o->n_stationary = o->epi_pipeline = o->epi_split = o->fuse = -1;
     o->early_weights = -1;
+    o->tail_split = -1;
 }
 
 }  // namespace lbc
@@ -573,6 +574,7 @@ lbc_status lbc_conv_plan_describe(const lbc_plan* plan, char* buf, size_t buf_le
                  : (c.warp_store && c.team_warps == 4) ? (c.fold ? "narrow-warp-stores,bias-in-mma" : "narrow-warp-stores")
                  : c.warp_store ? (c.epi_split ? (c.fold ? "warp-stores,split,bias-in-mma" : "warp-stores,split")
                                                : (c.fold ? "warp-stores,bias-in-mma" : "warp-stores"))
+                 : c.tail_first >= 0 ? "2x8-warp-teams,tail-split"
                  : (c.epi_split && c.team_warps == 8) ? (c.fold ? "2x8-warp-teams,split,bias-in-mma" : "2x8-warp-teams,split")
                  : c.team_warps == 4 ? (c.fold ? "4x4-warp-teams,bias-in-mma" : "4x4-warp-teams")
                                      : (c.fold ? "2x8-warp-teams,bias-in-mma" : "2x8-warp-teams"));

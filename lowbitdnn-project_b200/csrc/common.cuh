@@ -119,6 +119,7 @@ struct IgemmConfig {
     size_t smem_bytes;
     uint32_t tmem_cols;  // power of two >= n_acc*bn
     int32_t n_acc;       // TMEM accumulator stages (2, 4 or 8)
+    int32_t tail_first, tail_count, tail_m0;   // split last round of a CTA-pair launch (IgemmParams::tail_first), -1 = off
     int32_t reverse;     // lbc_plan_options::reverse: walk the tiles last-to-first
     int32_t pdl;         // programmatic dependent launch allowed
 };

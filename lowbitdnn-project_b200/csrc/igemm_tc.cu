@@ -127,6 +127,12 @@ struct IgemmParams {
     uint32_t off_fold;
     int32_t rev_m;                // ring modes: > 0 = number of M tiles, visited in reverse order (see TileIter::m0)
     int32_t early_b;              // resident filter matrix: fetch it before griddepcontrol.wait (nothing in the stream writes it)
+    // Tail split (CTA pairs, ring modes, one 256-wide N tile, int8 out): when the pair-steps do not divide by the pairs
+    // (stage 3 of ResNet-50: 392 steps for 74 pairs), the R leftover steps of the last round are run as 2R half-steps of
+    // 128 columns on 2R pairs, so the round lasts half a tile.  The half-tiles are virtual tiles behind the real ones:
+    // tile index tail_first + c belongs to CTA c (c < tail_count = 4R) and means M tile tail_m0 + 2*(c/4) + (c&1),
+    // columns [128*((c/2)&1), +128).  tail_first < 0: off.
+    int32_t tail_first, tail_count, tail_m0;
     int32_t k_mod;                // bias/scale index = channel % k_mod (pixel-group rewrite replicates them), 0 = plain
     // smem carve-up (byte offsets from the 1024-aligned base)
     uint32_t off_b, off_stage, off_ctl;
@@ -619,8 +625,17 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
     // pair mode counts the padded tile space (dummy tiles of the padding image load zeros and store nothing)
-    const int32_t num_tiles = n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
+    const bool tail_on = CTA2 && !kWindow && prm.tail_first >= 0;       // see IgemmParams::tail_first
+    const int32_t num_tiles = tail_on ? prm.tail_first + prm.tail_count
+                              : n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
     const int32_t first_tile = pair_mode ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
+    // this CTA's half-tile of the split last round: first GEMM row (with the launch's traversal direction) and column half
+    int32_t tail_row0 = 0, tail_half = 0;
+    if (tail_on) {
+        const int32_t mt = prm.tail_m0 + 2 * (int32_t)(blockIdx.x >> 2) + (int32_t)(blockIdx.x & 1u);
+        tail_row0 = ((prm.rev_m > 0 && mt < prm.rev_m) ? prm.rev_m - 1 - mt : mt) * kBlockM;
+        tail_half = (int32_t)((blockIdx.x >> 1) & 1u);
+    }
 
     // The three issue roles below run with ALL 32 lanes of their warp executing the (warp-uniform) loops; only
     // the TMA / MMA / commit instructions themselves are predicated on one elected lane.  Keeping the loops
@@ -652,7 +667,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             bool ok = true;
             Iter it;
             for (it.init(prm, first_tile, n_major); it.tile < num_tiles && ok; it.next(prm)) {
-                const int32_t m0 = it.m0();
+                const bool tail = tail_on && it.tile >= prm.tail_first;
+                const int32_t m0 = tail ? tail_row0 : it.m0();
                 int32_t w_base = 0, h_base = 0, n0 = 0;
                 if (KM == A_IM2COL) {
                     const uint32_t um = (uint32_t)m0, uq = (uint32_t)prm.q, up = (uint32_t)prm.p;
@@ -663,7 +679,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     w_base = q0 * prm.stride_w - prm.pad_w;
                     h_base = p0 * prm.stride_h - prm.pad_h;
                 }
-                const int32_t brow = it.n_blk * prm.bn + brow_off;
+                // (a half-tile's MMA reads the first bn/4 rows of each CTA's B block: the box still brings bn/2, the rest is unused)
+                const int32_t brow = tail ? tail_half * (prm.bn >> 1) + (int32_t)cta_rank * (prm.bn >> 2) : it.n_blk * prm.bn + brow_off;
                 const uint32_t sub = (uint32_t)it.local & (uint32_t)(prm.n_mma - 1);
                 const uint32_t sub_base = sub * sub_len;
                 uint32_t stage = sub_base + (sub ? stage_o : stage_e), phase = sub ? phase_o : phase_e;
@@ -772,6 +789,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const uint32_t n_mma = (uint32_t)prm.n_mma;
         const uint32_t leader = ptx::elect_one() ? 1u : 0u;
         const uint32_t idesc = ptx::make_idesc_i8(CTA2 ? 2 * kBlockM : kBlockM, (uint32_t)prm.bn);
+        const uint32_t idesc_half = ptx::make_idesc_i8(CTA2 ? 2 * kBlockM : kBlockM, (uint32_t)prm.bn >> 1);
         const uint64_t db_base = ptx::make_kmajor_desc(ptx::smem_u32(smem_b), (uint32_t)prm.bkb);
         const uint64_t da_base = (KM != 3) ? ptx::make_kmajor_desc(ptx::smem_u32(smem_a), (uint32_t)prm.bkc)
                                            : ptx::make_kmajor_desc_nosw(ptx::smem_u32(smem_a), (uint32_t)prm.dil_w * 16u, 128u);
@@ -872,6 +890,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (leader) trace_ev(prm, tracing, local, EV_M_START);
             const uint32_t tmem_d = tmem_base + acc_stage * bn;
             uint32_t accumulate = 0;
+            const uint32_t idesc_t = (tail_on && tile >= prm.tail_first) ? idesc_half : idesc;     // split last round: N = bn / 2
             const uint32_t db_n = RESB ? db_lo + n_blk * b_tile16 : db_lo;
             if (MAYFOLD && fold) {      // D = ones-block x bias digits: the accumulator starts at the bias
                 ptx::mma_i8_ss_pred32(tmem_d, fa_lo, fa_hi, fb_lo + n_blk * fold_tile16, fb_hi, idesc, 0u, leader);
@@ -931,7 +950,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
                             for (int k = 0; k < KS; ++k) {
                                 const uint32_t a_lo = a_base + (uint32_t)prm.a_tab[kWindow ? j + k : k];
-                                mma_issue<CTA2>(tmem_d, a_lo, da_hi, b_lo + 2u * k, db_hi, idesc, accumulate, leader);
+                                mma_issue<CTA2>(tmem_d, a_lo, da_hi, b_lo + 2u * k, db_hi, idesc_t, accumulate, leader);
                                 accumulate = 1;
                             }
                             j += KS;
@@ -1261,8 +1280,11 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (; it.tile < num_tiles;) {
             // CTA-local tile index (it.local counts pairs / team steps / plain CTA steps)
             const int32_t tile = pair_mode ? 2 * it.local + (int32_t)team : split ? it.local : it.local * (int32_t)n_teams + (int32_t)team;
-            struct { int32_t n_blk, img, p0, q0, m0; } tc = {it.n_blk, it.image(), it.p0(prm), it.q0(prm), it.m0()};
-            const int32_t col0 = tc.n_blk * prm.bn;
+            const bool tail = tail_on && it.tile >= prm.tail_first;        // this CTA's half-tile of the split last round
+            struct { int32_t n_blk, img, p0, q0, m0; } tc = {tail ? 0x4000 + tail_half : it.n_blk, it.image(), it.p0(prm), it.q0(prm),
+                                                             tail ? tail_row0 : it.m0()};
+            const int32_t col0 = tail ? tail_half * (prm.bn >> 1) : tc.n_blk * prm.bn;
+            const int32_t n_panels_t = tail ? 1 : n_panels;                // a half-tile is one 128-byte panel
             // per-channel parameters of this N tile -> smem (only when the N tile changes)
             if (tc.n_blk != cur_nblk) {
                 ptx::named_bar_sync(bar_id, team_threads);       // everyone done with the previous parameters
@@ -1312,13 +1334,13 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const int32_t w_step = split ? (int32_t)n_teams * n_halves : n_halves;
                 EpiThread wt = et;
                 wt.valid = true;
-                for (int32_t pnl = w_first; pnl < n_panels; pnl += w_step) {
+                for (int32_t pnl = w_first; pnl < n_panels_t; pnl += w_step) {
                     const int32_t pbase = pnl * pcols;
                     const uint32_t wbuf = wbuf0 + sbuf * wbytes;
                     // (the wait for the buffer's last store to have read it out happens inside, before the first smem store)
                     epi_run<kFold>(true, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase, pbase + pcols, wt, wbuf, wrow_off, wswz,
                                   y32, -1, col0, nbufs >= 2 ? 2 : 1);
-                    if (pnl + w_step >= n_panels) {
+                    if (pnl + w_step >= n_panels_t) {
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -1338,7 +1360,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 }
                 if (issuer) trace_ev(prm, tracing, tile, EV_E_STORED);
             } else
-            for (int32_t pnl = p_first; pnl < n_panels; pnl += p_step) {
+            for (int32_t pnl = p_first; pnl < n_panels_t; pnl += p_step) {
                 const int32_t pbase = pnl * pcols + pbase0;
                 if (nbufs == 1 && int8_out) {
                     // a single staging panel (shared memory is tight): its previous store must have read it out
@@ -1348,7 +1370,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t staging_s = team_staging_s + sbuf * panel_smem;
                 epi_run<kFold>(int8_out, prm.relu != 0, kFold, prm, sc, bi, taddr, pbase, pbase + pc_begin, pbase + pc_end, et, staging_s,
                               row_off, swz_mask, y32, out_row, col0);
-                if (pnl + p_step >= n_panels) {
+                if (pnl + p_step >= n_panels_t) {
                     // accumulator drained: hand the TMEM stage back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
@@ -1378,7 +1400,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                 ptx::tma_store_2d_s(&tm_out, staging_s, cbyte, tc.m0);
                         }
                         ptx::tma_store_commit();
-                        if (pnl + p_step >= n_panels) trace_ev(prm, tracing, tile, EV_E_STORED);
+                        if (pnl + p_step >= n_panels_t) trace_ev(prm, tracing, tile, EV_E_STORED);
                     }
                     if (++sbuf == nbufs) sbuf = 0;
                 }
@@ -2170,6 +2192,18 @@ static lbc_status make_config_impl(const ConvGeom& g, const DeviceInfo& dev, con
     if (c.res_one) c.grid -= c.grid % c.tiles_n;      // >= tiles_n by the planner's check above
     c.reverse = o.reverse == 1 ? 1 : 0;
     c.pdl = o.pdl != 0 ? 1 : 0;
+    // ---- split last round (see IgemmParams::tail_first)
+    c.tail_first = -1; c.tail_count = 0; c.tail_m0 = 0;
+    if (c.cta2 && c.mode != A_WINDOW && c.tiles_n == 1 && c.bn == 256 && !c.res_b && !c.epi_split && !c.warp_store &&
+        d.out_mode == LBC_OUT_INT8 && o.tail_split != 0) {
+        const int pairs = c.grid / 2, steps = c.it_imgs / 2;           // (it_imgs: the M tiles, padded to an even count)
+        const int full = steps / pairs, rest = steps - full * pairs;
+        if (full >= 1 && rest > 0 && 2 * rest <= pairs) {
+            c.tail_first = full * c.grid;
+            c.tail_count = 4 * rest;
+            c.tail_m0 = 2 * full * pairs;
+        }
+    }
     *cfg = c;
     return LBC_OK;
 }
@@ -2332,6 +2366,7 @@ static void fill_params(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     // reversed traversal (IgemmLaunch::reverse, set by the network runner; lbc_plan_options::reverse for single layers)
     prm.rev_m = (l.reverse || c.reverse) ? (c.mode == A_WINDOW ? d.n : c.tiles_m) : 0;
     prm.early_b = (l.early_b && c.res_b && c.pdl) ? 1 : 0;
+    prm.tail_first = c.tail_first; prm.tail_count = c.tail_count; prm.tail_m0 = c.tail_m0;
     prm.trace = rt.trace; prm.trace_tiles = rt.trace_tiles;
     prm.flag = rt.flag;
     // TILED/IM2COL consume cblocks*inner ring blocks in [tap][chunk] order: present them to the MMA loop as one

@@ -342,6 +342,58 @@ def test_cta_pairs_with_resident_filter_halves(d):
     assert _check(d, options={"resident_filter": 2}) == "igemm_tc"
 
 
+# ---- split last round of a CTA-pair launch (r02): leftover pair-steps run as half-width tiles ------------------
+TAIL_SPLIT_CASES = [
+    # (layer, options): grid capped so that the pair-steps do not divide by the pairs; max_bn keeps the 256-wide tile
+    (D(n=5, h=16, w=16, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1), {"max_grid": 8}),          # 5 steps, 4 pairs
+    (D(n=5, h=16, w=16, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1), {"max_grid": 8, "reverse": 1}),
+    (D(n=7, h=14, w=14, c=1024, k=256, r=1, s=1), {"max_grid": 8}),                                   # tiled; 11 M tiles + padding twin
+    (D(n=3, h=33, w=33, c=256, k=256, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1), {"max_grid": 6}),
+    (D(n=15, h=16, w=16, c=512, k=256, r=1, s=1, relu=1), {"max_grid": 12}),                          # 15 steps, 6 pairs: 3 leftover
+]
+
+
+@pytest.mark.parametrize("case", TAIL_SPLIT_CASES, ids=lambda c: f"n{c[0].n}h{c[0].h}c{c[0].c}r{c[0].r}s{c[0].stride_h}g{c[1]['max_grid']}")
+def test_cta_pair_tail_split(case):
+    import lowbitdnn_project_b200 as lbc
+    d, opt = case
+    opt = {**opt, "max_bn": 256, "cta_pairs": 1}
+    plan = lbc.ConvPlan(lbc.ConvDesc(**d.__dict__), options=opt)
+    try:
+        assert "tail-split" in plan.describe(), plan.describe()
+    finally:
+        plan.close()
+    assert _check(d, options=opt) == "igemm_tc"
+    assert _check(d, options={**opt, "tail_split": 0}) == "igemm_tc"
+
+
+def test_tail_split_at_full_size_equals_the_unsplit_launch():
+    """ResNet-50 stage 3 at the benchmark batch (392 pair-steps on 74 pairs): the launch with the split last round writes
+    exactly the bytes of the launch without it."""
+    import torch
+    import lowbitdnn_project_b200 as lbc
+    dev = torch.device("cuda:0")
+    for d in (lbc.ConvDesc(n=512, h=14, w=14, c=256, k=256, r=3, s=3, pad_h=1, pad_w=1, relu=1),
+              lbc.ConvDesc(n=512, h=14, w=14, c=1024, k=256, r=1, s=1, relu=1)):
+        g = torch.Generator(device="cpu").manual_seed(7)
+        x = torch.randint(-128, 128, (d.n, d.h, d.w, d.c), dtype=torch.int8, generator=g).to(dev)
+        w = torch.randint(-127, 128, (d.k * d.r * d.s * d.c,), dtype=torch.int8, generator=g).to(dev)
+        bias = torch.randint(-30000, 30000, (d.k,), dtype=torch.int32, generator=g).to(dev)
+        scale = (torch.rand((d.k,), generator=g) * 1.5 + 0.5).mul(2.0**-7 / (d.r * d.s * d.c) ** 0.5).to(torch.float32).to(dev)
+        outs = []
+        for opt in ({"tail_split": 1}, {"tail_split": 0}, {"tail_split": 1, "reverse": 1}):
+            plan = lbc.ConvPlan(d, options=opt)
+            assert ("tail-split" in plan.describe()) == (opt["tail_split"] == 1), plan.describe()
+            y = plan.empty_output(dev)
+            plan.run(x, plan.prepack(w), bias, scale, out=y)
+            plan.run(x, plan.prepack(w), bias, scale, out=y)
+            torch.cuda.synchronize()
+            plan.check_status()
+            outs.append(y.clone())
+            plan.close()
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[2], outs[1])
+
+
 # ---- small-C tensor-core path (zero-pad + space-to-depth into 16-channel pixels) -------------------------
 STEM_CASES = [
     D(n=2, h=32, w=32, c=3, k=64, r=7, s=7, stride_h=2, stride_w=2, pad_h=3, pad_w=3, relu=1),    # ResNet stem
