@@ -2,7 +2,7 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > $O/r02g_pytest_gpu.log 2>&1; echo "all gpu tests rc=$? $(tail -1 $O/r02g_pytest_gpu.log)"
+echo "(gpu tests: run separately)"
 timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/r02g_smoke.log 2>&1; echo "smoke rc=$? $(tail -1 $O/r02g_smoke.log)"
 timeout 600 python bench.py --layer-report $O/r02g_layers_resnet50.json > $O/r02g_bench.json 2> $O/r02g_bench.err; echo "bench rc=$? $(cut -c1-160 $O/r02g_bench.json)"
 timeout 600 python bench.py --impl reference > $O/r02g_bench_reference.json 2> $O/r02g_bench_reference.err; echo "reference rc=$?"
