@@ -120,7 +120,7 @@ typedef struct lbc_plan_options {
     int32_t resident_kb;         /* largest filter matrix (KB) kept resident                                        */
     int32_t epi_split;           /* tri-state: both epilogue teams drain every tile (column split) on > 128-wide tiles */
     int32_t fuse;                /* networks: 1 = run conv(R x S -> 64) -> conv(1x1 -> 256) pairs as one fused launch (opt-in) */
-    int32_t early_weights;       /* networks: resident filter matrices are fetched before the programmatic-dependency wait  */
+    int32_t early_weights;       /* networks: filter blocks are fetched before the programmatic-dependency wait (2: resident matrices only) */
     int32_t tail_split;          /* CTA pairs: the leftover steps of the last round run as half-width tiles on twice the pairs */
     int32_t reserved[4];
 } lbc_plan_options;

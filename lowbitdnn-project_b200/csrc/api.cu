@@ -1023,7 +1023,7 @@ lbc_status net_resolve(lbc_net* net, int i, const int8_t* x_override)
     if (st == LBC_OK) {
         L.resolved = true;
         L.rl.ig.reverse = L.reverse ? 1 : 0;
-        L.rl.ig.early_b = L.plan->opt.early_weights != 0 ? 1 : 0;
+        L.rl.ig.early_b = L.plan->opt.early_weights == 2 ? 2 : L.plan->opt.early_weights != 0 ? 1 : 0;
         L.rl.dw.reverse = (L.reverse && L.rl.dw.tiled) ? 1 : 0;
     }
     return st;
@@ -1462,7 +1462,7 @@ lbc_status lbc_net_submit_host(lbc_net* net, const int8_t* x_host, void* y_host,
                 st = resolve(L.plan, (const int8_t*)pp.x_buf[b], L.w, L.bias, L.scale, L.y, &net->first_rl[b]);
                 if (st != LBC_OK) return st;
                 net->first_rl[b].ig.reverse = L.reverse ? 1 : 0;
-                net->first_rl[b].ig.early_b = L.plan->opt.early_weights != 0 ? 1 : 0;
+                net->first_rl[b].ig.early_b = L.plan->opt.early_weights == 2 ? 2 : L.plan->opt.early_weights != 0 ? 1 : 0;
                 net->first_rl[b].dw.reverse = (L.reverse && net->first_rl[b].dw.tiled) ? 1 : 0;
                 net->first_rl_ok[b] = true;
             }

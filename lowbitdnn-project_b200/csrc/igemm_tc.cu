@@ -593,6 +593,18 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     ptx::tc_fence_after();
     // Programmatic dependent launch: everything above is on-chip set-up (barriers, TMEM, descriptor prefetch) and may
     // overlap the tail of the previous kernel in the stream; from here on global memory is read and written.
+    const bool tail_on = CTA2 && !kWindow && prm.tail_first >= 0;       // see IgemmParams::tail_first
+    const int32_t num_tiles = tail_on ? prm.tail_first + prm.tail_count
+                              : n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
+    const int32_t first_tile = pair_mode ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
+    // this CTA's half-tile of the split last round: first GEMM row (with the launch's traversal direction) and column half
+    int32_t tail_row0 = 0, tail_half = 0;
+    if (tail_on) {
+        const int32_t mt = prm.tail_m0 + 2 * (int32_t)(blockIdx.x >> 2) + (int32_t)(blockIdx.x & 1u);
+        tail_row0 = ((prm.rev_m > 0 && mt < prm.rev_m) ? prm.rev_m - 1 - mt : mt) * kBlockM;
+        tail_half = (int32_t)((blockIdx.x >> 1) & 1u);
+    }
+
     // ... with one exception: a resident filter matrix that no kernel in the stream writes (IgemmLaunch::early_b, set by
     // the network runner, whose weights were uploaded long before) is fetched BEFORE the wait, so its 32-128 KB arrive
     // while the previous layer drains.
@@ -618,6 +630,33 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         __syncwarp();
     };
+    // The same for a STREAMED filter matrix: the B blocks of this CTA's first ring stages go out before the wait (the A
+    // blocks of those stages follow after it, onto the same transaction count), so the burst of first loads that all
+    // CTAs send to L2 at the moment of the release is only the A third of it.
+    constexpr bool kRingEarly = !(kWindow && RESB);
+    const int32_t ring_pre = (!RESB && kRingEarly && prm.early_b == 1)
+                                 ? min(prm.cblocks * prm.inner / prm.tps, prm.stages / prm.n_mma) : 0;
+    if (ring_pre > 0 && warp == 0 && first_tile < num_tiles) {
+        if (ptx::elect_one()) {
+            Iter it0;
+            it0.init(prm, first_tile, n_major);
+            const bool tail0 = tail_on && it0.tile >= prm.tail_first;
+            const int32_t brow = tail0 ? tail_half * (prm.bn >> 1) + (int32_t)cta_rank * (prm.bn >> 2)
+                                       : it0.n_blk * prm.bn + (CTA2 ? (int32_t)cta_rank * (prm.bn >> 1) : 0);
+            const uint32_t tx_all = (prm.b_stage_bytes + (kWindow ? 0u : prm.a_stage_bytes)) * (CTA2 ? 2u : 1u);
+            const uint32_t full0 = CTA2 ? ptx::mapa(ptx::smem_u32(&ctl->full[0]), 0) : 0u;
+            int32_t bcol = 0;
+            for (int32_t st = 0; st < ring_pre; ++st) {
+                if (cta_rank == 0) ptx::mbar_expect_tx(&ctl->full[st], tx_all);
+                uint8_t* dst_b = smem_b + (uint32_t)st * prm.b_stage_bytes;
+                for (int32_t t = 0; t < prm.tps; ++t, dst_b += prm.b_block_bytes, bcol += prm.bkb) {
+                    if (CTA2) ptx::tma_load_2d_2sm(dst_b, &tm_b, full0 + (uint32_t)st * 8u, bcol, brow);
+                    else ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[st], bcol, brow);
+                }
+            }
+        }
+        __syncwarp();
+    }
     if (RESB && prm.early_b && warp == 0) load_resident_b();
     if (LBC_TRACE && gt) gt[1] = (long long)ptx::globaltimer_ns();
     ptx::griddep_wait();
@@ -625,18 +664,6 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (LBC_TRACE && prm.trace != nullptr && threadIdx.x == 0) prm.trace[(size_t)prm.trace_tiles * 16 + 2 * blockIdx.x] = clock64();
     const uint32_t tmem_base = ctl->tmem_base;
     // pair mode counts the padded tile space (dummy tiles of the padding image load zeros and store nothing)
-    const bool tail_on = CTA2 && !kWindow && prm.tail_first >= 0;       // see IgemmParams::tail_first
-    const int32_t num_tiles = tail_on ? prm.tail_first + prm.tail_count
-                              : n_major ? prm.it_cols * prm.it_rows * prm.it_imgs * prm.tiles_n : prm.tiles_m * prm.tiles_n;
-    const int32_t first_tile = pair_mode ? 2 * (int32_t)blockIdx.x : (int32_t)blockIdx.x;
-    // this CTA's half-tile of the split last round: first GEMM row (with the launch's traversal direction) and column half
-    int32_t tail_row0 = 0, tail_half = 0;
-    if (tail_on) {
-        const int32_t mt = prm.tail_m0 + 2 * (int32_t)(blockIdx.x >> 2) + (int32_t)(blockIdx.x & 1u);
-        tail_row0 = ((prm.rev_m > 0 && mt < prm.rev_m) ? prm.rev_m - 1 - mt : mt) * kBlockM;
-        tail_half = (int32_t)((blockIdx.x >> 1) & 1u);
-    }
-
     // The three issue roles below run with ALL 32 lanes of their warp executing the (warp-uniform) loops; only
     // the TMA / MMA / commit instructions themselves are predicated on one elected lane.  Keeping the loops
     // convergent lets the compiler hold addresses and descriptors in uniform registers; a `lane == 0` branch
@@ -690,7 +717,8 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     ok = wait_or_quit(&ctl->empty[stage], phase ^ 1, tflag);
                     if (!ok) break;
                     if (st == 0 && leader) trace_ev(prm, tracing, it.local, EV_P_ISSUE);
-                    if (leader && cta_rank == 0) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
+                    const bool pre = it.local == 0 && st < ring_pre;      // B block and transaction count already out (above)
+                    if (!pre && leader && cta_rank == 0) ptx::mbar_expect_tx(&ctl->full[stage], tx_bytes);
                     uint8_t* dst_a = smem_a + stage * a_stage;
                     uint8_t* dst_b = smem_b + stage * b_stage;
                     for (int32_t t = 0; t < tps; ++t) {
@@ -701,7 +729,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                     ptx::tma_load_im2col_4d_2sm(dst_a, &tm_a, fbar, c0, w_base, h_base, n0, (uint16_t)off_w, (uint16_t)off_h);
                                 else if (KM == A_TILED)
                                     ptx::tma_load_2d_2sm(dst_a, &tm_a, fbar, c0, m0);
-                                if (!RESB) ptx::tma_load_2d_2sm(dst_b, &tm_b, fbar, bcol, brow);
+                                if (!RESB && !pre) ptx::tma_load_2d_2sm(dst_b, &tm_b, fbar, bcol, brow);
                             }
                         } else if (leader) {
                             if (KM == A_IM2COL)
@@ -709,7 +737,7 @@ igemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                                         (uint16_t)off_h);
                             else if (KM == A_TILED)
                                 ptx::tma_load_2d(dst_a, &tm_a, &ctl->full[stage], c0, m0);
-                            if (!RESB) ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
+                            if (!RESB && !pre) ptx::tma_load_2d(dst_b, &tm_b, &ctl->full[stage], bcol, brow);
                         }
                         dst_a += a_block;
                         dst_b += b_block;
@@ -2365,7 +2393,7 @@ static void fill_params(const ConvGeom& g, const IgemmLaunch& l, const EpilogueP
     prm.fold = c.fold; prm.off_fold = c.off_fold;
     // reversed traversal (IgemmLaunch::reverse, set by the network runner; lbc_plan_options::reverse for single layers)
     prm.rev_m = (l.reverse || c.reverse) ? (c.mode == A_WINDOW ? d.n : c.tiles_m) : 0;
-    prm.early_b = (l.early_b && c.res_b && c.pdl) ? 1 : 0;
+    prm.early_b = (l.early_b && c.pdl) ? l.early_b : 0;          // 2: resident matrices only (lbc_plan_options::early_weights = 2)
     prm.tail_first = c.tail_first; prm.tail_count = c.tail_count; prm.tail_m0 = c.tail_m0;
     prm.trace = rt.trace; prm.trace_tiles = rt.trace_tiles;
     prm.flag = rt.flag;

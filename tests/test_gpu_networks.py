@@ -156,8 +156,12 @@ def test_weights_replaced_between_runs_take_effect():
     layers = [l for l in lbc.networks.resnet50(2) if l[0].startswith(("l1.0", "l2.0")) and "downsample" not in l[0]]
     layers = [(n, d, (layers[i - 1][0] if i else None)) for i, (n, d, _) in enumerate(layers)]
     layers = [l for l in layers[:3]]                       # l1.0.conv1 -> conv2 -> conv3: all resident-filter layers
+    # ... and two layers that stream their filter matrix through the ring (256 -> 256 3x3 in CTA pairs, 256 -> 512 1x1)
+    CD = lbc.ConvDesc
+    layers += [("s.conv2", CD(n=2, h=56, w=56, c=256, k=256, r=3, s=3, stride_h=2, stride_w=2, pad_h=1, pad_w=1, relu=1), "l1.0.conv3"),
+               ("s.conv3", CD(n=2, h=28, w=28, c=256, k=512, r=1, s=1, relu=1), "s.conv2")]
     stream = torch.cuda.current_stream()
-    for options in (None, {"early_weights": 0}):
+    for options in (None, {"early_weights": 2}, {"early_weights": 0}):
         net = load_net(lbc, layers, options=options)
         for gen in range(3):
             if gen:
