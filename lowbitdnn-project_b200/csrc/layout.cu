@@ -115,6 +115,9 @@ template <int C, int SH, int SW>
 __global__ void __launch_bounds__(128) stem_xform_kernel(StemXformParams p, const int8_t* __restrict__ x,
                                                          uint4* __restrict__ out)
 {
+    // the convolution that follows is launched with programmatic stream serialisation: let its CTAs set up (and fetch their
+    // filter matrix) while this pass runs; its griddepcontrol.wait still orders every read of `out` after this grid
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int32_t ws = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
     if (ws >= p.ws) return;
     const int32_t hs0 = (int32_t)blockIdx.y * kXformRows, n = (int32_t)blockIdx.z;
