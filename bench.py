@@ -233,6 +233,12 @@ def reference_arm(args, layers):
     if not oracle.have_ref():
         emit_json({"impl": "reference", "unavailable": "oracle/_ref/libref_conv.so missing (built only where /root/reference exists)"})
         return
+    # all the host threads: torchrun exports OMP_NUM_THREADS=1 to every rank, and under it only rank 0 runs this arm
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception as e:  # noqa: BLE001
+        log("could not raise the OpenMP thread count:", e)
     b, ic, ih, iw, oc, oh, ow, kh, kw = REF_SAMPLE
     rng = np.random.default_rng(99)
     x = rng.integers(-128, 128, size=(b, ic, ih, iw), dtype=np.int8)
