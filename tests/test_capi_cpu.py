@@ -131,9 +131,9 @@ def test_planner_choices_on_resnet50(lbc):
         "l2.0.downsample": ["b=resident,n-stationary", "a=im2col", "tiles 3136x2"],                  # 256 -> 512, stride 2
         "l3.0.downsample": ["b=ring ", "a=im2col", "tiles 784x4"],                                   # 512 -> 1024: 128 KB tiles stream
         "l3.1.conv1": ["b=ring,cta-pair", "a=tiled"],                                                # 1024 -> 256: long K loop
-        "l3.1.conv2": ["b=ring,cta-pair", "a=im2col", "tile 128x256", "2x8-warp-teams"],             # wide 3x3 in pairs: im2col
+        "l3.1.conv2": ["b=ring,cta-pair", "a=im2col", "tile 128x256", "2x8-warp-teams,tail-split"],  # wide 3x3 in pairs: im2col; 392 steps on 74 pairs
         "l3.0.conv2": ["b=ring,cta-pair", "a=im2col"],                                               # stride 2
-        "l4.1.conv2": ["b=ring,cta-pair", "a=im2col"],
+        "l4.1.conv2": ["b=ring,cta-pair", "a=im2col", "2x8-warp-teams"],                             # two N tiles: no split last round
         "l4.0.conv3": ["b=ring ", "tiles 196x8", "2x8-warp-teams"],                                  # 512 -> 2048
     }
     for name, needles in expect.items():
